@@ -1,0 +1,540 @@
+"""Host-side mirror of GenParticleFilters.jl's exported API over libgenpf_cuda.so.
+
+Same names, argument meaning and error behaviour as the reference (file:line cited per
+function, relative to the reference root) so tests read like the reference's own.
+Two state types, as in BASELINE.json's north star:
+
+* ``ParticleFilterState``  -- arbitrary models: ``traces`` are host objects (anything with the
+  small generative-function protocol below); only ``log_weights`` and ancestor indices go to
+  the GPU and traces are gathered on the host (``new_traces .= view(traces, parents)``).
+* ``DevicePFState``        -- models registered as device plugins (``DeviceModel("object_motion")``,
+  ``DeviceModel("lingauss1d")``): state lives in HBM, every call is a CUDA kernel sequence.
+
+Python indices are 0-based (``parents``); the C ABI writes 1-based for Julia on request.
+The host-model protocol (stand-in for Gen's GFI, reference SURVEY 8b):
+  model.generate(args, observations) -> (trace, log_weight)
+  trace.update(new_args, argdiffs, observations) -> (new_trace, log_weight_increment, retdiff, discard)
+  kern(trace, *kern_args, **kwargs) -> (trace, accepted)            (move-accept)
+  kern(trace, *kern_args, **kwargs) -> (trace, rel_log_weight)      (move-reweight)
+  trace[addr] -> value
+"""
+import ctypes as C
+import logging
+import math
+import warnings
+
+import numpy as np
+
+from . import _lib as L
+
+log = logging.getLogger("genpf")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------- states
+class ParticleFilterState:
+    """Gen.ParticleFilterState restricted to what this path touches (initialize.jl:4-10,42-43)."""
+
+    def __init__(self, traces, log_weights=None, log_ml_est=0.0):
+        n = len(traces)
+        self.traces = list(traces)
+        self.new_traces = [None] * n
+        self.log_weights = np.zeros(n) if log_weights is None else _f64(log_weights).copy()
+        self.log_ml_est = float(log_ml_est)
+        self.parents = np.arange(n, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.traces)
+
+    def __getitem__(self, idxs):  # view.jl:35-48
+        return ParticleFilterSubState(self, idxs)
+
+
+class ParticleFilterSubState:
+    """ParticleFilterSubState (view.jl:16-22): a view on a subset of particles of `source`."""
+
+    def __init__(self, source, idxs):
+        n = len(source.traces)
+        if isinstance(idxs, slice):
+            idxs = np.arange(n)[idxs]
+        self.idxs = np.asarray(idxs, dtype=np.int64)
+        self.source = source
+
+    def __len__(self):
+        return len(self.idxs)
+
+    @property
+    def traces(self):
+        return [self.source.traces[i] for i in self.idxs]
+
+    @property
+    def log_weights(self):
+        return self.source.log_weights[self.idxs]
+
+    @property
+    def parents(self):
+        return self.source.parents[self.idxs]
+
+
+class DeviceModel:
+    """A model registered as a device plugin of libgenpf_cuda.so (include/genpf.h)."""
+
+    def __init__(self, name, params=None):
+        lib = L.load()
+        mid = C.c_int32()
+        L.check(lib.genpf_model_builtin(name.encode(), C.byref(mid)))
+        self.name, self.model_id = name, mid.value
+        nf, nb, npar, naux = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(lib.genpf_model_info(mid, C.byref(nf), C.byref(nb), C.byref(npar), C.byref(naux)))
+        self.n_f64, self.n_u8, self.n_params, self.n_aux = nf.value, nb.value, npar.value, naux.value
+        self.params = None if params is None else _f64(params)
+        self.fields = {"object_motion": {"y": 0, "moving": 1}, "lingauss1d": {"x": 0}}[name]
+
+    def aux(self, t):
+        # object_motion: vel_y = sin(t) with integer t in radians, computed by the caller (README.md:48)
+        return _f64([math.sin(float(t))]) if self.name == "object_motion" else None
+
+
+class DevicePFState:
+    """Device-resident population (n_filters independent filters of n_particles)."""
+
+    def __init__(self, model, n_particles, n_filters=1, seed=0, keep_history=False, noise="lean"):
+        lib = L.load()
+        self.model = model
+        flags = (L.KEEP_HISTORY if keep_history else 0) | (L.NOISE_PHILOX53 if noise == "philox53" else 0)
+        h = C.c_void_p()
+        L.check(lib.genpf_filter_create(model.model_id, L.ptr(model.params),
+                                        0 if model.params is None else len(model.params), n_particles, n_filters,
+                                        seed, flags, C.byref(h)))
+        self._h = h
+        self.n_filters = n_filters
+        self.t = 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                L.load().genpf_filter_destroy(h)
+            except Exception:
+                pass
+
+    def __len__(self):
+        n, f = C.c_int64(), C.c_int64()
+        L.check(L.load().genpf_filter_size(self._h, C.byref(n), C.byref(f)))
+        return n.value
+
+    def _obs(self, obs):
+        o = _f64(np.atleast_1d(obs))
+        if o.size != self.n_filters:
+            raise ValueError("need one observation per filter")
+        return o
+
+    # accessors
+    @property
+    def log_weights(self):
+        out = np.empty(len(self) * self.n_filters)
+        L.check(L.load().genpf_get_log_weights(self._h, L.ptr(out)))
+        return out
+
+    @log_weights.setter
+    def log_weights(self, v):
+        v = _f64(v)
+        assert v.size == len(self) * self.n_filters
+        L.check(L.load().genpf_set_log_weights(self._h, L.ptr(v)))
+
+    @property
+    def parents(self):
+        out = np.empty(len(self) * self.n_filters, dtype=np.int64)
+        L.check(L.load().genpf_get_parents(self._h, L.ptr(out), 0))
+        return out
+
+    @property
+    def log_ml_est(self):
+        return log_ml_estimate(self) - (logsumexp_host(self.log_weights) - math.log(len(self))) \
+            if self.n_filters == 1 else None
+
+    def field(self, name_or_idx, t=None):
+        f = self.model.fields[name_or_idx] if isinstance(name_or_idx, str) else name_or_idx
+        out = np.empty(len(self) * self.n_filters)
+        L.check(L.load().genpf_get_field(self._h, f, self.t if t is None else t, L.ptr(out)))
+        return out
+
+    def set_field(self, name_or_idx, t, values):
+        f = self.model.fields[name_or_idx] if isinstance(name_or_idx, str) else name_or_idx
+        v = _f64(values)
+        L.check(L.load().genpf_set_field(self._h, f, t, L.ptr(v)))
+
+    @property
+    def accepts(self):
+        out = np.empty(len(self) * self.n_filters, dtype=np.uint8)
+        L.check(L.load().genpf_get_accepts(self._h, L.ptr(out)))
+        return out.astype(bool)
+
+    def sync(self):
+        L.check(L.load().genpf_filter_sync(self._h))
+
+
+def logsumexp_host(v):
+    """Gen.logsumexp on the GPU (C ABI genpf_logsumexp)."""
+    v = _f64(v)
+    out = C.c_double()
+    L.check(L.load().genpf_logsumexp(L.ptr(v), v.size, 0, C.byref(out)))
+    return out.value
+
+
+# --------------------------------------------------------------------------- utils.jl
+def get_log_norm_weights(state):
+    """utils.jl:148"""
+    lw = _f64(state.log_weights)
+    out = np.empty_like(lw)
+    L.check(L.load().genpf_normalize(L.ptr(lw), lw.size, 0, L.ptr(out), None, None, None, None))
+    return out
+
+
+def get_norm_weights(state):
+    """utils.jl:156"""
+    lw = _f64(state.log_weights)
+    out = np.empty_like(lw)
+    L.check(L.load().genpf_normalize(L.ptr(lw), lw.size, 0, None, L.ptr(out), None, None, None))
+    return out
+
+
+def effective_sample_size(state):
+    """utils.jl:163-164 (per filter for a batched device state)."""
+    if isinstance(state, DevicePFState):
+        out = np.empty(state.n_filters)
+        L.check(L.load().genpf_ess_dev(state._h, L.ptr(out)))
+        return out[0] if state.n_filters == 1 else out
+    lw = _f64(state.log_weights)
+    out = C.c_double()
+    L.check(L.load().genpf_ess(L.ptr(lw), lw.size, 0, C.byref(out)))
+    return out.value
+
+
+get_ess = effective_sample_size  # utils.jl:171
+
+
+def log_ml_estimate(state):
+    """Gen.log_ml_estimate; sub-states use the source's estimate (utils.jl:174-178)."""
+    if isinstance(state, DevicePFState):
+        out = np.empty(state.n_filters)
+        L.check(L.load().genpf_lml_dev(state._h, L.ptr(out)))
+        return out[0] if state.n_filters == 1 else out
+    base = state.source.log_ml_est if isinstance(state, ParticleFilterSubState) else state.log_ml_est
+    return base + logsumexp_host(state.log_weights) - math.log(len(state))
+
+
+get_lml_est = log_ml_estimate  # utils.jl:186
+
+
+# --------------------------------------------------------------------------- initialize.jl / update.jl
+def pf_initialize(model, model_args, observations, n_particles, **kw):
+    """initialize.jl:31-44.  Device models: observations = y_obs_1 (one per filter)."""
+    if isinstance(model, DeviceModel):
+        state = DevicePFState(model, n_particles, **kw)
+        L.check(L.load().genpf_initialize(state._h, L.ptr(state._obs(observations)), L.ptr(model.aux(1))))
+        state.t = 1
+        return state
+    traces, lws = [], np.empty(n_particles)
+    for i in range(n_particles):
+        tr, w = model.generate(model_args, observations)
+        traces.append(tr)
+        lws[i] = w
+    return ParticleFilterState(traces, lws)
+
+
+def pf_update(state, new_args, argdiffs, observations):
+    """pf_update!, update.jl:12-25."""
+    if isinstance(state, DevicePFState):
+        t = int(new_args[0])
+        L.check(L.load().genpf_update(state._h, t, L.ptr(state._obs(observations)), L.ptr(state.model.aux(t))))
+        state.t = t
+        return state
+    src, idxs = _resolve(state)
+    for i in idxs:
+        new_tr, incr, _, discard = src.traces[i].update(new_args, argdiffs, observations)
+        if discard:
+            raise GenPFErrorException(f"Choices were updated or deleted: {discard}")  # update.jl:18-20
+        src.new_traces[i] = new_tr
+        src.log_weights[i] += incr
+    _update_refs(state)
+    return state
+
+
+class GenPFErrorException(RuntimeError):
+    """Julia's ErrorException (error(...)) on this path."""
+
+
+def _resolve(state):
+    if isinstance(state, ParticleFilterSubState):
+        return state.source, state.idxs
+    return state, np.arange(len(state.traces))
+
+
+def _update_refs(state):
+    """update_refs!, utils.jl:10-20: swap for a full state, copy-back for a view."""
+    if isinstance(state, ParticleFilterSubState):
+        for i in state.idxs:
+            state.source.traces[i] = state.source.new_traces[i]
+    else:
+        state.traces, state.new_traces = state.new_traces, state.traces
+
+
+# --------------------------------------------------------------------------- resample.jl / resize.jl
+def _emit_check(kind, check):
+    if kind == L.VALID:
+        return
+    if check is True:
+        raise GenPFErrorException("Invalid weights.")  # resample.jl:55,92,151
+    if check == "warn":
+        warnings.warn(L.WARNINGS[kind])  # utils.jl:120,124,132,135
+
+
+def pf_resample(state, method="multinomial", *, priority_fn=None, check="warn", sort_particles=True,
+                uniforms=None, seed=0, n_out=None):
+    """pf_resample!, resample.jl:19-30 (dispatch), 48-65 / 85-120 / 143-175.
+
+    `uniforms` (optional) are the reference RNG's draws exported per output slot / stratum; without
+    them the library draws Philox4x32-10(seed) on the device.
+    """
+    if method not in L.METHODS:
+        raise GenPFErrorException(f"Resampling method {method} not recognized.")  # resample.jl:28
+    m = L.METHODS[method]
+    lib = L.load()
+    flags = L.SORT_PARTICLES if (method == "stratified" and sort_particles) else 0
+    if isinstance(state, DevicePFState):
+        kinds = np.zeros(state.n_filters, dtype=np.int32)
+        prio_kind, prio_param, prio_col = L.PRIO_NONE, 1.0, None
+        if priority_fn is not None:
+            if isinstance(priority_fn, (int, float)):
+                prio_kind, prio_param = L.PRIO_SCALE, float(priority_fn)  # w -> alpha*w
+            else:
+                prio_kind, prio_col = L.PRIO_COLUMN, _f64(priority_fn(state.log_weights))
+        u = None if uniforms is None else _f64(uniforms)
+        st = lib.genpf_resample_dev(state._h, m, prio_kind, prio_param, L.ptr(prio_col),
+                                    0 if n_out is None else n_out, flags | (L.CHECK if check is True else 0),
+                                    L.ptr(u), L.ptr(kinds))
+        if st == L.ERR_INVALID_WEIGHTS:
+            raise GenPFErrorException("Invalid weights.")
+        L.check(st)
+        for k in kinds:
+            _emit_check(int(k), check)
+        return state
+    src, idxs = _resolve(state)
+    sub = isinstance(state, ParticleFilterSubState)
+    n_in = len(idxs)
+    n_out = n_in if n_out is None else int(n_out)
+    lw = _f64(src.log_weights[idxs])
+    lp = None if priority_fn is None else _f64(priority_fn(lw))
+    u = None if uniforms is None else _f64(uniforms)
+    parents = np.empty(n_out, dtype=np.int64)
+    lw_out = np.empty(n_out)
+    lml_inc, kind = C.c_double(), C.c_int32()
+    st = lib.genpf_resample(m, L.ptr(lw), L.ptr(lp), n_in, n_out, L.ptr(u), seed,
+                            flags | (L.SUBSTATE if sub else 0) | (L.CHECK if check is True else 0),
+                            L.ptr(parents), L.ptr(lw_out), C.byref(lml_inc), C.byref(kind))
+    if st == L.ERR_INVALID_WEIGHTS:
+        raise GenPFErrorException("Invalid weights.")
+    L.check(st)
+    _emit_check(kind.value, check)
+    if kind.value in (L.INV_NAN_INPUT, L.INV_NAN_TOTAL):
+        # the reference crashes inside Categorical/floor(Int, NaN) here
+        raise GenPFErrorException("NaN weights: cannot resample.")
+    if sub:
+        # local parents -> positions of the view; traces copied back in place (utils.jl:17-20)
+        new = [src.traces[idxs[p]] for p in parents]
+        for j, i in enumerate(idxs):
+            src.new_traces[i] = new[j]
+            src.traces[i] = new[j]
+        src.parents[idxs] = parents
+        src.log_weights[idxs] = lw_out
+    else:
+        src.log_ml_est += lml_inc.value  # update_lml_est!, resample.jl:178-182
+        src.new_traces = [src.traces[p] for p in parents]  # new_traces .= view(traces, parents)
+        src.parents = parents
+        src.log_weights = lw_out
+        src.traces, src.new_traces = src.new_traces, [None] * n_out  # update_refs! (+ resize.jl:441-449)
+    return state
+
+
+def pf_multinomial_resample(state, **kw):
+    return pf_resample(state, "multinomial", **kw)
+
+
+def pf_residual_resample(state, **kw):
+    return pf_resample(state, "residual", **kw)
+
+
+def pf_stratified_resample(state, **kw):
+    return pf_resample(state, "stratified", **kw)
+
+
+def pf_resize(state, n_particles, method="multinomial", **kw):
+    """pf_resize!, resize.jl:16-27 (:multinomial 46-67, :residual 87-124)."""
+    if method == "optimal":
+        raise GenPFErrorException("pf_optimal_resize! is outside the accelerated path (SURVEY 8f)")
+    if method not in ("multinomial", "residual"):
+        raise GenPFErrorException(f"Resampling method {method} not recognized.")  # resize.jl:25
+    if isinstance(state, ParticleFilterSubState):
+        raise TypeError("pf_resize! takes a full ParticleFilterState")
+    return pf_resample(state, method, n_out=n_particles, **kw)
+
+
+def pf_multinomial_resize(state, n_particles, **kw):
+    return pf_resize(state, n_particles, "multinomial", **kw)
+
+
+def pf_residual_resize(state, n_particles, **kw):
+    return pf_resize(state, n_particles, "residual", **kw)
+
+
+def pf_replicate(state, n_replicates, *, layout="contiguous"):
+    """pf_replicate!, resize.jl:236-244."""
+    lay = L.LAYOUT_CONTIGUOUS if layout == "contiguous" else L.LAYOUT_INTERLEAVED
+    if isinstance(state, DevicePFState):
+        L.check(L.load().genpf_replicate(state._h, n_replicates, lay))
+        return state
+    n = len(state.traces)
+    lw = _f64(state.log_weights)
+    parents = np.empty(n * n_replicates, dtype=np.int64)
+    lw_out = np.empty(n * n_replicates)
+    L.check(L.load().genpf_replicate_host(L.ptr(lw), n, n_replicates, lay, 0, L.ptr(parents), L.ptr(lw_out)))
+    _apply_resize(state, parents, lw_out)
+    return state
+
+
+def pf_dereplicate(state, n_replicates, *, layout="contiguous", method="keepfirst", uniforms=None, seed=0):
+    """pf_dereplicate!, resize.jl:267-297."""
+    lay = L.LAYOUT_CONTIGUOUS if layout == "contiguous" else L.LAYOUT_INTERLEAVED
+    meth = L.KEEPFIRST if method == "keepfirst" else L.SAMPLE
+    u = None if uniforms is None else _f64(uniforms)
+    if isinstance(state, DevicePFState):
+        L.check(L.load().genpf_dereplicate(state._h, n_replicates, lay, meth, L.ptr(u)))
+        return state
+    n = len(state.traces)
+    assert n % n_replicates == 0  # resize.jl:270
+    lw = _f64(state.log_weights)
+    parents = np.empty(n // n_replicates, dtype=np.int64)
+    lw_out = np.empty(n // n_replicates)
+    L.check(L.load().genpf_dereplicate_host(L.ptr(lw), n, n_replicates, lay, meth, L.ptr(u), seed, 0,
+                                            L.ptr(parents), L.ptr(lw_out)))
+    _apply_resize(state, parents, lw_out)
+    return state
+
+
+def pf_coalesce(state, *, by=None):
+    """pf_coalesce!, resize.jl:309-334.  `by(trace)` must return something hashable."""
+    if isinstance(state, DevicePFState):
+        n_new = C.c_int64()
+        L.check(L.load().genpf_coalesce(state._h, C.byref(n_new)))
+        return state
+    if not state.traces:
+        return state
+    vals = [tr if by is None else by(tr) for tr in state.traces]
+    codes = {}
+    keys = np.array([codes.setdefault(v, len(codes)) for v in vals], dtype=np.int64)
+    n = len(keys)
+    lw = _f64(state.log_weights)
+    parents = np.empty(n, dtype=np.int64)
+    lw_out = np.empty(n)
+    n_new = C.c_int64()
+    L.check(L.load().genpf_coalesce_host(L.ptr(lw), L.ptr(keys), n, 0, L.ptr(parents), L.ptr(lw_out), C.byref(n_new)))
+    _apply_resize(state, parents[: n_new.value].copy(), lw_out[: n_new.value].copy())
+    return state
+
+
+def _apply_resize(state, parents, lw_out):
+    state.new_traces = [state.traces[p] for p in parents]
+    state.parents = parents
+    state.log_weights = lw_out
+    state.traces, state.new_traces = state.new_traces, [None] * len(parents)
+
+
+# --------------------------------------------------------------------------- rejuvenate.jl
+def pf_rejuvenate(state, kern, kern_args=(), n_iters=1, *, method="move", **kwargs):
+    """pf_rejuvenate!, rejuvenate.jl:18-27."""
+    if method == "move":
+        return pf_move_accept(state, kern, kern_args, n_iters, **kwargs)
+    if method == "reweight":
+        return pf_move_reweight(state, kern, kern_args, n_iters, **kwargs)
+    raise GenPFErrorException(f"Method {method} not recognized.")  # rejuvenate.jl:25
+
+
+def mh(*a, **k):
+    """Marker for Gen.mh on a device state: pf_rejuvenate(state, mh, (tau, obs_tau))."""
+    raise TypeError("mh is only a marker for device states")
+
+
+def pf_move_accept(state, kern, kern_args=(), n_iters=1, **kwargs):
+    """pf_move_accept!, rejuvenate.jl:40-53."""
+    if isinstance(state, DevicePFState):
+        if kern is not mh:
+            raise TypeError("device states rejuvenate with the built-in mh kernel")
+        tau, obs = kern_args
+        acc = np.zeros(state.n_filters, dtype=np.int64)
+        L.check(L.load().genpf_rejuvenate_mh(state._h, int(tau), L.ptr(state._obs(obs)),
+                                             L.ptr(state.model.aux(tau)), n_iters, L.ptr(acc)))
+        state.last_n_accept = acc
+        return state
+    src, idxs = _resolve(state)
+    for i in idxs:
+        trace = src.traces[i]
+        for _ in range(n_iters):
+            trace, accept = kern(trace, *kern_args, **kwargs)
+            log.debug("Accepted: %s", accept)  # rejuvenate.jl:47
+        src.new_traces[i] = trace
+    _update_refs(state)
+    return state
+
+
+def pf_move_reweight(state, kern, kern_args=(), n_iters=1, **kwargs):
+    """pf_move_reweight!, rejuvenate.jl:74-90 (host kernels only)."""
+    src, idxs = _resolve(state)
+    for i in idxs:
+        trace = src.traces[i]
+        for _ in range(n_iters):
+            trace, rel_weight = kern(trace, *kern_args, **kwargs)
+            src.log_weights[i] += rel_weight
+            log.debug("Rel. Weight: %s", rel_weight)  # rejuvenate.jl:83
+        src.new_traces[i] = trace
+    _update_refs(state)
+    return state
+
+
+# --------------------------------------------------------------------------- statistics.jl
+def _mean_var(state, addr):
+    lib = L.load()
+    if isinstance(state, DevicePFState):
+        tau, name = addr  # (t, :field), like `5 => :moving`
+        m, v = np.empty(state.n_filters), np.empty(state.n_filters)
+        L.check(lib.genpf_mean_var(state._h, state.model.fields[name], int(tau), L.ptr(m), L.ptr(v)))
+        return (m[0], v[0]) if state.n_filters == 1 else (m, v)
+    lw = _f64(state.log_weights)
+    x = _f64([tr[addr] for tr in state.traces])
+    m, v = C.c_double(), C.c_double()
+    L.check(lib.genpf_weighted_mean_var(L.ptr(lw), L.ptr(x), lw.size, 0, C.byref(m), C.byref(v)))
+    return m.value, v.value
+
+
+def mean(state, addr):
+    """Statistics.mean(state, addr), statistics.jl:13-14."""
+    return _mean_var(state, addr)[0]
+
+
+def var(state, addr):
+    """Statistics.var(state, addr), statistics.jl:48-50 (uncorrected, two-pass)."""
+    return _mean_var(state, addr)[1]
+
+
+def pf_step(state, t, obs_prev, obs_t, *, method="stratified", ess_thresh=0.5, mh_iters=1, return_ess=True):
+    """One iteration of the README loop (README.md:66-77) in a single C-ABI call on a device state."""
+    m = state.model
+    ess = np.empty(state.n_filters) if return_ess else None
+    L.check(L.load().genpf_step(state._h, int(t), L.ptr(state._obs(obs_prev)), L.ptr(m.aux(t - 1)),
+                                L.ptr(state._obs(obs_t)), L.ptr(m.aux(t)), L.METHODS[method], float(ess_thresh),
+                                int(mh_iters), L.ptr(ess)))
+    state.t = int(t)
+    return ess

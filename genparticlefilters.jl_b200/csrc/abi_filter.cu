@@ -1,0 +1,867 @@
+// abi_filter.cu -- C ABI, device-resident path: particle state lives in HBM as struct-of-arrays columns
+// and pf_initialize / pf_update! / pf_resample! / pf_rejuvenate! / mean / var / resizing all run as CUDA
+// kernels on the filter's stream.  See include/genpf.h for the reference function each call replaces.
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "coalesce.cuh"
+#include "engine.cuh"
+
+namespace genpf {
+
+enum { kModelObjectMotion = 0, kModelLinGauss1D = 1, kNumModels = 2 };
+
+struct ModelInfo {
+    const char *name;
+    int nf, nb, np, naux;
+};
+static const ModelInfo kModels[kNumModels] = {
+    {"object_motion", ObjectMotion::NF, ObjectMotion::NB, ObjectMotion::NP, ObjectMotion::NAUX},
+    {"lingauss1d", LinGauss1D::NF, LinGauss1D::NB, LinGauss1D::NP, LinGauss1D::NAUX},
+};
+
+struct Slab {  // one time slice's columns in one buffer
+    Cols c;
+};
+
+struct HistSlice {  // a frozen slice (GENPF_KEEP_HISTORY): columns in the particle order of generation `gen`
+    int64_t tau;
+    Cols c;
+    int64_t n;
+    int64_t gen;
+};
+struct ParentLog {  // ancestry of resample number `gen` (1-based): population gen-1 -> gen
+    int32_t *parents;
+    int64_t n_prev, n_cur;
+};
+
+}  // namespace genpf
+
+using namespace genpf;
+
+struct genpf_filter_s {
+    int model = 0;
+    int NF = 0, NB = 0;
+    int64_t n = 0, nf = 0;
+    uint64_t seed = 0;
+    uint32_t flags = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ModelParams P{};
+    int64_t t_cur = 0;
+    int64_t n_resamples = 0;
+    int64_t rng_offset = 0;
+    Cols win[2][2];  // [buffer][slot parity]
+    int buf = 0;
+    double *lw = nullptr, *lw_alt = nullptr;
+    int32_t *parents = nullptr;
+    uint8_t *accepts = nullptr;
+    unsigned long long *n_accept = nullptr;
+    double *lml = nullptr;
+    double *obs_dev = nullptr;
+    double *noise_cols[3] = {nullptr, nullptr, nullptr};
+    DevBuf noise_buf[3], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf;
+    CoalesceBufs cb;
+    Scratch sc;
+    bool part_valid = false;
+    std::vector<HistSlice> hist;
+    std::vector<ParentLog> plog;
+    std::vector<void *> owned;
+    double *h_pinned = nullptr;  // pinned scratch: max(nf,16) doubles * 4
+    Stats *h_stats = nullptr;
+
+    template <typename T>
+    int32_t dalloc(T **p, size_t count) {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GENPF_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+        owned.push_back(q);
+        *p = reinterpret_cast<T *>(q);
+        return GENPF_OK;
+    }
+    void dfree(void *q) {
+        for (auto &o : owned)
+            if (o == q) {
+                cudaFree(q);
+                o = nullptr;
+            }
+    }
+    int32_t alloc_cols(Cols &c, int64_t total) {
+        memset(&c, 0, sizeof(c));
+        for (int i = 0; i < NF; ++i) GENPF_TRY(dalloc(&c.f[i], (size_t)total));
+        for (int i = 0; i < NB; ++i) GENPF_TRY(dalloc(&c.b[i], (size_t)total));
+        return GENPF_OK;
+    }
+    void free_cols(Cols &c) {
+        for (int i = 0; i < NF; ++i) dfree(c.f[i]);
+        for (int i = 0; i < NB; ++i) dfree(c.b[i]);
+        memset(&c, 0, sizeof(c));
+    }
+    int32_t alloc_population(int64_t n_new) {
+        const int64_t total = n_new * nf;
+        for (int b = 0; b < 2; ++b)
+            for (int sl = 0; sl < 2; ++sl) GENPF_TRY(alloc_cols(win[b][sl], total));
+        GENPF_TRY(dalloc(&lw, (size_t)total));
+        GENPF_TRY(dalloc(&lw_alt, (size_t)total));
+        GENPF_TRY(dalloc(&parents, (size_t)total));
+        GENPF_TRY(dalloc(&accepts, (size_t)total));
+        GENPF_TRY(sc.ensure(n_new, nf));
+        return GENPF_OK;
+    }
+    void free_population() {
+        for (int b = 0; b < 2; ++b)
+            for (int sl = 0; sl < 2; ++sl) free_cols(win[b][sl]);
+        dfree(lw); dfree(lw_alt); dfree(parents); dfree(accepts);
+        lw = lw_alt = nullptr; parents = nullptr; accepts = nullptr;
+    }
+    Cols &slice(int64_t tau) { return win[buf][tau & 1]; }
+    Cols &slice_alt(int64_t tau) { return win[buf ^ 1][tau & 1]; }
+};
+
+namespace genpf {
+
+static int32_t check_filter(genpf_filter_t pf) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    GENPF_CUDA_TRY(cudaSetDevice(pf->device));
+    return GENPF_OK;
+}
+
+static int32_t set_obs(genpf_filter_t pf, const double *obs, const double *aux, const double **obs_dev,
+                       double *obs_val) {
+    const ModelInfo &mi = kModels[pf->model];
+    if (!obs) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
+    if (mi.naux > 0 && !aux) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL but the model needs per-step scalars");
+    for (int i = 0; i < mi.naux; ++i) pf->P.aux[i] = aux[i];
+    if (pf->nf == 1) {
+        *obs_dev = nullptr;
+        *obs_val = obs[0];
+    } else {
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->obs_dev, obs, (size_t)pf->nf * 8, cudaMemcpyHostToDevice, pf->stream));
+        *obs_dev = pf->obs_dev;
+        *obs_val = 0.0;
+    }
+    return GENPF_OK;
+}
+
+static int32_t stage_noise(genpf_filter_t pf, int which, const double *host, const double **dev) {
+    if (!host) {
+        *dev = nullptr;
+        return GENPF_OK;
+    }
+    const size_t bytes = (size_t)(pf->n * pf->nf) * 8;
+    GENPF_TRY(pf->noise_buf[which].ensure(bytes));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->noise_buf[which].p, host, bytes, cudaMemcpyHostToDevice, pf->stream));
+    *dev = pf->noise_buf[which].as<double>();
+    return GENPF_OK;
+}
+
+template <class Model, class Noise>
+static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
+                                Noise noise) {
+    const int64_t tpf = ceil_div(pf->n, kTile);
+    const unsigned grid = (unsigned)(tpf * pf->nf);
+    if (init) {
+        GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
+                     pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
+    } else {
+        GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kThreads, pf->stream, pf->P, t, pf->slice(t - 1),
+                     pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
+    }
+    return GENPF_OK;
+}
+template <class Model>
+static int32_t propagate_model(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
+                               const double *U, const double *Z) {
+    if (U || Z) {
+        NoiseCols nz{U, Z, nullptr};
+        return launch_propagate<Model, NoiseCols>(pf, init, t, obs_dev, obs_val, nz);
+    }
+    const uint64_t stream_id = make_stream(kPurposeUpdate, (uint64_t)t);
+    if (pf->flags & GENPF_NOISE_PHILOX53) {
+        NoisePhilox53 nz{pf->seed, stream_id, pf->rng_offset};
+        return launch_propagate<Model, NoisePhilox53>(pf, init, t, obs_dev, obs_val, nz);
+    }
+    NoiseLean nz{pf->seed, stream_id, pf->rng_offset};
+    return launch_propagate<Model, NoiseLean>(pf, init, t, obs_dev, obs_val, nz);
+}
+
+// freeze the slice that is about to leave the 2-slot window (GENPF_KEEP_HISTORY)
+static int32_t archive_slice(genpf_filter_t pf, int64_t tau) {
+    if (!(pf->flags & GENPF_KEEP_HISTORY) || tau < 1) return GENPF_OK;
+    HistSlice h;
+    h.tau = tau;
+    h.n = pf->n;
+    h.gen = pf->n_resamples;
+    h.c = pf->slice(tau);  // steal the columns, give the window fresh ones
+    GENPF_TRY(pf->alloc_cols(pf->win[pf->buf][tau & 1], pf->n * pf->nf));
+    pf->hist.push_back(h);
+    return GENPF_OK;
+}
+
+static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const double *obs, const double *aux,
+                            const double *U, const double *Z) {
+    GENPF_TRY(check_filter(pf));
+    if (init) {
+        if (t != 1) return fail(GENPF_ERR_INVALID_ARG, "initialize must create time step 1");
+    } else {
+        if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+        if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "pf_update! must advance to t_cur + 1");
+    }
+    const double *obs_dev, *dU, *dZ;
+    double obs_val;
+    GENPF_TRY(set_obs(pf, obs, aux, &obs_dev, &obs_val));
+    GENPF_TRY(stage_noise(pf, 0, U, &dU));
+    GENPF_TRY(stage_noise(pf, 1, Z, &dZ));
+    if (init) {
+        GENPF_CUDA_TRY(cudaMemsetAsync(pf->lml, 0, (size_t)pf->nf * 8, pf->stream));
+        pf->n_resamples = 0;
+        GENPF_LAUNCH(k_iota32, grid_1d(pf->n * pf->nf), 256, pf->stream, pf->parents, pf->n, pf->n * pf->nf);
+    } else {
+        GENPF_TRY(archive_slice(pf, t - 2));
+    }
+    int32_t st;
+    switch (pf->model) {
+        case kModelObjectMotion: st = propagate_model<ObjectMotion>(pf, init, t, obs_dev, obs_val, dU, dZ); break;
+        case kModelLinGauss1D: st = propagate_model<LinGauss1D>(pf, init, t, obs_dev, obs_val, dU, dZ); break;
+        default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+    }
+    GENPF_TRY(st);
+    pf->t_cur = t;
+    pf->part_valid = true;
+    return GENPF_OK;
+}
+
+// make sure sc.partials(0) describes the current lw, then finalize into st(0)
+static int32_t ensure_stats(genpf_filter_t pf, double *tile_off, double ess_frac, double *lml_accum) {
+    if (!pf->part_valid) {
+        LwSrc src{pf->lw, 1.0};
+        GENPF_TRY(launch_reduce(pf->stream, src, pf->n, pf->nf, pf->sc.partials(0)));
+        pf->part_valid = true;
+    }
+    return launch_finalize(pf->stream, pf->sc.partials(0), pf->n, pf->nf, pf->sc.st(0, pf->nf), tile_off, ess_frac,
+                           lml_accum);
+}
+
+static int32_t read_stats(genpf_filter_t pf, int which) {
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_stats, pf->sc.st(which, pf->nf), sizeof(Stats) * (size_t)pf->nf,
+                                   cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+
+template <class Model, class Noise>
+static int32_t launch_mh(genpf_filter_t pf, int64_t tau, const double *obs_dev, double obs_val, Noise noise) {
+    const int64_t tpf = ceil_div(pf->n, kTile);
+    GENPF_LAUNCH((k_mh<Model, Noise>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, pf->P, tau, tau == 1 ? 1 : 0,
+                 pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept);
+    return GENPF_OK;
+}
+template <class Model>
+static int32_t mh_model(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val,
+                        const double *U2, const double *Z2, const double *U3) {
+    if (U2 || Z2 || U3) {
+        NoiseCols nz{U2, Z2, U3};
+        return launch_mh<Model, NoiseCols>(pf, tau, obs_dev, obs_val, nz);
+    }
+    const uint64_t stream_id = make_stream(kPurposeMH, ((uint64_t)tau << 8) | (uint64_t)(iter & 0xFF));
+    if (pf->flags & GENPF_NOISE_PHILOX53) {
+        NoisePhilox53 nz{pf->seed, stream_id, pf->rng_offset};
+        return launch_mh<Model, NoisePhilox53>(pf, tau, obs_dev, obs_val, nz);
+    }
+    NoiseLean nz{pf->seed, stream_id, pf->rng_offset};
+    return launch_mh<Model, NoiseLean>(pf, tau, obs_dev, obs_val, nz);
+}
+
+static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
+                     const double *U2, const double *Z2, const double *U3, int64_t *n_accept) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    if (tau != pf->t_cur) return fail(GENPF_ERR_UNSUPPORTED, "mh rejuvenation is implemented for tau == newest time step");
+    if (n_iters < 1) return GENPF_OK;
+    const double *obs_dev, *dU2, *dZ2, *dU3;
+    double obs_val;
+    GENPF_TRY(set_obs(pf, obs, aux, &obs_dev, &obs_val));
+    GENPF_TRY(stage_noise(pf, 0, U2, &dU2));
+    GENPF_TRY(stage_noise(pf, 1, Z2, &dZ2));
+    GENPF_TRY(stage_noise(pf, 2, U3, &dU3));
+    GENPF_CUDA_TRY(cudaMemsetAsync(pf->n_accept, 0, (size_t)pf->nf * 8, pf->stream));
+    for (int it = 0; it < n_iters; ++it) {
+        int32_t st;
+        switch (pf->model) {
+            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3); break;
+            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3); break;
+            default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+        }
+        GENPF_TRY(st);
+    }
+    if (n_accept) {
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, pf->n_accept, (size_t)pf->nf * 8, cudaMemcpyDeviceToHost, pf->stream));
+        GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+        for (int64_t f = 0; f < pf->nf; ++f) n_accept[f] = (int64_t)reinterpret_cast<unsigned long long *>(pf->h_pinned)[f];
+    }
+    return GENPF_OK;
+}
+
+static GatherCols window_gather_cols(genpf_filter_t pf) {
+    GatherCols g;
+    memset(&g, 0, sizeof(g));
+    int kf = 0, kb = 0;
+    for (int sl = 0; sl < 2; ++sl) {
+        for (int i = 0; i < pf->NF; ++i) {
+            g.sf[kf] = pf->win[pf->buf][sl].f[i];
+            g.df[kf] = pf->win[pf->buf ^ 1][sl].f[i];
+            ++kf;
+        }
+        for (int i = 0; i < pf->NB; ++i) {
+            g.sb[kb] = pf->win[pf->buf][sl].b[i];
+            g.db[kb] = pf->win[pf->buf ^ 1][sl].b[i];
+            ++kb;
+        }
+    }
+    g.nf = kf;
+    g.nb = kb;
+    return g;
+}
+
+// grow / shrink the population buffers of the *other* buffer set + lw_alt + parents to n_out
+static int32_t resize_target(genpf_filter_t pf, int64_t n_out) {
+    if (n_out == pf->n) return GENPF_OK;
+    const int64_t total = n_out * pf->nf;
+    for (int sl = 0; sl < 2; ++sl) {
+        pf->free_cols(pf->win[pf->buf ^ 1][sl]);
+        GENPF_TRY(pf->alloc_cols(pf->win[pf->buf ^ 1][sl], total));
+    }
+    pf->dfree(pf->lw_alt);
+    GENPF_TRY(pf->dalloc(&pf->lw_alt, (size_t)total));
+    pf->dfree(pf->parents);
+    GENPF_TRY(pf->dalloc(&pf->parents, (size_t)total));
+    GENPF_TRY(pf->sc.ensure(n_out > pf->n ? n_out : pf->n, pf->nf));
+    return GENPF_OK;
+}
+// after the swap: make the (now spare) old buffers match the new size (update_refs!, resize.jl:441-449)
+static int32_t resize_spare(genpf_filter_t pf, int64_t n_new) {
+    const int64_t total = n_new * pf->nf;
+    for (int sl = 0; sl < 2; ++sl) {
+        pf->free_cols(pf->win[pf->buf ^ 1][sl]);
+        GENPF_TRY(pf->alloc_cols(pf->win[pf->buf ^ 1][sl], total));
+    }
+    pf->dfree(pf->lw_alt);
+    GENPF_TRY(pf->dalloc(&pf->lw_alt, (size_t)total));
+    pf->dfree(pf->accepts);
+    GENPF_TRY(pf->dalloc(&pf->accepts, (size_t)total));
+    return GENPF_OK;
+}
+
+static int32_t log_parents(genpf_filter_t pf, int64_t n_prev, int64_t n_cur) {
+    pf->n_resamples += 1;
+    if (!(pf->flags & GENPF_KEEP_HISTORY)) return GENPF_OK;
+    ParentLog pl;
+    pl.n_prev = n_prev;
+    pl.n_cur = n_cur;
+    GENPF_TRY(pf->dalloc(&pl.parents, (size_t)(n_cur * pf->nf)));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pl.parents, pf->parents, (size_t)(n_cur * pf->nf) * 4, cudaMemcpyDeviceToDevice, pf->stream));
+    pf->plog.push_back(pl);
+    return GENPF_OK;
+}
+
+// pf_resample! / pf_resize! on device state.  gate: only filters whose device-side predicate fired are
+// resampled (the others are copied through unchanged so the buffer swap stays unconditional).
+static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind, double prio_param,
+                           const double *prio_column_host, int64_t n_out, uint32_t flags, const double *uniforms_host,
+                           int32_t *invalid_kinds, double ess_frac) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    if (method != GENPF_MULTINOMIAL && method != GENPF_RESIDUAL && method != GENPF_STRATIFIED)
+        return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
+    if (n_out <= 0) n_out = pf->n;
+    if (n_out != pf->n && method == GENPF_STRATIFIED)
+        return fail(GENPF_ERR_INVALID_ARG, "stratified resampling cannot resize (resize.jl:16-27)");
+    if (n_out != pf->n && pf->nf != 1) return fail(GENPF_ERR_UNSUPPORTED, "resize needs n_filters == 1");
+    const int gate = ess_frac >= 0.0 ? 1 : 0;
+    const int64_t n = pf->n, nf = pf->nf;
+    cudaStream_t s = pf->stream;
+    Scratch &sc = pf->sc;
+    const bool substate = flags & GENPF_SUBSTATE;
+    const bool want_host_check = (flags & GENPF_CHECK) || invalid_kinds;
+    GENPF_TRY(resize_target(pf, n_out));
+
+    // selection source
+    LwSrc lw_src{pf->lw, 1.0}, sel = lw_src;
+    bool has_prio = false;
+    if (prio_kind == GENPF_PRIO_SCALE) {
+        sel = LwSrc{pf->lw, prio_param};
+        has_prio = true;
+    } else if (prio_kind == GENPF_PRIO_COLUMN) {
+        if (!prio_column_host) return fail(GENPF_ERR_INVALID_ARG, "prio_column is NULL");
+        GENPF_TRY(pf->prio_buf.ensure((size_t)(n * nf) * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->prio_buf.p, prio_column_host, (size_t)(n * nf) * 8, cudaMemcpyHostToDevice, s));
+        sel = LwSrc{pf->prio_buf.as<double>(), 1.0};
+        has_prio = true;
+    } else if (prio_kind != GENPF_PRIO_NONE) {
+        return fail(GENPF_ERR_INVALID_ARG, "unknown priority kind");
+    }
+    if (has_prio && gate) return fail(GENPF_ERR_UNSUPPORTED, "gated resample with priorities is not supported");
+    Stats *st_lw = sc.st(0, nf), *st_sel = has_prio ? sc.st(1, nf) : st_lw, *st_d = sc.st(2, nf);
+    double *lml_now = (substate || want_host_check) ? nullptr : pf->lml;
+    GENPF_TRY(ensure_stats(pf, has_prio ? nullptr : sc.tile_off.as<double>(), ess_frac, lml_now));
+    if (has_prio) {
+        GENPF_TRY(launch_reduce(s, sel, n, nf, sc.partials(1)));
+        GENPF_TRY(launch_finalize(s, sc.partials(1), n, nf, st_sel, sc.tile_off.as<double>(), -1.0, nullptr));
+    }
+    if (want_host_check) {
+        GENPF_TRY(read_stats(pf, has_prio ? 1 : 0));
+        bool any_invalid = false, any_nan = false;
+        for (int64_t f = 0; f < nf; ++f) {
+            int k = pf->h_stats[f].invalid_kind;
+            if (invalid_kinds) invalid_kinds[f] = k;
+            any_invalid |= (k != GENPF_VALID);
+            any_nan |= (k == GENPF_INV_NAN_INPUT || k == GENPF_INV_NAN_TOTAL);
+        }
+        if ((flags & GENPF_CHECK) && any_invalid) return fail(GENPF_ERR_INVALID_WEIGHTS, "Invalid weights.");
+        if (!substate) {  // update_lml_est! (resample.jl:178-182), after the check like the reference
+            GENPF_TRY(launch_finalize(s, sc.partials(0), n, nf, st_lw, nullptr, ess_frac, pf->lml));
+        }
+        if (any_nan && nf == 1) return GENPF_OK;
+    }
+    // uniforms
+    const double *d_u = nullptr;
+    if (uniforms_host) {
+        GENPF_TRY(pf->uni_buf.ensure((size_t)(n_out * nf) * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms_host, (size_t)(n_out * nf) * 8, cudaMemcpyHostToDevice, s));
+        d_u = pf->uni_buf.as<double>();
+    }
+    UniSrc uni{d_u, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    GENPF_TRY(select_ancestors<int32_t>(s, sc, method, sel, n, n_out, nf, st_sel, uni, flags, pf->parents, 0, gate));
+    // gather the window into the other buffer; no-priority reweight fused in
+    const int64_t tpf_out = ceil_div(n_out, kTile);
+    GatherCols g = window_gather_cols(pf);
+    GENPF_LAUNCH(k_gather, (unsigned)(tpf_out * nf), kThreads, s, g, pf->parents, n, n_out, tpf_out, (const double *)pf->lw,
+                 has_prio ? (double *)nullptr : pf->lw_alt, (const Stats *)st_lw, gate, substate ? 1 : 0);
+    if (has_prio) {
+        GENPF_LAUNCH((k_prio_ratio<int32_t>), dim3(grid_1d(n_out), (unsigned)nf), 256, s, pf->lw, sel, pf->parents,
+                     (int64_t)0, n, n_out, pf->lw_alt);
+        LwSrc dsrc{pf->lw_alt, 1.0};
+        GENPF_TRY(launch_reduce(s, dsrc, n_out, nf, sc.partials(2)));
+        GENPF_TRY(launch_finalize(s, sc.partials(2), n_out, nf, st_d, nullptr, -1.0, nullptr));
+        GENPF_LAUNCH(k_prio_shift, dim3(grid_1d(n_out), (unsigned)nf), 256, s, pf->lw_alt, n_out, st_d, st_lw, substate ? 1 : 0);
+    }
+    // update_refs!: swap (utils.jl:10-15)
+    pf->buf ^= 1;
+    std::swap(pf->lw, pf->lw_alt);
+    pf->part_valid = false;
+    GENPF_TRY(log_parents(pf, n, n_out));
+    if (n_out != n) {
+        pf->n = n_out;
+        GENPF_TRY(resize_spare(pf, n_out));
+    }
+    return GENPF_OK;
+}
+
+}  // namespace genpf
+
+extern "C" {
+
+int32_t genpf_model_builtin(const char *name, int32_t *model_id) {
+    if (!name || !model_id) return fail(GENPF_ERR_INVALID_ARG, "genpf_model_builtin: NULL argument");
+    for (int i = 0; i < kNumModels; ++i)
+        if (strcmp(name, kModels[i].name) == 0) {
+            *model_id = i;
+            return GENPF_OK;
+        }
+    return fail(GENPF_ERR_INVALID_ARG, std::string("unknown built-in model: ") + name);
+}
+
+int32_t genpf_model_info(int32_t model_id, int32_t *n_f64_fields, int32_t *n_u8_fields, int32_t *n_params,
+                         int32_t *n_aux) {
+    if (model_id < 0 || model_id >= kNumModels) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
+    if (n_f64_fields) *n_f64_fields = kModels[model_id].nf;
+    if (n_u8_fields) *n_u8_fields = kModels[model_id].nb;
+    if (n_params) *n_params = kModels[model_id].np;
+    if (n_aux) *n_aux = kModels[model_id].naux;
+    return GENPF_OK;
+}
+
+int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_params, int64_t n_particles,
+                            int64_t n_filters, uint64_t seed, uint32_t flags, genpf_filter_t *out) {
+    if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");
+    if (model_id < 0 || model_id >= kNumModels) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
+    if (n_particles <= 0 || n_filters <= 0) return fail(GENPF_ERR_INVALID_ARG, "n_particles and n_filters must be > 0");
+    if (n_particles >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "n_particles per filter must be < 2^31");
+    const ModelInfo &mi = kModels[model_id];
+    if (params && n_params != mi.np) return fail(GENPF_ERR_INVALID_ARG, "wrong number of model parameters");
+    std::unique_ptr<genpf_filter_s> pf(new genpf_filter_s());
+    pf->model = model_id;
+    pf->NF = mi.nf;
+    pf->NB = mi.nb;
+    pf->n = n_particles;
+    pf->nf = n_filters;
+    pf->seed = seed;
+    pf->flags = flags;
+    GENPF_CUDA_TRY(cudaGetDevice(&pf->device));
+    memset(&pf->P, 0, sizeof(pf->P));
+    if (model_id == kModelObjectMotion) {
+        const double def[4] = {0.75, 0.25, 0.01, 0.25};  // README.md:47-50
+        for (int i = 0; i < 4; ++i) pf->P.v[i] = params ? params[i] : def[i];
+        pf->P.v[4] = log(pf->P.v[3]);
+    } else {
+        const double def[5] = {0.9, 1.0, 1.0, 0.0, 1.0};
+        for (int i = 0; i < 5; ++i) pf->P.v[i] = params ? params[i] : def[i];
+        pf->P.v[5] = log(pf->P.v[2]);
+        pf->P.v[6] = sqrt(pf->P.v[0] * pf->P.v[0] * pf->P.v[4] * pf->P.v[4] + pf->P.v[1] * pf->P.v[1]);
+    }
+    GENPF_CUDA_TRY(cudaStreamCreateWithFlags(&pf->stream, cudaStreamNonBlocking));
+    int32_t st = pf->alloc_population(n_particles);
+    if (st == GENPF_OK) st = pf->dalloc(&pf->lml, (size_t)n_filters);
+    if (st == GENPF_OK) st = pf->dalloc(&pf->obs_dev, (size_t)n_filters);
+    if (st == GENPF_OK) st = pf->dalloc(&pf->n_accept, (size_t)n_filters);
+    if (st != GENPF_OK) {
+        genpf_filter_destroy(pf.release());
+        return st;
+    }
+    const size_t pin = (size_t)(n_filters > 16 ? n_filters : 16);
+    GENPF_CUDA_TRY(cudaMallocHost(&pf->h_pinned, pin * 8 * 4));
+    GENPF_CUDA_TRY(cudaMallocHost(&pf->h_stats, pin * sizeof(Stats)));
+    GENPF_CUDA_TRY(cudaMemsetAsync(pf->lml, 0, (size_t)n_filters * 8, pf->stream));
+    *out = pf.release();
+    return GENPF_OK;
+}
+
+int32_t genpf_filter_destroy(genpf_filter_t pf) {
+    if (!pf) return GENPF_OK;
+    cudaSetDevice(pf->device);
+    if (pf->stream) cudaStreamSynchronize(pf->stream);
+    for (void *p : pf->owned)
+        if (p) cudaFree(p);
+    pf->sc.release();
+    pf->cb.release();
+    pf->key_buf.release();
+    for (DevBuf *b : {&pf->noise_buf[0], &pf->noise_buf[1], &pf->noise_buf[2], &pf->uni_buf, &pf->tmp_col, &pf->tmp_idx, &pf->prio_buf})
+        b->release();
+    if (pf->h_pinned) cudaFreeHost(pf->h_pinned);
+    if (pf->h_stats) cudaFreeHost(pf->h_stats);
+    if (pf->stream) cudaStreamDestroy(pf->stream);
+    delete pf;
+    return GENPF_OK;
+}
+
+int32_t genpf_filter_size(genpf_filter_t pf, int64_t *n_particles, int64_t *n_filters) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    if (n_particles) *n_particles = pf->n;
+    if (n_filters) *n_filters = pf->nf;
+    return GENPF_OK;
+}
+
+int32_t genpf_filter_sync(genpf_filter_t pf) {
+    GENPF_TRY(check_filter(pf));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+int32_t genpf_filter_stream(genpf_filter_t pf, void **cuda_stream) {
+    if (!pf || !cuda_stream) return fail(GENPF_ERR_INVALID_ARG, "NULL argument");
+    *cuda_stream = (void *)pf->stream;
+    return GENPF_OK;
+}
+
+int32_t genpf_initialize(genpf_filter_t pf, const double *obs, const double *aux) {
+    return do_propagate(pf, true, 1, obs, aux, nullptr, nullptr);
+}
+int32_t genpf_initialize_with_noise(genpf_filter_t pf, const double *obs, const double *aux, const double *U,
+                                    const double *Z) {
+    if (!U || !Z) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    return do_propagate(pf, true, 1, obs, aux, U, Z);
+}
+int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux) {
+    return do_propagate(pf, false, t, obs, aux, nullptr, nullptr);
+}
+int32_t genpf_update_with_noise(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
+                                const double *Z) {
+    if (!U || !Z) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    return do_propagate(pf, false, t, obs, aux, U, Z);
+}
+
+int32_t genpf_ess_dev(genpf_filter_t pf, double *ess) {
+    GENPF_TRY(check_filter(pf));
+    if (!ess) return fail(GENPF_ERR_INVALID_ARG, "ess is NULL");
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    GENPF_TRY(ensure_stats(pf, nullptr, -1.0, nullptr));
+    GENPF_TRY(read_stats(pf, 0));
+    for (int64_t f = 0; f < pf->nf; ++f) ess[f] = pf->h_stats[f].invalid_kind == GENPF_VALID ? pf->h_stats[f].ess : NAN;
+    return GENPF_OK;
+}
+
+// log_ml_estimate(state) = log_ml_est + logsumexp(lw) - log(n)  (Gen; utils.jl:174-178)
+int32_t genpf_lml_dev(genpf_filter_t pf, double *lml) {
+    GENPF_TRY(check_filter(pf));
+    if (!lml) return fail(GENPF_ERR_INVALID_ARG, "lml is NULL");
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    GENPF_TRY(ensure_stats(pf, nullptr, -1.0, nullptr));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, pf->lml, (size_t)pf->nf * 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_TRY(read_stats(pf, 0));
+    for (int64_t f = 0; f < pf->nf; ++f) lml[f] = pf->h_pinned[f] + pf->h_stats[f].lse - log((double)pf->n);
+    return GENPF_OK;
+}
+
+int32_t genpf_resample_dev(genpf_filter_t pf, int32_t method, int32_t prio_kind, double prio_param,
+                           const double *prio_column, int64_t n_out, uint32_t flags, const double *uniforms,
+                           int32_t *invalid_kinds) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    return do_resample(pf, method, prio_kind, prio_param, prio_column, n_out, flags, uniforms, invalid_kinds, -1.0);
+}
+
+int32_t genpf_rejuvenate_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
+                            int64_t *n_accept) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    return do_mh(pf, tau, obs, aux, n_iters, nullptr, nullptr, nullptr, n_accept);
+}
+int32_t genpf_rejuvenate_mh_with_noise(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
+                                       const double *U2, const double *Z2, const double *U3, int64_t *n_accept) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    if (!U2 || !Z2 || !U3) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    return do_mh(pf, tau, obs, aux, 1, U2, Z2, U3, n_accept);
+}
+
+int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                   const double *obs_t, const double *aux_t, int32_t method, double ess_frac, int32_t mh_iters,
+                   double *ess_out) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_step must advance to t_cur + 1");
+    // README.md:68-74: the resample + rejuvenation happen only when ESS < ess_frac * n.  The ESS decides on
+    // the host exactly like the reference loop; (ess_frac >= 1 means "always").
+    GENPF_TRY(ensure_stats(pf, nullptr, -1.0, nullptr));
+    bool any = false, every = true;
+    if (ess_frac >= 1.0 && !ess_out) {
+        any = true;  // "always": no host round trip at all
+    } else {
+        GENPF_TRY(read_stats(pf, 0));
+        for (int64_t f = 0; f < pf->nf; ++f) {
+            if (ess_out) ess_out[f] = pf->h_stats[f].ess;
+            const bool r = ess_frac >= 1.0 || pf->h_stats[f].ess < ess_frac * (double)pf->n;
+            any |= r;
+            every &= r;
+        }
+        if (any && !every)
+            return fail(GENPF_ERR_UNSUPPORTED,
+                        "filters of one batch disagree on resampling; use the separate entry points per view");
+    }
+    if (any) {
+        GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, nullptr, nullptr, -1.0));
+        GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, mh_iters, nullptr, nullptr, nullptr, nullptr));
+    }
+    return do_propagate(pf, false, t, obs_t, aux_t, nullptr, nullptr);
+}
+
+// resolve which column holds (tau, field) and, for archived slices, the lineage index into it
+static int32_t locate_field(genpf_filter_t pf, int32_t field, int64_t tau, XSrc *x, const int32_t **idx,
+                            int64_t *n_src) {
+    if (field < 0 || field >= pf->NF + pf->NB) return fail(GENPF_ERR_INVALID_ARG, "field index out of range");
+    if (tau < 0 || tau > pf->t_cur) return fail(GENPF_ERR_INVALID_ARG, "time step out of range");
+    const Cols *c = nullptr;
+    *idx = nullptr;
+    *n_src = pf->n;
+    if (tau >= pf->t_cur - 1 && tau >= 1) {
+        c = &pf->slice(tau);
+    } else {
+        const HistSlice *h = nullptr;
+        for (const auto &hs : pf->hist)
+            if (hs.tau == tau) h = &hs;
+        if (!h) return fail(GENPF_ERR_STATE, "time slice is not resident (create the filter with GENPF_KEEP_HISTORY)");
+        c = &h->c;
+        *n_src = h->n;
+        if (h->gen < pf->n_resamples) {
+            // compose ancestry backwards: anc_j = parents_{g+1}[ ... parents_R[j] ]
+            const int64_t total = pf->n * pf->nf;
+            GENPF_TRY(pf->tmp_idx.ensure((size_t)total * 4));
+            int32_t *anc = pf->tmp_idx.as<int32_t>();
+            GENPF_LAUNCH(k_iota32, grid_1d(total), 256, pf->stream, anc, pf->n, total);
+            for (int64_t r = pf->n_resamples; r > h->gen; --r) {
+                const ParentLog &pl = pf->plog[(size_t)r - 1];
+                GENPF_LAUNCH(k_compose_lineage, dim3(grid_1d(pf->n), (unsigned)pf->nf), 256, pf->stream, anc, pl.parents,
+                             pl.n_cur, pf->n);
+            }
+            *idx = anc;
+        }
+    }
+    x->d = field < pf->NF ? c->f[field] : nullptr;
+    x->b = field < pf->NF ? nullptr : c->b[field - pf->NF];
+    return GENPF_OK;
+}
+
+int32_t genpf_mean_var(genpf_filter_t pf, int32_t field, int64_t tau, double *mean, double *var) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    XSrc x;
+    const int32_t *idx;
+    int64_t n_src;
+    GENPF_TRY(locate_field(pf, field, tau, &x, &idx, &n_src));
+    if (idx || n_src != pf->n) {  // materialise the lineage-resolved column
+        const int64_t total = pf->n * pf->nf;
+        GENPF_TRY(pf->tmp_col.ensure((size_t)total * 8));
+        GENPF_LAUNCH(k_read_field, dim3(grid_1d(pf->n), (unsigned)pf->nf), 256, pf->stream, x, idx, n_src, pf->n,
+                     pf->tmp_col.as<double>());
+        x.d = pf->tmp_col.as<double>();
+        x.b = nullptr;
+    }
+    GENPF_TRY(ensure_stats(pf, nullptr, -1.0, nullptr));
+    GENPF_TRY(launch_mean_var(pf->stream, pf->sc, pf->lw, x, pf->n, pf->nf, pf->sc.st(0, pf->nf)));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, pf->sc.moment_out.p, (size_t)pf->nf * 16, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    for (int64_t f = 0; f < pf->nf; ++f) {
+        if (mean) mean[f] = pf->h_pinned[f];
+        if (var) var[f] = pf->h_pinned[pf->nf + f];
+    }
+    return GENPF_OK;
+}
+
+int32_t genpf_get_log_weights(genpf_filter_t pf, double *out) {
+    GENPF_TRY(check_filter(pf));
+    if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");
+    GENPF_CUDA_TRY(cudaMemcpyAsync(out, pf->lw, (size_t)(pf->n * pf->nf) * 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+int32_t genpf_set_log_weights(genpf_filter_t pf, const double *in) {
+    GENPF_TRY(check_filter(pf));
+    if (!in) return fail(GENPF_ERR_INVALID_ARG, "in is NULL");
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->lw, in, (size_t)(pf->n * pf->nf) * 8, cudaMemcpyHostToDevice, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    pf->part_valid = false;
+    return GENPF_OK;
+}
+int32_t genpf_get_parents(genpf_filter_t pf, int64_t *out, uint32_t flags) {
+    GENPF_TRY(check_filter(pf));
+    if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");
+    const int64_t total = pf->n * pf->nf;
+    GENPF_TRY(pf->tmp_col.ensure((size_t)total * 8));
+    GENPF_LAUNCH((k_convert_idx<int32_t, long long>), grid_1d(total), 256, pf->stream, pf->parents,
+                 pf->tmp_col.as<long long>(), total, (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(out, pf->tmp_col.p, (size_t)total * 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+int32_t genpf_get_field(genpf_filter_t pf, int32_t field, int64_t tau, double *out) {
+    GENPF_TRY(check_filter(pf));
+    if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    XSrc x;
+    const int32_t *idx;
+    int64_t n_src;
+    GENPF_TRY(locate_field(pf, field, tau, &x, &idx, &n_src));
+    const int64_t total = pf->n * pf->nf;
+    GENPF_TRY(pf->tmp_col.ensure((size_t)total * 8));
+    GENPF_LAUNCH(k_read_field, dim3(grid_1d(pf->n), (unsigned)pf->nf), 256, pf->stream, x, idx, n_src, pf->n,
+                 pf->tmp_col.as<double>());
+    GENPF_CUDA_TRY(cudaMemcpyAsync(out, pf->tmp_col.p, (size_t)total * 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+int32_t genpf_set_field(genpf_filter_t pf, int32_t field, int64_t tau, const double *in) {
+    GENPF_TRY(check_filter(pf));
+    if (!in) return fail(GENPF_ERR_INVALID_ARG, "in is NULL");
+    if (field < 0 || field >= pf->NF + pf->NB) return fail(GENPF_ERR_INVALID_ARG, "field index out of range");
+    if (pf->t_cur < 1 || tau < pf->t_cur - 1 || tau > pf->t_cur || tau < 0)
+        return fail(GENPF_ERR_INVALID_ARG, "only the resident window {t_cur-1, t_cur} can be written");
+    const int64_t total = pf->n * pf->nf;
+    GENPF_TRY(pf->tmp_col.ensure((size_t)total * 8));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->tmp_col.p, in, (size_t)total * 8, cudaMemcpyHostToDevice, pf->stream));
+    Cols &c = pf->slice(tau);
+    GENPF_LAUNCH(k_write_field, grid_1d(total), 256, pf->stream, pf->tmp_col.as<double>(),
+                 field < pf->NF ? c.f[field] : (double *)nullptr,
+                 field < pf->NF ? (uint8_t *)nullptr : c.b[field - pf->NF], total);
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+int32_t genpf_get_accepts(genpf_filter_t pf, uint8_t *out) {
+    GENPF_TRY(check_filter(pf));
+    if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");
+    GENPF_CUDA_TRY(cudaMemcpyAsync(out, pf->accepts, (size_t)(pf->n * pf->nf), cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+
+}  // extern "C"
+
+// ---- resizing on device state (resize.jl:236-334); parents already written for n_out slots, new weights in lw_alt
+namespace genpf {
+static int32_t apply_parents_and_swap(genpf_filter_t pf, int64_t n_out) {
+    const int64_t tpf_out = ceil_div(n_out, kTile);
+    GatherCols g = window_gather_cols(pf);
+    GENPF_LAUNCH(k_gather, (unsigned)(tpf_out * pf->nf), kThreads, pf->stream, g, pf->parents, pf->n, n_out, tpf_out,
+                 (const double *)nullptr, (double *)nullptr, (const Stats *)nullptr, 0, 0);
+    pf->buf ^= 1;
+    std::swap(pf->lw, pf->lw_alt);
+    pf->part_valid = false;
+    const int64_t n_prev = pf->n;
+    GENPF_TRY(log_parents(pf, n_prev, n_out));
+    if (n_out != n_prev) {
+        pf->n = n_out;
+        GENPF_TRY(resize_spare(pf, n_out));
+    }
+    return GENPF_OK;
+}
+static int32_t check_resizable(genpf_filter_t pf) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    if (pf->nf != 1) return fail(GENPF_ERR_UNSUPPORTED, "resizing needs n_filters == 1");
+    return GENPF_OK;
+}
+}  // namespace genpf
+
+extern "C" {
+
+int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout) {
+    GENPF_TRY(check_resizable(pf));
+    if (k < 1) return fail(GENPF_ERR_INVALID_ARG, "n_replicates must be >= 1");
+    const int64_t n_out = pf->n * k;
+    if (n_out >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "replicated population must stay < 2^31");
+    GENPF_TRY(resize_target(pf, n_out));
+    GENPF_LAUNCH((k_replicate<int32_t>), grid_1d(n_out), 256, pf->stream, (const double *)pf->lw, pf->n, k,
+                 layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, pf->parents, (int64_t)0, pf->lw_alt);
+    return apply_parents_and_swap(pf, n_out);
+}
+
+int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms) {
+    GENPF_TRY(check_resizable(pf));
+    if (k < 1 || pf->n % k != 0) return fail(GENPF_ERR_INVALID_ARG, "n must be a multiple of n_replicates (resize.jl:270)");
+    const int64_t n_out = pf->n / k;
+    const double *d_u = nullptr;
+    if (uniforms) {
+        GENPF_TRY(pf->uni_buf.ensure((size_t)n_out * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms, (size_t)n_out * 8, cudaMemcpyHostToDevice, pf->stream));
+        d_u = pf->uni_buf.as<double>();
+    }
+    GENPF_TRY(resize_target(pf, n_out));
+    UniSrc uni{d_u, pf->seed, make_stream(kPurposeDerep, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    GENPF_LAUNCH((k_dereplicate<int32_t>), grid_1d(n_out), 256, pf->stream, (const double *)pf->lw, pf->n, k,
+                 layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, method == GENPF_SAMPLE ? 1 : 0, uni, pf->parents,
+                 (int64_t)0, pf->lw_alt);
+    return apply_parents_and_swap(pf, n_out);
+}
+
+int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new) {
+    GENPF_TRY(check_resizable(pf));
+    const int64_t n = pf->n;
+    GENPF_TRY(pf->key_buf.ensure((size_t)n * 8));
+    HashCols hc;
+    memset(&hc, 0, sizeof(hc));
+    for (int sl = 0; sl < 2; ++sl) {
+        if (pf->t_cur == 1 && sl == 0) continue;  // slice 0 is the constant initial slice
+        for (int i = 0; i < pf->NF; ++i) hc.f[hc.nf++] = pf->win[pf->buf][sl].f[i];
+        for (int i = 0; i < pf->NB; ++i) hc.b[hc.nb++] = pf->win[pf->buf][sl].b[i];
+    }
+    GENPF_LAUNCH(k_hash_window, grid_1d(n), 256, pf->stream, hc, n, pf->key_buf.as<int64_t>());
+    long long *n_new_dev = nullptr;
+    GENPF_TRY(launch_coalesce<int32_t>(pf->stream, pf->cb, pf->lw, pf->key_buf.as<int64_t>(), n, pf->parents, 0,
+                                       pf->lw_alt, &n_new_dev));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, n_new_dev, 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    const int64_t n_out = (int64_t) * reinterpret_cast<long long *>(pf->h_pinned);
+    if (n_new) *n_new = n_out;
+    return apply_parents_and_swap(pf, n_out);
+}
+
+}  // extern "C"

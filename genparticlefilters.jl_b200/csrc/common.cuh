@@ -1,0 +1,211 @@
+// common.cuh -- shared device primitives for libgenpf_cuda.so (sm_100a).
+//
+// Tile geometry: every weight-vector kernel works on tiles of kTile = 2048 particles,
+// 256 threads x 8 fp64 each, "striped by 16-byte vector": thread t owns elements
+// (j*256 + t)*2 + {0,1}, j = 0..3, so every global access is a fully coalesced
+// 128-bit load/store (4 KB per warp-instruction group) with no shared-memory transpose.
+// The reduce, scan and propagate kernels all use the SAME partition so the per-tile
+// partials one kernel writes are the tile offsets the next one consumes.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace genpf {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 8;
+constexpr int kVecs = kItems / 2;
+constexpr int kTile = kThreads * kItems;  // 2048 particles per tile
+constexpr int kWarps = kThreads / 32;
+
+// per-filter result of the weight reduction (device resident; utils.jl:117-140,163-164, resample.jl:178-182)
+struct Stats {
+    double M;    // maximum(v)
+    double S;    // sum(exp.(v .- M))
+    double S2;   // sum(exp.(2 .* (v .- M)))
+    double lse;  // logsumexp(v)
+    double ess;  // S^2 / S2 == exp(-logsumexp(2 .* lognorm(v)))
+    int32_t invalid_kind;
+    int32_t do_resample;  // device-side predicate of the fused README step (ess < ess_frac * n)
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 philox_at(uint64_t seed, uint64_t stream, uint64_t idx) {
+    return philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)stream, (uint32_t)(stream >> 32),
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+// 53-bit uniform in [0,1): (x >> 11) * 2^-53
+__device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 11) * 0x1.0p-53;
+}
+__host__ __device__ __forceinline__ uint64_t make_stream(uint32_t purpose, uint64_t step) {
+    return ((uint64_t)purpose << 56) | (step & 0x00FFFFFFFFFFFFFFull);
+}
+enum : uint32_t { kPurposeResample = 1, kPurposeUpdate = 2, kPurposeMH = 3, kPurposeDerep = 4 };
+
+// source of uniforms for selection: a column, or Philox(seed, stream, counter = slot)
+struct UniSrc {
+    const double *col;  // nullable
+    uint64_t seed, stream;
+    int64_t offset;  // global slot offset of local slot 0 (batches / shards)
+    __device__ __forceinline__ double operator()(int64_t i) const {
+        if (col) return col[i];
+        uint4 o = philox_at(seed, stream, (uint64_t)(i + offset));
+        return u53(o.x, o.y);
+    }
+};
+
+// ------------------------------------------------------------------ warp / block reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// all threads get the result; smem must hold kWarps doubles; deterministic order
+__device__ __forceinline__ double block_sum(double v, double *smem) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) r += smem[w];
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double *smem) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = smem[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) r = fmax(r, smem[w]);
+    return r;
+}
+__device__ __forceinline__ int block_or(int v, int *smem) {
+    v = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) r |= smem[w];
+    return r;
+}
+
+// ------------------------------------------------------------------ tile load / store (striped by 16 B vector)
+// value source: a column, optionally scaled (priority_fn = w -> alpha*w, resample.jl:51-52)
+struct LwSrc {
+    const double *p;
+    double scale;  // 1.0 => identity
+    __device__ __forceinline__ double fix(double v) const { return scale == 1.0 ? v : v * scale; }
+};
+
+__device__ __forceinline__ void load_tile(const LwSrc &src, int64_t base, int64_t valid, double (&v)[kItems],
+                                          double fill) {
+    const double *p = src.p + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+        if (vec_ok && e + 1 < valid) {
+            double2 d = __ldg(reinterpret_cast<const double2 *>(p + e));
+            v[2 * j] = src.fix(d.x);
+            v[2 * j + 1] = src.fix(d.y);
+        } else {
+            v[2 * j] = e < valid ? src.fix(__ldg(p + e)) : fill;
+            v[2 * j + 1] = e + 1 < valid ? src.fix(__ldg(p + e + 1)) : fill;
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store_tile(T *out, int64_t base, int64_t valid, const T (&v)[kItems]) {
+    T *p = out + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0);
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+        if (vec_ok && e + 1 < valid) {
+            struct alignas(2 * sizeof(T)) V2 { T a, b; };
+            V2 d{v[2 * j], v[2 * j + 1]};
+            *reinterpret_cast<V2 *>(p + e) = d;
+        } else {
+            if (e < valid) p[e] = v[2 * j];
+            if (e + 1 < valid) p[e + 1] = v[2 * j + 1];
+        }
+    }
+}
+// element index (within the tile) of register slot k of this thread
+__device__ __forceinline__ int tile_elem(int k) { return ((k >> 1) * kThreads + threadIdx.x) * 2 + (k & 1); }
+
+// In-tile inclusive prefix sum over the striped layout.  On return incl[k] is the inclusive sum of all
+// tile elements up to and including this thread's slot k; returns the tile total to all threads.
+// smem: 32 values of T.  Deterministic association.
+template <typename T>
+__device__ __forceinline__ T tile_scan(const T (&x)[kItems], T (&incl)[kItems], T *smem) {
+    T lane_excl[kVecs], inc[kVecs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        T s = x[2 * j] + x[2 * j + 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        inc[j] = s;
+        T e = __shfl_up_sync(0xffffffffu, s, 1);  // exact exclusive prefix (no subtraction: fp64)
+        lane_excl[j] = lane == 0 ? T(0) : e;
+    }
+    __syncthreads();
+    if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < kVecs; ++j) smem[j * kWarps + warp] = inc[j];
+    }
+    __syncthreads();
+    T total;
+    {
+        // exclusive scan over the 32 (row j, warp w) cells, row-major == element order
+        T c = smem[lane];
+        T s = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        total = __shfl_sync(0xffffffffu, s, 31);
+        T e = __shfl_up_sync(0xffffffffu, s, 1);
+        (void)c;
+        __syncthreads();
+        if (warp == 0) smem[lane] = lane == 0 ? T(0) : e;  // exclusive
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        T excl = smem[j * kWarps + warp] + lane_excl[j];
+        incl[2 * j] = excl + x[2 * j];
+        incl[2 * j + 1] = incl[2 * j] + x[2 * j + 1];
+    }
+    return total;
+}
+
+}  // namespace genpf

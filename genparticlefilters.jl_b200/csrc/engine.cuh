@@ -1,0 +1,165 @@
+// engine.cuh -- host-side launch sequences over the weight-vector kernels, shared by the host-array
+// ABI (abi_host.cu) and the device-resident filter (abi_filter.cu).  Everything here takes DEVICE
+// pointers and a stream and never synchronises.
+#pragma once
+#include "filter.cuh"
+#include "host.hpp"
+
+namespace genpf {
+
+// scratch owned by a workspace / filter; all grow-only
+struct Scratch {
+    DevBuf part[3][4];  // three partial sets (lw, selection source, ratio d): m, s, s2, flags
+    DevBuf stats;       // Stats[4 * nf]: [0] lw  [1] selection  [2] ratio d  [3] sorted selection
+    DevBuf tile_off, W, O;
+    DevBuf resid_c, resid_r, resid_coff, resid_roff, resid_rtot;
+    DevBuf sort_tmp, sorted_keys, order, prio_col;
+    DevBuf moment_partial, moment_out;
+    DevBuf misc;
+    int64_t cap_n = -1, cap_nf = -1;
+
+    int32_t ensure(int64_t n, int64_t nf) {
+        const int64_t tpf = ceil_div(n, kTile);
+        const size_t np = (size_t)(tpf * nf);
+        for (int k = 0; k < 3; ++k) {
+            GENPF_TRY(part[k][0].ensure(np * 8));
+            GENPF_TRY(part[k][1].ensure(np * 8));
+            GENPF_TRY(part[k][2].ensure(np * 8));
+            GENPF_TRY(part[k][3].ensure(np * 4));
+        }
+        GENPF_TRY(stats.ensure(sizeof(Stats) * 4 * (size_t)nf));
+        GENPF_TRY(tile_off.ensure(np * 8));
+        GENPF_TRY(moment_partial.ensure(np * 8));
+        GENPF_TRY(moment_out.ensure((size_t)nf * 8 * 2));
+        return GENPF_OK;
+    }
+    Partials partials(int k) { return Partials{part[k][0].as<double>(), part[k][1].as<double>(), part[k][2].as<double>(), part[k][3].as<int>()}; }
+    Stats *st(int k, int64_t nf) { return stats.as<Stats>() + (size_t)k * nf; }
+    void release() {
+        for (auto &a : part) for (auto &b : a) b.release();
+        for (DevBuf *b : {&stats, &tile_off, &W, &O, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
+                          &sort_tmp, &sorted_keys, &order, &prio_col, &moment_partial, &moment_out, &misc})
+            b->release();
+    }
+};
+
+inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, Partials part) {
+    const int64_t tpf = ceil_div(n, kTile);
+    GENPF_LAUNCH(k_reduce, (unsigned)(tpf * nf), kThreads, s, src, n, tpf, part);
+    return GENPF_OK;
+}
+inline int32_t launch_finalize(cudaStream_t s, Partials part, int64_t n, int64_t nf, Stats *st, double *tile_off,
+                               double ess_frac, double *lml_accum) {
+    const int64_t tpf = ceil_div(n, kTile);
+    GENPF_LAUNCH(k_finalize, (unsigned)nf, kThreads, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+    return GENPF_OK;
+}
+
+inline StratArgs make_strat(UniSrc uni, int64_t n) {
+    StratArgs a;
+    a.uni = uni;
+    a.step = 1.0 / (double)n;
+    a.n = n;
+    a.pow2 = (n & (n - 1)) == 0;
+    return a;
+}
+
+// Ancestor selection given selection statistics `st_sel` + `tile_off` already computed for `sel`
+// (unsorted order).  Writes parents (0-based + out_base), local to each filter.
+//   stratified : scan -> offspring counts O -> expand                      (resample.jl:156-170)
+//   multinomial: scan -> W -> inverse-CDF search per uniform                (resample.jl:59)
+//   residual   : counts + residual scan -> expand + search on the tail      (resample.jl:96-115)
+template <typename IdxT, typename OutT>
+int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, int64_t n_in, int64_t n_out,
+                           int64_t nf, Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base,
+                           int gate) {
+    const int64_t tpf_in = ceil_div(n_in, kTile), tpf_out = ceil_div(n_out, kTile);
+    GENPF_TRY(sc.O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
+    IdxT *O = sc.O.as<IdxT>();
+    double *tile_off = sc.tile_off.as<double>();
+    if (method == GENPF_STRATIFIED) {
+        const int32_t *order = nullptr;
+        if (flags & GENPF_SORT_PARTICLES) {
+            // sortperm(log_priorities, rev=true): materialise keys, sort per filter, re-reduce in sorted order
+            GENPF_TRY(sc.prio_col.ensure((size_t)(n_in * nf) * 8));
+            GENPF_TRY(sc.sorted_keys.ensure((size_t)(n_in * nf) * 8));
+            GENPF_TRY(sc.order.ensure((size_t)(n_in * nf) * 4));
+            if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated resample with sort_particles is not supported");
+            double *keys = sc.prio_col.as<double>();
+            GENPF_LAUNCH(k_materialize, grid_1d(n_in * nf), 256, s, sel, n_in * nf, keys);
+            for (int64_t f = 0; f < nf; ++f)
+                GENPF_TRY(sort_desc_stable(keys + f * n_in, n_in, sc.sorted_keys.as<double>() + f * n_in,
+                                           sc.order.as<int32_t>() + f * n_in, sc.sort_tmp, s));
+            LwSrc sorted{sc.sorted_keys.as<double>(), 1.0};
+            Stats *st_sorted = sc.st(3, nf);
+            GENPF_TRY(launch_reduce(s, sorted, n_in, nf, sc.partials(1)));
+            GENPF_TRY(launch_finalize(s, sc.partials(1), n_in, nf, st_sorted, tile_off, -1.0, nullptr));
+            sel = sorted;
+            st_sel = st_sorted;
+            order = sc.order.as<int32_t>();
+        }
+        StratArgs strat = make_strat(uni, n_in);
+        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
+                     (double *)nullptr, O, strat, gate);
+        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, n_in, n_out, tpf_out, order,
+                     parents, out_base, st_sel, gate, 0);
+    } else if (method == GENPF_MULTINOMIAL) {
+        GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
+        StratArgs none = make_strat(uni, n_in);
+        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
+                     sc.W.as<double>(), (IdxT *)nullptr, none, gate);
+        GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
+                     tpf_out, uni, (const IdxT *)nullptr, parents, out_base, st_sel, gate);
+    } else if (method == GENPF_RESIDUAL) {
+        if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated residual resample is not supported");
+        const size_t np = (size_t)(tpf_in * nf);
+        GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
+        GENPF_TRY(sc.resid_c.ensure(np * 8));
+        GENPF_TRY(sc.resid_r.ensure(np * 8));
+        GENPF_TRY(sc.resid_coff.ensure(np * 8));
+        GENPF_TRY(sc.resid_roff.ensure(np * 8));
+        GENPF_TRY(sc.resid_rtot.ensure((size_t)nf * 8));
+        ResidPartials rp{sc.resid_c.as<long long>(), sc.resid_r.as<double>()};
+        GENPF_LAUNCH(k_resid_partials, (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel, rp);
+        GENPF_LAUNCH(k_resid_finalize, (unsigned)nf, kThreads, s, rp, tpf_in, sc.resid_rtot.as<double>(),
+                     sc.resid_coff.as<long long>(), sc.resid_roff.as<double>());
+        GENPF_LAUNCH((k_resid_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel,
+                     sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
+                     sc.W.as<double>());
+        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, n_in, n_out, tpf_out,
+                     (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1);
+        GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
+                     tpf_out, uni, (const IdxT *)O, parents, out_base, st_sel, 0);
+    } else {
+        return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
+    }
+    return GENPF_OK;
+}
+
+template <typename OutT>
+int32_t select_ancestors(cudaStream_t s, Scratch &sc, int method, LwSrc sel, int64_t n_in, int64_t n_out, int64_t nf,
+                         Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base, int gate) {
+    if (n_in < 0x7FFFFFF0ll && n_out < 0x7FFFFFF0ll)
+        return select_ancestors_t<int32_t, OutT>(s, sc, method, sel, n_in, n_out, nf, st_sel, uni, flags, parents,
+                                                 out_base, gate);
+    return select_ancestors_t<long long, OutT>(s, sc, method, sel, n_in, n_out, nf, st_sel, uni, flags, parents,
+                                               out_base, gate);
+}
+
+// mean / var of column x under softmax(lw) (statistics.jl:13-17,48-54); results in sc.moment_out[0..nf) and [nf..2nf)
+inline int32_t launch_mean_var(cudaStream_t s, Scratch &sc, const double *lw, XSrc x, int64_t n, int64_t nf,
+                               Stats *st) {
+    const int64_t tpf = ceil_div(n, kTile);
+    LwSrc src{lw, 1.0};
+    double *partial = sc.moment_partial.as<double>();
+    double *mean = sc.moment_out.as<double>(), *var = mean + nf;
+    GENPF_LAUNCH(k_weighted_moment, (unsigned)(tpf * nf), kThreads, s, src, x, n, tpf, st, (const double *)nullptr,
+                 partial);
+    GENPF_LAUNCH(k_sum_partials, (unsigned)nf, kThreads, s, partial, tpf, mean);
+    GENPF_LAUNCH(k_weighted_moment, (unsigned)(tpf * nf), kThreads, s, src, x, n, tpf, st, (const double *)mean,
+                 partial);
+    GENPF_LAUNCH(k_sum_partials, (unsigned)nf, kThreads, s, partial, tpf, var);
+    return GENPF_OK;
+}
+
+}  // namespace genpf

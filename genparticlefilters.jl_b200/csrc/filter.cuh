@@ -1,0 +1,303 @@
+// filter.cuh -- device-resident particle population kernels (K8, K10, K11).
+//
+// HBM layout (struct of arrays, one column per field per time slice, particles of filter f at [f*n, (f+1)*n)):
+//   f64 fields  : double  col[slot][field][n_filters*n]
+//   u8  fields  : uint8_t col[slot][field][n_filters*n]
+//   log_weights : double  lw[n_filters*n]
+//   parents     : int32   parents[n_filters*n]      (ancestor of each particle in the last resample, 0-based local)
+// `slot` is a ring over time (slot = t mod K, K = 2 unless GENPF_KEEP_HISTORY): the fixed-lag window the
+// README loop touches is {t-1, t}.  Every column exists twice (buffer A/B): the ancestor gather writes the
+// other buffer and the two swap, exactly like `traces`/`new_traces` (utils.jl:10-15).
+#pragma once
+#include "kernels.cuh"
+#include "models.cuh"
+
+namespace genpf {
+
+struct Cols {
+    double *f[kMaxF];
+    uint8_t *b[kMaxB];
+};
+
+__device__ __forceinline__ void load_tile_u8(const uint8_t *col, int64_t base, int64_t valid, uint8_t (&v)[kItems]) {
+    const uint8_t *p = col + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 1) == 0);
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+        if (vec_ok && e + 1 < valid) {
+            uchar2 d = *reinterpret_cast<const uchar2 *>(p + e);
+            v[2 * j] = d.x;
+            v[2 * j + 1] = d.y;
+        } else {
+            v[2 * j] = e < valid ? p[e] : 0;
+            v[2 * j + 1] = e + 1 < valid ? p[e + 1] : 0;
+        }
+    }
+}
+__device__ __forceinline__ void store_tile_u8(uint8_t *col, int64_t base, int64_t valid, const uint8_t (&v)[kItems]) {
+    uint8_t *p = col + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 1) == 0);
+#pragma unroll
+    for (int j = 0; j < kVecs; ++j) {
+        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+        if (vec_ok && e + 1 < valid) {
+            *reinterpret_cast<uchar2 *>(p + e) = make_uchar2(v[2 * j], v[2 * j + 1]);
+        } else {
+            if (e < valid) p[e] = v[2 * j];
+            if (e + 1 < valid) p[e + 1] = v[2 * j + 1];
+        }
+    }
+}
+
+template <class Model>
+__device__ __forceinline__ void load_slices(const Cols &c, int64_t base, int64_t valid,
+                                            typename Model::Slice (&s)[kItems]) {
+#pragma unroll
+    for (int fld = 0; fld < Model::NF; ++fld) {
+        double v[kItems];
+        LwSrc src{c.f[fld], 1.0};
+        load_tile(src, base, valid, v, 0.0);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) s[k].f[fld] = v[k];
+    }
+#pragma unroll
+    for (int fld = 0; fld < Model::NB; ++fld) {
+        uint8_t v[kItems];
+        load_tile_u8(c.b[fld], base, valid, v);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) s[k].b[fld] = v[k];
+    }
+}
+template <class Model>
+__device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_t valid,
+                                             const typename Model::Slice (&s)[kItems]) {
+#pragma unroll
+    for (int fld = 0; fld < Model::NF; ++fld) {
+        double v[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) v[k] = s[k].f[fld];
+        store_tile<double>(c.f[fld], base, valid, v);
+    }
+#pragma unroll
+    for (int fld = 0; fld < Model::NB; ++fld) {
+        uint8_t v[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) v[k] = s[k].b[fld];
+        store_tile_u8(c.b[fld], base, valid, v);
+    }
+}
+
+// tile epilogue shared by every kernel that produces log-weights: the K1 partials of the tile
+__device__ __forceinline__ void emit_partials(const double (&v)[kItems], const Partials &out, double *sm, int *smi) {
+    int fl = 0;
+    double m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        fl |= isnan(v[k]) ? 1 : 0;
+        m = fmax(m, v[k]);
+    }
+    m = block_max(m, sm);
+    fl = block_or(fl, smi);
+    double s = 0.0, s2 = 0.0;
+    if (m == INFINITY) {
+        fl |= 2;
+    } else if (m > -INFINITY) {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            double e = exp(v[k] - m);
+            s += e;
+            s2 += e * e;
+        }
+    }
+    s = block_sum(s, sm);
+    s2 = block_sum(s2, sm);
+    if (threadIdx.x == 0) {
+        out.m[blockIdx.x] = m;
+        out.s[blockIdx.x] = s;
+        out.s2[blockIdx.x] = s2;
+        out.flags[blockIdx.x] = fl;
+    }
+}
+
+// ------------------------------------------------------------------ K10 propagate + weight (+ K1 partials)
+// INIT: pf_initialize (initialize.jl:39-41): slice_1 = transition(initial), lw = obs_logpdf
+// else: pf_update!    (update.jl:15-21):     slice_t = transition(slice_{t-1}), lw += obs_logpdf
+template <class Model, class Noise, bool INIT>
+static __global__ void __launch_bounds__(kThreads)
+    k_propagate(ModelParams P, int64_t t, Cols prev, Cols next, double *lw, const double *obs_dev, double obs_val,
+                int64_t n, int64_t tpf, Noise noise, Partials partials) {
+    __shared__ double sm[kWarps];
+    __shared__ int smi[kWarps];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    const int64_t base = f * n + start;
+    const double obs = obs_dev ? obs_dev[f] : obs_val;
+    typename Model::Slice sp[kItems], sn[kItems];
+    double v[kItems];
+    if (INIT) {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) Model::initial(P, sp[k]);
+    } else {
+        load_slices<Model>(prev, base, valid, sp);
+        LwSrc src{lw, 1.0};
+        load_tile(src, base, valid, v, -INFINITY);
+    }
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        int e = tile_elem(k);
+        double U = 0.5, Z = 0.0, U3;
+        if (e < valid) noise.get(base + e, U, Z, U3);
+        Model::transition(P, t, sp[k], sn[k], U, Z);
+        double l = Model::obs_logpdf(P, sn[k], obs);
+        if (e < valid) v[k] = INIT ? l : v[k] + l;
+        else v[k] = -INFINITY;
+    }
+    store_slices<Model>(next, base, valid, sn);
+    store_tile<double>(lw, base, valid, v);
+    emit_partials(v, partials, sm, smi);
+}
+
+// ------------------------------------------------------------------ K11 MH rejuvenation (move-accept)
+// pf_move_accept! (rejuvenate.jl:40-53) with kern = Gen.mh on select(tau => latents), tau the newest
+// slice: regenerate slice tau from the prior given slice tau-1; weight = obs log-density ratio;
+// accept iff log(rand()) < weight.  Log-weights are untouched.
+template <class Model, class Noise>
+static __global__ void __launch_bounds__(kThreads)
+    k_mh(ModelParams P, int64_t tau, int first_step, Cols prevprev, Cols cur, const double *obs_dev, double obs_val,
+         int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept) {
+    __shared__ double sm[kWarps];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    const int64_t base = f * n + start;
+    const double obs = obs_dev ? obs_dev[f] : obs_val;
+    typename Model::Slice sp[kItems], sc[kItems];
+    if (first_step) {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) Model::initial(P, sp[k]);
+    } else {
+        load_slices<Model>(prevprev, base, valid, sp);
+    }
+    load_slices<Model>(cur, base, valid, sc);
+    uint8_t acc[kItems];
+    double cnt = 0.0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        int e = tile_elem(k);
+        double U = 0.5, Z = 0.0, U3 = 1.0;
+        if (e < valid) noise.get(base + e, U, Z, U3);
+        typename Model::Slice q;
+        Model::transition(P, tau, sp[k], q, U, Z);
+        double alpha = Model::obs_logpdf(P, q, obs) - Model::obs_logpdf(P, sc[k], obs);
+        bool a = (e < valid) && (log(U3) < alpha);
+        if (a) sc[k] = q;
+        acc[k] = a ? 1 : 0;
+        cnt += a ? 1.0 : 0.0;
+    }
+    store_slices<Model>(cur, base, valid, sc);
+    if (accepts) store_tile_u8(accepts, base, valid, acc);
+    if (n_accept) {
+        cnt = block_sum(cnt, sm);
+        if (threadIdx.x == 0 && cnt > 0.0) atomicAdd(&n_accept[f], (unsigned long long)cnt);
+    }
+}
+
+// ------------------------------------------------------------------ K8 ancestor gather
+// new_traces .= view(traces, parents) (resample.jl:60,102-104,114,169) over the window's columns.
+// Output centric, coalesced 16-byte stores; reads follow the (monotone for stratified/residual) parents.
+// Also applies update_weights! for the no-priority case (lw .= 0 | lse - log n, resample.jl:193-195,208-210).
+struct GatherCols {
+    const double *sf[2 * kMaxF];
+    double *df[2 * kMaxF];
+    const uint8_t *sb[2 * kMaxB];
+    uint8_t *db[2 * kMaxB];
+    int nf, nb;
+};
+static __global__ void __launch_bounds__(kThreads)
+    k_gather(GatherCols c, int32_t *parents, int64_t n_in, int64_t n_out, int64_t tpf_out, const double *lw_src,
+             double *lw_fill, const Stats *stats, int gate, int substate) {
+    int64_t f, tile;
+    blk_to_tile(tpf_out, f, tile);
+    bool pass = false;  // gated and this filter keeps its population: identity parents, weights copied through
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) pass = true;
+        if (gate && !stats[f].do_resample) pass = true;
+    }
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n_out - start);
+    const int64_t obase = f * n_out + start;
+    int64_t p[kItems];
+    if (pass) {
+        int32_t id[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            int e = tile_elem(k);
+            id[k] = (int32_t)(start + e);
+            p[k] = e < valid ? f * n_in + start + e : f * n_in;
+        }
+        store_tile<int32_t>(parents, obase, valid, id);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            int e = tile_elem(k);
+            p[k] = e < valid ? f * n_in + (int64_t)parents[obase + e] : f * n_in;
+        }
+    }
+    for (int col = 0; col < c.nf; ++col) {
+        double v[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) v[k] = __ldg(c.sf[col] + p[k]);
+        store_tile<double>(c.df[col], obase, valid, v);
+    }
+    for (int col = 0; col < c.nb; ++col) {
+        uint8_t v[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) v[k] = __ldg(c.sb[col] + p[k]);
+        store_tile_u8(c.db[col], obase, valid, v);
+    }
+    if (lw_fill) {
+        const double val = substate ? stats[f].lse - log((double)n_in) : 0.0;
+        double v[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) v[k] = pass ? __ldg(lw_src + p[k]) : val;
+        store_tile<double>(lw_fill, obase, valid, v);
+    }
+}
+
+// gather of one fp64 column through parents (priorities: lw[parents], and lineage resolution)
+static __global__ void k_gather_f64(const double *src, const int32_t *idx, int64_t n_in, int64_t n_out, double *dst) {
+    int64_t f = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x)
+        dst[f * n_out + j] = src[f * n_in + idx[f * n_out + j]];
+}
+// lineage composition: anc[j] = parents_prev[anc[j]]
+static __global__ void k_compose_lineage(int32_t *anc, const int32_t *parents_prev, int64_t n_prev, int64_t n_cur) {
+    int64_t f = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_cur; j += (int64_t)gridDim.x * blockDim.x)
+        anc[f * n_cur + j] = parents_prev[f * n_prev + anc[f * n_cur + j]];
+}
+static __global__ void k_iota32(int32_t *a, int64_t n, int64_t total) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x)
+        a[j] = (int32_t)(j % n);
+}
+// read a field through an index column as fp64 (u8 promoted)
+static __global__ void k_read_field(XSrc x, const int32_t *idx, int64_t n_src, int64_t n, double *out) {
+    int64_t f = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = idx ? f * n_src + idx[f * n + j] : f * n + j;
+        out[f * n + j] = x(s);
+    }
+}
+static __global__ void k_write_field(const double *in, double *dcol, uint8_t *bcol, int64_t total) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+        if (dcol) dcol[j] = in[j];
+        else bcol[j] = in[j] != 0.0 ? 1 : 0;
+    }
+}
+
+}  // namespace genpf

@@ -1,0 +1,94 @@
+// host.hpp -- host-side plumbing shared by the ABI translation units: errors, launch counting,
+// grow-only device buffers.  No torch types anywhere: the library only needs the CUDA runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/genpf.h"
+
+namespace genpf {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<int64_t> g_launches;
+
+inline int32_t fail(int32_t code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define GENPF_CUDA_TRY(expr)                                                                                 \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) {                                                                             \
+            char _b[512];                                                                                    \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, \
+                     #expr);                                                                                 \
+            cudaGetLastError();                                                                              \
+            return ::genpf::fail(GENPF_ERR_CUDA, _b);                                                        \
+        }                                                                                                    \
+    } while (0)
+
+#define GENPF_TRY(expr)               \
+    do {                              \
+        int32_t _s = (expr);          \
+        if (_s != GENPF_OK) return _s; \
+    } while (0)
+
+// kernel launch + count (bench.py's gpu_launches) + launch-error check
+#define GENPF_LAUNCH(kernel, grid, block, stream, ...)           \
+    do {                                                         \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);   \
+        ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        GENPF_CUDA_TRY(cudaGetLastError());                      \
+    } while (0)
+
+// grow-only device allocation
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int32_t ensure(size_t bytes) {
+        if (bytes <= cap) return GENPF_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(GENPF_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return GENPF_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline unsigned grid_1d(int64_t n, int block = 256, int64_t max_blocks = 148 * 16) {
+    int64_t g = ceil_div(n, block);
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (unsigned)g;
+}
+
+// stable descending sort of fp64 keys with Julia `isless` ordering (sort.cu; K7).
+// order32[k] = original index of the k-th largest key; ties keep ascending original index.
+int32_t sort_desc_stable(const double *keys, int64_t n, double *keys_sorted, int32_t *order32, DevBuf &tmp,
+                         cudaStream_t stream);
+// stable ascending sort of int64 keys with index payload (coalesce)
+int32_t sort_keys_i64(const int64_t *keys, int64_t n, int64_t *keys_sorted, int32_t *order32, DevBuf &tmp,
+                      cudaStream_t stream);
+
+}  // namespace genpf

@@ -1,0 +1,595 @@
+// kernels.cuh -- weight-vector kernels (K1-K6, K9, K12, K13).
+//
+// Pipeline of one resample over n particles (per filter f; tile = 2048 particles):
+//   k_reduce    : tile partials (max, sum e^{v-max}, sum e^{2(v-max)}, NaN/+Inf flags)     [R 8 B/particle]
+//   k_finalize  : per filter M, S, S2, lse, ESS, invalid kind, exclusive tile offsets      [tiny]
+//   k_scan      : w_i = e^{v_i-M}/S, in-tile fp64 inclusive scan + tile offset -> W_k,
+//                 and/or cumulative offspring counts O_k = #{i : u_i <= W_k}                [R 8, W 8 or 4]
+//   k_expand    : parent_i = min{k : O_k > i}  (load-balanced search, output centric)       [R ~4, W 4|8]
+//   k_search    : parent_j = min{k : W_k > u_j} (multinomial, residual tail)                [R 8 + search, W 4|8]
+// The normalisation needs the global (M, S) before any cumulative weight exists, so a reduce pass is
+// unavoidable; given that pass, "reduce-then-scan" with a shared tile partition gives every tile its
+// exclusive prefix without the spinning of a decoupled look-back and is bit-deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace genpf {
+
+struct Partials {
+    double *m, *s, *s2;
+    int *flags;  // bit0: NaN seen, bit1: +Inf seen
+};
+
+__device__ __forceinline__ void blk_to_tile(int64_t tpf, int64_t &f, int64_t &tile) {
+    int64_t b = blockIdx.x;
+    f = b / tpf;
+    tile = b - f * tpf;
+}
+
+// ------------------------------------------------------------------ K1/K2 reduce
+// Replaces: Gen.logsumexp, lognorm/softmax (utils.jl:100-107), safe_softmax's validity scan
+// (utils.jl:119-137), effective_sample_size (utils.jl:163-164).
+static __global__ void __launch_bounds__(kThreads) k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out) {
+    __shared__ double sm[kWarps];
+    __shared__ int smi[kWarps];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    double v[kItems];
+    load_tile(src, f * n + start, valid, v, -INFINITY);
+    int fl = 0;
+    double m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        fl |= isnan(v[k]) ? 1 : 0;
+        m = fmax(m, v[k]);
+    }
+    m = block_max(m, sm);
+    fl = block_or(fl, smi);
+    double s = 0.0, s2 = 0.0;
+    if (m == INFINITY) {
+        fl |= 2;
+    } else if (m > -INFINITY) {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            double e = exp(v[k] - m);
+            s += e;
+            s2 += e * e;
+        }
+    }
+    s = block_sum(s, sm);
+    s2 = block_sum(s2, sm);
+    if (threadIdx.x == 0) {
+        out.m[blockIdx.x] = m;
+        out.s[blockIdx.x] = s;
+        out.s2[blockIdx.x] = s2;
+        out.flags[blockIdx.x] = fl;
+    }
+}
+
+// One block per filter.  Combines tile partials, classifies validity (utils.jl:119-137) and writes the
+// exclusive tile offsets of the NORMALISED weights (the scan's carry-in).
+//   lml_accum != null: log_ml_est[f] += lse - log(n)  (update_lml_est!, resample.jl:178-182), gated by do_resample
+//   ess_frac < 0 => do_resample = 1, else do_resample = (ess < ess_frac * n)   (README.md:68)
+static __global__ void __launch_bounds__(kThreads)
+    k_finalize(Partials in, int64_t n, int64_t tpf, Stats *stats, double *tile_off, double ess_frac,
+               double *lml_accum) {
+    __shared__ double sm[kWarps];
+    __shared__ int smi[kWarps];
+    __shared__ double carry_s;
+    const int64_t f = blockIdx.x;
+    const double *pm = in.m + f * tpf, *ps = in.s + f * tpf, *ps2 = in.s2 + f * tpf;
+    const int *pf = in.flags + f * tpf;
+    double m = -INFINITY;
+    int fl = 0;
+    for (int64_t b = threadIdx.x; b < tpf; b += kThreads) {
+        m = fmax(m, pm[b]);
+        fl |= pf[b];
+    }
+    const double M = block_max(m, sm);
+    fl = block_or(fl, smi);
+    double s = 0.0, s2 = 0.0;
+    if (M > -INFINITY && M < INFINITY) {
+        for (int64_t b = threadIdx.x; b < tpf; b += kThreads) {
+            double mb = pm[b];
+            if (mb > -INFINITY) {
+                double sc = exp(mb - M);
+                s += ps[b] * sc;
+                s2 += ps2[b] * (sc * sc);
+            }
+        }
+    }
+    const double S = block_sum(s, sm);
+    const double S2 = block_sum(s2, sm);
+    int kind = 0;
+    if (fl & 1) kind = 1;                        // NaN in input
+    else if (M == -INFINITY) kind = 2;           // all -Inf
+    else if ((fl & 2) || isnan(S)) kind = 4;     // +Inf entry => Inf-Inf = NaN total
+    else if (S == 0.0) kind = 3;                 // zero total (unreachable: e_max = 1)
+    const double lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    const double ess = S * S / S2;
+    int do_rs = 1;
+    if (ess_frac >= 0.0) do_rs = (ess < ess_frac * (double)n) ? 1 : 0;
+    if (kind == 1 || kind == 4) do_rs = 0;
+    if (threadIdx.x == 0) {
+        Stats st;
+        st.M = M; st.S = S; st.S2 = S2; st.lse = lse; st.ess = ess;
+        st.invalid_kind = kind; st.do_resample = do_rs;
+        stats[f] = st;
+        if (lml_accum && do_rs) lml_accum[f] += lse - log((double)n);
+        carry_s = 0.0;
+    }
+    if (!tile_off) return;
+    __syncthreads();
+    // exclusive scan of the normalised tile totals, 256 tiles per round, sequential carry
+    const bool uniform = (kind == 2 || kind == 3);
+    const double inv_n = 1.0 / (double)n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b0 = 0; b0 < tpf; b0 += kThreads) {
+        int64_t b = b0 + threadIdx.x;
+        double t = 0.0;
+        if (b < tpf) {
+            if (uniform) {
+                int64_t cnt = min((int64_t)kTile, n - b * kTile);
+                t = (double)cnt * inv_n;
+            } else if (kind == 0 && pm[b] > -INFINITY) {
+                t = ps[b] * exp(pm[b] - M) / S;
+            }
+        }
+        double inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0.0;
+        __syncthreads();
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads();
+        double woff = 0.0, tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            if (w < warp) woff += sm[w];
+            tot += sm[w];
+        }
+        const double c = carry_s;
+        if (b < tpf) tile_off[f * tpf + b] = c + (woff + ex);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = c + tot;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ stratified thresholds
+// u_i = r_i*(1/n) + lower_i with two roundings and no FMA (resample.jl:162); lower_i = element i of
+// 0.0:1/n:1.0-1/n, i.e. (i-1)/n (exact for power-of-two n).
+struct StratArgs {
+    UniSrc uni;
+    double step;  // 1/n
+    int64_t n;
+    int pow2;
+};
+__device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t i1) {
+    double r = a.uni(f * a.n + i1 - 1);
+    double lower = a.pow2 ? (double)(i1 - 1) * a.step : (double)(i1 - 1) / (double)a.n;
+    return __dadd_rn(__dmul_rn(r, a.step), lower);
+}
+// C(W) = #{i in 1..n : u_i <= W}.  Because u is non-decreasing in i this is a prefix count, and
+// parent_i = min{k : W_k >= u_i} (resample.jl:163-168) == min{k : C(W_k) >= i}.
+__device__ __forceinline__ int64_t strat_count(const StratArgs &a, int64_t f, double W) {
+    double x = W * (double)a.n;
+    int64_t j = x >= (double)a.n ? a.n : (x <= 0.0 ? 0 : (int64_t)x);
+    const bool near_edge = (x - (double)j) < 1e-6;
+    while (j < a.n && strat_u(a, f, j + 1) <= W) ++j;
+    if (near_edge)
+        while (j > 0 && strat_u(a, f, j) > W) --j;
+    return j;
+}
+
+// ------------------------------------------------------------------ K3 normalise + scan
+// Replaces safe_softmax line utils.jl:139 and the running accum_weight of resample.jl:163-166.
+// Writes W (normalised inclusive cumulative weights) and/or O (cumulative offspring counts, stratified).
+template <typename IdxT>
+static __global__ void __launch_bounds__(kThreads)
+    k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, double *W_out, IdxT *O_out,
+           StratArgs strat, int gate) {
+    __shared__ double sm[32];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const Stats st = stats[f];
+    if (st.invalid_kind == 1 || st.invalid_kind == 4) return;
+    if (gate && !st.do_resample) return;
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    double v[kItems], w[kItems], W[kItems];
+    load_tile(src, f * n + start, valid, v, -INFINITY);
+    const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
+    const double inv_n = 1.0 / (double)n;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        if (uniform) w[k] = tile_elem(k) < valid ? inv_n : 0.0;
+        else w[k] = exp(v[k] - st.M) / st.S;
+    }
+    tile_scan<double>(w, W, sm);
+    const double off = tile_off[f * tpf + tile];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) W[k] = off + W[k];
+    if (W_out) store_tile<double>(W_out, f * n + start, valid, W);
+    if (O_out) {
+        IdxT O[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) O[k] = tile_elem(k) < valid ? (IdxT)strat_count(strat, f, W[k]) : (IdxT)0;
+        store_tile<IdxT>(O_out, f * n + start, valid, O);
+    }
+}
+
+// ------------------------------------------------------------------ searches
+// smallest k in [0, n) with a[k] > t, clamped to n-1 (the reference would throw BoundsError, App. C)
+template <typename T, typename Q>
+__device__ __forceinline__ int64_t upper_bound_clamped(const T *a, int64_t n, Q t) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// K4/K6 expand: parent_i = min{k : O_k > i} for output slot i (0-based).  Output centric, so a particle
+// owning millions of offspring costs nothing extra.  The block brackets its 2048 outputs with two
+// searches, stages that slice of O in shared memory when it fits, and searches there.
+constexpr int kExpandCap = 4096;
+template <typename IdxT, typename OutT>
+static __global__ void __launch_bounds__(kThreads)
+    k_expand(const IdxT *O, int64_t n_src, int64_t n_out, int64_t tpf_out, const int32_t *order, OutT *parents,
+             int64_t out_base, const Stats *stats, int gate, int residual) {
+    __shared__ int64_t range[2];
+    __shared__ IdxT sO[kExpandCap];
+    int64_t f, tile;
+    blk_to_tile(tpf_out, f, tile);
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+        if (gate && !stats[f].do_resample) return;
+    }
+    const IdxT *Of = O + f * n_src;
+    const int64_t i0 = tile * kTile;
+    int64_t valid = min((int64_t)kTile, n_out - i0);
+    if (residual) {  // only the deterministic copies: slots [0, C), C = O[n_src-1]
+        int64_t C = (int64_t)Of[n_src - 1];
+        valid = min(valid, C - i0);
+        if (valid <= 0) return;
+    }
+    if (threadIdx.x < 2) {
+        int64_t target = threadIdx.x == 0 ? i0 : i0 + valid - 1;
+        range[threadIdx.x] = upper_bound_clamped<IdxT, int64_t>(Of, n_src, target);
+    }
+    __syncthreads();
+    const int64_t k_lo = range[0], k_hi = range[1];
+    const int64_t L = k_hi - k_lo + 1;
+    const bool staged = L <= kExpandCap;
+    if (staged) {
+        for (int64_t j = threadIdx.x; j < L; j += kThreads) sO[j] = Of[k_lo + j];
+        __syncthreads();
+    }
+    OutT out[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        int e = tile_elem(k);
+        int64_t p = 0;
+        if (e < valid) {
+            int64_t i = i0 + e;
+            p = k_lo + (staged ? upper_bound_clamped<IdxT, int64_t>(sO, L, i)
+                               : upper_bound_clamped<IdxT, int64_t>(Of + k_lo, L, i));
+            if (order) p = order[f * n_src + p];
+        }
+        out[k] = (OutT)(p + out_base);
+    }
+    store_tile<OutT>(parents, f * n_out + i0, valid, out);
+}
+
+// W-based stratified selection (debug / cross-check of the O path): parent_i = min{k : W_k >= u_i}
+template <typename OutT>
+static __global__ void __launch_bounds__(kThreads)
+    k_select_stratified_w(const double *W, int64_t n, const int32_t *order, StratArgs strat, OutT *parents,
+                          int64_t out_base) {
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    double u = strat_u(strat, 0, i + 1);
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (W[mid] >= u) hi = mid; else lo = mid + 1;
+    }
+    parents[i] = (OutT)((order ? order[lo] : lo) + out_base);
+}
+
+// K5 inverse-CDF search for arbitrary (unsorted) uniforms: parent_j = min{k : W_k > u_j}, capped at n
+// (Distributions' single-draw rule, resize.jl:284).  Slots below first_slot (residual: the
+// deterministic copies) are left alone.  A coarse table of every 256-th W lives in shared memory so
+// only the last 8 steps touch global/L2.
+constexpr int kCoarseStride = 256;
+constexpr int kCoarseCap = 4096;  // covers n <= 2^20 fully in smem; larger n search the coarse table in global
+template <typename IdxT, typename OutT>
+static __global__ void __launch_bounds__(kThreads)
+    k_search(const double *W, int64_t n_src, int64_t n_out, int64_t bpf, UniSrc uni, const IdxT *first_slot_O,
+             OutT *parents, int64_t out_base, const Stats *stats, int gate) {
+    __shared__ double sW[kCoarseCap];
+    int64_t f = blockIdx.x / bpf;
+    int64_t blk = blockIdx.x - f * bpf;
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+        if (gate && !stats[f].do_resample) return;
+    }
+    const double *Wf = W + f * n_src;
+    const int64_t n_coarse = (n_src + kCoarseStride - 1) / kCoarseStride;  // coarse[c] = W[min((c+1)*stride, n) - 1]
+    const bool coarse_in_smem = n_coarse <= kCoarseCap;
+    if (coarse_in_smem) {
+        for (int64_t c = threadIdx.x; c < n_coarse; c += kThreads)
+            sW[c] = Wf[min((c + 1) * (int64_t)kCoarseStride, n_src) - 1];
+        __syncthreads();
+    }
+    const int64_t first = first_slot_O ? (int64_t)first_slot_O[f * n_src + n_src - 1] : 0;
+    for (int64_t j = blk * (int64_t)kTile + threadIdx.x; j < min(n_out, (blk + 1) * (int64_t)kTile); j += kThreads) {
+        if (j < first) continue;
+        const double u = uni(f * n_out + j);
+        int64_t lo = 0, hi = n_src - 1;
+        if (coarse_in_smem) {
+            int64_t c = upper_bound_clamped<double, double>(sW, n_coarse, u);
+            lo = c * kCoarseStride;
+            hi = min(lo + kCoarseStride, n_src) - 1;
+        }
+        while (lo < hi) {
+            int64_t mid = lo + ((hi - lo) >> 1);
+            if (Wf[mid] > u) hi = mid; else lo = mid + 1;
+        }
+        parents[f * n_out + j] = (OutT)(lo + out_base);
+    }
+}
+
+// ------------------------------------------------------------------ K6 residual
+// c_i = floor(n_out * w_i) literally (resample.jl:99, resize.jl:103); r_i = n_out*w_i - floor(n_out*w_i).
+struct ResidPartials {
+    long long *c;  // per tile sum of copies
+    double *r;     // per tile sum of residual weights
+};
+__device__ __forceinline__ void resid_terms(const Stats &st, double v, bool in_range, double n_out_d, double inv_n,
+                                            long long &c, double &r) {
+    const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
+    double w = uniform ? (in_range ? inv_n : 0.0) : exp(v - st.M) / st.S;
+    double nw = n_out_d * w;
+    double fl = floor(nw);
+    c = (long long)fl;
+    r = nw - fl;
+}
+static __global__ void __launch_bounds__(kThreads)
+    k_resid_partials(LwSrc src, int64_t n, int64_t n_out, int64_t tpf, const Stats *stats, ResidPartials out) {
+    __shared__ double sm[kWarps];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const Stats st = stats[f];
+    if (st.invalid_kind == 1 || st.invalid_kind == 4) return;
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    double v[kItems];
+    load_tile(src, f * n + start, valid, v, -INFINITY);
+    long long cs = 0;
+    double rs = 0.0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        long long c;
+        double r;
+        resid_terms(st, v[k], tile_elem(k) < valid, (double)n_out, 1.0 / (double)n, c, r);
+        cs += c;
+        rs += r;
+    }
+    rs = block_sum(rs, sm);
+    double csd = block_sum((double)cs, sm);  // exact: counts < 2^53
+    if (threadIdx.x == 0) {
+        out.c[blockIdx.x] = (long long)csd;
+        out.r[blockIdx.x] = rs;
+    }
+}
+// one block per filter: total residual mass, exclusive tile offsets for counts and normalised residuals
+static __global__ void __launch_bounds__(kThreads)
+    k_resid_finalize(ResidPartials in, int64_t tpf, double *r_total, long long *c_off, double *r_off) {
+    __shared__ double sm[kWarps];
+    const int64_t f = blockIdx.x;
+    double rs = 0.0;
+    for (int64_t b = threadIdx.x; b < tpf; b += kThreads) rs += in.r[f * tpf + b];
+    const double R = block_sum(rs, sm);
+    if (threadIdx.x == 0) {
+        r_total[f] = R;
+        long long c = 0;
+        double r = 0.0;
+        for (int64_t b = 0; b < tpf; ++b) {  // tpf <= n/2048: short serial carry chain
+            c_off[f * tpf + b] = c;
+            r_off[f * tpf + b] = r;
+            c += in.c[f * tpf + b];
+            r += (R > 0.0) ? in.r[f * tpf + b] / R : 0.0;
+        }
+    }
+}
+template <typename IdxT>
+static __global__ void __launch_bounds__(kThreads)
+    k_resid_scan(LwSrc src, int64_t n, int64_t n_out, int64_t tpf, const Stats *stats, const double *r_total,
+                 const long long *c_off, const double *r_off, IdxT *O_out, double *R_out) {
+    __shared__ double sm[32];
+    __shared__ long long smi[32];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const Stats st = stats[f];
+    if (st.invalid_kind == 1 || st.invalid_kind == 4) return;
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    double v[kItems], r[kItems], R[kItems];
+    long long c[kItems], C[kItems];
+    load_tile(src, f * n + start, valid, v, -INFINITY);
+    const double Rt = r_total[f];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        resid_terms(st, v[k], tile_elem(k) < valid, (double)n_out, 1.0 / (double)n, c[k], r[k]);
+        r[k] = Rt > 0.0 ? r[k] / Rt : 0.0;  // r_weights / sum(r_weights), resample.jl:110
+    }
+    tile_scan<long long>(c, C, smi);
+    tile_scan<double>(r, R, sm);
+    const long long co = c_off[f * tpf + tile];
+    const double ro = r_off[f * tpf + tile];
+    IdxT O[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        long long cc = co + C[k];
+        if (cc > n_out) cc = n_out;  // clamp (App. C)
+        O[k] = (IdxT)cc;
+        R[k] = ro + R[k];
+    }
+    store_tile<IdxT>(O_out, f * n + start, valid, O);
+    store_tile<double>(R_out, f * n + start, valid, R);
+}
+
+// ------------------------------------------------------------------ K9 reweight after resample
+// update_weights! without priorities: full state lw .= 0.0 (resample.jl:193-195); sub-state
+// lw .= logsumexp(lw) - log(n_v) (resample.jl:208-210).
+static __global__ void k_fill_weights(double *lw_out, int64_t n_out, const Stats *stats, int substate, int64_t n_in, int gate) {
+    int64_t f = blockIdx.y;
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+        if (gate && !stats[f].do_resample) return;
+    }
+    const double val = substate ? stats[f].lse - log((double)n_in) : 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x)
+        lw_out[f * n_out + j] = val;
+}
+// with priorities: d_j = lw[parent_j] - lp[parent_j] (resample.jl:197,212)
+template <typename InT>
+static __global__ void k_prio_ratio(const double *lw, LwSrc lp, const InT *parents, int64_t in_base, int64_t n_in,
+                             int64_t n_out, double *d_out) {
+    int64_t f = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = (int64_t)parents[f * n_out + j] - in_base;
+        d_out[f * n_out + j] = lw[f * n_in + p] - lp.fix(lp.p[f * n_in + p]);
+    }
+}
+// lw_j = d_j + (log(n_out) - lse(d))  full (resample.jl:201, resize.jl:436)
+//      = d_j + (lse(lw_old) - lse(d)) sub-state (resample.jl:215-216)
+static __global__ void k_prio_shift(double *d, int64_t n_out, const Stats *st_d, const Stats *st_lw, int substate) {
+    int64_t f = blockIdx.y;
+    const double shift = substate ? (st_lw[f].lse - st_d[f].lse) : (log((double)n_out) - st_d[f].lse);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x)
+        d[f * n_out + j] = d[f * n_out + j] + shift;
+}
+
+// get_log_norm_weights (utils.jl:148) / get_norm_weights (utils.jl:156)
+static __global__ void k_normalize_out(const double *lw, int64_t n, const Stats *stats, double *log_norm, double *norm) {
+    const Stats st = stats[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = lw[i];
+        if (log_norm) log_norm[i] = v - st.lse;
+        if (norm) norm[i] = exp(v - st.M) / st.S;
+    }
+}
+
+// ------------------------------------------------------------------ K12 weighted mean / variance
+// mean = sum(softmax(lw) .* x); var = sum(softmax(lw) .* (x .- mean).^2)  -- two pass, like statistics.jl:13-17,48-54
+struct XSrc {
+    const double *d;   // fp64 column, or
+    const uint8_t *b;  // Bool column promoted to fp64 (README.md:97)
+    __device__ __forceinline__ double operator()(int64_t i) const { return d ? d[i] : (double)b[i]; }
+};
+static __global__ void __launch_bounds__(kThreads)
+    k_weighted_moment(LwSrc lw, XSrc x, int64_t n, int64_t tpf, const Stats *stats, const double *center,
+                      double *partial) {
+    __shared__ double sm[kWarps];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const Stats st = stats[f];
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    double v[kItems];
+    load_tile(lw, f * n + start, valid, v, -INFINITY);
+    const double c = center ? center[f] : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        int e = tile_elem(k);
+        if (e < valid) {
+            double xv = x(f * n + start + e);
+            double wv = exp(v[k] - st.M) / st.S;
+            double t = center ? (xv - c) * (xv - c) : xv;
+            acc += wv * t;
+        }
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+static __global__ void __launch_bounds__(kThreads) k_sum_partials(const double *partial, int64_t tpf, double *out) {
+    __shared__ double sm[kWarps];
+    const int64_t f = blockIdx.x;
+    double s = 0.0;
+    for (int64_t b = threadIdx.x; b < tpf; b += kThreads) s += partial[f * tpf + b];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) out[f] = s;
+}
+
+// ------------------------------------------------------------------ K13 replicate / dereplicate
+// pf_replicate! resize.jl:236-244: repeat(x; inner=k) | repeat(x, k); weights copied unchanged
+template <typename OutT>
+static __global__ void k_replicate(const double *lw, int64_t n, int64_t k, int interleaved, OutT *parents, int64_t out_base,
+                            double *lw_out) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n * k; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t src = interleaved ? (j % n) : (j / k);
+        if (parents) parents[j] = (OutT)(src + out_base);
+        if (lw_out) lw_out[j] = lw[src];
+    }
+}
+// pf_dereplicate! resize.jl:267-297.  One thread per retained particle; the block of k replicas is walked
+// sequentially exactly like the reference (softmax, then single inverse-CDF draw `cp <= u`, lse - log k).
+template <typename OutT>
+static __global__ void k_dereplicate(const double *lw, int64_t n, int64_t k, int interleaved, int sample, UniSrc uni,
+                              OutT *parents, int64_t out_base, double *lw_out) {
+    const int64_t n_new = n / k;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_new; b += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t first = interleaved ? b : b * k;
+        const int64_t stride = interleaved ? n_new : 1;
+        if (!sample) {
+            if (parents) parents[b] = (OutT)(first + out_base);
+            lw_out[b] = lw[first];
+            continue;
+        }
+        double m = -INFINITY;
+        for (int64_t j = 0; j < k; ++j) m = fmax(m, lw[first + j * stride]);
+        double s = 0.0;
+        for (int64_t j = 0; j < k; ++j) s += exp(lw[first + j * stride] - m);
+        const double u = uni(b);
+        int64_t i = 0;
+        double cp = exp(lw[first] - m) / s;
+        while (cp <= u && i < k - 1) {
+            i += 1;
+            cp += exp(lw[first + i * stride] - m) / s;
+        }
+        if (parents) parents[b] = (OutT)(first + i * stride + out_base);
+        lw_out[b] = (m == -INFINITY ? -INFINITY : m + log(s)) - log((double)k);
+    }
+}
+
+static __global__ void k_materialize(LwSrc src, int64_t n, double *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = src.fix(src.p[i]);
+}
+
+static __global__ void k_uniforms(UniSrc uni, int64_t n, double *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = uni(i);
+}
+
+template <typename A, typename B>
+static __global__ void k_convert_idx(const A *in, B *out, int64_t n, int64_t add) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (B)((int64_t)in[i] + add);
+}
+
+}  // namespace genpf

@@ -1,0 +1,220 @@
+/*
+ * genpf.h -- C ABI of libgenpf_cuda.so, the B200 (sm_100a) particle-filter engine
+ * that stands behind GenParticleFilters.jl's weight / propagate / resample /
+ * rejuvenate / statistics / resize path.
+ *
+ * The reference (Julia) has no FFI boundary; the cut line is the
+ * plain-bits part of `ParticleFilterState`: log_weights::Vector{Float64},
+ * parents::Vector{Int64}, log_ml_est::Float64 (reference src/view.jl:16-22,
+ * src/initialize.jl:4-10).  Every entry point below names the reference
+ * function it replaces (paths relative to the reference root).  Julia binds
+ * these with `ccall((:genpf_xxx, "libgenpf_cuda"), Int32, (...), ...)`; see
+ * INTEGRATION.md and genparticlefilters.jl_b200/julia/GenPFCuda.jl.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; all sizes int64_t; weights fp64.
+ *  - every function returns an int32 status (0 ok, <0 error), never throws or
+ *    exits; genpf_last_error() returns a thread-local message.
+ *  - host-array calls take HOST pointers (valid only during the call) unless
+ *    GENPF_DEVICE_PTRS is set; they are synchronous on return.
+ *  - parents are written 1-based when GENPF_INDEX_BASE1 is set (Julia), else 0-based.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails
+ *    with GENPF_ERR_CUDA.
+ */
+#ifndef GENPF_H
+#define GENPF_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENPF_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---- */
+#define GENPF_OK 0
+#define GENPF_ERR_INVALID_ARG (-1)
+#define GENPF_ERR_CUDA (-2)
+#define GENPF_ERR_INVALID_WEIGHTS (-3) /* error("Invalid weights."), resample.jl:55,92,151 (check=true) */
+#define GENPF_ERR_UNKNOWN_METHOD (-4)  /* error("Resampling method ... not recognized."), resample.jl:28 */
+#define GENPF_ERR_NOMEM (-5)
+#define GENPF_ERR_UNSUPPORTED (-6)
+#define GENPF_ERR_STATE (-7)
+
+/* ---- method / option enums (mirror the reference's Symbols, SURVEY.md section 5 "config") ---- */
+#define GENPF_MULTINOMIAL 0 /* :multinomial  resample.jl:48-65,  resize.jl:46-67  */
+#define GENPF_RESIDUAL 1    /* :residual     resample.jl:85-120, resize.jl:87-124 */
+#define GENPF_STRATIFIED 2  /* :stratified   resample.jl:143-175 */
+
+#define GENPF_SORT_PARTICLES 1u /* sort_particles=true, resample.jl:143-145,156-157 */
+#define GENPF_SUBSTATE 2u       /* ParticleFilterSubState semantics, resample.jl:184-187,205-218 */
+#define GENPF_INDEX_BASE1 4u    /* parents written 1-based (Vector{Int}, view.jl:21) */
+#define GENPF_DEVICE_PTRS 8u    /* array arguments are device pointers (CUDA.jl CuArray) */
+#define GENPF_CHECK 16u         /* check=true: invalid weights => GENPF_ERR_INVALID_WEIGHTS */
+
+/* invalid_kind: which branch of safe_softmax fired, utils.jl:119-137 */
+#define GENPF_VALID 0
+#define GENPF_INV_NAN_INPUT 1  /* utils.jl:119-122 "NaN found in input values."            */
+#define GENPF_INV_ALL_NEGINF 2 /* utils.jl:123-126 "All input values are -Inf."  (uniform) */
+#define GENPF_INV_ZERO_TOTAL 3 /* utils.jl:130-133 "All weights are zero."       (uniform) */
+#define GENPF_INV_NAN_TOTAL 4  /* utils.jl:134-137 "Total weight is NaN."                  */
+
+#define GENPF_LAYOUT_CONTIGUOUS 0  /* layout=:contiguous,  resize.jl:236-238 */
+#define GENPF_LAYOUT_INTERLEAVED 1 /* layout=:interleaved */
+#define GENPF_KEEPFIRST 0          /* method=:keepfirst, resize.jl:272-276 */
+#define GENPF_SAMPLE 1             /* method=:sample,    resize.jl:278-291 */
+
+#define GENPF_PRIO_NONE 0   /* priority_fn === nothing, resample.jl:51-52 */
+#define GENPF_PRIO_SCALE 1  /* priority_fn = w -> alpha*w (the documented w/2 case) */
+#define GENPF_PRIO_COLUMN 2 /* caller-supplied device/host column of log priorities */
+
+/* device-filter creation flags */
+#define GENPF_NOISE_LEAN 0u     /* one Philox4x32-10 call per particle per purpose, fp32 Box-Muller */
+#define GENPF_NOISE_PHILOX53 1u /* 53-bit uniforms + fp64 Box-Muller */
+#define GENPF_KEEP_HISTORY 2u   /* keep every time slice + ancestry log (mean/var of past addresses) */
+
+/* ---- library ---- */
+int32_t genpf_version(void);
+const char *genpf_last_error(void);
+int32_t genpf_device_count(int32_t *count);
+int32_t genpf_set_device(int32_t device);
+int32_t genpf_synchronize(void);
+
+/* =====================================================================
+ * Host-array path (arbitrary Gen models: traces stay in Julia, only the
+ * weight vector and the ancestor indices cross the boundary)
+ * ===================================================================== */
+
+/* Gen.logsumexp(log_weights)   (called at resample.jl:180,200,210,215; utils.jl:100,177) */
+int32_t genpf_logsumexp(const double *lw, int64_t n, uint32_t flags, double *out);
+
+/* effective_sample_size / get_ess, utils.jl:163-171 */
+int32_t genpf_ess(const double *lw, int64_t n, uint32_t flags, double *out);
+
+/* get_log_norm_weights (utils.jl:148), get_norm_weights (utils.jl:156) and safe_softmax's
+ * validity (utils.jl:117-140) in one pass pair.  log_norm / norm may be NULL. */
+int32_t genpf_normalize(const double *lw, int64_t n, uint32_t flags, double *log_norm, double *norm, double *lse,
+                        double *ess, int32_t *invalid_kind);
+
+/* pf_resample! (resample.jl:19-30) and pf_resize! for :multinomial/:residual (resize.jl:16-27):
+ *   prologue  safe_softmax(log_prio or lw), update_lml_est!   resample.jl:51-57,178-187
+ *   select    ancestors into parents_out[n_out]               resample.jl:59,96-115,156-170
+ *   epilogue  update_weights! into lw_out[n_out]              resample.jl:190-218, resize.jl:424-438
+ * log_prio == NULL  <=>  `log_priorities === state.log_weights` (resample.jl:193).
+ * uniforms: n_out doubles in [0,1) (stratified: one per stratum; residual: slot j uses uniforms[j]);
+ *           NULL => Philox4x32-10(seed, stream 0, counter = slot), 53-bit.
+ * lml_increment = logsumexp(lw) - log(n_in)  (0 for GENPF_SUBSTATE); caller adds it to state.log_ml_est.
+ * NaN weights (kinds 1, 4) leave parents_out / lw_out untouched (the reference crashes there). */
+int32_t genpf_resample(int32_t method, const double *lw, const double *log_prio, int64_t n_in, int64_t n_out,
+                       const double *uniforms, uint64_t seed, uint32_t flags, int64_t *parents_out, double *lw_out,
+                       double *lml_increment, int32_t *invalid_kind);
+
+/* The same over n_seg disjoint views of one state (`state[idxs]`, view.jl:35-48; test/resample.jl:130-162):
+ * segment s = [seg_offsets[s], seg_offsets[s+1]); parents are LOCAL to the segment; GENPF_SUBSTATE implied. */
+int32_t genpf_resample_segmented(int32_t method, const double *lw, const double *log_prio, int64_t n,
+                                 const int64_t *seg_offsets, int64_t n_seg, const double *uniforms, uint64_t seed,
+                                 uint32_t flags, int64_t *parents_out, double *lw_out, int32_t *invalid_kinds);
+
+/* mean(state, addr) / var(state, addr), statistics.jl:13-17,48-54 (x = getindex.(traces, addr) as fp64) */
+int32_t genpf_weighted_mean_var(const double *lw, const double *x, int64_t n, uint32_t flags, double *mean,
+                                double *var);
+
+/* pf_replicate! index/weight arithmetic, resize.jl:236-244 (n -> n*k) */
+int32_t genpf_replicate_host(const double *lw, int64_t n, int64_t k, int32_t layout, uint32_t flags,
+                             int64_t *parents_out, double *lw_out);
+/* pf_dereplicate!, resize.jl:267-297 (n -> n/k); uniforms (n/k) only for GENPF_SAMPLE, NULL => Philox(seed) */
+int32_t genpf_dereplicate_host(const double *lw, int64_t n, int64_t k, int32_t layout, int32_t method,
+                               const double *uniforms, uint64_t seed, uint32_t flags, int64_t *parents_out,
+                               double *lw_out);
+/* pf_coalesce!, resize.jl:309-334, with int64 keys standing for by(trace); returns n_new; output in
+ * ascending first-index order (the reference's Dict order is unspecified). */
+int32_t genpf_coalesce_host(const double *lw, const int64_t *keys, int64_t n, uint32_t flags, int64_t *parents_out,
+                            double *lw_out, int64_t *n_new);
+
+/* Philox uniforms exactly as the library generates them (for exporting / parity) */
+int32_t genpf_uniforms(uint64_t seed, uint64_t stream, int64_t n, uint32_t flags, double *out);
+
+/* debug / parity: normalised cumulative weights W_k the selection kernels search (device order) */
+int32_t genpf_debug_cumweights(const double *lw, int64_t n, uint32_t flags, double *W_out);
+
+/* =====================================================================
+ * Device-resident path (models registered as device plugins)
+ * ===================================================================== */
+typedef struct genpf_filter_s *genpf_filter_t;
+
+/* built-in plugins: "object_motion" (README.md:43-54; params p_stay,p_start,sigma_proc,sigma_obs),
+ *                   "lingauss1d"    (SURVEY B.2;      params a,q,r,m0,s0) */
+int32_t genpf_model_builtin(const char *name, int32_t *model_id);
+int32_t genpf_model_info(int32_t model_id, int32_t *n_f64_fields, int32_t *n_u8_fields, int32_t *n_params,
+                         int32_t *n_aux);
+
+/* n_filters independent filters of n_particles each (views / batches, view.jl:16-48).  params may be NULL
+ * (README constants). */
+int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_params, int64_t n_particles,
+                            int64_t n_filters, uint64_t seed, uint32_t flags, genpf_filter_t *out);
+int32_t genpf_filter_destroy(genpf_filter_t pf);
+int32_t genpf_filter_size(genpf_filter_t pf, int64_t *n_particles, int64_t *n_filters);
+
+/* pf_initialize(model, (1,), obs_1, n), initialize.jl:31-44.  obs[n_filters], aux[n_aux] (object_motion:
+ * aux[0] = sin(1.0) computed by the caller so Julia's sin is used). */
+int32_t genpf_initialize(genpf_filter_t pf, const double *obs, const double *aux);
+int32_t genpf_initialize_with_noise(genpf_filter_t pf, const double *obs, const double *aux, const double *U,
+                                    const double *Z);
+
+/* pf_update!(state, (t,), (UnknownChange(),), obs_t), update.jl:12-25 */
+int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux);
+int32_t genpf_update_with_noise(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
+                                const double *Z);
+
+/* effective_sample_size(state) / log_ml_estimate(state): out[n_filters] */
+int32_t genpf_ess_dev(genpf_filter_t pf, double *ess);
+int32_t genpf_lml_dev(genpf_filter_t pf, double *lml);
+
+/* pf_resample!(state, method; priority_fn, check, sort_particles) on device state, resample.jl:19-30;
+ * n_out != n_particles gives pf_resize! (resize.jl:16-27) for multinomial/residual (n_filters == 1). */
+int32_t genpf_resample_dev(genpf_filter_t pf, int32_t method, int32_t prio_kind, double prio_param,
+                           const double *prio_column, int64_t n_out, uint32_t flags, const double *uniforms,
+                           int32_t *invalid_kinds);
+
+/* pf_rejuvenate!(state, mh, (select(tau=>latents),), n_iters), rejuvenate.jl:18-27,40-53, with tau the newest
+ * slice; obs/aux are those of step tau.  n_accept[n_filters] may be NULL. */
+int32_t genpf_rejuvenate_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
+                            int64_t *n_accept);
+int32_t genpf_rejuvenate_mh_with_noise(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
+                                       const double *U2, const double *Z2, const double *U3, int64_t *n_accept);
+
+/* One README loop iteration (README.md:66-77) fused on the device:
+ *   ess = effective_sample_size(state); if ess < ess_frac*n: pf_resample!(method); pf_rejuvenate!(mh) end;
+ *   pf_update!(t).  Results are identical to the three separate calls.  ess_out[n_filters] may be NULL
+ * (then nothing is copied back and the call is asynchronous on the filter's stream). */
+int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                   const double *obs_t, const double *aux_t, int32_t method, double ess_frac, int32_t mh_iters,
+                   double *ess_out);
+
+/* mean(state, tau=>field) / var(...), statistics.jl:13-17,48-54.  field: 0..n_f64-1 are the fp64 fields,
+ * n_f64.. the u8 (Bool) fields promoted to fp64 (README.md:97).  out[n_filters]. */
+int32_t genpf_mean_var(genpf_filter_t pf, int32_t field, int64_t tau, double *mean, double *var);
+
+/* pf_replicate! / pf_dereplicate! / pf_coalesce!, resize.jl:236-334, on device state (n_filters == 1) */
+int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout);
+int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms);
+int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new);
+
+/* accessors (also checkpoint I/O): out sized n_particles*n_filters */
+int32_t genpf_get_log_weights(genpf_filter_t pf, double *out);
+int32_t genpf_set_log_weights(genpf_filter_t pf, const double *in);
+int32_t genpf_get_parents(genpf_filter_t pf, int64_t *out, uint32_t flags);
+int32_t genpf_get_field(genpf_filter_t pf, int32_t field, int64_t tau, double *out);
+int32_t genpf_set_field(genpf_filter_t pf, int32_t field, int64_t tau, const double *in);
+int32_t genpf_get_accepts(genpf_filter_t pf, uint8_t *out);
+int32_t genpf_filter_sync(genpf_filter_t pf);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t genpf_launch_count(void);
+
+/* raw device pointers for multi-GPU plumbing (CUDA IPC / NCCL are driven by the host language) */
+int32_t genpf_filter_stream(genpf_filter_t pf, void **cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENPF_H */

@@ -1,0 +1,36 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import oracle
+    oracle.load()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def g():
+    """The product package; GPU tests only.  Fails loudly if the CUDA library is missing."""
+    import genpf_b200
+    genpf_b200.load()
+    return genpf_b200
+
+
+GOLDEN_CASES = ["n100_s1", "n1000_s5", "n2048_s2", "n3000_s1"]

@@ -1,0 +1,204 @@
+"""Generates tests/golden/golden_v1.npz.
+
+The reference (Julia) cannot run in this image and ships no seeded vectors, so these
+fixtures are produced by a SECOND, independent restatement of the reference algorithms written in
+pure-Python IEEE-double arithmetic (math.exp/log = the same libm as the C oracle, no FMA, literal
+loops), each function citing the reference file:line.  tests/test_oracle_kat.py requires the C oracle
+to reproduce them bit-for-bit; the GPU tests then check the CUDA path against the same files.
+Run:  python tests/golden/make_golden.py
+"""
+import math
+import os
+import struct
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+M32 = 0xFFFFFFFF
+
+
+# ---- Philox4x32-10 (shared RNG convention; not reference arithmetic)
+def philox(ctr, key):
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M32, p1 & M32, ((p0 >> 32) ^ c3 ^ k1) & M32, p0 & M32
+        k0 = (k0 + 0x9E3779B9) & M32
+        k1 = (k1 + 0xBB67AE85) & M32
+    return c0, c1, c2, c3
+
+
+def uniform53(seed, stream, idx):
+    o = philox((idx & M32, idx >> 32, stream & M32, stream >> 32), (seed & M32, seed >> 32))
+    x = (o[1] << 32) | o[0]
+    return (x >> 11) * 2.0 ** -53
+
+
+def normal_from(seed, stream, idx):  # inputs only; any deterministic generator would do
+    u1 = 1.0 - uniform53(seed, stream, 2 * idx)
+    u2 = uniform53(seed, stream, 2 * idx + 1)
+    return math.sqrt(-2.0 * math.log(u1)) * math.cos(2.0 * math.pi * u2)
+
+
+# ---- Julia Base.sum (pairwise, 1024 block) and Gen.logsumexp
+def jl_sum(a, lo=0, hi=None):
+    hi = len(a) - 1 if hi is None else hi
+    if lo == hi:
+        return a[lo]
+    if hi - lo < 1024:
+        v = a[lo] + a[lo + 1]
+        for i in range(lo + 2, hi + 1):
+            v += a[i]
+        return v
+    mid = lo + ((hi - lo) >> 1)
+    return jl_sum(a, lo, mid) + jl_sum(a, mid + 1, hi)
+
+
+def logsumexp(v):
+    m = max(v)
+    if m == -math.inf:
+        return -math.inf
+    return m + math.log(jl_sum([math.exp(x - m) for x in v]))
+
+
+def softmax(v):  # utils.jl:103-107
+    m = max(v)
+    ws = [math.exp(x - m) for x in v]
+    s = jl_sum(ws)
+    return [w / s for w in ws]
+
+
+def safe_softmax(v):  # utils.jl:117-140
+    n = len(v)
+    if any(math.isnan(x) for x in v):
+        return [math.nan] * n, 1
+    if all(x == -math.inf for x in v):
+        return [1.0 / n] * n, 2
+    m = max(v)
+    ws = [math.exp(x - m) for x in v]
+    total = jl_sum(ws)
+    if total == 0.0:
+        return [1.0 / n] * n, 3
+    if math.isnan(total):
+        return [math.nan] * n, 4
+    s = jl_sum(ws)
+    return [w / s for w in ws], 0
+
+
+def ess(lw):  # utils.jl:163-164 + Gen.effective_sample_size
+    l = logsumexp(lw)
+    return math.exp(-logsumexp([2.0 * (x - l) for x in lw]))
+
+
+def sortperm_desc(keys):  # sortperm(v, rev=true): stable, ties by ascending index
+    return sorted(range(len(keys)), key=lambda i: (-keys[i], i))
+
+
+def stratified(w, r, order=None):  # resample.jl:159-170, literal
+    n = len(w)
+    order = list(range(n)) if order is None else order
+    parents = [0] * n
+    i_old, step, accum = 0, 1.0 / n, 0.0
+    for i_new in range(1, n + 1):
+        lower = (i_new - 1) / n
+        if lower + step > accum:
+            u = r[i_new - 1] * step
+            u = u + lower
+            while accum < u and i_old < n:
+                accum += w[order[i_old]]
+                i_old += 1
+        parents[i_new - 1] = order[max(i_old, 1) - 1]
+    return parents
+
+
+def multinomial(w, us):  # inverse CDF, Distributions single-draw rule (resize.jl:284): first W_i > u
+    out = []
+    n = len(w)
+    W, acc = [], 0.0
+    for x in w:
+        acc += x
+        W.append(acc)
+    for u in us:
+        i = 0
+        while W[i] <= u and i < n - 1:
+            i += 1
+        out.append(i)
+    return out
+
+
+def residual(w, us, n_out):  # resample.jl:96-115 / resize.jl:100-119
+    parents = []
+    for i, x in enumerate(w):
+        c = int(math.floor(n_out * x))
+        parents += [i] * c
+    parents = parents[:n_out]
+    nd = len(parents)
+    if nd < n_out:
+        rw = [n_out * x - math.floor(n_out * x) for x in w]
+        s = jl_sum(rw)
+        rw = [x / s for x in rw]
+        parents += multinomial(rw, us[nd:n_out])
+    return parents, nd
+
+
+def reweight(lw, lp, parents, n_out, substate):  # resample.jl:190-218, resize.jl:424-438
+    if lp is None:
+        v = logsumexp(lw) - math.log(len(lw)) if substate else 0.0
+        return [v] * n_out
+    d = [lw[p] - lp[p] for p in parents]
+    shift = (logsumexp(lw) - logsumexp(d)) if substate else (math.log(n_out) - logsumexp(d))
+    return [x + shift for x in d]
+
+
+def mean_var(lw, x):  # statistics.jl:13-17,48-54
+    w = softmax(lw)
+    mu = jl_sum([a * b for a, b in zip(w, x)])
+    return mu, jl_sum([a * ((b - mu) * (b - mu)) for a, b in zip(w, x)])
+
+
+def main():
+    out = {}
+    cases = [("n100_s1", 100, 1.0, 11), ("n1000_s5", 1000, 5.0, 12), ("n2048_s2", 2048, 2.0, 13),
+             ("n3000_s1", 3000, 1.0, 14)]
+    for name, n, sigma, seed in cases:
+        lw = [sigma * normal_from(seed, 7, i) for i in range(n)]
+        u = [uniform53(seed, 0, i) for i in range(n)]
+        out[f"{name}/lw"] = np.array(lw)
+        out[f"{name}/u"] = np.array(u)
+        out[f"{name}/lse"] = np.array(logsumexp(lw))
+        out[f"{name}/ess"] = np.array(ess(lw))
+        w, kind = safe_softmax(lw)
+        assert kind == 0
+        out[f"{name}/w"] = np.array(w)
+        x = [normal_from(seed, 9, i) for i in range(n)]
+        out[f"{name}/x"] = np.array(x)
+        out[f"{name}/mean_var"] = np.array(mean_var(lw, x))
+        # stratified, unsorted and sorted, with and without priorities w -> w/2 (test/resample.jl:90-119)
+        p = stratified(w, u)
+        out[f"{name}/strat/parents"] = np.array(p)
+        order = sortperm_desc(lw)
+        out[f"{name}/order"] = np.array(order)
+        out[f"{name}/strat_sorted/parents"] = np.array(stratified(w, u, order))
+        lp = [x_ / 2 for x_ in lw]
+        wp, _ = safe_softmax(lp)
+        pp = stratified(wp, u)
+        out[f"{name}/strat_prio/parents"] = np.array(pp)
+        out[f"{name}/strat_prio/lw_out"] = np.array(reweight(lw, lp, pp, n, False))
+        out[f"{name}/strat_prio/lw_out_sub"] = np.array(reweight(lw, lp, pp, n, True))
+        out[f"{name}/lw_out_sub"] = np.array(reweight(lw, None, p, n, True))
+        # multinomial and residual, plus resize to n/2 and 3n/2 (test/resize.jl:3-84)
+        for n_out in (n, n // 2, n + n // 2):
+            us = [uniform53(seed, 1, i) for i in range(n_out)]
+            out[f"{name}/u_{n_out}"] = np.array(us)
+            out[f"{name}/multi_{n_out}/parents"] = np.array(multinomial(w, us))
+            rp, nd = residual(w, us, n_out)
+            out[f"{name}/resid_{n_out}/parents"] = np.array(rp)
+            out[f"{name}/resid_{n_out}/n_det"] = np.array(nd)
+    np.savez_compressed(os.path.join(HERE, "golden_v1.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,361 @@
+"""GPU parity tests of the device-resident path (plugin models): pf_initialize / pf_update! /
+pf_resample! / pf_rejuvenate!(mh) / mean / var / resizing, against the CPU oracle with the SAME noise
+columns (parity mode) and against closed forms (README posterior flip, Kalman filter)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from util import check_parents, strat_u
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def noisy_init(g, pf, obs, U, Z):
+    L = g._lib
+    L.check(g.load().genpf_initialize_with_noise(pf._h, L.ptr(pf._obs(obs)), L.ptr(pf.model.aux(1)), L.ptr(U), L.ptr(Z)))
+    pf.t = 1
+
+
+def noisy_update(g, pf, t, obs, U, Z):
+    L = g._lib
+    L.check(g.load().genpf_update_with_noise(pf._h, t, L.ptr(pf._obs(obs)), L.ptr(pf.model.aux(t)), L.ptr(U), L.ptr(Z)))
+    pf.t = t
+
+
+def noisy_mh(g, pf, tau, obs, U2, Z2, U3):
+    L = g._lib
+    acc = np.zeros(pf.n_filters, dtype=np.int64)
+    L.check(g.load().genpf_rejuvenate_mh_with_noise(pf._h, tau, L.ptr(pf._obs(obs)), L.ptr(pf.model.aux(tau)),
+                                                    L.ptr(U2), L.ptr(Z2), L.ptr(U3), L.ptr(acc)))
+    return acc
+
+
+@pytest.mark.parametrize("n", [100, 2048, 5000, (1 << 17) + 7])
+def test_object_motion_parity_with_noise(g, orc, n):
+    """Full README-style sequence with supplied noise: state columns bit-identical, log-weights 1e-10."""
+    rng = np.random.default_rng(n)
+    model = g.DeviceModel("object_motion")
+    pf = g.DevicePFState(model, n, seed=1)
+    T = 6
+    obs = np.concatenate([rng.normal(0, 0.3, 3), np.sin(np.arange(4, T + 1)).cumsum() + rng.normal(0, 0.3, T - 3)])
+    vel = [math.sin(float(t)) for t in range(0, T + 1)]
+    # t = 1
+    U, Z = rng.random(n), rng.normal(size=n)
+    noisy_init(g, pf, obs[0], U, Z)
+    y1, m1 = orc.om_transition(None, None, vel[1], U, Z)
+    lw = orc.om_obs_logpdf(y1, obs[0])
+    np.testing.assert_array_equal(pf.field("y", 1), y1)
+    np.testing.assert_array_equal(pf.field("moving", 1), m1)
+    np.testing.assert_allclose(pf.log_weights, lw, rtol=RTOL)
+    ys, ms = {0: np.zeros(n), 1: y1}, {0: np.zeros(n, dtype=np.uint8), 1: m1}
+    lml = 0.0
+    for t in range(2, T + 1):
+        # ESS
+        assert g.effective_sample_size(pf) == pytest.approx(orc.ess(lw), rel=RTOL)
+        assert g.log_ml_estimate(pf) == pytest.approx(lml + orc.logsumexp(lw) - math.log(n), rel=RTOL, abs=1e-9)
+        # resample (alternate the three methods), then MH on tau = t-1, then update to t
+        method = ["stratified", "residual", "multinomial"][t % 3]
+        r = rng.random(n)
+        g.pf_resample(pf, method, sort_particles=False, uniforms=r)
+        p_ref, lw_new, inc, _ = orc.resample(method, lw, r)
+        p = pf.parents
+        W_ref = orc.cumweights(orc.softmax(lw))
+        if method == "stratified":
+            nm, _ = check_parents(p, p_ref, W_ref, strat_u(r, n))
+        elif method == "multinomial":
+            nm, _ = check_parents(p, p_ref, W_ref, r)
+        else:
+            nm = int(np.sum(p != p_ref))
+        assert nm == 0  # no ties expected at these sizes
+        lml += inc
+        for tau in (t - 2, t - 1):
+            ys[tau], ms[tau] = ys[tau][p_ref], ms[tau][p_ref]
+        lw = lw_new
+        np.testing.assert_array_equal(pf.field("y", t - 1), ys[t - 1])
+        np.testing.assert_array_equal(pf.log_weights, lw)
+        U2, Z2, U3 = rng.random(n), rng.normal(size=n), rng.random(n)
+        acc = noisy_mh(g, pf, t - 1, obs[t - 2], U2, Z2, U3)
+        yq, mq, a_ref = orc.om_mh(ys[t - 2] if t > 2 else None, ms[t - 2] if t > 2 else None, ys[t - 1], ms[t - 1],
+                                  vel[t - 1], obs[t - 2], U2, Z2, U3)
+        ys[t - 1], ms[t - 1] = yq, mq
+        np.testing.assert_array_equal(pf.accepts, a_ref)  # trace changes iff accepted (test/rejuvenate.jl:30-50)
+        assert acc[0] == a_ref.sum()
+        np.testing.assert_array_equal(pf.field("y", t - 1), yq)
+        np.testing.assert_array_equal(pf.field("moving", t - 1), mq)
+        np.testing.assert_array_equal(pf.log_weights, lw)  # move-accept leaves weights alone
+        U, Z = rng.random(n), rng.normal(size=n)
+        noisy_update(g, pf, t, obs[t - 1], U, Z)
+        ys[t], ms[t] = orc.om_transition(ys[t - 1], ms[t - 1], vel[t], U, Z)
+        lw = orc.om_obs_logpdf(ys[t], obs[t - 1], lw)
+        np.testing.assert_array_equal(pf.field("y", t), ys[t])
+        np.testing.assert_array_equal(pf.field("moving", t), ms[t])
+        np.testing.assert_allclose(pf.log_weights, lw, rtol=RTOL, atol=1e-12)
+    m_gpu, v_gpu = g.mean(pf, (T, "y")), g.var(pf, (T, "y"))
+    m_ref, v_ref = orc.mean_var(lw, ys[T])
+    assert m_gpu == pytest.approx(m_ref, rel=RTOL) and v_gpu == pytest.approx(v_ref, rel=RTOL)
+    m_gpu = g.mean(pf, (T, "moving"))  # Bool promoted to fp64 (README.md:97)
+    assert m_gpu == pytest.approx(orc.mean_var(lw, ms[T].astype(float))[0], rel=RTOL, abs=1e-15)
+
+
+def test_lingauss_parity_with_noise(g, orc):
+    rng = np.random.default_rng(5)
+    n = 10_000
+    params = (0.9, 1.0, 1.0, 0.0, 1.0)
+    model = g.DeviceModel("lingauss1d", params)
+    pf = g.DevicePFState(model, n)
+    sig1 = math.sqrt(0.9 ** 2 * 1.0 + 1.0)
+    Z = rng.normal(size=n)
+    noisy_init(g, pf, 0.3, np.zeros(n), Z)
+    x1 = orc.lg_transition(np.zeros(n), Z, (0.9, sig1, 1.0, 0.0, 1.0))
+    lw = orc.lg_obs_logpdf(x1, 0.3, params)
+    np.testing.assert_array_equal(pf.field("x", 1), x1)
+    np.testing.assert_allclose(pf.log_weights, lw, rtol=RTOL)
+    Z = rng.normal(size=n)
+    noisy_update(g, pf, 2, -0.2, np.zeros(n), Z)
+    x2 = orc.lg_transition(x1, Z, params)
+    lw = orc.lg_obs_logpdf(x2, -0.2, params, lw)
+    np.testing.assert_array_equal(pf.field("x", 2), x2)
+    np.testing.assert_allclose(pf.log_weights, lw, rtol=RTOL)
+    Z2, U3 = rng.normal(size=n), rng.random(n)
+    noisy_mh(g, pf, 2, -0.2, np.zeros(n), Z2, U3)
+    xq, acc = orc.lg_mh(x1, x2, -0.2, Z2, U3, params)
+    np.testing.assert_array_equal(pf.field("x", 2), xq)
+    np.testing.assert_array_equal(pf.accepts, acc)
+
+
+def readme_observations(T=10, seed=3):
+    """README.md:87-89: moving = t > 5, one fixed draw."""
+    rng = np.random.default_rng(seed)
+    y, obs = 0.0, []
+    for t in range(1, T + 1):
+        y = y + (math.sin(t) if t > 5 else 0.0) + 0.01 * rng.normal()
+        obs.append(y + 0.25 * rng.normal())
+    return np.array(obs)
+
+
+def run_readme_filter(g, n, seed, method="residual", keep_history=True, noise="lean"):
+    """README.md:60-79."""
+    obs = readme_observations()
+    model = g.DeviceModel("object_motion")
+    state = g.pf_initialize(model, (1,), obs[0], n, seed=seed, keep_history=keep_history, noise=noise)
+    for t in range(2, len(obs) + 1):
+        if g.effective_sample_size(state) < 0.5 * n:
+            g.pf_resample(state, method, sort_particles=False)
+            g.pf_rejuvenate(state, g.mh, (t - 1, obs[t - 2]))
+        g.pf_update(state, (t,), None, obs[t - 1])
+    return state
+
+
+@pytest.mark.parametrize("noise", ["lean", "philox53"])
+def test_readme_posterior_flip(g, noise):
+    """README.md:97-104: P(moving) flips from low at t=5 to high at t=6 (their draw: 0.07 / 0.95)."""
+    for n in (100, 100_000):
+        flips = 0
+        for seed in range(5):
+            state = run_readme_filter(g, n, seed, noise=noise)
+            m5, m6 = g.mean(state, (5, "moving")), g.mean(state, (6, "moving"))
+            v5 = g.var(state, (5, "moving"))
+            assert 0.0 <= m5 <= 1.0 and 0.0 <= m6 <= 1.0
+            assert v5 == pytest.approx(m5 * (1 - m5), abs=1e-9)  # Bernoulli variance
+            flips += (m5 < 0.5 < m6)
+        assert flips >= 4, f"posterior flip seen in only {flips}/5 runs at n={n}"
+
+
+def kalman(obs, a, q, r, m0, s0):
+    m, P, lz = m0, s0 ** 2, 0.0
+    for y in obs:
+        mp, Pp = a * m, a * a * P + q * q
+        S = Pp + r * r
+        K = Pp / S
+        lz += -0.5 * ((y - mp) ** 2 / S + math.log(2 * math.pi * S))
+        m, P = mp + K * (y - mp), (1 - K) * Pp
+    return m, P, lz
+
+
+@pytest.mark.parametrize("method", ["stratified", "multinomial", "residual"])
+def test_lingauss_kalman(g, method):
+    """bootstrap PF on the linear-Gaussian tracker against the Kalman filter."""
+    a, q, r, m0, s0 = 0.9, 1.0, 1.0, 0.0, 1.0
+    rng = np.random.default_rng(2)
+    T, n = 30, 1 << 18
+    x, obs = rng.normal(m0, s0), []
+    for _ in range(T):
+        x = a * x + q * rng.normal()
+        obs.append(x + r * rng.normal())
+    model = g.DeviceModel("lingauss1d", (a, q, r, m0, s0))
+    state = g.pf_initialize(model, (1,), obs[0], n, seed=9)
+    for t in range(2, T + 1):
+        g.pf_resample(state, method, sort_particles=False)
+        g.pf_update(state, (t,), None, obs[t - 1])
+    m, P, lz = kalman(obs, a, q, r, m0, s0)
+    ess = g.effective_sample_size(state)
+    se = math.sqrt(P / ess)
+    assert abs(g.mean(state, (T, "x")) - m) < 6 * se
+    assert g.var(state, (T, "x")) == pytest.approx(P, rel=0.05)
+    assert g.log_ml_estimate(state) == pytest.approx(lz, abs=0.05)
+
+
+def test_production_noise_distribution(g):
+    """Philox noise checked distributionally: KS on Z, Bernoulli rate on U."""
+    from scipy import stats
+    n = 1 << 20
+    for noise in ("lean", "philox53"):
+        model = g.DeviceModel("lingauss1d", (0.0, 1.0, 1.0, 0.0, 0.0))  # x_1 = Z exactly
+        state = g.pf_initialize(model, (1,), 0.0, n, seed=123, noise=noise)
+        z = state.field("x", 1)
+        assert stats.kstest(z, "norm").pvalue > 1e-3
+        assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+        model = g.DeviceModel("object_motion")
+        state = g.pf_initialize(model, (1,), 0.0, n, seed=7, noise=noise)
+        frac = state.field("moving", 1).mean()
+        assert abs(frac - 0.25) < 4 * math.sqrt(0.25 * 0.75 / n)
+        # different seeds / steps give different streams
+        s2 = g.pf_initialize(model, (1,), 0.0, n, seed=8, noise=noise)
+        assert np.mean(s2.field("y", 1) == state.field("y", 1)) < 0.01
+
+
+def test_step_equals_separate_calls(g):
+    """genpf_step (one C call per README iteration) == ESS / resample / mh / update issued separately."""
+    obs = readme_observations()
+    n = 50_000
+    model = g.DeviceModel("object_motion")
+    for method in ("stratified", "residual", "multinomial"):
+        a = g.pf_initialize(model, (1,), obs[0], n, seed=11)
+        b = g.pf_initialize(model, (1,), obs[0], n, seed=11)
+        for t in range(2, len(obs) + 1):
+            ess_a = g.pf_step(a, t, obs[t - 2], obs[t - 1], method=method, ess_thresh=0.5)
+            ess_b = g.effective_sample_size(b)
+            assert ess_a[0] == ess_b
+            if ess_b < 0.5 * n:
+                g.pf_resample(b, method, sort_particles=False)
+                g.pf_rejuvenate(b, g.mh, (t - 1, obs[t - 2]))
+            g.pf_update(b, (t,), None, obs[t - 1])
+            np.testing.assert_array_equal(a.log_weights, b.log_weights)
+            np.testing.assert_array_equal(a.field("y", t), b.field("y", t))
+            np.testing.assert_array_equal(a.field("moving", t - 1), b.field("moving", t - 1))
+        assert g.log_ml_estimate(a) == g.log_ml_estimate(b)
+
+
+def test_batched_filters_match_single(g, orc):
+    """n_filters independent filters (views, view.jl:16-48; config 5) == each filter run alone."""
+    rng = np.random.default_rng(13)
+    nf, n = 7, 3000
+    model = g.DeviceModel("object_motion")
+    batch = g.DevicePFState(model, n, n_filters=nf)
+    obs1, obs2 = rng.normal(0, 0.3, nf), rng.normal(0, 0.3, nf)
+    U, Z = rng.random(nf * n), rng.normal(size=nf * n)
+    U2, Z2 = rng.random(nf * n), rng.normal(size=nf * n)
+    r = rng.random(nf * n)
+    noisy_init(g, batch, obs1, U, Z)
+    ess = g.effective_sample_size(batch)
+    g.pf_resample(batch, "stratified", sort_particles=False, uniforms=r)
+    noisy_update(g, batch, 2, obs2, U2, Z2)
+    lml = g.log_ml_estimate(batch)
+    mean_b = g.mean(batch, (2, "y"))
+    for f in range(nf):
+        sl = slice(f * n, (f + 1) * n)
+        one = g.DevicePFState(model, n)
+        noisy_init(g, one, obs1[f], U[sl], Z[sl])
+        assert g.effective_sample_size(one) == ess[f]
+        g.pf_resample(one, "stratified", sort_particles=False, uniforms=r[sl])
+        noisy_update(g, one, 2, obs2[f], U2[sl], Z2[sl])
+        np.testing.assert_array_equal(batch.parents[sl], one.parents)  # local parents
+        np.testing.assert_array_equal(batch.log_weights[sl], one.log_weights)
+        np.testing.assert_array_equal(batch.field("y", 2)[sl], one.field("y", 2))
+        assert g.log_ml_estimate(one) == lml[f]
+        assert g.mean(one, (2, "y")) == mean_b[f]
+
+
+def test_device_resizing(g, orc):
+    """pf_replicate! / pf_dereplicate! / pf_coalesce! / pf_resize! on device state (test/resize.jl)."""
+    rng = np.random.default_rng(17)
+    n, k = 1000, 4
+    model = g.DeviceModel("object_motion")
+    for layout in ("contiguous", "interleaved"):
+        pf = g.pf_initialize(model, (1,), 0.1, n, seed=5)
+        g.pf_update(pf, (2,), None, 0.2)
+        lw0, y0, lml0 = pf.log_weights, pf.field("y", 2), g.log_ml_estimate(pf)
+        g.pf_replicate(pf, k, layout=layout)
+        assert len(pf) == n * k
+        expect = np.repeat(np.arange(n), k) if layout == "contiguous" else np.tile(np.arange(n), k)
+        np.testing.assert_array_equal(pf.parents, expect)
+        np.testing.assert_array_equal(pf.field("y", 2), y0[expect])
+        np.testing.assert_array_equal(pf.log_weights, lw0[expect])
+        assert g.log_ml_estimate(pf) == pytest.approx(lml0, abs=1e-10)  # test/resize.jl:131,144
+        g.pf_update(pf, (3,), None, 0.3)  # the replicated population keeps working
+        g.pf_dereplicate(pf, k, layout=layout)
+        assert len(pf) == n
+        np.testing.assert_array_equal(pf.field("y", 2), y0)
+    # coalesce: replicas are identical particles and collapse back (test/resize.jl:227-254)
+    pf = g.pf_initialize(model, (1,), 0.1, n, seed=6)
+    lml0 = g.log_ml_estimate(pf)
+    y0 = pf.field("y", 1)
+    g.pf_replicate(pf, 3)
+    g.pf_coalesce(pf)
+    assert len(pf) == len(np.unique(y0))
+    assert g.log_ml_estimate(pf) == pytest.approx(lml0, abs=1e-6)
+    # resize through residual / multinomial resampling (test/resize.jl:3-84)
+    for method in ("multinomial", "residual"):
+        for n_new in (n // 2, n + n // 2):
+            pf = g.pf_initialize(model, (1,), 0.1, n, seed=7)
+            lw0, y0, lml0 = pf.log_weights, pf.field("y", 1), g.log_ml_estimate(pf)
+            u = rng.random(n_new)
+            g.pf_resize(pf, n_new, method, uniforms=u)
+            p_ref, lw_ref, _, _ = orc.resample(method, lw0, u, n_out=n_new)
+            assert len(pf) == n_new
+            np.testing.assert_array_equal(pf.parents, p_ref)
+            np.testing.assert_array_equal(pf.field("y", 1), y0[p_ref])
+            assert g.log_ml_estimate(pf) == pytest.approx(lml0, abs=1e-10)
+            g.pf_update(pf, (2,), None, 0.0)
+
+
+def test_history_lineage(g):
+    """mean(state, tau=>addr) for a slice that left the window is resolved through the ancestry log."""
+    obs = readme_observations()
+    n = 4000
+    model = g.DeviceModel("object_motion")
+    state = g.pf_initialize(model, (1,), obs[0], n, seed=2, keep_history=True)
+    cols, par = {}, []
+    for t in range(2, 8):
+        g.pf_resample(state, "stratified", sort_particles=False)
+        p = state.parents
+        for tau in cols:
+            cols[tau] = cols[tau][p]
+        g.pf_rejuvenate(state, g.mh, (t - 1, obs[t - 2]))
+        cols[t - 1] = state.field("moving", t - 1)
+        g.pf_update(state, (t,), None, obs[t - 1])
+    for tau in (1, 3, 5):
+        np.testing.assert_array_equal(state.field("moving", tau), cols[tau])
+        w = np.exp(state.log_weights - state.log_weights.max())
+        w /= w.sum()
+        assert g.mean(state, (tau, "moving")) == pytest.approx(float(np.sum(w * cols[tau])), rel=1e-9, abs=1e-12)
+    plain = g.pf_initialize(model, (1,), obs[0], n, seed=2)
+    g.pf_update(plain, (2,), None, obs[1])
+    g.pf_update(plain, (3,), None, obs[2])
+    with pytest.raises(g.GenPFError):
+        plain.field("moving", 1)  # not resident without GENPF_KEEP_HISTORY
+
+
+def test_device_priorities_and_check(g, orc):
+    rng = np.random.default_rng(23)
+    n = 20_000
+    model = g.DeviceModel("object_motion")
+    pf = g.pf_initialize(model, (1,), 0.4, n, seed=3)
+    lw0, lml0 = pf.log_weights, g.log_ml_estimate(pf)
+    u = rng.random(n)
+    g.pf_resample(pf, "stratified", priority_fn=0.5, sort_particles=False, uniforms=u)  # w -> w/2
+    p_ref, lw_ref, _, _ = orc.resample("stratified", lw0, u, lp=lw0 / 2)
+    np.testing.assert_array_equal(pf.parents, p_ref)
+    np.testing.assert_allclose(pf.log_weights, lw_ref, rtol=RTOL, atol=1e-11)
+    assert g.log_ml_estimate(pf) == pytest.approx(lml0, abs=1e-9)
+    pf.log_weights = np.full(n, -np.inf)
+    with pytest.raises(g.GenPFErrorException, match="Invalid weights."):
+        g.pf_resample(pf, "stratified", check=True)
+    with pytest.warns(UserWarning, match="All input values are -Inf"):
+        g.pf_resample(pf, "stratified", sort_particles=False)
+    assert np.all(pf.log_weights == 0.0)
+    with pytest.raises(g.GenPFErrorException, match="not recognized"):
+        g.pf_resample(pf, "systematic")
