@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: particle-updates/s of the object_motion filter at 2^24 particles per GPU.
+
+One "step" = one README loop iteration (README.md:66-77) with the resample forced:
+    ESS -> pf_resample!(:stratified, sort_particles=false) -> pf_rejuvenate!(mh) -> pf_update!
+over 2^24 particles (BASELINE.json configs).  One JSON line on stdout:
+    value        whole-job particle-updates/s, state resident in HBM, CUDA events on the filter's stream
+    e2e          the same through the public API (genpf_b200.pf_step) with host observation buffers in and
+                 the ESS read back every step
+    roofline     dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+    cpu_baseline the CPU oracle (OpenMP port of the reference algorithms) on a bounded sample, same box
+`--impl reference` times that CPU port alone (the Julia reference cannot run in this image: no julia).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec"
+N_PARTICLES = 1 << 24
+# SURVEY.md 8(d) algorithmic bytes per particle-update, per kernel of the step (sum = 117)
+KERNEL_ALGO_BYTES = {
+    "k_propagate": 34,  # R y,m,lw 17 + W y,m,lw 17
+    "k_scan": 8,        # R lw
+    "k_expand": 4,      # W parents (int32)
+    "k_gather": 44,     # R window 18 + W window 18 + W lw 8
+    "k_mh": 27,         # R window 18 + W slice 9
+    "k_step_fused": 117 - 8,  # everything but the scan's read of lw
+}
+STEP_ALGO_BYTES = 117
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def observations(T, seed=3):
+    """README.md:87-89 generator extended to T steps (moving for t > 5)."""
+    rng = np.random.default_rng(seed)
+    y, obs = 0.0, []
+    for t in range(1, T + 1):
+        y = y + (math.sin(t) if t > 5 else 0.0) + 0.01 * rng.normal()
+        obs.append(y + 0.25 * rng.normal())
+    return np.array(obs)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def cpu_arm(steps, warmup, n_sample, omp=True):
+    """The CPU port of the reference path (oracle/) on the host cores: same step, bounded sample."""
+    from oracle import oracle as orc
+    T = warmup + steps + 1
+    obs = observations(T)
+    f = orc.OMFilter(n_sample, seed=0, omp=omp)
+    f.init(math.sin(1.0), obs[0])
+    t = 2
+    for _ in range(warmup):
+        f.step(t, math.sin(t - 1.0), obs[t - 2], math.sin(float(t)), obs[t - 1])
+        t += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f.step(t, math.sin(t - 1.0), obs[t - 2], math.sin(float(t)), obs[t - 1])
+        t += 1
+    dt = time.perf_counter() - t0
+    return n_sample * steps / dt, dt / steps, f.threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 1 << 22
+    value, sec_per_step, cores = cpu_arm(args.steps, args.warmup, n_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "object_motion 2^24 particles: ESS + stratified resample(sort=false) + MH + update",
+                   "note": "Julia/Gen cannot run here (no julia in the image); this is the C/OpenMP port of the "
+                           "reference algorithms (oracle/), faster than the real reference (no trace overhead)"},
+        "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} particles per step (1/4 of the 2^24 workload), {args.steps} steps"},
+        "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="genpf")
+    ap.add_argument("--particles", type=int, default=N_PARTICLES)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes as C
+
+    import torch
+
+    import genpf_b200 as g
+    L = g._lib
+    lib = g.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    L.check(lib.genpf_set_device(local_rank))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.particles
+    K, W = args.steps, args.warmup
+    T = W + 3 * K + 6
+    obs = observations(T)
+    model = g.DeviceModel("object_motion")
+    # particles shard across ranks: rank r owns global slots [r*n, (r+1)*n) of the Philox counter space
+    state = g.pf_initialize(model, (1,), obs[0], n, seed=1234 + rank)
+    sp = C.c_void_p()
+    L.check(lib.genpf_filter_stream(state._h, C.byref(sp)))
+    stream = torch.cuda.ExternalStream(sp.value)
+    auxs = [np.array([math.sin(float(t))]) for t in range(T + 2)]
+    obs_arr = [np.array([o]) for o in obs]
+    method = L.STRATIFIED
+
+    def raw_step(t):  # asynchronous: nothing is copied back
+        L.check(lib.genpf_step(state._h, t, L.ptr(obs_arr[t - 2]), L.ptr(auxs[t - 1]), L.ptr(obs_arr[t - 1]),
+                               L.ptr(auxs[t]), method, 1.0, 1, None))
+        state.t = t
+
+    t = 2
+    for _ in range(W):
+        raw_step(t)
+        t += 1
+    # ---- timed region 1: device-resident throughput
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.genpf_launch_count()
+    e0.record(stream)
+    for _ in range(K):
+        raw_step(t)
+        t += 1
+    e1.record(stream)
+    barrier()
+    launches = lib.genpf_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
+    L.check(lib.genpf_profile_begin())
+    for _ in range(K):
+        raw_step(t)
+        t += 1
+    buf = C.create_string_buffer(1 << 16)
+    L.check(lib.genpf_profile_end(buf, len(buf)))
+    prof = {}
+    for row in buf.value.decode().strip().splitlines():
+        name, cnt, tot = row.split("\t")
+        name = name.strip("()").split("<")[0]
+        c, tt = prof.get(name, (0, 0.0))
+        prof[name] = (c + int(cnt), tt + float(tot))
+    # ---- timed region 3: end to end through the public API: host obs in, ESS back, every step
+    pin_prev, pin_t = np.empty(1), np.empty(1)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(K):
+        pin_prev[0], pin_t[0] = obs[t - 2], obs[t - 1]
+        ess = g.pf_step(state, t, pin_prev, pin_t, method="stratified", ess_thresh=1.0, mh_iters=1, return_ess=True)
+        t += 1
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    assert np.isfinite(ess).all()
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = times.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_updates = float(n) * world * K
+    value = total_updates / (ms_max * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    # dominant kernel by device time
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_cnt, dom_ms) = dom
+    per_launch_ms = dom_ms / dom_cnt
+    algo_b = KERNEL_ALGO_BYTES.get(dom_name, 0) * n
+    achieved = algo_b / (per_launch_ms * 1e-3) / 1e9
+    prof_total = sum(v[1] for v in prof.values())
+    line = {
+        "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "object_motion 2^24 particles/GPU: ESS + stratified resample(sort_particles=false) "
+                               "+ MH rejuvenation + update per step (README.md:66-77, resample forced)",
+                   "particles_per_gpu": n, "l2": "inputs larger than L2 (>=1.2 GB touched per step)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent particle shards (no cross-GPU "
+                                                              "ancestor exchange yet)",
+                   "noise": "lean Philox4x32-10 (1 call/particle/purpose)", "algo_bytes_per_update": STEP_ALGO_BYTES},
+        "clocks": clocks,
+        "e2e": {"value": total_updates / (e2e_ms_max * 1e-3), "unit": "particle-updates/s",
+                "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 48,
+                "note": "genpf_b200.pf_step: obs/aux scalars in (kernel arguments), Stats(ESS) read back per step"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algo_bytes_per_launch": algo_b, "ms_per_launch": per_launch_ms,
+                     "share_of_step": dom_ms / prof_total,
+                     "step_frac": (STEP_ALGO_BYTES * n / (ms_max / K * 1e-3) / 1e9) / peak,
+                     "kernels_ms_per_step": {k: v[1] / K for k, v in sorted(prof.items())}},
+    }
+    if world == 1 and not args.no_cpu:
+        n_sample = 1 << 22
+        v1, s1, cores = cpu_arm(2, 1, n_sample)
+        steps_cpu = max(2, min(40, int(12.0 / max(s1, 1e-3))))
+        v, s, cores = cpu_arm(steps_cpu, 1, n_sample)
+        line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_sample} particles x {steps_cpu} steps of the same step "
+                                          "(C/OpenMP port of the reference algorithms; Julia absent from the image)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

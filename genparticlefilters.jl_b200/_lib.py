@@ -84,6 +84,8 @@ SIGNATURES = {
     "genpf_filter_sync": (i32, [_vp]),
     "genpf_launch_count": (i64, []),
     "genpf_filter_stream": (i32, [_vp, C.POINTER(_vp)]),
+    "genpf_profile_begin": (i32, []),
+    "genpf_profile_end": (i32, [C.c_char_p, i64]),
 }
 
 _lib = None

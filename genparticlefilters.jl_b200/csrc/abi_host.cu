@@ -10,6 +10,8 @@ namespace genpf {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
 
 // per-host-thread workspace: one stream, staging buffers, scratch
 struct HostWs {
@@ -102,6 +104,54 @@ extern "C" {
 int32_t genpf_version(void) { return GENPF_VERSION; }
 const char *genpf_last_error(void) { return g_last_error.c_str(); }
 int64_t genpf_launch_count(void) { return g_launches.load(); }
+
+// per-kernel device timing of everything launched between begin and end (single host thread)
+int32_t genpf_profile_begin(void) {
+    for (auto &r : g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    g_prof_on = true;
+    return GENPF_OK;
+}
+// writes "name count total_ms\n" lines into buf (NUL terminated); returns GENPF_OK
+int32_t genpf_profile_end(char *buf, int64_t buf_len) {
+    g_prof_on = false;
+    GENPF_CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<std::string> names;
+    std::vector<double> total;
+    std::vector<int64_t> count;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        size_t k = 0;
+        for (; k < names.size(); ++k)
+            if (names[k] == r.name) break;
+        if (k == names.size()) {
+            names.push_back(r.name);
+            total.push_back(0.0);
+            count.push_back(0);
+        }
+        total[k] += ms;
+        count[k] += 1;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    std::string out;
+    for (size_t k = 0; k < names.size(); ++k) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", names[k].c_str(), (long long)count[k], total[k]);
+        out += line;
+    }
+    if (buf && buf_len > 0) {
+        size_t m = out.size() < (size_t)buf_len - 1 ? out.size() : (size_t)buf_len - 1;
+        memcpy(buf, out.data(), m);
+        buf[m] = 0;
+    }
+    return GENPF_OK;
+}
 
 int32_t genpf_device_count(int32_t *count) {
     if (!count) return fail(GENPF_ERR_INVALID_ARG, "count is NULL");

@@ -39,12 +39,30 @@ inline int32_t fail(int32_t code, const std::string &msg) {
         if (_s != GENPF_OK) return _s; \
     } while (0)
 
+// optional per-kernel CUDA-event timing (genpf_profile_begin/end): events are recorded on the launching
+// stream around every kernel, so the durations are device times of exactly the launches of the timed region
+struct ProfRec {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+extern bool g_prof_on;
+extern std::vector<ProfRec> g_prof;
+inline cudaEvent_t prof_mark(cudaStream_t s) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    return e;
+}
+
 // kernel launch + count (bench.py's gpu_launches) + launch-error check
-#define GENPF_LAUNCH(kernel, grid, block, stream, ...)           \
-    do {                                                         \
-        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);   \
-        ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed); \
-        GENPF_CUDA_TRY(cudaGetLastError());                      \
+#define GENPF_LAUNCH(kernel, grid, block, stream, ...)                       \
+    do {                                                                     \
+        cudaEvent_t _e0 = nullptr;                                           \
+        if (::genpf::g_prof_on) _e0 = ::genpf::prof_mark(stream);            \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);               \
+        if (::genpf::g_prof_on) ::genpf::g_prof.push_back({#kernel, _e0, ::genpf::prof_mark(stream)}); \
+        ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed);         \
+        GENPF_CUDA_TRY(cudaGetLastError());                                  \
     } while (0)
 
 // grow-only device allocation

@@ -211,6 +211,11 @@ int32_t genpf_filter_sync(genpf_filter_t pf);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t genpf_launch_count(void);
 
+/* per-kernel device time (CUDA events on the launching stream) of every kernel launched between begin and
+ * end; end writes "kernel<TAB>count<TAB>total_ms" lines into buf.  Used by bench.py's roofline. */
+int32_t genpf_profile_begin(void);
+int32_t genpf_profile_end(char *buf, int64_t buf_len);
+
 /* raw device pointers for multi-GPU plumbing (CUDA IPC / NCCL are driven by the host language) */
 int32_t genpf_filter_stream(genpf_filter_t pf, void **cuda_stream);
 
