@@ -34,7 +34,7 @@ KERNEL_ALGO_BYTES = {
     "k_expand": 4,      # W parents (int32)
     "k_gather": 44,     # R window 18 + W window 18 + W lw 8
     "k_mh": 27,         # R window 18 + W slice 9
-    "k_step_fused": 117 - 8,  # everything but the scan's read of lw
+    "k_step_fused": 117 - 8,  # the whole step but the scan's read of lw
 }
 STEP_ALGO_BYTES = 117
 
@@ -57,39 +57,69 @@ def observations(T, seed=3):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, device):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, device, period=0.05):
+        import threading
+        self.rows, self.stop_flag, self.err = [], False, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(device)
+            self.nv, self.h = nv, h
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                    try:
+                        rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    pw = self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    self.rows.append((sm, rs, pw))
+                except Exception as e:  # noqa: BLE001
+                    self.err = repr(e)
+                    return
+                time.sleep(period)
+
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
-        os.unlink(self.f.name)
-        if not rows:
+        self.stop_flag = True
+        if self.err and not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err]}
+        self.t.join(timeout=2)
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm,
+                "reasons": [nm for b, nm in names.items() if bits & b], "samples": len(self.rows),
+                "power_w_max": max(r[2] for r in self.rows)}
 
 
 def cpu_arm(steps, warmup, n_sample, omp=True):
@@ -203,7 +233,6 @@ def main():
     barrier()
     launches = lib.genpf_launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
     # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
     L.check(lib.genpf_profile_begin())
     for _ in range(K):
@@ -228,6 +257,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - w0
     assert np.isfinite(ess).all()
+    clocks = sampler.stop() if sampler else None
 
     times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -7,6 +7,7 @@
 
 #include "coalesce.cuh"
 #include "engine.cuh"
+#include "fused.cuh"
 
 namespace genpf {
 
@@ -461,6 +462,95 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     return GENPF_OK;
 }
 
+
+// ---- fused README iteration (stratified, resample taken, Philox noise): finalize -> scan -> k_step_fused
+template <class Model, class Noise>
+static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise nmh, Noise nup) {
+    const int64_t tpf = ceil_div(pf->n, kTile);
+    const int64_t t = a.t;
+    GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, a,
+                 (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
+                 pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
+                 pf->n, tpf, nmh, nup, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
+    return GENPF_OK;
+}
+template <class Model>
+static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a) {
+    const uint64_t s_mh = make_stream(kPurposeMH, ((uint64_t)(a.t - 1) << 8));
+    const uint64_t s_up = make_stream(kPurposeUpdate, (uint64_t)a.t);
+    if (pf->flags & GENPF_NOISE_PHILOX53) {
+        NoisePhilox53 nmh{pf->seed, s_mh, pf->rng_offset}, nup{pf->seed, s_up, pf->rng_offset};
+        return launch_step_fused<Model, NoisePhilox53>(pf, a, nmh, nup);
+    }
+    NoiseLean nmh{pf->seed, s_mh, pf->rng_offset}, nup{pf->seed, s_up, pf->rng_offset};
+    return launch_step_fused<Model, NoiseLean>(pf, a, nmh, nup);
+}
+
+static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                             const double *obs_t, const double *aux_t, int32_t mh_iters, bool finalized) {
+    const ModelInfo &mi = kModels[pf->model];
+    const int64_t n = pf->n, nf = pf->nf;
+    cudaStream_t s = pf->stream;
+    Scratch &sc = pf->sc;
+    if (!obs_prev || !obs_t) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
+    if (mi.naux > 0 && (!aux_prev || !aux_t)) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL");
+    StepArgs a;
+    a.P_prev = pf->P;
+    a.P_t = pf->P;
+    for (int i = 0; i < mi.naux; ++i) {
+        a.P_prev.aux[i] = aux_prev[i];
+        a.P_t.aux[i] = aux_t[i];
+    }
+    a.t = t;
+    a.mh_iters = mh_iters;
+    if (nf == 1) {
+        a.obs_prev_dev = a.obs_t_dev = nullptr;
+        a.obs_prev = obs_prev[0];
+        a.obs_t = obs_t[0];
+    } else {
+        GENPF_TRY(pf->uni_buf.ensure((size_t)nf * 16));
+        double *d = pf->uni_buf.as<double>();
+        GENPF_CUDA_TRY(cudaMemcpyAsync(d, obs_prev, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(d + nf, obs_t, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
+        a.obs_prev_dev = d;
+        a.obs_t_dev = d + nf;
+        a.obs_prev = a.obs_t = 0.0;
+    }
+    const int64_t tpf = ceil_div(n, kTile);
+    GENPF_TRY(sc.O.ensure((size_t)(n * nf) * 4));
+    GENPF_TRY(sc.tile_last.ensure((size_t)(tpf * nf) * 4));
+    if (!finalized) GENPF_TRY(ensure_stats(pf, sc.tile_off.as<double>(), -1.0, pf->lml));
+    UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    StratArgs strat = make_strat(uni, n);
+    LwSrc lw_src{pf->lw, 1.0};
+    GENPF_LAUNCH((k_scan<int32_t>), (unsigned)(tpf * nf), kThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
+                 (const double *)sc.tile_off.as<double>(), (double *)nullptr, sc.O.as<int32_t>(),
+                 sc.tile_last.as<int32_t>(), strat, 0);
+    int32_t st;
+    switch (pf->model) {
+        case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a); break;
+        case kModelLinGauss1D: st = step_fused_model<LinGauss1D>(pf, a); break;
+        default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+    }
+    GENPF_TRY(st);
+    pf->buf ^= 1;
+    std::swap(pf->lw, pf->lw_alt);
+    GENPF_TRY(log_parents(pf, n, n));
+    if ((pf->flags & GENPF_KEEP_HISTORY) && t - 2 >= 1) {
+        // slice t-2 left the window: it stays in the (now spare) old buffer, in pre-resample order
+        HistSlice h;
+        h.tau = t - 2;
+        h.n = n;
+        h.gen = pf->n_resamples - 1;
+        h.c = pf->win[pf->buf ^ 1][(t - 2) & 1];
+        GENPF_TRY(pf->alloc_cols(pf->win[pf->buf ^ 1][(t - 2) & 1], n * nf));
+        pf->hist.push_back(h);
+    }
+    pf->t_cur = t;
+    pf->part_valid = true;
+    return GENPF_OK;
+}
+
 }  // namespace genpf
 
 extern "C" {
@@ -507,11 +597,13 @@ int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_pa
         const double def[4] = {0.75, 0.25, 0.01, 0.25};  // README.md:47-50
         for (int i = 0; i < 4; ++i) pf->P.v[i] = params ? params[i] : def[i];
         pf->P.v[4] = log(pf->P.v[3]);
+        pf->P.v[5] = 1.0 / pf->P.v[3];
     } else {
         const double def[5] = {0.9, 1.0, 1.0, 0.0, 1.0};
         for (int i = 0; i < 5; ++i) pf->P.v[i] = params ? params[i] : def[i];
         pf->P.v[5] = log(pf->P.v[2]);
         pf->P.v[6] = sqrt(pf->P.v[0] * pf->P.v[0] * pf->P.v[4] * pf->P.v[4] + pf->P.v[1] * pf->P.v[1]);
+        pf->P.v[7] = 1.0 / pf->P.v[2];
     }
     GENPF_CUDA_TRY(cudaStreamCreateWithFlags(&pf->stream, cudaStreamNonBlocking));
     int32_t st = pf->alloc_population(n_particles);
@@ -630,17 +722,22 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
     GENPF_TRY(check_filter(pf));
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
     if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_step must advance to t_cur + 1");
-    // README.md:68-74: the resample + rejuvenation happen only when ESS < ess_frac * n.  The ESS decides on
-    // the host exactly like the reference loop; (ess_frac >= 1 means "always").
-    GENPF_TRY(ensure_stats(pf, nullptr, -1.0, nullptr));
-    bool any = false, every = true;
+    // README.md:68-74: the resample + rejuvenation happen only when ESS < ess_frac * n.  ess_frac >= 1 means
+    // "always" and needs no host round trip; otherwise the ESS decides on the host like the reference loop.
+    const bool fusable = (method == GENPF_STRATIFIED) && mh_iters >= 0 && mh_iters < 256;
+    bool any = false, every = true, finalized = false;
     if (ess_frac >= 1.0 && !ess_out) {
-        any = true;  // "always": no host round trip at all
+        any = true;
     } else {
+        // one finalize serves the decision, the scan's tile offsets and (if taken) update_lml_est!
+        GENPF_TRY(pf->sc.O.ensure(4));
+        GENPF_TRY(ensure_stats(pf, pf->sc.tile_off.as<double>(), ess_frac >= 1.0 ? -1.0 : ess_frac,
+                               fusable ? pf->lml : nullptr));
+        finalized = fusable;
         GENPF_TRY(read_stats(pf, 0));
         for (int64_t f = 0; f < pf->nf; ++f) {
             if (ess_out) ess_out[f] = pf->h_stats[f].ess;
-            const bool r = ess_frac >= 1.0 || pf->h_stats[f].ess < ess_frac * (double)pf->n;
+            const bool r = pf->h_stats[f].do_resample != 0;
             any |= r;
             every &= r;
         }
@@ -648,6 +745,7 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
             return fail(GENPF_ERR_UNSUPPORTED,
                         "filters of one batch disagree on resampling; use the separate entry points per view");
     }
+    if (any && fusable) return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, finalized);
     if (any) {
         GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, nullptr, nullptr, -1.0));
         GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, mh_iters, nullptr, nullptr, nullptr, nullptr));

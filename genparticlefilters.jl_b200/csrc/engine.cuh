@@ -11,7 +11,7 @@ namespace genpf {
 struct Scratch {
     DevBuf part[3][4];  // three partial sets (lw, selection source, ratio d): m, s, s2, flags
     DevBuf stats;       // Stats[4 * nf]: [0] lw  [1] selection  [2] ratio d  [3] sorted selection
-    DevBuf tile_off, W, O;
+    DevBuf tile_off, W, O, tile_last;
     DevBuf resid_c, resid_r, resid_coff, resid_roff, resid_rtot;
     DevBuf sort_tmp, sorted_keys, order, prio_col;
     DevBuf moment_partial, moment_out;
@@ -37,7 +37,7 @@ struct Scratch {
     Stats *st(int k, int64_t nf) { return stats.as<Stats>() + (size_t)k * nf; }
     void release() {
         for (auto &a : part) for (auto &b : a) b.release();
-        for (DevBuf *b : {&stats, &tile_off, &W, &O, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
+        for (DevBuf *b : {&stats, &tile_off, &W, &O, &tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
                           &sort_tmp, &sorted_keys, &order, &prio_col, &moment_partial, &moment_out, &misc})
             b->release();
     }
@@ -51,7 +51,13 @@ inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, P
 inline int32_t launch_finalize(cudaStream_t s, Partials part, int64_t n, int64_t nf, Stats *st, double *tile_off,
                                double ess_frac, double *lml_accum) {
     const int64_t tpf = ceil_div(n, kTile);
-    GENPF_LAUNCH(k_finalize, (unsigned)nf, kThreads, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+    if (tpf <= 8 * 64) {
+        GENPF_LAUNCH((k_finalize_fast<64>), (unsigned)nf, 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+    } else if (tpf <= 8 * 1024) {
+        GENPF_LAUNCH((k_finalize_fast<1024>), (unsigned)nf, 1024, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+    } else {
+        GENPF_LAUNCH(k_finalize, (unsigned)nf, kThreads, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+    }
     return GENPF_OK;
 }
 
@@ -75,7 +81,9 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                            int gate) {
     const int64_t tpf_in = ceil_div(n_in, kTile), tpf_out = ceil_div(n_out, kTile);
     GENPF_TRY(sc.O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
+    GENPF_TRY(sc.tile_last.ensure((size_t)(tpf_in * nf) * sizeof(IdxT)));
     IdxT *O = sc.O.as<IdxT>();
+    IdxT *tile_last = sc.tile_last.as<IdxT>();
     double *tile_off = sc.tile_off.as<double>();
     if (method == GENPF_STRATIFIED) {
         const int32_t *order = nullptr;
@@ -100,14 +108,14 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         }
         StratArgs strat = make_strat(uni, n_in);
         GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     (double *)nullptr, O, strat, gate);
-        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, n_in, n_out, tpf_out, order,
+                     (double *)nullptr, O, tile_last, strat, gate);
+        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0);
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         StratArgs none = make_strat(uni, n_in);
         GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     sc.W.as<double>(), (IdxT *)nullptr, none, gate);
+                     sc.W.as<double>(), (IdxT *)nullptr, (IdxT *)nullptr, none, gate);
         GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
                      tpf_out, uni, (const IdxT *)nullptr, parents, out_base, st_sel, gate);
     } else if (method == GENPF_RESIDUAL) {
@@ -125,8 +133,8 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      sc.resid_coff.as<long long>(), sc.resid_roff.as<double>());
         GENPF_LAUNCH((k_resid_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel,
                      sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
-                     sc.W.as<double>());
-        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, n_in, n_out, tpf_out,
+                     tile_last, sc.W.as<double>());
+        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
                      (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1);
         GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
                      tpf_out, uni, (const IdxT *)O, parents, out_base, st_sel, 0);

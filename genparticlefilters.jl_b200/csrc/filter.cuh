@@ -193,7 +193,7 @@ static __global__ void __launch_bounds__(kThreads)
         typename Model::Slice q;
         Model::transition(P, tau, sp[k], q, U, Z);
         double alpha = Model::obs_logpdf(P, q, obs) - Model::obs_logpdf(P, sc[k], obs);
-        bool a = (e < valid) && (log(U3) < alpha);
+        bool a = (e < valid) && mh_accept(U3, alpha);
         if (a) sc[k] = q;
         acc[k] = a ? 1 : 0;
         cnt += a ? 1.0 : 0.0;

@@ -162,6 +162,123 @@ static __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Register-resident finalize for tpf <= 8*THREADS tiles per filter: each thread owns 8 CONTIGUOUS tiles,
+// loads their partials once (all loads in flight together), and the three phases (max, rescaled sums,
+// exclusive tile offsets) need only four block-level combines.  Same outputs as k_finalize.
+template <int THREADS>
+static __global__ void __launch_bounds__(THREADS)
+    k_finalize_fast(Partials in, int64_t n, int64_t tpf, Stats *stats, double *tile_off, double ess_frac,
+                    double *lml_accum) {
+    constexpr int C = 8, NW = THREADS / 32;
+    __shared__ double sm[3][NW];
+    __shared__ int smi[NW];
+    const int64_t f = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b0 = (int64_t)threadIdx.x * C;
+    double pm[C], ps[C], ps2[C];
+    int fl = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int64_t b = b0 + c;
+        const bool ok = b < tpf;
+        pm[c] = ok ? in.m[f * tpf + b] : -INFINITY;
+        ps[c] = ok ? in.s[f * tpf + b] : 0.0;
+        ps2[c] = ok ? in.s2[f * tpf + b] : 0.0;
+        fl |= ok ? in.flags[f * tpf + b] : 0;
+    }
+    double m = pm[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmax(m, pm[c]);
+    m = warp_max(m);
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    if (lane == 0) {
+        sm[0][warp] = m;
+        smi[warp] = fl;
+    }
+    __syncthreads();
+    double M = sm[0][0];
+    fl = smi[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+        M = fmax(M, sm[0][w]);
+        fl |= smi[w];
+    }
+    __syncthreads();
+    double sc[C], s = 0.0, s2 = 0.0;
+    const bool finite_max = (M > -INFINITY && M < INFINITY);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        sc[c] = (finite_max && pm[c] > -INFINITY) ? exp(pm[c] - M) : 0.0;
+        s += ps[c] * sc[c];
+        s2 += ps2[c] * (sc[c] * sc[c]);
+    }
+    s = warp_sum(s);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        sm[0][warp] = s;
+        sm[1][warp] = s2;
+    }
+    __syncthreads();
+    double S = 0.0, S2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        S += sm[0][w];
+        S2 += sm[1][w];
+    }
+    __syncthreads();
+    int kind = 0;
+    if (fl & 1) kind = 1;
+    else if (M == -INFINITY) kind = 2;
+    else if ((fl & 2) || isnan(S)) kind = 4;
+    else if (S == 0.0) kind = 3;
+    const double lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    const double ess = S * S / S2;
+    int do_rs = 1;
+    if (ess_frac >= 0.0) do_rs = (ess < ess_frac * (double)n) ? 1 : 0;
+    if (kind == 1 || kind == 4) do_rs = 0;
+    if (threadIdx.x == 0) {
+        Stats st;
+        st.M = M; st.S = S; st.S2 = S2; st.lse = lse; st.ess = ess;
+        st.invalid_kind = kind; st.do_resample = do_rs;
+        stats[f] = st;
+        if (lml_accum && do_rs) lml_accum[f] += lse - log((double)n);
+    }
+    if (!tile_off) return;
+    const bool uniform = (kind == 2 || kind == 3);
+    const double inv_n = 1.0 / (double)n;
+    double t[C], run = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int64_t b = b0 + c;
+        double v = 0.0;
+        if (b < tpf) {
+            if (uniform) v = (double)min((int64_t)kTile, n - b * kTile) * inv_n;
+            else if (kind == 0) v = ps[c] * sc[c] / S;
+        }
+        t[c] = run;  // exclusive within the thread
+        run += v;
+    }
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = 0.0;
+    if (lane == 31) sm[2][warp] = inc;
+    __syncthreads();
+    double woff = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (w < warp) woff += sm[2][w];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int64_t b = b0 + c;
+        if (b < tpf) tile_off[f * tpf + b] = (woff + ex) + t[c];
+    }
+}
+
 // ------------------------------------------------------------------ stratified thresholds
 // u_i = r_i*(1/n) + lower_i with two roundings and no FMA (resample.jl:162); lower_i = element i of
 // 0.0:1/n:1.0-1/n, i.e. (i-1)/n (exact for power-of-two n).
@@ -194,7 +311,7 @@ __device__ __forceinline__ int64_t strat_count(const StratArgs &a, int64_t f, do
 template <typename IdxT>
 static __global__ void __launch_bounds__(kThreads)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, double *W_out, IdxT *O_out,
-           StratArgs strat, int gate) {
+           IdxT *tile_last_O, StratArgs strat, int gate) {
     __shared__ double sm[32];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
@@ -207,10 +324,13 @@ static __global__ void __launch_bounds__(kThreads)
     load_tile(src, f * n + start, valid, v, -INFINITY);
     const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
     const double inv_n = 1.0 / (double)n;
+    // w_i = e_i / S evaluated as e_i * (1/S): at most 1 ulp from the reference's division, far inside the
+    // sequential-vs-parallel cumulative-sum noise that defines the documented tie class
+    const double inv_S = 1.0 / st.S;
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
         if (uniform) w[k] = tile_elem(k) < valid ? inv_n : 0.0;
-        else w[k] = exp(v[k] - st.M) / st.S;
+        else w[k] = exp(v[k] - st.M) * inv_S;
     }
     tile_scan<double>(w, W, sm);
     const double off = tile_off[f * tpf + tile];
@@ -220,7 +340,13 @@ static __global__ void __launch_bounds__(kThreads)
     if (O_out) {
         IdxT O[kItems];
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) O[k] = tile_elem(k) < valid ? (IdxT)strat_count(strat, f, W[k]) : (IdxT)0;
+        for (int k = 0; k < kItems; ++k) {
+            const int e = tile_elem(k);
+            O[k] = e < valid ? (IdxT)strat_count(strat, f, W[k]) : (IdxT)0;
+            // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
+            if (start + e == n - 1) O[k] = (IdxT)n;
+            if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];
+        }
         store_tile<IdxT>(O_out, f * n + start, valid, O);
     }
 }
@@ -237,16 +363,126 @@ __device__ __forceinline__ int64_t upper_bound_clamped(const T *a, int64_t n, Q 
     return lo;
 }
 
-// K4/K6 expand: parent_i = min{k : O_k > i} for output slot i (0-based).  Output centric, so a particle
-// owning millions of offspring costs nothing extra.  The block brackets its 2048 outputs with two
-// searches, stages that slice of O in shared memory when it fits, and searches there.
-constexpr int kExpandCap = 4096;
+// K4/K6 expand: parent_i = min{k : O_k > i} for output slot i (0-based), output centric so a particle
+// owning millions of offspring costs nothing extra.  Per block of 2048 outputs:
+//   1. two coarse searches over the per-tile closing counts (tile_last_O) bracket the source tiles,
+//   2. those tiles' O values are staged in shared memory (<= 3 tiles; else per-thread global search),
+//   3. every source with offspring in the block drops its index at its first output slot (scatter of
+//      run heads), and a block-wide max-scan fills the runs -- no per-output binary search.
+template <typename IdxT>
+struct ExpandSmem {
+    static constexpr int kStageCap = (sizeof(IdxT) == 4 ? 3 : 2) * kTile;  // stays under 48 KB static smem
+    IdxT sO[kStageCap + 1];
+    int32_t sParent[kTile];
+    int32_t warp_max[kWarps];
+    int64_t brk[2];
+};
+
+// first tile b in [0, tpf) with tile_last[b] > target (clamped to tpf-1)
+template <typename IdxT>
+__device__ __forceinline__ int64_t coarse_search(const IdxT *tile_last, int64_t tpf, int64_t target, int64_t guess) {
+    // gallop outwards from the guess: resampled populations keep parent ~ output index
+    int64_t lo = 0, hi = tpf - 1;
+    if (guess > hi) guess = hi;
+    if ((int64_t)tile_last[guess] > target) {
+        hi = guess;
+        int64_t step = 1;
+        while (hi - step >= 0 && (int64_t)tile_last[hi - step] > target) {
+            hi -= step;
+            step <<= 1;
+        }
+        lo = max((int64_t)0, hi - step + 1);
+    } else {
+        lo = guess + 1;
+        if (lo > hi) return hi;
+        int64_t step = 1;
+        while (lo + step <= hi && (int64_t)tile_last[lo + step - 1] <= target) {
+            lo += step;
+            step <<= 1;
+        }
+        hi = min(hi, lo + step - 1);
+    }
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if ((int64_t)tile_last[mid] > target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// On return p[k] = source index (local to the filter) of this thread's striped output slot k.
+template <typename IdxT>
+__device__ __forceinline__ void block_expand(const IdxT *Of, const IdxT *tile_last, int64_t n_src, int64_t tpf_src,
+                                             int64_t i0, int64_t valid, ExpandSmem<IdxT> &sm, int64_t (&p)[kItems]) {
+    if (threadIdx.x < 2) {
+        const int64_t target = threadIdx.x == 0 ? i0 : i0 + valid - 1;
+        sm.brk[threadIdx.x] = coarse_search<IdxT>(tile_last, tpf_src, target, i0 / kTile);
+    }
+    __syncthreads();
+    const int64_t b_lo = sm.brk[0], b_hi = sm.brk[1];
+    const int64_t s0 = b_lo * kTile, s1 = min((b_hi + 1) * (int64_t)kTile, n_src);
+    const int64_t len = s1 - s0;
+    if (len <= ExpandSmem<IdxT>::kStageCap) {
+        if (threadIdx.x == 0) sm.sO[0] = b_lo > 0 ? tile_last[b_lo - 1] : (IdxT)0;
+        for (int64_t j = threadIdx.x; j < len; j += kThreads) sm.sO[1 + j] = Of[s0 + j];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) sm.sParent[k * kThreads + threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t iend = i0 + valid;
+        for (int64_t j = threadIdx.x; j < len; j += kThreads) {
+            const int64_t prev = (int64_t)sm.sO[j], cur = (int64_t)sm.sO[j + 1];
+            const int64_t pos = max(prev, i0), end = min(cur, iend);
+            if (pos < end) sm.sParent[pos - i0] = (int32_t)j;
+        }
+        __syncthreads();
+        // block-wide inclusive max-scan over sParent (blocked 8 per thread, then warp + cross-warp)
+        int32_t a[kItems];
+        {
+            const int4 q0 = reinterpret_cast<const int4 *>(sm.sParent)[2 * threadIdx.x];
+            const int4 q1 = reinterpret_cast<const int4 *>(sm.sParent)[2 * threadIdx.x + 1];
+            a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w;
+            a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+        }
+#pragma unroll
+        for (int k = 1; k < kItems; ++k) a[k] = max(a[k], a[k - 1]);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int32_t run = a[kItems - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t t = __shfl_up_sync(0xffffffffu, run, o);
+            if (lane >= o) run = max(run, t);
+        }
+        if (lane == 31) sm.warp_max[warp] = run;
+        int32_t excl = __shfl_up_sync(0xffffffffu, run, 1);
+        if (lane == 0) excl = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+            if (w < warp) excl = max(excl, sm.warp_max[w]);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) a[k] = max(a[k], excl);
+        reinterpret_cast<int4 *>(sm.sParent)[2 * threadIdx.x] = make_int4(a[0], a[1], a[2], a[3]);
+        reinterpret_cast<int4 *>(sm.sParent)[2 * threadIdx.x + 1] = make_int4(a[4], a[5], a[6], a[7]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const int e = tile_elem(k);
+            p[k] = s0 + (e < valid ? (int64_t)sm.sParent[e] : 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const int e = tile_elem(k);
+            p[k] = s0 + (e < valid ? upper_bound_clamped<IdxT, int64_t>(Of + s0, len, i0 + e) : 0);
+        }
+    }
+    __syncthreads();
+}
+
 template <typename IdxT, typename OutT>
 static __global__ void __launch_bounds__(kThreads)
-    k_expand(const IdxT *O, int64_t n_src, int64_t n_out, int64_t tpf_out, const int32_t *order, OutT *parents,
-             int64_t out_base, const Stats *stats, int gate, int residual) {
-    __shared__ int64_t range[2];
-    __shared__ IdxT sO[kExpandCap];
+    k_expand(const IdxT *O, const IdxT *tile_last_O, int64_t n_src, int64_t n_out, int64_t tpf_out,
+             const int32_t *order, OutT *parents, int64_t out_base, const Stats *stats, int gate, int residual) {
+    __shared__ ExpandSmem<IdxT> sm;
     int64_t f, tile;
     blk_to_tile(tpf_out, f, tile);
     if (stats) {
@@ -254,6 +490,7 @@ static __global__ void __launch_bounds__(kThreads)
         if (kind == 1 || kind == 4) return;
         if (gate && !stats[f].do_resample) return;
     }
+    const int64_t tpf_src = (n_src + kTile - 1) / kTile;
     const IdxT *Of = O + f * n_src;
     const int64_t i0 = tile * kTile;
     int64_t valid = min((int64_t)kTile, n_out - i0);
@@ -262,30 +499,14 @@ static __global__ void __launch_bounds__(kThreads)
         valid = min(valid, C - i0);
         if (valid <= 0) return;
     }
-    if (threadIdx.x < 2) {
-        int64_t target = threadIdx.x == 0 ? i0 : i0 + valid - 1;
-        range[threadIdx.x] = upper_bound_clamped<IdxT, int64_t>(Of, n_src, target);
-    }
-    __syncthreads();
-    const int64_t k_lo = range[0], k_hi = range[1];
-    const int64_t L = k_hi - k_lo + 1;
-    const bool staged = L <= kExpandCap;
-    if (staged) {
-        for (int64_t j = threadIdx.x; j < L; j += kThreads) sO[j] = Of[k_lo + j];
-        __syncthreads();
-    }
+    int64_t p[kItems];
+    block_expand<IdxT>(Of, tile_last_O + f * tpf_src, n_src, tpf_src, i0, valid, sm, p);
     OutT out[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
-        int e = tile_elem(k);
-        int64_t p = 0;
-        if (e < valid) {
-            int64_t i = i0 + e;
-            p = k_lo + (staged ? upper_bound_clamped<IdxT, int64_t>(sO, L, i)
-                               : upper_bound_clamped<IdxT, int64_t>(Of + k_lo, L, i));
-            if (order) p = order[f * n_src + p];
-        }
-        out[k] = (OutT)(p + out_base);
+        int64_t q = p[k];
+        if (order && tile_elem(k) < valid) q = order[f * n_src + q];
+        out[k] = (OutT)(q + out_base);
     }
     store_tile<OutT>(parents, f * n_out + i0, valid, out);
 }
@@ -416,7 +637,7 @@ static __global__ void __launch_bounds__(kThreads)
 template <typename IdxT>
 static __global__ void __launch_bounds__(kThreads)
     k_resid_scan(LwSrc src, int64_t n, int64_t n_out, int64_t tpf, const Stats *stats, const double *r_total,
-                 const long long *c_off, const double *r_off, IdxT *O_out, double *R_out) {
+                 const long long *c_off, const double *r_off, IdxT *O_out, IdxT *tile_last_O, double *R_out) {
     __shared__ double sm[32];
     __shared__ long long smi[32];
     int64_t f, tile;
@@ -445,6 +666,7 @@ static __global__ void __launch_bounds__(kThreads)
         if (cc > n_out) cc = n_out;  // clamp (App. C)
         O[k] = (IdxT)cc;
         R[k] = ro + R[k];
+        if (tile_elem(k) == valid - 1) tile_last_O[f * tpf + tile] = O[k];
     }
     store_tile<IdxT>(O_out, f * n + start, valid, O);
     store_tile<double>(R_out, f * n + start, valid, R);

@@ -31,13 +31,25 @@ struct SliceT {
 #define GENPF_LOG_2PI 1.8378770664093453  // log(2*pi) as computed by Julia/glibc in fp64
 
 // Gen: logpdf(normal, x, mu, sigma) = -(((x-mu)/sigma)^2 + log(2pi))/2 - log(sigma)
-__device__ __forceinline__ double normal_logpdf(double x, double mu, double sigma, double log_sigma) {
-    double z = (x - mu) / sigma;
+// (x-mu)/sigma is evaluated as (x-mu)*(1/sigma): exact for the README's sigma = 0.25, <= 1 ulp otherwise
+// (log-weights are compared at 1e-10 relative).
+__device__ __forceinline__ double normal_logpdf(double x, double mu, double inv_sigma, double log_sigma) {
+    double z = (x - mu) * inv_sigma;
     return -(__dmul_rn(z, z) + GENPF_LOG_2PI) / 2.0 - log_sigma;
 }
 
+// accept iff log(U3) < alpha (Gen mh).  Decision-exact fast path: an fp32 log with a conservative error
+// bound decides unless it lands within the bound of alpha, in which case the fp64 log is evaluated.
+__device__ __forceinline__ bool mh_accept(double U3, double alpha) {
+    if (alpha > 0.0) return true;  // log(U3) <= 0 < alpha
+    const float lf = __logf((float)U3);
+    const float af = (float)alpha;
+    if (fabsf(lf - af) > 1e-4f * (1.0f + fabsf(lf))) return lf < af;
+    return log(U3) < alpha;
+}
+
 // README.md:43-54 object_motion.  params: v[0]=p_stay .75, v[1]=p_start .25, v[2]=sigma_proc .01,
-// v[3]=sigma_obs .25, v[4]=log(sigma_obs) (filled by the host).  aux[0] = vel_t = sin(t) from the caller.
+// v[3]=sigma_obs .25, v[4]=log(sigma_obs), v[5]=1/sigma_obs (host filled).  aux[0] = vel_t = sin(t) from the caller.
 struct ObjectMotion {
     static constexpr int NF = 1, NB = 1, NP = 4, NAUX = 1;
     using Slice = SliceT<NF, NB>;
@@ -53,13 +65,13 @@ struct ObjectMotion {
         nxt.b[0] = m;
     }
     static __device__ __forceinline__ double obs_logpdf(const ModelParams &p, const Slice &s, double obs) {
-        return normal_logpdf(obs, s.f[0], p.v[3], p.v[4]);
+        return normal_logpdf(obs, s.f[0], p.v[5], p.v[4]);
     }
 };
 
 // 1-D linear-Gaussian tracker: x_0 ~ N(m0, s0) marginalised into the first transition,
 // x_t ~ N(a x_{t-1}, q), y_t ~ N(x_t, r).  params: v[0]=a, v[1]=q, v[2]=r, v[3]=m0, v[4]=s0,
-// v[5]=log(r), v[6]=sqrt(a^2 s0^2 + q^2) (host filled).
+// v[5]=log(r), v[6]=sqrt(a^2 s0^2 + q^2), v[7]=1/r (host filled).
 struct LinGauss1D {
     static constexpr int NF = 1, NB = 0, NP = 5, NAUX = 0;
     using Slice = SliceT<NF, NB>;
@@ -74,7 +86,7 @@ struct LinGauss1D {
         nxt.b[0] = 0;
     }
     static __device__ __forceinline__ double obs_logpdf(const ModelParams &p, const Slice &s, double obs) {
-        return normal_logpdf(obs, s.f[0], p.v[2], p.v[5]);
+        return normal_logpdf(obs, s.f[0], p.v[7], p.v[5]);
     }
 };
 
@@ -91,7 +103,7 @@ struct NoiseLean {
         float ua = ((float)(o.y >> 8) + 0.5f) * 0x1.0p-24f;
         float ub = ((float)(o.z >> 8) + 0.5f) * 0x1.0p-24f;
         float rr = sqrtf(-2.0f * __logf(ua));
-        Z = (double)(rr * cospif(2.0f * ub));
+        Z = (double)(rr * __cosf(6.28318530717958647692f * (ub - 0.5f)));  // angle in [-pi, pi): MUFU range
         U3 = ((double)o.w + 0.5) * 0x1.0p-32;
     }
 };
