@@ -59,7 +59,7 @@ def observations(T, seed=3):
 class ClockSampler:
     """SM clock + throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, device, period=0.05):
+    def __init__(self, device, period=0.004):
         import threading
         self.rows, self.stop_flag, self.err = [], False, None
         try:
@@ -164,8 +164,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="genpf")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -181,12 +181,11 @@ static int32_t propagate_model(genpf_filter_t pf, bool init, int64_t t, const do
         NoiseCols nz{U, Z, nullptr};
         return launch_propagate<Model, NoiseCols>(pf, init, t, obs_dev, obs_val, nz);
     }
-    const uint64_t stream_id = make_stream(kPurposeUpdate, (uint64_t)t);
     if (pf->flags & GENPF_NOISE_PHILOX53) {
-        NoisePhilox53 nz{pf->seed, stream_id, pf->rng_offset};
+        NoisePhilox53 nz{pf->seed, (uint64_t)t, pf->rng_offset};
         return launch_propagate<Model, NoisePhilox53>(pf, init, t, obs_dev, obs_val, nz);
     }
-    NoiseLean nz{pf->seed, stream_id, pf->rng_offset};
+    NoiseLean nz{pf->seed, (uint64_t)t, pf->rng_offset};
     return launch_propagate<Model, NoiseLean>(pf, init, t, obs_dev, obs_val, nz);
 }
 
@@ -255,9 +254,9 @@ static int32_t read_stats(genpf_filter_t pf, int which) {
 }
 
 template <class Model, class Noise>
-static int32_t launch_mh(genpf_filter_t pf, int64_t tau, const double *obs_dev, double obs_val, Noise noise) {
+static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise) {
     const int64_t tpf = ceil_div(pf->n, kTile);
-    GENPF_LAUNCH((k_mh<Model, Noise>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, pf->P, tau, tau == 1 ? 1 : 0,
+    GENPF_LAUNCH((k_mh<Model, Noise>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
                  pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept);
     return GENPF_OK;
 }
@@ -266,15 +265,15 @@ static int32_t mh_model(genpf_filter_t pf, int64_t tau, int iter, const double *
                         const double *U2, const double *Z2, const double *U3) {
     if (U2 || Z2 || U3) {
         NoiseCols nz{U2, Z2, U3};
-        return launch_mh<Model, NoiseCols>(pf, tau, obs_dev, obs_val, nz);
+        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz);
     }
-    const uint64_t stream_id = make_stream(kPurposeMH, ((uint64_t)tau << 8) | (uint64_t)(iter & 0xFF));
+    // the mh move on slice tau belongs to README iteration s = tau + 1 (it runs right before pf_update!(s))
     if (pf->flags & GENPF_NOISE_PHILOX53) {
-        NoisePhilox53 nz{pf->seed, stream_id, pf->rng_offset};
-        return launch_mh<Model, NoisePhilox53>(pf, tau, obs_dev, obs_val, nz);
+        NoisePhilox53 nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
+        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz);
     }
-    NoiseLean nz{pf->seed, stream_id, pf->rng_offset};
-    return launch_mh<Model, NoiseLean>(pf, tau, obs_dev, obs_val, nz);
+    NoiseLean nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
+    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz);
 }
 
 static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
@@ -465,25 +464,23 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
 
 // ---- fused README iteration (stratified, resample taken, Philox noise): finalize -> scan -> k_step_fused
 template <class Model, class Noise>
-static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise nmh, Noise nup) {
+static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noise) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     const int64_t t = a.t;
     GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, a,
                  (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                  pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
-                 pf->n, tpf, nmh, nup, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
+                 pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
     return GENPF_OK;
 }
 template <class Model>
 static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a) {
-    const uint64_t s_mh = make_stream(kPurposeMH, ((uint64_t)(a.t - 1) << 8));
-    const uint64_t s_up = make_stream(kPurposeUpdate, (uint64_t)a.t);
     if (pf->flags & GENPF_NOISE_PHILOX53) {
-        NoisePhilox53 nmh{pf->seed, s_mh, pf->rng_offset}, nup{pf->seed, s_up, pf->rng_offset};
-        return launch_step_fused<Model, NoisePhilox53>(pf, a, nmh, nup);
+        NoisePhilox53 nz{pf->seed, (uint64_t)a.t, pf->rng_offset};
+        return launch_step_fused<Model, NoisePhilox53>(pf, a, nz);
     }
-    NoiseLean nmh{pf->seed, s_mh, pf->rng_offset}, nup{pf->seed, s_up, pf->rng_offset};
-    return launch_step_fused<Model, NoiseLean>(pf, a, nmh, nup);
+    NoiseLean nz{pf->seed, (uint64_t)a.t, pf->rng_offset};
+    return launch_step_fused<Model, NoiseLean>(pf, a, nz);
 }
 
 static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,

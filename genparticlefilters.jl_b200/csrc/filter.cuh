@@ -148,8 +148,8 @@ static __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
         int e = tile_elem(k);
-        double U = 0.5, Z = 0.0, U3;
-        if (e < valid) noise.get(base + e, U, Z, U3);
+        double U = 0.5, Z = 0.0;
+        if (e < valid) noise.up(base + e, U, Z);
         Model::transition(P, t, sp[k], sn[k], U, Z);
         double l = Model::obs_logpdf(P, sn[k], obs);
         if (e < valid) v[k] = INIT ? l : v[k] + l;
@@ -166,8 +166,8 @@ static __global__ void __launch_bounds__(kThreads)
 // accept iff log(rand()) < weight.  Log-weights are untouched.
 template <class Model, class Noise>
 static __global__ void __launch_bounds__(kThreads)
-    k_mh(ModelParams P, int64_t tau, int first_step, Cols prevprev, Cols cur, const double *obs_dev, double obs_val,
-         int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept) {
+    k_mh(ModelParams P, int64_t tau, int iter, int first_step, Cols prevprev, Cols cur, const double *obs_dev,
+         double obs_val, int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept) {
     __shared__ double sm[kWarps];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
@@ -189,7 +189,7 @@ static __global__ void __launch_bounds__(kThreads)
     for (int k = 0; k < kItems; ++k) {
         int e = tile_elem(k);
         double U = 0.5, Z = 0.0, U3 = 1.0;
-        if (e < valid) noise.get(base + e, U, Z, U3);
+        if (e < valid) noise.mh(base + e, iter, U, Z, U3);
         typename Model::Slice q;
         Model::transition(P, tau, sp[k], q, U, Z);
         double alpha = Model::obs_logpdf(P, q, obs) - Model::obs_logpdf(P, sc[k], obs);

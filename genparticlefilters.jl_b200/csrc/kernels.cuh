@@ -162,9 +162,9 @@ static __global__ void __launch_bounds__(kThreads)
     }
 }
 
-// Register-resident finalize for tpf <= 8*THREADS tiles per filter: each thread owns 8 CONTIGUOUS tiles,
-// loads their partials once (all loads in flight together), and the three phases (max, rescaled sums,
-// exclusive tile offsets) need only four block-level combines.  Same outputs as k_finalize.
+// Register-resident finalize for tpf <= 8*THREADS tiles per filter: thread t owns tiles {c*THREADS + t}
+// (coalesced loads, all in flight together); the three phases (max, rescaled sums, exclusive tile offsets)
+// need only a handful of block-level combines.  Same outputs as k_finalize.
 template <int THREADS>
 static __global__ void __launch_bounds__(THREADS)
     k_finalize_fast(Partials in, int64_t n, int64_t tpf, Stats *stats, double *tile_off, double ess_frac,
@@ -172,14 +172,15 @@ static __global__ void __launch_bounds__(THREADS)
     constexpr int C = 8, NW = THREADS / 32;
     __shared__ double sm[3][NW];
     __shared__ int smi[NW];
+    __shared__ double row_cell[C][NW];  // inclusive warp totals per row -> exclusive offsets
+    __shared__ double row_total[C];
     const int64_t f = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t b0 = (int64_t)threadIdx.x * C;
     double pm[C], ps[C], ps2[C];
     int fl = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int64_t b = b0 + c;
+        const int64_t b = (int64_t)c * THREADS + threadIdx.x;
         const bool ok = b < tpf;
         pm[c] = ok ? in.m[f * tpf + b] : -INFINITY;
         ps[c] = ok ? in.s[f * tpf + b] : 0.0;
@@ -225,7 +226,6 @@ static __global__ void __launch_bounds__(THREADS)
         S += sm[0][w];
         S2 += sm[1][w];
     }
-    __syncthreads();
     int kind = 0;
     if (fl & 1) kind = 1;
     else if (M == -INFINITY) kind = 2;
@@ -244,38 +244,48 @@ static __global__ void __launch_bounds__(THREADS)
         if (lml_accum && do_rs) lml_accum[f] += lse - log((double)n);
     }
     if (!tile_off) return;
+    // exclusive scan over tiles in index order b = c*THREADS + t: rows c are contiguous runs of THREADS tiles
     const bool uniform = (kind == 2 || kind == 3);
     const double inv_n = 1.0 / (double)n;
-    double t[C], run = 0.0;
+    double ex[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int64_t b = b0 + c;
+        const int64_t b = (int64_t)c * THREADS + threadIdx.x;
         double v = 0.0;
         if (b < tpf) {
             if (uniform) v = (double)min((int64_t)kTile, n - b * kTile) * inv_n;
             else if (kind == 0) v = ps[c] * sc[c] / S;
         }
-        t[c] = run;  // exclusive within the thread
-        run += v;
-    }
-    double inc = run;
+        double inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
+        for (int o = 1; o < 32; o <<= 1) {
+            double u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        double e = __shfl_up_sync(0xffffffffu, inc, 1);
+        ex[c] = lane == 0 ? 0.0 : e;
+        if (lane == 31) row_cell[c][warp] = inc;
     }
-    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) ex = 0.0;
-    if (lane == 31) sm[2][warp] = inc;
     __syncthreads();
-    double woff = 0.0;
+    for (int row = warp; row < C; row += NW) {  // one warp scans a row's NW warp totals
+        double t = lane < NW ? row_cell[row][lane] : 0.0;
+        double inc = t;
 #pragma unroll
-    for (int w = 0; w < NW; ++w)
-        if (w < warp) woff += sm[2][w];
+        for (int o = 1; o < 32; o <<= 1) {
+            double u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        double e = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane < NW) row_cell[row][lane] = lane == 0 ? 0.0 : e;
+        if (lane == 31) row_total[row] = inc;
+    }
+    __syncthreads();
+    double roff = 0.0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int64_t b = b0 + c;
-        if (b < tpf) tile_off[f * tpf + b] = (woff + ex) + t[c];
+        const int64_t b = (int64_t)c * THREADS + threadIdx.x;
+        if (b < tpf) tile_off[f * tpf + b] = roff + (row_cell[c][warp] + ex[c]);
+        roff += row_total[c];
     }
 }
 
@@ -288,10 +298,12 @@ struct StratArgs {
     int64_t n;
     int pow2;
 };
+__device__ __forceinline__ double strat_lower(const StratArgs &a, int64_t i1) {
+    return a.pow2 ? (double)(i1 - 1) * a.step : (double)(i1 - 1) / (double)a.n;
+}
 __device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t i1) {
     double r = a.uni(f * a.n + i1 - 1);
-    double lower = a.pow2 ? (double)(i1 - 1) * a.step : (double)(i1 - 1) / (double)a.n;
-    return __dadd_rn(__dmul_rn(r, a.step), lower);
+    return __dadd_rn(__dmul_rn(r, a.step), strat_lower(a, i1));
 }
 // C(W) = #{i in 1..n : u_i <= W}.  Because u is non-decreasing in i this is a prefix count, and
 // parent_i = min{k : W_k >= u_i} (resample.jl:163-168) == min{k : C(W_k) >= i}.
@@ -299,7 +311,8 @@ __device__ __forceinline__ int64_t strat_count(const StratArgs &a, int64_t f, do
     double x = W * (double)a.n;
     int64_t j = x >= (double)a.n ? a.n : (x <= 0.0 ? 0 : (int64_t)x);
     const bool near_edge = (x - (double)j) < 1e-6;
-    while (j < a.n && strat_u(a, f, j + 1) <= W) ++j;
+    // u_i >= lower_i, so a stratum whose lower bound already exceeds W needs no draw
+    while (j < a.n && strat_lower(a, j + 1) <= W && strat_u(a, f, j + 1) <= W) ++j;
     if (near_edge)
         while (j > 0 && strat_u(a, f, j) > W) --j;
     return j;
@@ -372,10 +385,10 @@ __device__ __forceinline__ int64_t upper_bound_clamped(const T *a, int64_t n, Q 
 template <typename IdxT>
 struct ExpandSmem {
     static constexpr int kStageCap = (sizeof(IdxT) == 4 ? 3 : 2) * kTile;  // stays under 48 KB static smem
-    IdxT sO[kStageCap + 1];
-    int32_t sParent[kTile];
-    int32_t warp_max[kWarps];
+    alignas(16) int32_t sParent[kTile];  // accessed as int4
     int64_t brk[2];
+    int32_t warp_max[kWarps];
+    IdxT sO[kStageCap + 1];
 };
 
 // first tile b in [0, tpf) with tile_last[b] > target (clamped to tpf-1)
@@ -423,15 +436,15 @@ __device__ __forceinline__ void block_expand(const IdxT *Of, const IdxT *tile_la
     const int64_t len = s1 - s0;
     if (len <= ExpandSmem<IdxT>::kStageCap) {
         if (threadIdx.x == 0) sm.sO[0] = b_lo > 0 ? tile_last[b_lo - 1] : (IdxT)0;
-        for (int64_t j = threadIdx.x; j < len; j += kThreads) sm.sO[1 + j] = Of[s0 + j];
+        for (int j = threadIdx.x; j < (int)len; j += kThreads) sm.sO[1 + j] = Of[s0 + j];
 #pragma unroll
         for (int k = 0; k < kItems; ++k) sm.sParent[k * kThreads + threadIdx.x] = 0;
         __syncthreads();
-        const int64_t iend = i0 + valid;
-        for (int64_t j = threadIdx.x; j < len; j += kThreads) {
-            const int64_t prev = (int64_t)sm.sO[j], cur = (int64_t)sm.sO[j + 1];
-            const int64_t pos = max(prev, i0), end = min(cur, iend);
-            if (pos < end) sm.sParent[pos - i0] = (int32_t)j;
+        const IdxT ibeg = (IdxT)i0, iend = (IdxT)(i0 + valid);
+        for (int j = threadIdx.x; j < (int)len; j += kThreads) {
+            const IdxT prev = sm.sO[j], cur = sm.sO[j + 1];
+            const IdxT pos = prev > ibeg ? prev : ibeg, end = cur < iend ? cur : iend;
+            if (pos < end) sm.sParent[(int)(pos - ibeg)] = j;
         }
         __syncthreads();
         // block-wide inclusive max-scan over sParent (blocked 8 per thread, then warp + cross-warp)

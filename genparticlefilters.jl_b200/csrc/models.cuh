@@ -92,43 +92,95 @@ struct LinGauss1D {
 
 // ------------------------------------------------------------------ noise policies
 // Draw order per particle: init/update = [U1 (bernoulli), Z1 (normal)]; mh = [U2, Z2, U3 (accept)].
-// Lean: ONE Philox4x32-10 call per particle per purpose: U = (w0+.5)2^-32, Z = fp32 Box-Muller(w1, w2),
-//       U3 = (w3+.5)2^-32.  Counter = global particle slot, stream = (purpose, step).
+// A policy serves one README iteration "step s": the update to time s and the mh move applied right before
+// it (on slice s-1).  Interface:
+//   up(i, U, Z)              noise of pf_update!/pf_initialize to time s
+//   mh(i, it, U, Z, U3)      noise of mh iteration `it` on slice s-1
+//   both(i, ...)             the two at once (fused step, iteration 0)
+__device__ __forceinline__ float fast_bm_radius(float ua) { return sqrtf(-2.0f * __logf(ua)); }
+
+// Lean (default): ONE Philox4x32-10 call per particle per step s serves BOTH moves (128 bits):
+//   w0[31:8] U_mh (24 b)   w1[31:8] U_up (24 b)   w2 U_acc (32 b)   w3[31:8] Box-Muller angle (24 b)
+//   {w0[7:0], w1[7:0], w3[7:0]} Box-Muller radius uniform (24 b);  Z_mh = r cos(theta), Z_up = r sin(theta)
+// (the two outputs of one Box-Muller transform are independent normals).  fp32 transcendental units.
+// mh iterations it >= 1 draw their own call: U = w0, radius w1, angle w2, U_acc = w3.
 struct NoiseLean {
-    uint64_t seed, stream;
+    uint64_t seed;
+    uint64_t step;  // s
     int64_t offset;
-    __device__ __forceinline__ void get(int64_t i, double &U, double &Z, double &U3) const {
-        uint4 o = philox_at(seed, stream, (uint64_t)(i + offset));
+    __device__ __forceinline__ void both(int64_t i, double &U_mh, double &Z_mh, double &U_acc, double &U_up,
+                                         double &Z_up) const {
+        const uint4 o = philox_at(seed, make_stream(kPurposeUpdate, step), (uint64_t)(i + offset));
+        U_mh = ((double)(o.x >> 8) + 0.5) * 0x1.0p-24;
+        U_up = ((double)(o.y >> 8) + 0.5) * 0x1.0p-24;
+        U_acc = ((double)o.z + 0.5) * 0x1.0p-32;
+        const uint32_t rb = ((o.x & 0xFFu) << 16) | ((o.y & 0xFFu) << 8) | (o.w & 0xFFu);
+        const float ua = ((float)rb + 0.5f) * 0x1.0p-24f;
+        const float th = (((float)(o.w >> 8) + 0.5f) * 0x1.0p-24f - 0.5f) * 6.28318530717958647692f;  // [-pi, pi)
+        const float rr = fast_bm_radius(ua);
+        float sn, cs;
+        __sincosf(th, &sn, &cs);
+        Z_mh = (double)(rr * cs);
+        Z_up = (double)(rr * sn);
+    }
+    __device__ __forceinline__ void up(int64_t i, double &U, double &Z) const {
+        double a, b, c;
+        both(i, a, b, c, U, Z);
+    }
+    __device__ __forceinline__ void mh(int64_t i, int it, double &U, double &Z, double &U3) const {
+        if (it == 0) {
+            double a, b;
+            both(i, U, Z, U3, a, b);
+            return;
+        }
+        const uint4 o = philox_at(seed, make_stream(kPurposeMH, (step << 8) | (uint64_t)(it & 0xFF)), (uint64_t)(i + offset));
         U = ((double)o.x + 0.5) * 0x1.0p-32;
-        float ua = ((float)(o.y >> 8) + 0.5f) * 0x1.0p-24f;
-        float ub = ((float)(o.z >> 8) + 0.5f) * 0x1.0p-24f;
-        float rr = sqrtf(-2.0f * __logf(ua));
-        Z = (double)(rr * __cosf(6.28318530717958647692f * (ub - 0.5f)));  // angle in [-pi, pi): MUFU range
+        const float ua = ((float)(o.y >> 8) + 0.5f) * 0x1.0p-24f;
+        const float th = (((float)(o.z >> 8) + 0.5f) * 0x1.0p-24f - 0.5f) * 6.28318530717958647692f;
+        Z = (double)(fast_bm_radius(ua) * __cosf(th));
         U3 = ((double)o.w + 0.5) * 0x1.0p-32;
     }
 };
-// 53-bit uniforms + fp64 Box-Muller (two Philox calls)
+// High-fidelity: 53-bit uniforms + fp64 Box-Muller, two Philox calls per move
 struct NoisePhilox53 {
-    uint64_t seed, stream;
+    uint64_t seed;
+    uint64_t step;
     int64_t offset;
-    __device__ __forceinline__ void get(int64_t i, double &U, double &Z, double &U3) const {
-        uint4 a = philox_at(seed, stream, (uint64_t)(i + offset));
-        uint4 b = philox_at(seed, stream ^ (1ull << 55), (uint64_t)(i + offset));
+    __device__ __forceinline__ void draw(uint64_t stream, int64_t i, double &U, double &Z, double &U3) const {
+        const uint4 a = philox_at(seed, stream, (uint64_t)(i + offset));
+        const uint4 b = philox_at(seed, stream ^ (1ull << 55), (uint64_t)(i + offset));
         U = u53(a.x, a.y);
-        double ua = 1.0 - u53(a.z, a.w);  // (0,1]
-        double ub = u53(b.x, b.y);
+        const double ua = 1.0 - u53(a.z, a.w);  // (0,1]
+        const double ub = u53(b.x, b.y);
         Z = sqrt(-2.0 * log(ua)) * cospi(2.0 * ub);
         U3 = 1.0 - u53(b.z, b.w);  // (0,1]
+    }
+    __device__ __forceinline__ void up(int64_t i, double &U, double &Z) const {
+        double u3;
+        draw(make_stream(kPurposeUpdate, step), i, U, Z, u3);
+    }
+    __device__ __forceinline__ void mh(int64_t i, int it, double &U, double &Z, double &U3) const {
+        draw(make_stream(kPurposeMH, (step << 8) | (uint64_t)(it & 0xFF)), i, U, Z, U3);
+    }
+    __device__ __forceinline__ void both(int64_t i, double &U_mh, double &Z_mh, double &U_acc, double &U_up,
+                                         double &Z_up) const {
+        mh(i, 0, U_mh, Z_mh, U_acc);
+        up(i, U_up, Z_up);
     }
 };
 // parity mode: noise supplied as columns (exported from the reference's RNG)
 struct NoiseCols {
     const double *U, *Z, *U3;
-    __device__ __forceinline__ void get(int64_t i, double &u, double &z, double &u3) const {
+    __device__ __forceinline__ void up(int64_t i, double &u, double &z) const {
+        u = U ? U[i] : 0.0;
+        z = Z ? Z[i] : 0.0;
+    }
+    __device__ __forceinline__ void mh(int64_t i, int, double &u, double &z, double &u3) const {
         u = U ? U[i] : 0.0;
         z = Z ? Z[i] : 0.0;
         u3 = U3 ? U3[i] : 1.0;
     }
+    __device__ __forceinline__ void both(int64_t, double &, double &, double &, double &, double &) const {}
 };
 
 }  // namespace genpf

@@ -531,17 +531,23 @@ void orc_lg_mh(const orc_lg_params *p, int64_t n, const double *x_pp, double *x_
 }
 
 /* ------------------------------------------------------------------ CPU baseline filter (bench only) */
-/* Production-noise convention shared with the CUDA library ("lean" Philox noise):
- * one Philox call per particle per purpose; U = (w0+0.5)*2^-32, Z = fp32 Box-Muller of w1,w2, U' from w3. */
-static inline void lean_noise(uint64_t seed, uint64_t stream, uint64_t idx, double *U, double *Z, double *U3) {
+/* Production-noise convention shared with the CUDA library ("lean" Philox noise, models.cuh NoiseLean):
+ * ONE Philox call per particle per README iteration serves the mh move and the update:
+ * w0[31:8] U_mh, w1[31:8] U_up, w2 U_acc, w3[31:8] Box-Muller angle, {w0,w1,w3}[7:0] radius uniform;
+ * Z_mh = r cos(theta), Z_up = r sin(theta). */
+static inline void lean_noise(uint64_t seed, uint64_t stream, uint64_t idx, double *U_mh, double *Z_mh, double *U_acc,
+                              double *U_up, double *Z_up) {
     uint32_t o[4];
     philox_at(seed, stream, idx, o);
-    *U = ((double)o[0] + 0.5) * 0x1.0p-32;
-    float ua = ((float)(o[1] >> 8) + 0.5f) * 0x1.0p-24f;
-    float ub = ((float)(o[2] >> 8) + 0.5f) * 0x1.0p-24f;
+    *U_mh = ((double)(o[0] >> 8) + 0.5) * 0x1.0p-24;
+    *U_up = ((double)(o[1] >> 8) + 0.5) * 0x1.0p-24;
+    *U_acc = ((double)o[2] + 0.5) * 0x1.0p-32;
+    uint32_t rb = ((o[0] & 0xFFu) << 16) | ((o[1] & 0xFFu) << 8) | (o[3] & 0xFFu);
+    float ua = ((float)rb + 0.5f) * 0x1.0p-24f;
+    float th = (((float)(o[3] >> 8) + 0.5f) * 0x1.0p-24f - 0.5f) * 6.28318530717958647692f;
     float rr = sqrtf(-2.0f * logf(ua));
-    *Z = (double)(rr * cosf(6.28318530717958647692f * ub));
-    *U3 = ((double)o[3] + 0.5) * 0x1.0p-32;
+    *Z_mh = (double)(rr * cosf(th));
+    *Z_up = (double)(rr * sinf(th));
 }
 #define ORC_STREAM(purpose, step) (((uint64_t)(purpose) << 56) | ((uint64_t)(step) & 0x00FFFFFFFFFFFFFFull))
 
@@ -577,8 +583,8 @@ void orc_om_filter_init(orc_om_filter *f, const orc_om_params *p, double vel1, d
     f->log_ml_est = 0.0;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
-        double U, Z, U3;
-        lean_noise(f->seed, ORC_STREAM(2, 1), (uint64_t)i, &U, &Z, &U3);
+        double U, Z, a_, b_, c_;
+        lean_noise(f->seed, ORC_STREAM(2, 1), (uint64_t)i, &a_, &b_, &c_, &U, &Z);
         f->y[0][i] = 0.0;
         f->m[0][i] = 0;
         uint8_t m = U < p->p_start;
@@ -624,14 +630,13 @@ double orc_om_filter_step(orc_om_filter *f, const orc_om_params *p, int64_t t, d
         int64_t a = f->parents[i] - 1;
         double y_pp = f->y[prv][a], y_c = f->y[cur][a];
         uint8_t m_pp = f->m[prv][a], m_c = f->m[cur][a];
-        double U2, Z2, U3, U1, Z1, unused;
-        lean_noise(f->seed, ORC_STREAM(3, t - 1), (uint64_t)i, &U2, &Z2, &U3);
+        double U2, Z2, U3, U1, Z1;
+        lean_noise(f->seed, ORC_STREAM(2, t), (uint64_t)i, &U2, &Z2, &U3, &U1, &Z1);
         uint8_t mq = U2 < (m_pp ? p->p_stay : p->p_start);
         double sz = p->sigma_proc * Z2;
         double yq = (y_pp + (mq ? vel_prev : 0.0)) + sz;
         double alpha = orc_normal_logpdf(obs_prev, yq, p->sigma_obs) - orc_normal_logpdf(obs_prev, y_c, p->sigma_obs);
         if (log(U3) < alpha) { y_c = yq; m_c = mq; }
-        lean_noise(f->seed, ORC_STREAM(2, t), (uint64_t)i, &U1, &Z1, &unused);
         uint8_t mn = U1 < (m_c ? p->p_stay : p->p_start);
         double sz1 = p->sigma_proc * Z1;
         double yn = (y_c + (mn ? vel_t : 0.0)) + sz1;
