@@ -166,10 +166,10 @@ static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const d
     const int64_t tpf = ceil_div(pf->n, kTile);
     const unsigned grid = (unsigned)(tpf * pf->nf);
     if (init) {
-        GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
+        GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
                      pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
     } else {
-        GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kThreads, pf->stream, pf->P, t, pf->slice(t - 1),
+        GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(t - 1),
                      pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
     }
     return GENPF_OK;
@@ -256,7 +256,7 @@ static int32_t read_stats(genpf_filter_t pf, int which) {
 template <class Model, class Noise>
 static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise) {
     const int64_t tpf = ceil_div(pf->n, kTile);
-    GENPF_LAUNCH((k_mh<Model, Noise>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
+    GENPF_LAUNCH((k_mh<Model, Noise>), (unsigned)(tpf * pf->nf), kStateThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
                  pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept);
     return GENPF_OK;
 }
@@ -467,7 +467,15 @@ template <class Model, class Noise>
 static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noise) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     const int64_t t = a.t;
-    GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t>), (unsigned)(tpf * pf->nf), kThreads, pf->stream, a,
+    if (a.mh_iters == 1) {
+        GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 1>), (unsigned)(tpf * pf->nf), kStateThreads, pf->stream, a,
+                     (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
+                     pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents,
+                     pf->lw_alt, pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr,
+                     pf->sc.partials(0));
+        return GENPF_OK;
+    }
+    GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), (unsigned)(tpf * pf->nf), kStateThreads, pf->stream, a,
                  (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                  pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
                  pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));

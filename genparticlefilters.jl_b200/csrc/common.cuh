@@ -70,6 +70,9 @@ struct UniSrc {
 };
 
 // ------------------------------------------------------------------ warp / block reductions
+// All block-level helpers are templated on the block size T (threads); a tile is always kTile = 2048
+// particles, so a thread owns kTile/T of them.  T = 256 (8 each) is the default; the fused step kernel
+// runs T = 512 (4 each) for occupancy.
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -80,7 +83,8 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// all threads get the result; smem must hold kWarps doubles; deterministic order
+// all threads get the result; smem must hold T/32 values; deterministic order
+template <int T = kThreads>
 __device__ __forceinline__ double block_sum(double v, double *smem) {
     v = warp_sum(v);
     __syncthreads();
@@ -88,9 +92,10 @@ __device__ __forceinline__ double block_sum(double v, double *smem) {
     __syncthreads();
     double r = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) r += smem[w];
+    for (int w = 0; w < T / 32; ++w) r += smem[w];
     return r;
 }
+template <int T = kThreads>
 __device__ __forceinline__ double block_max(double v, double *smem) {
     v = warp_max(v);
     __syncthreads();
@@ -98,9 +103,10 @@ __device__ __forceinline__ double block_max(double v, double *smem) {
     __syncthreads();
     double r = smem[0];
 #pragma unroll
-    for (int w = 1; w < kWarps; ++w) r = fmax(r, smem[w]);
+    for (int w = 1; w < T / 32; ++w) r = fmax(r, smem[w]);
     return r;
 }
+template <int T = kThreads>
 __device__ __forceinline__ int block_or(int v, int *smem) {
     v = __reduce_or_sync(0xffffffffu, (unsigned)v);
     __syncthreads();
@@ -108,7 +114,7 @@ __device__ __forceinline__ int block_or(int v, int *smem) {
     __syncthreads();
     int r = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) r |= smem[w];
+    for (int w = 0; w < T / 32; ++w) r |= smem[w];
     return r;
 }
 
@@ -120,13 +126,18 @@ struct LwSrc {
     __device__ __forceinline__ double fix(double v) const { return scale == 1.0 ? v : v * scale; }
 };
 
-__device__ __forceinline__ void load_tile(const LwSrc &src, int64_t base, int64_t valid, double (&v)[kItems],
+// element index (within the tile) of register slot k of this thread
+template <int T = kThreads>
+__device__ __forceinline__ int tile_elem(int k) { return ((k >> 1) * T + threadIdx.x) * 2 + (k & 1); }
+
+template <int T = kThreads>
+__device__ __forceinline__ void load_tile(const LwSrc &src, int64_t base, int64_t valid, double (&v)[kTile / T],
                                           double fill) {
     const double *p = src.p + base;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 #pragma unroll
-    for (int j = 0; j < kVecs; ++j) {
-        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+    for (int j = 0; j < kTile / T / 2; ++j) {
+        int64_t e = (int64_t)(j * T + threadIdx.x) * 2;
         if (vec_ok && e + 1 < valid) {
             double2 d = __ldg(reinterpret_cast<const double2 *>(p + e));
             v[2 * j] = src.fix(d.x);
@@ -137,15 +148,15 @@ __device__ __forceinline__ void load_tile(const LwSrc &src, int64_t base, int64_
         }
     }
 }
-template <typename T>
-__device__ __forceinline__ void store_tile(T *out, int64_t base, int64_t valid, const T (&v)[kItems]) {
-    T *p = out + base;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0);
+template <typename X, int T = kThreads>
+__device__ __forceinline__ void store_tile(X *out, int64_t base, int64_t valid, const X (&v)[kTile / T]) {
+    X *p = out + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & (2 * sizeof(X) - 1)) == 0);
 #pragma unroll
-    for (int j = 0; j < kVecs; ++j) {
-        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+    for (int j = 0; j < kTile / T / 2; ++j) {
+        int64_t e = (int64_t)(j * T + threadIdx.x) * 2;
         if (vec_ok && e + 1 < valid) {
-            struct alignas(2 * sizeof(T)) V2 { T a, b; };
+            struct alignas(2 * sizeof(X)) V2 { X a, b; };
             V2 d{v[2 * j], v[2 * j + 1]};
             *reinterpret_cast<V2 *>(p + e) = d;
         } else {
@@ -154,54 +165,52 @@ __device__ __forceinline__ void store_tile(T *out, int64_t base, int64_t valid, 
         }
     }
 }
-// element index (within the tile) of register slot k of this thread
-__device__ __forceinline__ int tile_elem(int k) { return ((k >> 1) * kThreads + threadIdx.x) * 2 + (k & 1); }
 
 // In-tile inclusive prefix sum over the striped layout.  On return incl[k] is the inclusive sum of all
 // tile elements up to and including this thread's slot k; returns the tile total to all threads.
-// smem: 32 values of T.  Deterministic association.
-template <typename T>
-__device__ __forceinline__ T tile_scan(const T (&x)[kItems], T (&incl)[kItems], T *smem) {
-    T lane_excl[kVecs], inc[kVecs];
+// smem: 32 values of X ((kTile/T/2 rows) x (T/32 warps) = 32 cells for every T).  Deterministic association.
+template <typename X, int T = kThreads>
+__device__ __forceinline__ X tile_scan(const X (&x)[kTile / T], X (&incl)[kTile / T], X *smem) {
+    constexpr int V = kTile / T / 2, NW = T / 32;
+    static_assert(V * NW == 32, "tile_scan needs 32 (row, warp) cells");
+    X lane_excl[V], inc[V];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int j = 0; j < kVecs; ++j) {
-        T s = x[2 * j] + x[2 * j + 1];
+    for (int j = 0; j < V; ++j) {
+        X s = x[2 * j] + x[2 * j + 1];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            T t = __shfl_up_sync(0xffffffffu, s, o);
+            X t = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += t;
         }
         inc[j] = s;
-        T e = __shfl_up_sync(0xffffffffu, s, 1);  // exact exclusive prefix (no subtraction: fp64)
-        lane_excl[j] = lane == 0 ? T(0) : e;
+        X e = __shfl_up_sync(0xffffffffu, s, 1);  // exact exclusive prefix (no subtraction: fp64)
+        lane_excl[j] = lane == 0 ? X(0) : e;
     }
     __syncthreads();
     if (lane == 31) {
 #pragma unroll
-        for (int j = 0; j < kVecs; ++j) smem[j * kWarps + warp] = inc[j];
+        for (int j = 0; j < V; ++j) smem[j * NW + warp] = inc[j];
     }
     __syncthreads();
-    T total;
+    X total;
     {
         // exclusive scan over the 32 (row j, warp w) cells, row-major == element order
-        T c = smem[lane];
-        T s = c;
+        X s = smem[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            T t = __shfl_up_sync(0xffffffffu, s, o);
+            X t = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += t;
         }
         total = __shfl_sync(0xffffffffu, s, 31);
-        T e = __shfl_up_sync(0xffffffffu, s, 1);
-        (void)c;
+        X e = __shfl_up_sync(0xffffffffu, s, 1);
         __syncthreads();
-        if (warp == 0) smem[lane] = lane == 0 ? T(0) : e;  // exclusive
+        if (warp == 0) smem[lane] = lane == 0 ? X(0) : e;  // exclusive
         __syncthreads();
     }
 #pragma unroll
-    for (int j = 0; j < kVecs; ++j) {
-        T excl = smem[j * kWarps + warp] + lane_excl[j];
+    for (int j = 0; j < V; ++j) {
+        X excl = smem[j * NW + warp] + lane_excl[j];
         incl[2 * j] = excl + x[2 * j];
         incl[2 * j + 1] = incl[2 * j] + x[2 * j + 1];
     }

@@ -19,12 +19,16 @@ struct Cols {
     uint8_t *b[kMaxB];
 };
 
-__device__ __forceinline__ void load_tile_u8(const uint8_t *col, int64_t base, int64_t valid, uint8_t (&v)[kItems]) {
+constexpr int kStateThreads = 512;  // block size of every kernel that produces particle state + K1 partials
+
+template <int T = kThreads>
+__device__ __forceinline__ void load_tile_u8(const uint8_t *col, int64_t base, int64_t valid,
+                                             uint8_t (&v)[kTile / T]) {
     const uint8_t *p = col + base;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 1) == 0);
 #pragma unroll
-    for (int j = 0; j < kVecs; ++j) {
-        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+    for (int j = 0; j < kTile / T / 2; ++j) {
+        int64_t e = (int64_t)(j * T + threadIdx.x) * 2;
         if (vec_ok && e + 1 < valid) {
             uchar2 d = *reinterpret_cast<const uchar2 *>(p + e);
             v[2 * j] = d.x;
@@ -35,12 +39,14 @@ __device__ __forceinline__ void load_tile_u8(const uint8_t *col, int64_t base, i
         }
     }
 }
-__device__ __forceinline__ void store_tile_u8(uint8_t *col, int64_t base, int64_t valid, const uint8_t (&v)[kItems]) {
+template <int T = kThreads>
+__device__ __forceinline__ void store_tile_u8(uint8_t *col, int64_t base, int64_t valid,
+                                              const uint8_t (&v)[kTile / T]) {
     uint8_t *p = col + base;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 1) == 0);
 #pragma unroll
-    for (int j = 0; j < kVecs; ++j) {
-        int64_t e = (int64_t)(j * kThreads + threadIdx.x) * 2;
+    for (int j = 0; j < kTile / T / 2; ++j) {
+        int64_t e = (int64_t)(j * T + threadIdx.x) * 2;
         if (vec_ok && e + 1 < valid) {
             *reinterpret_cast<uchar2 *>(p + e) = make_uchar2(v[2 * j], v[2 * j + 1]);
         } else {
@@ -50,68 +56,70 @@ __device__ __forceinline__ void store_tile_u8(uint8_t *col, int64_t base, int64_
     }
 }
 
-template <class Model>
+template <class Model, int T = kThreads>
 __device__ __forceinline__ void load_slices(const Cols &c, int64_t base, int64_t valid,
-                                            typename Model::Slice (&s)[kItems]) {
+                                            typename Model::Slice (&s)[kTile / T]) {
 #pragma unroll
     for (int fld = 0; fld < Model::NF; ++fld) {
-        double v[kItems];
+        double v[kTile / T];
         LwSrc src{c.f[fld], 1.0};
-        load_tile(src, base, valid, v, 0.0);
+        load_tile<T>(src, base, valid, v, 0.0);
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) s[k].f[fld] = v[k];
+        for (int k = 0; k < kTile / T; ++k) s[k].f[fld] = v[k];
     }
 #pragma unroll
     for (int fld = 0; fld < Model::NB; ++fld) {
-        uint8_t v[kItems];
-        load_tile_u8(c.b[fld], base, valid, v);
+        uint8_t v[kTile / T];
+        load_tile_u8<T>(c.b[fld], base, valid, v);
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) s[k].b[fld] = v[k];
+        for (int k = 0; k < kTile / T; ++k) s[k].b[fld] = v[k];
     }
 }
-template <class Model>
+template <class Model, int T = kThreads>
 __device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_t valid,
-                                             const typename Model::Slice (&s)[kItems]) {
+                                             const typename Model::Slice (&s)[kTile / T]) {
 #pragma unroll
     for (int fld = 0; fld < Model::NF; ++fld) {
-        double v[kItems];
+        double v[kTile / T];
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) v[k] = s[k].f[fld];
-        store_tile<double>(c.f[fld], base, valid, v);
+        for (int k = 0; k < kTile / T; ++k) v[k] = s[k].f[fld];
+        store_tile<double, T>(c.f[fld], base, valid, v);
     }
 #pragma unroll
     for (int fld = 0; fld < Model::NB; ++fld) {
-        uint8_t v[kItems];
+        uint8_t v[kTile / T];
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) v[k] = s[k].b[fld];
-        store_tile_u8(c.b[fld], base, valid, v);
+        for (int k = 0; k < kTile / T; ++k) v[k] = s[k].b[fld];
+        store_tile_u8<T>(c.b[fld], base, valid, v);
     }
 }
 
 // tile epilogue shared by every kernel that produces log-weights: the K1 partials of the tile
-__device__ __forceinline__ void emit_partials(const double (&v)[kItems], const Partials &out, double *sm, int *smi) {
+template <int T = kThreads>
+__device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, double *sm,
+                                              int *smi) {
     int fl = 0;
     double m = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
+    for (int k = 0; k < kTile / T; ++k) {
         fl |= isnan(v[k]) ? 1 : 0;
         m = fmax(m, v[k]);
     }
-    m = block_max(m, sm);
-    fl = block_or(fl, smi);
+    m = block_max<T>(m, sm);
+    fl = block_or<T>(fl, smi);
     double s = 0.0, s2 = 0.0;
     if (m == INFINITY) {
         fl |= 2;
     } else if (m > -INFINITY) {
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
+        for (int k = 0; k < kTile / T; ++k) {
             double e = exp(v[k] - m);
             s += e;
             s2 += e * e;
         }
     }
-    s = block_sum(s, sm);
-    s2 = block_sum(s2, sm);
+    s = block_sum<T>(s, sm);
+    s2 = block_sum<T>(s2, sm);
     if (threadIdx.x == 0) {
         out.m[blockIdx.x] = m;
         out.s[blockIdx.x] = s;
@@ -124,30 +132,31 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kItems], const P
 // INIT: pf_initialize (initialize.jl:39-41): slice_1 = transition(initial), lw = obs_logpdf
 // else: pf_update!    (update.jl:15-21):     slice_t = transition(slice_{t-1}), lw += obs_logpdf
 template <class Model, class Noise, bool INIT>
-static __global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kStateThreads)
     k_propagate(ModelParams P, int64_t t, Cols prev, Cols next, double *lw, const double *obs_dev, double obs_val,
                 int64_t n, int64_t tpf, Noise noise, Partials partials) {
-    __shared__ double sm[kWarps];
-    __shared__ int smi[kWarps];
+    constexpr int T = kStateThreads, I = kTile / T;
+    __shared__ double sm[T / 32];
+    __shared__ int smi[T / 32];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t start = tile * kTile;
     const int64_t valid = min((int64_t)kTile, n - start);
     const int64_t base = f * n + start;
     const double obs = obs_dev ? obs_dev[f] : obs_val;
-    typename Model::Slice sp[kItems], sn[kItems];
-    double v[kItems];
+    typename Model::Slice sp[I], sn[I];
+    double v[I];
     if (INIT) {
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) Model::initial(P, sp[k]);
+        for (int k = 0; k < I; ++k) Model::initial(P, sp[k]);
     } else {
-        load_slices<Model>(prev, base, valid, sp);
+        load_slices<Model, T>(prev, base, valid, sp);
         LwSrc src{lw, 1.0};
-        load_tile(src, base, valid, v, -INFINITY);
+        load_tile<T>(src, base, valid, v, -INFINITY);
     }
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-        int e = tile_elem(k);
+    for (int k = 0; k < I; ++k) {
+        int e = tile_elem<T>(k);
         double U = 0.5, Z = 0.0;
         if (e < valid) noise.up(base + e, U, Z);
         Model::transition(P, t, sp[k], sn[k], U, Z);
@@ -155,9 +164,9 @@ static __global__ void __launch_bounds__(kThreads)
         if (e < valid) v[k] = INIT ? l : v[k] + l;
         else v[k] = -INFINITY;
     }
-    store_slices<Model>(next, base, valid, sn);
-    store_tile<double>(lw, base, valid, v);
-    emit_partials(v, partials, sm, smi);
+    store_slices<Model, T>(next, base, valid, sn);
+    store_tile<double, T>(lw, base, valid, v);
+    emit_partials<T>(v, partials, sm, smi);
 }
 
 // ------------------------------------------------------------------ K11 MH rejuvenation (move-accept)
@@ -165,29 +174,30 @@ static __global__ void __launch_bounds__(kThreads)
 // slice: regenerate slice tau from the prior given slice tau-1; weight = obs log-density ratio;
 // accept iff log(rand()) < weight.  Log-weights are untouched.
 template <class Model, class Noise>
-static __global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kStateThreads)
     k_mh(ModelParams P, int64_t tau, int iter, int first_step, Cols prevprev, Cols cur, const double *obs_dev,
          double obs_val, int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept) {
-    __shared__ double sm[kWarps];
+    constexpr int T = kStateThreads, I = kTile / T;
+    __shared__ double sm[T / 32];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t start = tile * kTile;
     const int64_t valid = min((int64_t)kTile, n - start);
     const int64_t base = f * n + start;
     const double obs = obs_dev ? obs_dev[f] : obs_val;
-    typename Model::Slice sp[kItems], sc[kItems];
+    typename Model::Slice sp[I], sc[I];
     if (first_step) {
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) Model::initial(P, sp[k]);
+        for (int k = 0; k < I; ++k) Model::initial(P, sp[k]);
     } else {
-        load_slices<Model>(prevprev, base, valid, sp);
+        load_slices<Model, T>(prevprev, base, valid, sp);
     }
-    load_slices<Model>(cur, base, valid, sc);
-    uint8_t acc[kItems];
+    load_slices<Model, T>(cur, base, valid, sc);
+    uint8_t acc[I];
     double cnt = 0.0;
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-        int e = tile_elem(k);
+    for (int k = 0; k < I; ++k) {
+        int e = tile_elem<T>(k);
         double U = 0.5, Z = 0.0, U3 = 1.0;
         if (e < valid) noise.mh(base + e, iter, U, Z, U3);
         typename Model::Slice q;
@@ -198,10 +208,10 @@ static __global__ void __launch_bounds__(kThreads)
         acc[k] = a ? 1 : 0;
         cnt += a ? 1.0 : 0.0;
     }
-    store_slices<Model>(cur, base, valid, sc);
-    if (accepts) store_tile_u8(accepts, base, valid, acc);
+    store_slices<Model, T>(cur, base, valid, sc);
+    if (accepts) store_tile_u8<T>(accepts, base, valid, acc);
     if (n_accept) {
-        cnt = block_sum(cnt, sm);
+        cnt = block_sum<T>(cnt, sm);
         if (threadIdx.x == 0 && cnt > 0.0) atomicAdd(&n_accept[f], (unsigned long long)cnt);
     }
 }

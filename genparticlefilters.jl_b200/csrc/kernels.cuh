@@ -387,7 +387,7 @@ struct ExpandSmem {
     static constexpr int kStageCap = (sizeof(IdxT) == 4 ? 3 : 2) * kTile;  // stays under 48 KB static smem
     alignas(16) int32_t sParent[kTile];  // accessed as int4
     int64_t brk[2];
-    int32_t warp_max[kWarps];
+    int32_t warp_max[32];
     IdxT sO[kStageCap + 1];
 };
 
@@ -422,10 +422,13 @@ __device__ __forceinline__ int64_t coarse_search(const IdxT *tile_last, int64_t 
     return lo;
 }
 
-// On return p[k] = source index (local to the filter) of this thread's striped output slot k.
-template <typename IdxT>
-__device__ __forceinline__ void block_expand(const IdxT *Of, const IdxT *tile_last, int64_t n_src, int64_t tpf_src,
-                                             int64_t i0, int64_t valid, ExpandSmem<IdxT> &sm, int64_t (&p)[kItems]) {
+// On return rel[k] + (returned s0) = source index (local to the filter) of this thread's striped output
+// slot k (block of T threads, kTile/T slots each).
+template <typename IdxT, int T = kThreads>
+__device__ __forceinline__ int64_t block_expand(const IdxT *Of, const IdxT *tile_last, int64_t n_src, int64_t tpf_src,
+                                                int64_t i0, int64_t valid, ExpandSmem<IdxT> &sm,
+                                                int32_t (&rel)[kTile / T]) {
+    constexpr int I = kTile / T;
     if (threadIdx.x < 2) {
         const int64_t target = threadIdx.x == 0 ? i0 : i0 + valid - 1;
         sm.brk[threadIdx.x] = coarse_search<IdxT>(tile_last, tpf_src, target, i0 / kTile);
@@ -436,29 +439,35 @@ __device__ __forceinline__ void block_expand(const IdxT *Of, const IdxT *tile_la
     const int64_t len = s1 - s0;
     if (len <= ExpandSmem<IdxT>::kStageCap) {
         if (threadIdx.x == 0) sm.sO[0] = b_lo > 0 ? tile_last[b_lo - 1] : (IdxT)0;
-        for (int j = threadIdx.x; j < (int)len; j += kThreads) sm.sO[1 + j] = Of[s0 + j];
+        for (int j = threadIdx.x; j < (int)len; j += T) sm.sO[1 + j] = Of[s0 + j];
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) sm.sParent[k * kThreads + threadIdx.x] = 0;
+        for (int k = 0; k < I; ++k) sm.sParent[k * T + threadIdx.x] = 0;
         __syncthreads();
         const IdxT ibeg = (IdxT)i0, iend = (IdxT)(i0 + valid);
-        for (int j = threadIdx.x; j < (int)len; j += kThreads) {
+        for (int j = threadIdx.x; j < (int)len; j += T) {
             const IdxT prev = sm.sO[j], cur = sm.sO[j + 1];
             const IdxT pos = prev > ibeg ? prev : ibeg, end = cur < iend ? cur : iend;
             if (pos < end) sm.sParent[(int)(pos - ibeg)] = j;
         }
         __syncthreads();
-        // block-wide inclusive max-scan over sParent (blocked 8 per thread, then warp + cross-warp)
-        int32_t a[kItems];
-        {
+        // block-wide inclusive max-scan over sParent (blocked I per thread, then warp + cross-warp)
+        int32_t a[I];
+        if (I == 8) {
             const int4 q0 = reinterpret_cast<const int4 *>(sm.sParent)[2 * threadIdx.x];
             const int4 q1 = reinterpret_cast<const int4 *>(sm.sParent)[2 * threadIdx.x + 1];
             a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w;
-            a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+            a[4 % I] = q1.x; a[5 % I] = q1.y; a[6 % I] = q1.z; a[7 % I] = q1.w;
+        } else if (I == 4) {
+            const int4 q0 = reinterpret_cast<const int4 *>(sm.sParent)[threadIdx.x];
+            a[0] = q0.x; a[1] = q0.y; a[2 % I] = q0.z; a[3 % I] = q0.w;
+        } else {
+            const int2 q0 = reinterpret_cast<const int2 *>(sm.sParent)[threadIdx.x];
+            a[0] = q0.x; a[1] = q0.y;
         }
 #pragma unroll
-        for (int k = 1; k < kItems; ++k) a[k] = max(a[k], a[k - 1]);
+        for (int k = 1; k < I; ++k) a[k] = max(a[k], a[k - 1]);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        int32_t run = a[kItems - 1];
+        int32_t run = a[I - 1];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int32_t t = __shfl_up_sync(0xffffffffu, run, o);
@@ -469,26 +478,33 @@ __device__ __forceinline__ void block_expand(const IdxT *Of, const IdxT *tile_la
         if (lane == 0) excl = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w)
+        for (int w = 0; w < T / 32; ++w)
             if (w < warp) excl = max(excl, sm.warp_max[w]);
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) a[k] = max(a[k], excl);
-        reinterpret_cast<int4 *>(sm.sParent)[2 * threadIdx.x] = make_int4(a[0], a[1], a[2], a[3]);
-        reinterpret_cast<int4 *>(sm.sParent)[2 * threadIdx.x + 1] = make_int4(a[4], a[5], a[6], a[7]);
+        for (int k = 0; k < I; ++k) a[k] = max(a[k], excl);
+        if (I == 8) {
+            reinterpret_cast<int4 *>(sm.sParent)[2 * threadIdx.x] = make_int4(a[0], a[1], a[2], a[3]);
+            reinterpret_cast<int4 *>(sm.sParent)[2 * threadIdx.x + 1] = make_int4(a[4 % I], a[5 % I], a[6 % I], a[7 % I]);
+        } else if (I == 4) {
+            reinterpret_cast<int4 *>(sm.sParent)[threadIdx.x] = make_int4(a[0], a[1], a[2 % I], a[3 % I]);
+        } else {
+            reinterpret_cast<int2 *>(sm.sParent)[threadIdx.x] = make_int2(a[0], a[1]);
+        }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-            const int e = tile_elem(k);
-            p[k] = s0 + (e < valid ? (int64_t)sm.sParent[e] : 0);
+        for (int k = 0; k < I; ++k) {
+            const int e = tile_elem<T>(k);
+            rel[k] = e < valid ? sm.sParent[e] : 0;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-            const int e = tile_elem(k);
-            p[k] = s0 + (e < valid ? upper_bound_clamped<IdxT, int64_t>(Of + s0, len, i0 + e) : 0);
+        for (int k = 0; k < I; ++k) {
+            const int e = tile_elem<T>(k);
+            rel[k] = e < valid ? (int32_t)upper_bound_clamped<IdxT, int64_t>(Of + s0, len, i0 + e) : 0;
         }
     }
     __syncthreads();
+    return s0;
 }
 
 template <typename IdxT, typename OutT>
@@ -512,12 +528,12 @@ static __global__ void __launch_bounds__(kThreads)
         valid = min(valid, C - i0);
         if (valid <= 0) return;
     }
-    int64_t p[kItems];
-    block_expand<IdxT>(Of, tile_last_O + f * tpf_src, n_src, tpf_src, i0, valid, sm, p);
+    int32_t rel[kItems];
+    const int64_t s0 = block_expand<IdxT>(Of, tile_last_O + f * tpf_src, n_src, tpf_src, i0, valid, sm, rel);
     OutT out[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
-        int64_t q = p[k];
+        int64_t q = s0 + rel[k];
         if (order && tile_elem(k) < valid) q = order[f * n_src + q];
         out[k] = (OutT)(q + out_base);
     }

@@ -40,12 +40,13 @@ __device__ __forceinline__ double normal_logpdf(double x, double mu, double inv_
 
 // accept iff log(U3) < alpha (Gen mh).  Decision-exact fast path: an fp32 log with a conservative error
 // bound decides unless it lands within the bound of alpha, in which case the fp64 log is evaluated.
+static __device__ __noinline__ bool mh_accept_slow(double U3, double alpha) { return log(U3) < alpha; }
 __device__ __forceinline__ bool mh_accept(double U3, double alpha) {
     if (alpha > 0.0) return true;  // log(U3) <= 0 < alpha
     const float lf = __logf((float)U3);
     const float af = (float)alpha;
     if (fabsf(lf - af) > 1e-4f * (1.0f + fabsf(lf))) return lf < af;
-    return log(U3) < alpha;
+    return mh_accept_slow(U3, alpha);
 }
 
 // README.md:43-54 object_motion.  params: v[0]=p_stay .75, v[1]=p_start .25, v[2]=sigma_proc .01,
@@ -97,7 +98,10 @@ struct LinGauss1D {
 //   up(i, U, Z)              noise of pf_update!/pf_initialize to time s
 //   mh(i, it, U, Z, U3)      noise of mh iteration `it` on slice s-1
 //   both(i, ...)             the two at once (fused step, iteration 0)
-__device__ __forceinline__ float fast_bm_radius(float ua) { return sqrtf(-2.0f * __logf(ua)); }
+__device__ __forceinline__ float fast_bm_radius(float ua) {
+    const float x = -2.0f * __logf(ua);  // >= 0 (ua can round up to 1.0f)
+    return x * rsqrtf(fmaxf(x, 1e-30f));
+}
 
 // Lean (default): ONE Philox4x32-10 call per particle per step s serves BOTH moves (128 bits):
 //   w0[31:8] U_mh (24 b)   w1[31:8] U_up (24 b)   w2 U_acc (32 b)   w3[31:8] Box-Muller angle (24 b)
