@@ -528,7 +528,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
-    GENPF_LAUNCH((k_scan<int32_t>), (unsigned)(tpf * nf), kThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
+    GENPF_LAUNCH((k_scan<int32_t>), (unsigned)(tpf * nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
                  (const double *)sc.tile_off.as<double>(), (double *)nullptr, sc.O.as<int32_t>(),
                  sc.tile_last.as<int32_t>(), strat, 0);
     int32_t st;

@@ -438,7 +438,7 @@ int32_t genpf_debug_cumweights(const double *lw, int64_t n, uint32_t flags, doub
     GENPF_TRY(launch_finalize(ws.stream, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), ws.sc.tile_off.as<double>(), -1.0, nullptr));
     UniSrc uni{nullptr, 0, 0, 0};
     StratArgs none = make_strat(uni, n);
-    GENPF_LAUNCH((k_scan<int32_t>), (unsigned)tpf, kThreads, ws.stream, src, n, tpf, ws.sc.st(0, 1),
+    GENPF_LAUNCH((k_scan<int32_t>), (unsigned)tpf, kScanThreads, ws.stream, src, n, tpf, ws.sc.st(0, 1),
                  ws.sc.tile_off.as<double>(), d_W, (int32_t *)nullptr, (int32_t *)nullptr, none, 0);
     GENPF_TRY(copy_out(ws, d_W, W_out, n, dp));
     GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));

@@ -49,8 +49,8 @@ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint64_t stream, uint6
 }
 // 53-bit uniform in [0,1): (x >> 11) * 2^-53
 __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
-    uint64_t x = ((uint64_t)hi << 32) | lo;
-    return (double)(x >> 11) * 0x1.0p-53;
+    // x >> 11 = hi * 2^21 + (lo >> 11): two exact 32-bit conversions and one exact fma
+    return fma((double)hi, 0x1.0p-32, (double)(lo >> 11) * 0x1.0p-53);
 }
 __host__ __device__ __forceinline__ uint64_t make_stream(uint32_t purpose, uint64_t step) {
     return ((uint64_t)purpose << 56) | (step & 0x00FFFFFFFFFFFFFFull);

@@ -107,14 +107,14 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
             order = sc.order.as<int32_t>();
         }
         StratArgs strat = make_strat(uni, n_in);
-        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
+        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
                      (double *)nullptr, O, tile_last, strat, gate);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0);
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         StratArgs none = make_strat(uni, n_in);
-        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
+        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
                      sc.W.as<double>(), (IdxT *)nullptr, (IdxT *)nullptr, none, gate);
         GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
                      tpf_out, uni, (const IdxT *)nullptr, parents, out_base, st_sel, gate);

@@ -299,7 +299,8 @@ struct StratArgs {
     int pow2;
 };
 __device__ __forceinline__ double strat_lower(const StratArgs &a, int64_t i1) {
-    return a.pow2 ? (double)(i1 - 1) * a.step : (double)(i1 - 1) / (double)a.n;
+    const double im1 = a.n < 0x7FFFFFFFll ? (double)(int)(i1 - 1) : (double)(i1 - 1);
+    return a.pow2 ? im1 * a.step : im1 / (double)a.n;
 }
 __device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t i1) {
     double r = a.uni(f * a.n + i1 - 1);
@@ -307,24 +308,29 @@ __device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t
 }
 // C(W) = #{i in 1..n : u_i <= W}.  Because u is non-decreasing in i this is a prefix count, and
 // parent_i = min{k : W_k >= u_i} (resample.jl:163-168) == min{k : C(W_k) >= i}.
-__device__ __forceinline__ int64_t strat_count(const StratArgs &a, int64_t f, double W) {
-    double x = W * (double)a.n;
-    int64_t j = x >= (double)a.n ? a.n : (x <= 0.0 ? 0 : (int64_t)x);
+// J = int32 when n < 2^31 (single-instruction fp64<->int conversions), else int64.
+template <typename J>
+__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t f, double W) {
+    const double nd = (double)a.n;
+    const double x = W * nd;
+    J j = x >= nd ? (J)a.n : (x <= 0.0 ? (J)0 : (J)x);
     const bool near_edge = (x - (double)j) < 1e-6;
     // u_i >= lower_i, so a stratum whose lower bound already exceeds W needs no draw
-    while (j < a.n && strat_lower(a, j + 1) <= W && strat_u(a, f, j + 1) <= W) ++j;
+    while (j < (J)a.n && strat_lower(a, (int64_t)j + 1) <= W && strat_u(a, f, (int64_t)j + 1) <= W) ++j;
     if (near_edge)
-        while (j > 0 && strat_u(a, f, j) > W) --j;
+        while (j > 0 && strat_u(a, f, (int64_t)j) > W) --j;
     return j;
 }
 
 // ------------------------------------------------------------------ K3 normalise + scan
 // Replaces safe_softmax line utils.jl:139 and the running accum_weight of resample.jl:163-166.
 // Writes W (normalised inclusive cumulative weights) and/or O (cumulative offspring counts, stratified).
+constexpr int kScanThreads = 512;  // every launch of k_scan uses this block size (fixed summation order)
 template <typename IdxT>
-static __global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kScanThreads, 2)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, double *W_out, IdxT *O_out,
            IdxT *tile_last_O, StratArgs strat, int gate) {
+    constexpr int T = kScanThreads, I = kTile / T;
     __shared__ double sm[32];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
@@ -333,34 +339,34 @@ static __global__ void __launch_bounds__(kThreads)
     if (gate && !st.do_resample) return;
     const int64_t start = tile * kTile;
     const int64_t valid = min((int64_t)kTile, n - start);
-    double v[kItems], w[kItems], W[kItems];
-    load_tile(src, f * n + start, valid, v, -INFINITY);
+    double v[I], w[I], W[I];
+    load_tile<T>(src, f * n + start, valid, v, -INFINITY);
     const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
     const double inv_n = 1.0 / (double)n;
     // w_i = e_i / S evaluated as e_i * (1/S): at most 1 ulp from the reference's division, far inside the
     // sequential-vs-parallel cumulative-sum noise that defines the documented tie class
     const double inv_S = 1.0 / st.S;
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-        if (uniform) w[k] = tile_elem(k) < valid ? inv_n : 0.0;
+    for (int k = 0; k < I; ++k) {
+        if (uniform) w[k] = tile_elem<T>(k) < valid ? inv_n : 0.0;
         else w[k] = exp(v[k] - st.M) * inv_S;
     }
-    tile_scan<double>(w, W, sm);
+    tile_scan<double, T>(w, W, sm);
     const double off = tile_off[f * tpf + tile];
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) W[k] = off + W[k];
-    if (W_out) store_tile<double>(W_out, f * n + start, valid, W);
+    for (int k = 0; k < I; ++k) W[k] = off + W[k];
+    if (W_out) store_tile<double, T>(W_out, f * n + start, valid, W);
     if (O_out) {
-        IdxT O[kItems];
+        IdxT O[I];
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-            const int e = tile_elem(k);
-            O[k] = e < valid ? (IdxT)strat_count(strat, f, W[k]) : (IdxT)0;
+        for (int k = 0; k < I; ++k) {
+            const int e = tile_elem<T>(k);
+            O[k] = e < valid ? strat_count<IdxT>(strat, f, W[k]) : (IdxT)0;
             // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
             if (start + e == n - 1) O[k] = (IdxT)n;
             if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];
         }
-        store_tile<IdxT>(O_out, f * n + start, valid, O);
+        store_tile<IdxT, T>(O_out, f * n + start, valid, O);
     }
 }
 
