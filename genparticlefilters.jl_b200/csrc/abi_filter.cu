@@ -164,7 +164,7 @@ template <class Model, class Noise>
 static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
                                 Noise noise) {
     const int64_t tpf = ceil_div(pf->n, kTile);
-    const unsigned grid = (unsigned)(tpf * pf->nf);
+    const dim3 grid((unsigned)tpf, (unsigned)pf->nf);
     if (init) {
         GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
                      pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
@@ -256,7 +256,7 @@ static int32_t read_stats(genpf_filter_t pf, int which) {
 template <class Model, class Noise>
 static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise) {
     const int64_t tpf = ceil_div(pf->n, kTile);
-    GENPF_LAUNCH((k_mh<Model, Noise>), (unsigned)(tpf * pf->nf), kStateThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
+    GENPF_LAUNCH((k_mh<Model, Noise>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
                  pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept);
     return GENPF_OK;
 }
@@ -439,7 +439,7 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     // gather the window into the other buffer; no-priority reweight fused in
     const int64_t tpf_out = ceil_div(n_out, kTile);
     GatherCols g = window_gather_cols(pf);
-    GENPF_LAUNCH(k_gather, (unsigned)(tpf_out * nf), kThreads, s, g, pf->parents, n, n_out, tpf_out, (const double *)pf->lw,
+    GENPF_LAUNCH(k_gather, dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, g, pf->parents, n, n_out, tpf_out, (const double *)pf->lw,
                  has_prio ? (double *)nullptr : pf->lw_alt, (const Stats *)st_lw, gate, substate ? 1 : 0);
     if (has_prio) {
         GENPF_LAUNCH((k_prio_ratio<int32_t>), dim3(grid_1d(n_out), (unsigned)nf), 256, s, pf->lw, sel, pf->parents,
@@ -468,14 +468,14 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
     const int64_t tpf = ceil_div(pf->n, kTile);
     const int64_t t = a.t;
     if (a.mh_iters == 1) {
-        GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 1>), (unsigned)(tpf * pf->nf), kStateThreads, pf->stream, a,
+        GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                      pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents,
                      pf->lw_alt, pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr,
                      pf->sc.partials(0));
         return GENPF_OK;
     }
-    GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), (unsigned)(tpf * pf->nf), kStateThreads, pf->stream, a,
+    GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
                  (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                  pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
                  pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
@@ -528,7 +528,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
-    GENPF_LAUNCH((k_scan<int32_t>), (unsigned)(tpf * nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
+    GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, (unsigned)nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
                  (const double *)sc.tile_off.as<double>(), (double *)nullptr, sc.O.as<int32_t>(),
                  sc.tile_last.as<int32_t>(), strat, 0);
     int32_t st;
@@ -586,6 +586,7 @@ int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_pa
     if (model_id < 0 || model_id >= kNumModels) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
     if (n_particles <= 0 || n_filters <= 0) return fail(GENPF_ERR_INVALID_ARG, "n_particles and n_filters must be > 0");
     if (n_particles >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "n_particles per filter must be < 2^31");
+    if (n_filters > 65535) return fail(GENPF_ERR_UNSUPPORTED, "n_filters must be <= 65535 (grid.y)");
     const ModelInfo &mi = kModels[model_id];
     if (params && n_params != mi.np) return fail(GENPF_ERR_INVALID_ARG, "wrong number of model parameters");
     std::unique_ptr<genpf_filter_s> pf(new genpf_filter_s());
@@ -893,7 +894,7 @@ namespace genpf {
 static int32_t apply_parents_and_swap(genpf_filter_t pf, int64_t n_out) {
     const int64_t tpf_out = ceil_div(n_out, kTile);
     GatherCols g = window_gather_cols(pf);
-    GENPF_LAUNCH(k_gather, (unsigned)(tpf_out * pf->nf), kThreads, pf->stream, g, pf->parents, pf->n, n_out, tpf_out,
+    GENPF_LAUNCH(k_gather, dim3((unsigned)tpf_out, (unsigned)pf->nf), kThreads, pf->stream, g, pf->parents, pf->n, n_out, tpf_out,
                  (const double *)nullptr, (double *)nullptr, (const Stats *)nullptr, 0, 0);
     pf->buf ^= 1;
     std::swap(pf->lw, pf->lw_alt);

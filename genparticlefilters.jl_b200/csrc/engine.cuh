@@ -45,7 +45,7 @@ struct Scratch {
 
 inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, Partials part) {
     const int64_t tpf = ceil_div(n, kTile);
-    GENPF_LAUNCH(k_reduce, (unsigned)(tpf * nf), kThreads, s, src, n, tpf, part);
+    GENPF_LAUNCH(k_reduce, dim3((unsigned)tpf, (unsigned)nf), kThreads, s, src, n, tpf, part);
     return GENPF_OK;
 }
 inline int32_t launch_finalize(cudaStream_t s, Partials part, int64_t n, int64_t nf, Stats *st, double *tile_off,
@@ -107,16 +107,16 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
             order = sc.order.as<int32_t>();
         }
         StratArgs strat = make_strat(uni, n_in);
-        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
+        GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
                      (double *)nullptr, O, tile_last, strat, gate);
-        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
+        GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0);
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         StratArgs none = make_strat(uni, n_in);
-        GENPF_LAUNCH((k_scan<IdxT>), (unsigned)(tpf_in * nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
+        GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
                      sc.W.as<double>(), (IdxT *)nullptr, (IdxT *)nullptr, none, gate);
-        GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
+        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
                      tpf_out, uni, (const IdxT *)nullptr, parents, out_base, st_sel, gate);
     } else if (method == GENPF_RESIDUAL) {
         if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated residual resample is not supported");
@@ -128,15 +128,15 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         GENPF_TRY(sc.resid_roff.ensure(np * 8));
         GENPF_TRY(sc.resid_rtot.ensure((size_t)nf * 8));
         ResidPartials rp{sc.resid_c.as<long long>(), sc.resid_r.as<double>()};
-        GENPF_LAUNCH(k_resid_partials, (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel, rp);
+        GENPF_LAUNCH(k_resid_partials, dim3((unsigned)tpf_in, (unsigned)nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel, rp);
         GENPF_LAUNCH(k_resid_finalize, (unsigned)nf, kThreads, s, rp, tpf_in, sc.resid_rtot.as<double>(),
                      sc.resid_coff.as<long long>(), sc.resid_roff.as<double>());
-        GENPF_LAUNCH((k_resid_scan<IdxT>), (unsigned)(tpf_in * nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel,
+        GENPF_LAUNCH((k_resid_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel,
                      sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
                      tile_last, sc.W.as<double>());
-        GENPF_LAUNCH((k_expand<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
+        GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
                      (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1);
-        GENPF_LAUNCH((k_search<IdxT, OutT>), (unsigned)(tpf_out * nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
+        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
                      tpf_out, uni, (const IdxT *)O, parents, out_base, st_sel, 0);
     } else {
         return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
@@ -161,10 +161,10 @@ inline int32_t launch_mean_var(cudaStream_t s, Scratch &sc, const double *lw, XS
     LwSrc src{lw, 1.0};
     double *partial = sc.moment_partial.as<double>();
     double *mean = sc.moment_out.as<double>(), *var = mean + nf;
-    GENPF_LAUNCH(k_weighted_moment, (unsigned)(tpf * nf), kThreads, s, src, x, n, tpf, st, (const double *)nullptr,
+    GENPF_LAUNCH(k_weighted_moment, dim3((unsigned)tpf, (unsigned)nf), kThreads, s, src, x, n, tpf, st, (const double *)nullptr,
                  partial);
     GENPF_LAUNCH(k_sum_partials, (unsigned)nf, kThreads, s, partial, tpf, mean);
-    GENPF_LAUNCH(k_weighted_moment, (unsigned)(tpf * nf), kThreads, s, src, x, n, tpf, st, (const double *)mean,
+    GENPF_LAUNCH(k_weighted_moment, dim3((unsigned)tpf, (unsigned)nf), kThreads, s, src, x, n, tpf, st, (const double *)mean,
                  partial);
     GENPF_LAUNCH(k_sum_partials, (unsigned)nf, kThreads, s, partial, tpf, var);
     return GENPF_OK;

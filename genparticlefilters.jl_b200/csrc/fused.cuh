@@ -45,7 +45,7 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
-    __shared__ double smd[T / 32];
+    __shared__ double smd[2 * (T / 32)];
     __shared__ int smi[T / 32];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);

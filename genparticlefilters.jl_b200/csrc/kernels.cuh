@@ -20,10 +20,10 @@ struct Partials {
     int *flags;  // bit0: NaN seen, bit1: +Inf seen
 };
 
-__device__ __forceinline__ void blk_to_tile(int64_t tpf, int64_t &f, int64_t &tile) {
-    int64_t b = blockIdx.x;
-    f = b / tpf;
-    tile = b - f * tpf;
+// grid = (tiles per filter, filters): no 64-bit division in any prologue
+__device__ __forceinline__ void blk_to_tile(int64_t, int64_t &f, int64_t &tile) {
+    f = blockIdx.y;
+    tile = blockIdx.x;
 }
 
 // ------------------------------------------------------------------ K1/K2 reduce
@@ -53,7 +53,7 @@ static __global__ void __launch_bounds__(kThreads) k_reduce(LwSrc src, int64_t n
     } else if (m > -INFINITY) {
 #pragma unroll
         for (int k = 0; k < kItems; ++k) {
-            double e = exp(v[k] - m);
+            double e = exp_nonpos(v[k] - m);
             s += e;
             s2 += e * e;
         }
@@ -61,10 +61,10 @@ static __global__ void __launch_bounds__(kThreads) k_reduce(LwSrc src, int64_t n
     s = block_sum(s, sm);
     s2 = block_sum(s2, sm);
     if (threadIdx.x == 0) {
-        out.m[blockIdx.x] = m;
-        out.s[blockIdx.x] = s;
-        out.s2[blockIdx.x] = s2;
-        out.flags[blockIdx.x] = fl;
+        out.m[blockIdx.y * gridDim.x + blockIdx.x] = m;
+        out.s[blockIdx.y * gridDim.x + blockIdx.x] = s;
+        out.s2[blockIdx.y * gridDim.x + blockIdx.x] = s2;
+        out.flags[blockIdx.y * gridDim.x + blockIdx.x] = fl;
     }
 }
 
@@ -309,17 +309,36 @@ __device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t
 // C(W) = #{i in 1..n : u_i <= W}.  Because u is non-decreasing in i this is a prefix count, and
 // parent_i = min{k : W_k >= u_i} (resample.jl:163-168) == min{k : C(W_k) >= i}.
 // J = int32 when n < 2^31 (single-instruction fp64<->int conversions), else int64.
+// Deliberately ONE out-of-line copy per J: inlined at every unrolled item (Philox rounds, the
+// non-power-of-two division, two fix-up loops) k_scan grew past 100 KB of SASS and thrashed the I-cache.
+template <typename J>
+static __device__ __noinline__ J strat_count_impl(const double *col, uint64_t seed, uint64_t stream, int64_t slot0,
+                                                  double step, J n, int pow2, double W) {
+    const double nd = (double)n;
+    const double x = W * nd;
+    J j = x >= nd ? n : (x <= 0.0 ? (J)0 : (J)x);
+    const bool near_edge = (x - (double)j) < 1e-6;
+    auto lower_of = [&](J i1) { return pow2 ? (double)(i1 - 1) * step : (double)(i1 - 1) / nd; };
+    auto u_of = [&](J i1) {
+        double r;
+        if (col) {
+            r = col[slot0 + (int64_t)i1 - 1];
+        } else {
+            const uint4 o = philox_at(seed, stream, (uint64_t)(slot0 + (int64_t)i1 - 1));
+            r = u53(o.x, o.y);
+        }
+        return __dadd_rn(__dmul_rn(r, step), lower_of(i1));
+    };
+    // u_i >= lower_i, so a stratum whose lower bound already exceeds W needs no draw
+    while (j < n && lower_of(j + 1) <= W && u_of(j + 1) <= W) ++j;
+    if (near_edge)
+        while (j > 0 && u_of(j) > W) --j;
+    return j;
+}
 template <typename J>
 __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t f, double W) {
-    const double nd = (double)a.n;
-    const double x = W * nd;
-    J j = x >= nd ? (J)a.n : (x <= 0.0 ? (J)0 : (J)x);
-    const bool near_edge = (x - (double)j) < 1e-6;
-    // u_i >= lower_i, so a stratum whose lower bound already exceeds W needs no draw
-    while (j < (J)a.n && strat_lower(a, (int64_t)j + 1) <= W && strat_u(a, f, (int64_t)j + 1) <= W) ++j;
-    if (near_edge)
-        while (j > 0 && strat_u(a, f, (int64_t)j) > W) --j;
-    return j;
+    return strat_count_impl<J>(a.uni.col, a.uni.seed, a.uni.stream, f * a.n + (a.uni.col ? 0 : a.uni.offset), a.step,
+                               (J)a.n, a.pow2, W);
 }
 
 // ------------------------------------------------------------------ K3 normalise + scan
@@ -349,7 +368,7 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
 #pragma unroll
     for (int k = 0; k < I; ++k) {
         if (uniform) w[k] = tile_elem<T>(k) < valid ? inv_n : 0.0;
-        else w[k] = exp(v[k] - st.M) * inv_S;
+        else w[k] = exp_nonpos(v[k] - st.M) * inv_S;
     }
     tile_scan<double, T>(w, W, sm);
     const double off = tile_off[f * tpf + tile];
@@ -573,8 +592,9 @@ static __global__ void __launch_bounds__(kThreads)
     k_search(const double *W, int64_t n_src, int64_t n_out, int64_t bpf, UniSrc uni, const IdxT *first_slot_O,
              OutT *parents, int64_t out_base, const Stats *stats, int gate) {
     __shared__ double sW[kCoarseCap];
-    int64_t f = blockIdx.x / bpf;
-    int64_t blk = blockIdx.x - f * bpf;
+    int64_t f = blockIdx.y;
+    int64_t blk = blockIdx.x;
+    (void)bpf;
     if (stats) {
         const int kind = stats[f].invalid_kind;
         if (kind == 1 || kind == 4) return;
@@ -645,8 +665,8 @@ static __global__ void __launch_bounds__(kThreads)
     rs = block_sum(rs, sm);
     double csd = block_sum((double)cs, sm);  // exact: counts < 2^53
     if (threadIdx.x == 0) {
-        out.c[blockIdx.x] = (long long)csd;
-        out.r[blockIdx.x] = rs;
+        out.c[blockIdx.y * gridDim.x + blockIdx.x] = (long long)csd;
+        out.r[blockIdx.y * gridDim.x + blockIdx.x] = rs;
     }
 }
 // one block per filter: total residual mass, exclusive tile offsets for counts and normalised residuals
@@ -781,7 +801,7 @@ static __global__ void __launch_bounds__(kThreads)
         }
     }
     acc = block_sum(acc, sm);
-    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 static __global__ void __launch_bounds__(kThreads) k_sum_partials(const double *partial, int64_t tpf, double *out) {
     __shared__ double sm[kWarps];
