@@ -84,6 +84,15 @@ SIGNATURES = {
     "genpf_filter_sync": (i32, [_vp]),
     "genpf_launch_count": (i64, []),
     "genpf_filter_stream": (i32, [_vp, C.POINTER(_vp)]),
+    "genpf_shard_ipc_export": (i32, [_vp, _vp, _ip]),
+    "genpf_shard_attach": (i32, [_vp, i32, i32, _vp, _vp, _vp, _vp, _vp]),
+    "genpf_shard_detach": (i32, [_vp]),
+    "genpf_shard_initialize": (i32, [_vp, _vp, _vp]),
+    "genpf_shard_begin_step": (i32, [_vp]),
+    "genpf_shard_scan": (i32, [_vp]),
+    "genpf_shard_push": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32]),
+    "genpf_shard_finish": (i32, [_vp]),
+    "genpf_shard_stats": (i32, [_vp, _dp, _dp, _i32p]),
     "genpf_profile_begin": (i32, []),
     "genpf_profile_end": (i32, [C.c_char_p, i64]),
 }

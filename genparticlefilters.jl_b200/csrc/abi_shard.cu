@@ -1,0 +1,266 @@
+// abi_shard.cu -- C ABI, multi-GPU particle sharding.  One process per GPU; rank r owns global
+// particle slots [r*n_loc, (r+1)*n_loc) of ONE filter of world*n_loc particles.  The library launches kernels
+// on the filter's stream; the three tiny collectives of a step (all-gather of 3 doubles, all-gather of one
+// int64, one barrier) are issued by the host language (torch.distributed/NCCL, or NCCL.jl) ON THE SAME STREAM
+// on device buffers it owns, so a step needs no host synchronisation:
+//
+//   genpf_shard_begin_step   K1 partials -> local (max, sum e, sum e^2)        -> stats_local   [allgather]
+//   genpf_shard_scan         global (M,S,ESS,lml), shard prefix, scan -> O_k    -> oend_local    [allgather]
+//   genpf_shard_push         offspring of local parents -> owner's buffers over NVLink P2P       [barrier]
+//   genpf_shard_finish       swap buffers, K1 partials of the received population
+#include "filter_state.hpp"
+
+namespace genpf {
+
+struct ShardCtx {
+    int rank = 0, world = 1;
+    int64_t n_loc = 0, n_total = 0;
+    PeerDst peer[2];  // destination tables for push into buffer set b (b = the owners' spare set)
+    double *stats_local = nullptr;
+    const double *stats_all = nullptr;
+    long long *oend_local = nullptr;
+    const long long *oend_all = nullptr;
+    double *shard_info = nullptr;
+    ShardRange *range = nullptr;
+    std::vector<void *> opened;
+};
+
+static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3; }
+
+// fixed export order: for buf in {0,1}: for slot in {0,1}: f64 fields, u8 fields; then lw[buf 0], lw[buf 1], parents
+static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
+    for (int b = 0; b < 2; ++b)
+        for (int sl = 0; sl < 2; ++sl) {
+            for (int i = 0; i < pf->NF; ++i) out.push_back(pf->win[b][sl].f[i]);
+            for (int i = 0; i < pf->NB; ++i) out.push_back(pf->win[b][sl].b[i]);
+        }
+    out.push_back(pf->lw_by_buf[0]);
+    out.push_back(pf->lw_by_buf[1]);
+    out.push_back(pf->parents);
+}
+
+template <class Model, class Noise>
+static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, Noise noise) {
+    const int64_t tpf = ceil_div(pf->n, kTile);
+    const int64_t t = a.t;
+    // upper bound on the tiles this rank can parent is unknown on the host (device-resident range): launch
+    // enough blocks for the whole population; blocks beyond the range exit immediately
+    const unsigned grid = (unsigned)(ceil_div(sh->n_total, kTile) + 1);
+    const PeerDst &pd = sh->peer[pf->buf ^ 1];
+    PeerDst d = pd;
+    // the owner's spare set holds slice t-1 at parity (t-1)&1 and receives slice t at parity t&1
+    for (int g = 0; g < sh->world; ++g) {
+        if (((t - 1) & 1) == 1) std::swap(d.dst_cur[g], d.dst_new[g]);
+    }
+    if (a.mh_iters == 1) {
+        GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, 1>), grid, kStateThreads, pf->stream, a,
+                     (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
+                     pf->slice(t - 2), pf->slice(t - 1), d, (const ShardRange *)sh->range, pf->n, tpf, sh->rank, noise);
+    } else {
+        GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, -1>), grid, kStateThreads, pf->stream, a,
+                     (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
+                     pf->slice(t - 2), pf->slice(t - 1), d, (const ShardRange *)sh->range, pf->n, tpf, sh->rank, noise);
+    }
+    return GENPF_OK;
+}
+template <class Model>
+static int32_t push_model(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a) {
+    if (pf->flags & GENPF_NOISE_PHILOX53) {
+        NoisePhilox53 nz{pf->seed, (uint64_t)a.t, 0};
+        return launch_push<Model, NoisePhilox53>(pf, sh, a, nz);
+    }
+    NoiseLean nz{pf->seed, (uint64_t)a.t, 0};
+    return launch_push<Model, NoiseLean>(pf, sh, a, nz);
+}
+
+}  // namespace genpf
+
+using namespace genpf;
+
+extern "C" {
+
+int32_t genpf_shard_ipc_export(genpf_filter_t pf, void *handles, int64_t *n_bufs) {
+    GENPF_TRY(check_filter(pf));
+    if (!n_bufs) return fail(GENPF_ERR_INVALID_ARG, "n_bufs is NULL");
+    *n_bufs = n_export_bufs(pf);
+    if (!handles) return GENPF_OK;
+    std::vector<void *> bufs;
+    list_bufs(pf, bufs);
+    cudaIpcMemHandle_t *h = reinterpret_cast<cudaIpcMemHandle_t *>(handles);
+    for (size_t i = 0; i < bufs.size(); ++i) GENPF_CUDA_TRY(cudaIpcGetMemHandle(&h[i], bufs[i]));
+    return GENPF_OK;
+}
+
+int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const void *all_handles,
+                           double *stats_local_dev, const double *stats_all_dev, long long *oend_local_dev,
+                           const long long *oend_all_dev) {
+    GENPF_TRY(check_filter(pf));
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_attach: need 1 <= world <= 8 and 0 <= rank < world");
+    if (pf->nf != 1) return fail(GENPF_ERR_UNSUPPORTED, "sharding needs n_filters == 1");
+    if (pf->n % kTile != 0) return fail(GENPF_ERR_INVALID_ARG, "particles per shard must be a multiple of 2048");
+    if (pf->flags & GENPF_KEEP_HISTORY) return fail(GENPF_ERR_UNSUPPORTED, "sharding with GENPF_KEEP_HISTORY");
+    if ((int64_t)world * pf->n >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "total population must be < 2^31");
+    if (!stats_local_dev || !stats_all_dev || !oend_local_dev || !oend_all_dev)
+        return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_attach: NULL exchange buffer");
+    if (world > 1 && !all_handles) return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_attach: NULL handles");
+    ShardCtx *sh = new ShardCtx();
+    sh->rank = rank;
+    sh->world = world;
+    sh->n_loc = pf->n;
+    sh->n_total = (int64_t)world * pf->n;
+    sh->stats_local = stats_local_dev;
+    sh->stats_all = stats_all_dev;
+    sh->oend_local = oend_local_dev;
+    sh->oend_all = oend_all_dev;
+    const int nb = n_export_bufs(pf);
+    std::vector<void *> mine;
+    list_bufs(pf, mine);
+    for (int g = 0; g < world; ++g) {
+        std::vector<void *> ptrs(nb);
+        if (g == rank) {
+            ptrs = mine;
+        } else {
+            const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles) + (size_t)g * nb;
+            for (int i = 0; i < nb; ++i) {
+                GENPF_CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], h[i], cudaIpcMemLazyEnablePeerAccess));
+                sh->opened.push_back(ptrs[i]);
+            }
+        }
+        int k = 0;
+        for (int b = 0; b < 2; ++b) {
+            // parity 0 -> "dst_cur" slot table, parity 1 -> "dst_new"; launch_push swaps per time step
+            Cols c0, c1;
+            memset(&c0, 0, sizeof(c0));
+            memset(&c1, 0, sizeof(c1));
+            for (int i = 0; i < pf->NF; ++i) c0.f[i] = (double *)ptrs[k++];
+            for (int i = 0; i < pf->NB; ++i) c0.b[i] = (uint8_t *)ptrs[k++];
+            for (int i = 0; i < pf->NF; ++i) c1.f[i] = (double *)ptrs[k++];
+            for (int i = 0; i < pf->NB; ++i) c1.b[i] = (uint8_t *)ptrs[k++];
+            sh->peer[b].dst_cur[g] = c0;
+            sh->peer[b].dst_new[g] = c1;
+        }
+        sh->peer[0].lw[g] = (double *)ptrs[k++];
+        sh->peer[1].lw[g] = (double *)ptrs[k++];
+        sh->peer[0].parents[g] = sh->peer[1].parents[g] = (int32_t *)ptrs[k++];
+    }
+    GENPF_TRY(pf->dalloc(&sh->shard_info, 2));
+    GENPF_TRY(pf->dalloc(&sh->range, 1));
+    pf->rng_offset = 0;  // Philox counters are GLOBAL particle slots
+    pf->shard = sh;
+    return GENPF_OK;
+}
+
+int32_t genpf_shard_detach(genpf_filter_t pf) {
+    if (!pf || !pf->shard) return GENPF_OK;
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    cudaSetDevice(pf->device);
+    cudaStreamSynchronize(pf->stream);
+    for (void *p : sh->opened) cudaIpcCloseMemHandle(p);
+    delete sh;
+    pf->shard = nullptr;
+    return GENPF_OK;
+}
+
+// pf_initialize for a shard: Philox counters are global slots rank*n_loc + i
+int32_t genpf_shard_initialize(genpf_filter_t pf, const double *obs, const double *aux) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    pf->rng_offset = (int64_t)sh->rank * sh->n_loc;
+    return genpf_initialize(pf, obs, aux);
+}
+
+int32_t genpf_shard_begin_step(genpf_filter_t pf) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    // local statistics + locally normalised tile offsets; Stats starts with the three doubles (M, S, S2)
+    GENPF_TRY(ensure_stats(pf, pf->sc.tile_off.as<double>(), -1.0, nullptr));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(sh->stats_local, pf->sc.st(0, 1), 3 * sizeof(double), cudaMemcpyDeviceToDevice,
+                                   pf->stream));
+    return GENPF_OK;
+}
+
+int32_t genpf_shard_scan(genpf_filter_t pf) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    const int64_t n = pf->n, tpf = ceil_div(n, kTile);
+    Scratch &sc = pf->sc;
+    GENPF_TRY(sc.O.ensure((size_t)n * 4));
+    GENPF_TRY(sc.tile_last.ensure((size_t)tpf * 4));
+    GENPF_LAUNCH(k_shard_combine, 1, 32, pf->stream, sh->stats_all, sh->world, sh->rank, sh->n_total, sc.st(0, 1),
+                 sh->shard_info, pf->lml);
+    UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), 0};
+    StratArgs strat = make_strat(uni, sh->n_total);
+    LwSrc lw_src{pf->lw, 1.0};
+    GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, pf->stream, lw_src, n, tpf,
+                 (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), (double *)nullptr,
+                 sc.O.as<int32_t>(), sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info,
+                 (int64_t)sh->rank * n);
+    GENPF_LAUNCH(k_shard_oend, 1, 32, pf->stream, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->oend_local);
+    return GENPF_OK;
+}
+
+int32_t genpf_shard_push(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                         const double *obs_t, const double *aux_t, int32_t mh_iters) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_push must advance to t_cur + 1");
+    if (!obs_prev || !obs_t) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
+    if (mh_iters < 0 || mh_iters > 255) return fail(GENPF_ERR_INVALID_ARG, "mh_iters out of range");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    const ModelInfo &mi = kModels[pf->model];
+    if (mi.naux > 0 && (!aux_prev || !aux_t)) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL");
+    StepArgs a;
+    a.P_prev = pf->P;
+    a.P_t = pf->P;
+    for (int i = 0; i < mi.naux; ++i) {
+        a.P_prev.aux[i] = aux_prev[i];
+        a.P_t.aux[i] = aux_t[i];
+    }
+    a.t = t;
+    a.mh_iters = mh_iters;
+    a.obs_prev_dev = a.obs_t_dev = nullptr;
+    a.obs_prev = obs_prev[0];
+    a.obs_t = obs_t[0];
+    GENPF_LAUNCH(k_shard_ranges, 1, 32, pf->stream, sh->oend_all, sh->world, sh->rank, (long long)sh->n_total, sh->range);
+    int32_t st;
+    switch (pf->model) {
+        case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a); break;
+        case kModelLinGauss1D: st = push_model<LinGauss1D>(pf, sh, a); break;
+        default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+    }
+    GENPF_TRY(st);
+    pf->t_cur = t;  // slices now live in the spare buffer set; genpf_shard_finish swaps after the barrier
+    return GENPF_OK;
+}
+
+int32_t genpf_shard_finish(genpf_filter_t pf) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    pf->buf ^= 1;
+    std::swap(pf->lw, pf->lw_alt);
+    pf->n_resamples += 1;
+    // the received population's K1 partials (its tiles may have been written by two different ranks)
+    LwSrc src{pf->lw, 1.0};
+    GENPF_TRY(launch_reduce(pf->stream, src, pf->n, 1, pf->sc.partials(0)));
+    pf->part_valid = true;
+    return GENPF_OK;
+}
+
+// global ESS / log_ml_estimate of the sharded population as of the last genpf_shard_scan
+int32_t genpf_shard_stats(genpf_filter_t pf, double *ess, double *lml_est, int32_t *invalid_kind) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, pf->lml, 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_TRY(read_stats(pf, 0));
+    if (ess) *ess = pf->h_stats[0].ess;
+    if (lml_est) *lml_est = pf->h_pinned[0];  // log_ml_est accumulated by the resamples so far
+    if (invalid_kind) *invalid_kind = pf->h_stats[0].invalid_kind;
+    return GENPF_OK;
+}
+
+}  // extern "C"

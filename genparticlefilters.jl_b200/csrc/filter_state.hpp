@@ -1,0 +1,135 @@
+// filter_state.hpp -- the device-resident filter object behind genpf_filter_t (shared by abi_filter.cu
+// and abi_shard.cu).
+#pragma once
+#include <cstring>
+#include <vector>
+
+#include "coalesce.cuh"
+#include "engine.cuh"
+#include "fused.cuh"
+
+namespace genpf {
+
+enum { kModelObjectMotion = 0, kModelLinGauss1D = 1, kNumModels = 2 };
+
+struct ModelInfo {
+    const char *name;
+    int nf, nb, np, naux;
+};
+static const ModelInfo kModels[kNumModels] __attribute__((unused)) = {
+    {"object_motion", ObjectMotion::NF, ObjectMotion::NB, ObjectMotion::NP, ObjectMotion::NAUX},
+    {"lingauss1d", LinGauss1D::NF, LinGauss1D::NB, LinGauss1D::NP, LinGauss1D::NAUX},
+};
+
+struct Slab {  // one time slice's columns in one buffer
+    Cols c;
+};
+
+struct HistSlice {  // a frozen slice (GENPF_KEEP_HISTORY): columns in the particle order of generation `gen`
+    int64_t tau;
+    Cols c;
+    int64_t n;
+    int64_t gen;
+};
+struct ParentLog {  // ancestry of resample number `gen` (1-based): population gen-1 -> gen
+    int32_t *parents;
+    int64_t n_prev, n_cur;
+};
+
+}  // namespace genpf
+
+using namespace genpf;
+
+struct genpf_filter_s {
+    int model = 0;
+    int NF = 0, NB = 0;
+    int64_t n = 0, nf = 0;
+    uint64_t seed = 0;
+    uint32_t flags = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ModelParams P{};
+    int64_t t_cur = 0;
+    int64_t n_resamples = 0;
+    int64_t rng_offset = 0;
+    Cols win[2][2];  // [buffer][slot parity]
+    int buf = 0;
+    double *lw = nullptr, *lw_alt = nullptr;
+    double *lw_by_buf[2] = {nullptr, nullptr};  // identity of the two weight buffers (lw == lw_by_buf[buf])
+    void *shard = nullptr;                      // ShardCtx (abi_shard.cu)
+    int32_t *parents = nullptr;
+    uint8_t *accepts = nullptr;
+    unsigned long long *n_accept = nullptr;
+    double *lml = nullptr;
+    double *obs_dev = nullptr;
+    double *noise_cols[3] = {nullptr, nullptr, nullptr};
+    DevBuf noise_buf[3], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf;
+    CoalesceBufs cb;
+    Scratch sc;
+    bool part_valid = false;
+    std::vector<HistSlice> hist;
+    std::vector<ParentLog> plog;
+    std::vector<void *> owned;
+    double *h_pinned = nullptr;  // pinned scratch: max(nf,16) doubles * 4
+    Stats *h_stats = nullptr;
+
+    template <typename T>
+    int32_t dalloc(T **p, size_t count) {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GENPF_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+        owned.push_back(q);
+        *p = reinterpret_cast<T *>(q);
+        return GENPF_OK;
+    }
+    void dfree(void *q) {
+        for (auto &o : owned)
+            if (o == q) {
+                cudaFree(q);
+                o = nullptr;
+            }
+    }
+    int32_t alloc_cols(Cols &c, int64_t total) {
+        memset(&c, 0, sizeof(c));
+        for (int i = 0; i < NF; ++i) GENPF_TRY(dalloc(&c.f[i], (size_t)total));
+        for (int i = 0; i < NB; ++i) GENPF_TRY(dalloc(&c.b[i], (size_t)total));
+        return GENPF_OK;
+    }
+    void free_cols(Cols &c) {
+        for (int i = 0; i < NF; ++i) dfree(c.f[i]);
+        for (int i = 0; i < NB; ++i) dfree(c.b[i]);
+        memset(&c, 0, sizeof(c));
+    }
+    int32_t alloc_population(int64_t n_new) {
+        const int64_t total = n_new * nf;
+        for (int b = 0; b < 2; ++b)
+            for (int sl = 0; sl < 2; ++sl) GENPF_TRY(alloc_cols(win[b][sl], total));
+        GENPF_TRY(dalloc(&lw, (size_t)total));
+        GENPF_TRY(dalloc(&lw_alt, (size_t)total));
+        lw_by_buf[0] = lw;
+        lw_by_buf[1] = lw_alt;
+        GENPF_TRY(dalloc(&parents, (size_t)total));
+        GENPF_TRY(dalloc(&accepts, (size_t)total));
+        GENPF_TRY(sc.ensure(n_new, nf));
+        return GENPF_OK;
+    }
+    void free_population() {
+        for (int b = 0; b < 2; ++b)
+            for (int sl = 0; sl < 2; ++sl) free_cols(win[b][sl]);
+        dfree(lw); dfree(lw_alt); dfree(parents); dfree(accepts);
+        lw = lw_alt = nullptr; parents = nullptr; accepts = nullptr;
+    }
+    Cols &slice(int64_t tau) { return win[buf][tau & 1]; }
+    Cols &slice_alt(int64_t tau) { return win[buf ^ 1][tau & 1]; }
+};
+
+
+namespace genpf {
+int32_t check_filter(genpf_filter_t pf);
+int32_t log_parents(genpf_filter_t pf, int64_t n_prev, int64_t n_cur);
+int32_t ensure_stats(genpf_filter_t pf, double *tile_off, double ess_frac, double *lml_accum);
+int32_t read_stats(genpf_filter_t pf, int which);
+}  // namespace genpf

@@ -125,4 +125,163 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
     emit_partials<T>(v, partials, smd, smi);
 }
 
+// ------------------------------------------------------------------ multi-GPU: source-side push
+// Particle sharding: rank r owns global particle slots [r*n_loc, (r+1)*n_loc).  After the shard-aware scan the
+// local O_k are GLOBAL cumulative offspring counts, so this rank's particles parent the contiguous global
+// output range [out_begin, out_end).  The kernel computes those offspring (gather from the LOCAL parent, mh,
+// update -- exactly k_step_fused's arithmetic, Philox keyed by the GLOBAL output slot, so the population is
+// independent of the number of GPUs) and stores them straight into the OWNER's buffers through peer-mapped
+// pointers (NVLink P2P stores; n_loc is a multiple of the 2048 tile so a tile never straddles two owners).
+// No all-to-all, no staging: stores are fire-and-forget, the ranks meet at one stream-ordered barrier after.
+constexpr int kMaxPeers = 8;
+struct PeerDst {
+    Cols dst_cur[kMaxPeers], dst_new[kMaxPeers];
+    double *lw[kMaxPeers];
+    int32_t *parents[kMaxPeers];
+};
+struct ShardRange {  // device resident: written by k_shard_ranges
+    long long out_begin, out_end;
+};
+
+template <class Model, class Noise, typename IdxT, int MH>
+static __global__ void __launch_bounds__(kStateThreads, 2)
+    k_step_push(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, PeerDst peer,
+                const ShardRange *range, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise) {
+    constexpr int T = kStateThreads, I = kTile / T;
+    __shared__ ExpandSmem<IdxT> sm;
+    const int64_t out_begin = range->out_begin, out_end = range->out_end;
+    const int64_t tile = out_begin / kTile + blockIdx.x;  // global output tile
+    const int64_t t0 = tile * kTile;
+    const int64_t i0 = max(t0, out_begin);
+    const int64_t i1 = min(t0 + (int64_t)kTile, out_end);
+    if (i1 <= i0) return;  // uniform: beyond this rank's range
+    const int valid = (int)(i1 - i0);
+    const int owner = (int)(t0 / n_loc);
+    const int64_t lbase = i0 - (int64_t)owner * n_loc;  // slot of output i0 inside the owner's shard
+    int32_t rel[I];
+    const int64_t guess = max((int64_t)0, i0 / kTile - (int64_t)rank * tpf_loc);  // balanced shards: parent ~ output
+    const int64_t s0 = block_expand<IdxT, T>(O, tile_last_O, n_loc, tpf_loc, i0, valid, sm, rel, (IdxT)out_begin, guess);
+    const bool fast = (valid == kTile);  // interior tiles are full and 2048-aligned
+    const double obs_prev = a.obs_prev, obs_t = a.obs_t;
+    const bool first = (a.t - 1) == 1;
+    const int iters = MH >= 0 ? MH : a.mh_iters;
+    const Cols dst_cur = peer.dst_cur[owner], dst_new = peer.dst_new[owner];
+    double *lw_dst = peer.lw[owner];
+    int32_t *par_dst = peer.parents[owner];
+    const int64_t gsrc = (int64_t)rank * n_loc + s0;  // global index of local source s0
+#pragma unroll
+    for (int j = 0; j < I / 2; ++j) {
+        typename Model::Slice sc[2], sn[2];
+        double v[2];
+        const int e0 = (j * T + threadIdx.x) * 2;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int k = 2 * j + c2;
+            const int e = e0 + c2;
+            const bool live = e < valid;
+            const int64_t s = s0 + rel[k];
+            typename Model::Slice pp, cur;
+            if (first) {
+                Model::initial(a.P_prev, pp);
+            } else {
+#pragma unroll
+                for (int c = 0; c < Model::NF; ++c) pp.f[c] = __ldg(src_pp.f[c] + s);
+#pragma unroll
+                for (int c = 0; c < Model::NB; ++c) pp.b[c] = __ldg(src_pp.b[c] + s);
+            }
+#pragma unroll
+            for (int c = 0; c < Model::NF; ++c) cur.f[c] = __ldg(src_cur.f[c] + s);
+#pragma unroll
+            for (int c = 0; c < Model::NB; ++c) cur.b[c] = __ldg(src_cur.b[c] + s);
+            double U_mh, Z_mh, U_acc, U_up, Z_up;
+            noise.both(i0 + e, U_mh, Z_mh, U_acc, U_up, Z_up);  // GLOBAL output slot
+            for (int it = 0; it < iters; ++it) {
+                if (MH < 0 && it > 0) noise.mh(i0 + e, it, U_mh, Z_mh, U_acc);
+                typename Model::Slice q;
+                Model::transition(a.P_prev, a.t - 1, pp, q, U_mh, Z_mh);
+                const double alpha =
+                    Model::obs_logpdf(a.P_prev, q, obs_prev) - Model::obs_logpdf(a.P_prev, cur, obs_prev);
+                if (live && mh_accept(U_acc, alpha)) cur = q;
+            }
+            Model::transition(a.P_t, a.t, cur, sn[c2], U_up, Z_up);
+            sc[c2] = cur;
+            v[c2] = 0.0 + Model::obs_logpdf(a.P_t, sn[c2], obs_t);
+        }
+        store_pair<int32_t>(par_dst + lbase, e0, valid, fast, (int32_t)(gsrc + rel[2 * j]), (int32_t)(gsrc + rel[2 * j + 1]));
+#pragma unroll
+        for (int c = 0; c < Model::NF; ++c) {
+            store_pair<double>(dst_cur.f[c] + lbase, e0, valid, fast, sc[0].f[c], sc[1].f[c]);
+            store_pair<double>(dst_new.f[c] + lbase, e0, valid, fast, sn[0].f[c], sn[1].f[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < Model::NB; ++c) {
+            store_pair<uint8_t>(dst_cur.b[c] + lbase, e0, valid, fast, sc[0].b[c], sc[1].b[c]);
+            store_pair<uint8_t>(dst_new.b[c] + lbase, e0, valid, fast, sn[0].b[c], sn[1].b[c]);
+        }
+        store_pair<double>(lw_dst + lbase, e0, valid, fast, v[0], v[1]);
+    }
+}
+
+// global statistics from the all-gathered per-shard (max, sum e, sum e^2); one thread (world <= 8)
+static __global__ void k_shard_combine(const double *gathered, int world, int rank, int64_t n_total, Stats *stats,
+                                       double *shard_info, double *lml_accum) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double M = -INFINITY;
+    bool nan = false;
+    for (int g = 0; g < world; ++g) {
+        double m = gathered[3 * g];
+        if (isnan(m) || isnan(gathered[3 * g + 1])) nan = true;
+        M = fmax(M, m);
+    }
+    double S = 0.0, S2 = 0.0, prefix = 0.0, mine = 0.0;
+    const bool finite = M > -INFINITY && M < INFINITY;
+    for (int g = 0; g < world; ++g) {
+        double m = gathered[3 * g];
+        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
+        S += gathered[3 * g + 1] * sc;
+        S2 += gathered[3 * g + 2] * (sc * sc);
+    }
+    for (int g = 0; g < world; ++g) {
+        double m = gathered[3 * g];
+        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
+        double share = gathered[3 * g + 1] * sc / S;
+        if (g < rank) prefix += share;
+        if (g == rank) mine = share;
+    }
+    int kind = 0;
+    if (nan) kind = 1;
+    else if (M == -INFINITY) kind = 2;
+    else if (M == INFINITY || isnan(S)) kind = 4;
+    else if (S == 0.0) kind = 3;
+    Stats st;
+    st.M = M; st.S = S; st.S2 = S2;
+    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    st.ess = S * S / S2;
+    st.invalid_kind = kind;
+    st.do_resample = (kind == 1 || kind == 4) ? 0 : 1;
+    stats[0] = st;
+    if (kind == 2 || kind == 3) {  // uniform fallback (utils.jl:123-133): every shard carries 1/world
+        prefix = (double)rank / (double)world;
+        mine = 1.0 / (double)world;
+    }
+    shard_info[0] = prefix;
+    shard_info[1] = mine;  // local offsets are normalised to 1 over the shard: scale by the shard's global share
+    if (lml_accum && st.do_resample) lml_accum[0] += st.lse - log((double)n_total);
+}
+
+// output range [begin, end) this rank parents, from the all-gathered closing counts (monotone by construction)
+static __global__ void k_shard_ranges(const long long *oend_all, int world, int rank, long long n_total,
+                                      ShardRange *range) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long begin = 0;
+    for (int g = 0; g < rank; ++g) begin = max(begin, oend_all[g]);
+    long long end = max(begin, oend_all[rank]);
+    if (rank == world - 1) end = n_total;
+    range->out_begin = begin;
+    range->out_end = end;
+}
+static __global__ void k_shard_oend(const int32_t *tile_last_O, int64_t tpf, long long *oend_local) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *oend_local = (long long)tile_last_O[tpf - 1];
+}
+
 }  // namespace genpf

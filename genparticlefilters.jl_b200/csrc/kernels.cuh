@@ -348,7 +348,10 @@ constexpr int kScanThreads = 512;  // every launch of k_scan uses this block siz
 template <typename IdxT>
 static __global__ void __launch_bounds__(kScanThreads, 2)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, double *W_out, IdxT *O_out,
-           IdxT *tile_last_O, StratArgs strat, int gate) {
+           IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info = nullptr,
+           int64_t global_base = 0) {
+    // shard_info (multi-GPU particle sharding): {prefix, scale}: this shard's cumulative weights are
+    // prefix + scale * (locally normalised tile offsets) + in-tile sums of globally normalised weights.
     constexpr int T = kScanThreads, I = kTile / T;
     __shared__ double sm[32];
     int64_t f, tile;
@@ -361,7 +364,7 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
     double v[I], w[I], W[I];
     load_tile<T>(src, f * n + start, valid, v, -INFINITY);
     const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
-    const double inv_n = 1.0 / (double)n;
+    const double inv_n = 1.0 / (double)strat.n;  // == n except for a shard of a multi-GPU population
     // w_i = e_i / S evaluated as e_i * (1/S): at most 1 ulp from the reference's division, far inside the
     // sequential-vs-parallel cumulative-sum noise that defines the documented tie class
     const double inv_S = 1.0 / st.S;
@@ -371,7 +374,8 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
         else w[k] = exp_nonpos(v[k] - st.M) * inv_S;
     }
     tile_scan<double, T>(w, W, sm);
-    const double off = tile_off[f * tpf + tile];
+    double off = tile_off[f * tpf + tile];
+    if (shard_info) off = shard_info[0] + shard_info[1] * off;
 #pragma unroll
     for (int k = 0; k < I; ++k) W[k] = off + W[k];
     if (W_out) store_tile<double, T>(W_out, f * n + start, valid, W);
@@ -382,7 +386,7 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
             const int e = tile_elem<T>(k);
             O[k] = e < valid ? strat_count<IdxT>(strat, f, W[k]) : (IdxT)0;
             // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
-            if (start + e == n - 1) O[k] = (IdxT)n;
+            if (global_base + start + e == strat.n - 1) O[k] = (IdxT)strat.n;
             if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];
         }
         store_tile<IdxT, T>(O_out, f * n + start, valid, O);
@@ -452,18 +456,18 @@ __device__ __forceinline__ int64_t coarse_search(const IdxT *tile_last, int64_t 
 template <typename IdxT, int T = kThreads>
 __device__ __forceinline__ int64_t block_expand(const IdxT *Of, const IdxT *tile_last, int64_t n_src, int64_t tpf_src,
                                                 int64_t i0, int64_t valid, ExpandSmem<IdxT> &sm,
-                                                int32_t (&rel)[kTile / T]) {
+                                                int32_t (&rel)[kTile / T], IdxT O_base = 0, int64_t guess = -1) {
     constexpr int I = kTile / T;
     if (threadIdx.x < 2) {
         const int64_t target = threadIdx.x == 0 ? i0 : i0 + valid - 1;
-        sm.brk[threadIdx.x] = coarse_search<IdxT>(tile_last, tpf_src, target, i0 / kTile);
+        sm.brk[threadIdx.x] = coarse_search<IdxT>(tile_last, tpf_src, target, guess >= 0 ? guess : i0 / kTile);
     }
     __syncthreads();
     const int64_t b_lo = sm.brk[0], b_hi = sm.brk[1];
     const int64_t s0 = b_lo * kTile, s1 = min((b_hi + 1) * (int64_t)kTile, n_src);
     const int64_t len = s1 - s0;
     if (len <= ExpandSmem<IdxT>::kStageCap) {
-        if (threadIdx.x == 0) sm.sO[0] = b_lo > 0 ? tile_last[b_lo - 1] : (IdxT)0;
+        if (threadIdx.x == 0) sm.sO[0] = b_lo > 0 ? tile_last[b_lo - 1] : O_base;
         for (int j = threadIdx.x; j < (int)len; j += T) sm.sO[1 + j] = Of[s0 + j];
 #pragma unroll
         for (int k = 0; k < I; ++k) sm.sParent[k * T + threadIdx.x] = 0;

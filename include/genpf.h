@@ -211,6 +211,33 @@ int32_t genpf_filter_sync(genpf_filter_t pf);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t genpf_launch_count(void);
 
+/* =====================================================================
+ * Multi-GPU particle sharding: one process per GPU, rank r owns global particle slots
+ * [r*n_loc, (r+1)*n_loc) of ONE filter of world*n_loc particles (n_loc a multiple of 2048, world <= 8).
+ * Kernels run on the filter's stream; the host language issues three tiny collectives per step on that
+ * same stream (e.g. torch.distributed / NCCL.jl) over device buffers it owns:
+ *   genpf_shard_begin_step -> all_gather(stats_local[3] -> stats_all[world*3])
+ *   genpf_shard_scan       -> all_gather(oend_local[1]  -> oend_all[world])
+ *   genpf_shard_push       -> barrier (any collective)        offspring go to their owner over NVLink P2P
+ *   genpf_shard_finish
+ * The population is independent of the number of GPUs: Philox counters are global particle slots.
+ * ===================================================================== */
+/* 64-byte CUDA IPC handles of the filter's state buffers; handles == NULL just returns the count */
+int32_t genpf_shard_ipc_export(genpf_filter_t pf, void *handles, int64_t *n_bufs);
+/* all_handles: world * n_bufs handles, rank-major (all-gathered by the caller) */
+int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const void *all_handles,
+                           double *stats_local_dev, const double *stats_all_dev, long long *oend_local_dev,
+                           const long long *oend_all_dev);
+int32_t genpf_shard_detach(genpf_filter_t pf);
+int32_t genpf_shard_initialize(genpf_filter_t pf, const double *obs, const double *aux);
+int32_t genpf_shard_begin_step(genpf_filter_t pf);
+int32_t genpf_shard_scan(genpf_filter_t pf);
+int32_t genpf_shard_push(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                         const double *obs_t, const double *aux_t, int32_t mh_iters);
+int32_t genpf_shard_finish(genpf_filter_t pf);
+/* global ESS / accumulated log_ml_est / validity as of the last genpf_shard_scan (synchronises) */
+int32_t genpf_shard_stats(genpf_filter_t pf, double *ess, double *lml_est, int32_t *invalid_kind);
+
 /* per-kernel device time (CUDA events on the launching stream) of every kernel launched between begin and
  * end; end writes "kernel<TAB>count<TAB>total_ms" lines into buf.  Used by bench.py's roofline. */
 int32_t genpf_profile_begin(void);

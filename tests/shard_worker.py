@@ -1,0 +1,91 @@
+"""Worker for the multi-GPU sharding tests: launched by torchrun (one rank per GPU).
+Runs ONE object_motion filter of world*n_local particles sharded over the ranks and checks it against the
+same filter run unsharded on rank 0 (same seed): the population must not depend on the number of GPUs."""
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import genpf_b200 as g
+    from genpf_b200.sharded import ShardedFilter, cross_shard_fraction, exchange_plan
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    g._lib.check(g.load().genpf_set_device(int(os.environ.get("LOCAL_RANK", "0"))))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    n_local = int(os.environ.get("SHARD_N_LOCAL", str(1 << 16)))
+    T = 6
+    rng = np.random.default_rng(3)
+    y, obs = 0.0, []
+    for t in range(1, T + 1):
+        y = y + (math.sin(t) if t > 3 else 0.0) + 0.01 * rng.normal()
+        obs.append(y + 0.25 * rng.normal())
+    model = g.DeviceModel("object_motion")
+    sf = ShardedFilter(model, n_local, seed=77)
+    sf.initialize(obs[0])
+    ref = None
+    if rank == 0:
+        ref = g.pf_initialize(model, (1,), obs[0], n_local * world, seed=77)
+    sl = slice(rank * n_local, (rank + 1) * n_local)
+
+    def gather(col):
+        t_ = torch.from_numpy(np.ascontiguousarray(col)).cuda()
+        out = [torch.empty_like(t_) for _ in range(world)]
+        dist.all_gather(out, t_)
+        return np.concatenate([o.cpu().numpy() for o in out])
+
+    ok = True
+    y1 = gather(sf.state.field("y", 1))
+    lw1 = gather(sf.state.log_weights)
+    if rank == 0:
+        assert np.array_equal(y1, ref.field("y", 1)), "sharded init differs"
+        assert np.array_equal(lw1, ref.log_weights)
+    for t in range(2, T + 1):
+        sf.step(t, obs[t - 2], obs[t - 1])
+        ess, lml, kind = sf.stats()
+        ranges, frac = sf.exchange_summary()
+        par = gather(sf.state.parents)
+        yt = gather(sf.state.field("y", t))
+        ym = gather(sf.state.field("y", t - 1))
+        mt = gather(sf.state.field("moving", t))
+        lw = gather(sf.state.log_weights)
+        if rank == 0:
+            ess_ref = g.pf_step(ref, t, obs[t - 2], obs[t - 1], method="stratified", ess_thresh=1.0)
+            assert kind == 0
+            assert abs(ess - ess_ref[0]) <= 1e-9 * ess_ref[0], (ess, ess_ref)
+            p_ref = ref.parents
+            same = par == p_ref
+            n_bad = int((~same).sum())
+            assert n_bad <= 4, f"step {t}: {n_bad} ancestors differ between sharded and unsharded"
+            assert np.all(np.diff(par) >= 0) and par[0] >= 0 and par[-1] < n_local * world
+            assert np.array_equal(yt[same], ref.field("y", t)[same])
+            assert np.array_equal(ym[same], ref.field("y", t - 1)[same])
+            assert np.array_equal(mt[same], ref.field("moving", t)[same])
+            assert np.array_equal(lw[same], ref.log_weights[same])
+            assert ranges[0][0] == 0 and ranges[-1][1] == n_local * world
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            if n_bad:  # keep the two populations aligned for the next step
+                print(f"[shard_worker] step {t}: {n_bad} tie ancestors", flush=True)
+            print(f"[shard_worker] t={t} ess={ess:.3f} cross_shard_fraction={frac:.5f} ranges={ranges}", flush=True)
+    lml_s = sf.log_ml_estimate()
+    if rank == 0:
+        lml_r = g.log_ml_estimate(ref)
+        assert abs(lml_s - lml_r) <= 1e-9 * max(1.0, abs(lml_r)), (lml_s, lml_r)
+        print("[shard_worker] OK", flush=True)
+    dist.barrier()
+    sf.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
