@@ -35,6 +35,8 @@ KERNEL_ALGO_BYTES = {
     "k_gather": 44,     # R window 18 + W window 18 + W lw 8
     "k_mh": 27,         # R window 18 + W slice 9
     "k_step_fused": 117 - 8,  # the whole step but the scan's read of lw
+    "k_step_push": 117 - 8,   # the same arithmetic, stores routed to the owning GPU (multi-GPU)
+    "k_reduce": 8,
 }
 STEP_ALGO_BYTES = 117
 
@@ -44,6 +46,14 @@ def measured_peak_gbs():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_of(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+    return None
 
 
 def observations(T, seed=3):
@@ -202,19 +212,38 @@ def main():
     T = W + 3 * K + 6
     obs = observations(T)
     model = g.DeviceModel("object_motion")
-    # particles shard across ranks: rank r owns global slots [r*n, (r+1)*n) of the Philox counter space
-    state = g.pf_initialize(model, (1,), obs[0], n, seed=1234 + rank)
-    sp = C.c_void_p()
-    L.check(lib.genpf_filter_stream(state._h, C.byref(sp)))
-    stream = torch.cuda.ExternalStream(sp.value)
     auxs = [np.array([math.sin(float(t))]) for t in range(T + 2)]
     obs_arr = [np.array([o]) for o in obs]
     method = L.STRATIFIED
+    shard_info = None
+    if world == 1:
+        state = g.pf_initialize(model, (1,), obs[0], n, seed=1234)
+        sp = C.c_void_p()
+        L.check(lib.genpf_filter_stream(state._h, C.byref(sp)))
+        stream = torch.cuda.ExternalStream(sp.value)
 
-    def raw_step(t):  # asynchronous: nothing is copied back
-        L.check(lib.genpf_step(state._h, t, L.ptr(obs_arr[t - 2]), L.ptr(auxs[t - 1]), L.ptr(obs_arr[t - 1]),
-                               L.ptr(auxs[t]), method, 1.0, 1, None))
-        state.t = t
+        def raw_step(t):  # asynchronous: nothing is copied back
+            L.check(lib.genpf_step(state._h, t, L.ptr(obs_arr[t - 2]), L.ptr(auxs[t - 1]), L.ptr(obs_arr[t - 1]),
+                                   L.ptr(auxs[t]), method, 1.0, 1, None))
+            state.t = t
+
+        def e2e_step(t, pin_prev, pin_t):
+            return g.pf_step(state, t, pin_prev, pin_t, method="stratified", ess_thresh=1.0, mh_iters=1,
+                             return_ess=True)
+    else:
+        # ONE filter of world * n particles, slots sharded contiguously over the ranks:
+        # NCCL all-gathers of shard totals on the filter's stream + NVLink P2P push of offspring
+        from genpf_b200.sharded import ShardedFilter
+        sf = ShardedFilter(model, n, seed=1234)
+        sf.initialize(obs[0])
+        stream = sf.stream
+
+        def raw_step(t):
+            sf.step(t, obs[t - 2], obs[t - 1])
+
+        def e2e_step(t, pin_prev, pin_t):
+            sf.step(t, pin_prev[0], pin_t[0])
+            return np.array([sf.stats()[0]])
 
     t = 2
     for _ in range(W):
@@ -233,6 +262,11 @@ def main():
     barrier()
     launches = lib.genpf_launch_count() - launches0
     ms = e0.elapsed_time(e1)
+    if world > 1:
+        ranges, frac = sf.exchange_summary()
+        shard_info = {"cross_shard_offspring_fraction": frac,
+                      "nvlink_bytes_per_step_per_gpu": frac * n * 30.0,  # parents 4 + two slices 18 + lw 8
+                      "collectives_per_step": "2 all_gather (3 f64, 1 i64) + 1 barrier, NCCL on the filter stream"}
     # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
     L.check(lib.genpf_profile_begin())
     for _ in range(K):
@@ -252,7 +286,7 @@ def main():
     w0 = time.perf_counter()
     for _ in range(K):
         pin_prev[0], pin_t[0] = obs[t - 2], obs[t - 1]
-        ess = g.pf_step(state, t, pin_prev, pin_t, method="stratified", ess_thresh=1.0, mh_iters=1, return_ess=True)
+        ess = e2e_step(t, pin_prev, pin_t)
         t += 1
     barrier()
     e2e_s = time.perf_counter() - w0
@@ -284,16 +318,18 @@ def main():
         "config": {"workload": "object_motion 2^24 particles/GPU: ESS + stratified resample(sort_particles=false) "
                                "+ MH rejuvenation + update per step (README.md:66-77, resample forced)",
                    "particles_per_gpu": n, "l2": "inputs larger than L2 (>=1.2 GB touched per step)",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent particle shards (no cross-GPU "
-                                                              "ancestor exchange yet)",
+                   "parallelism": "1 GPU" if world == 1 else f"one filter of {world}x2^24 particles sharded over "
+                                  f"{world} GPUs: NCCL all-gather of shard totals + NVLink P2P push of offspring",
+                   "sharding": shard_info,
                    "noise": "lean Philox4x32-10 (1 call/particle/purpose)", "algo_bytes_per_update": STEP_ALGO_BYTES},
         "clocks": clocks,
         "e2e": {"value": total_updates / (e2e_ms_max * 1e-3), "unit": "particle-updates/s",
                 "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 48,
-                "note": "genpf_b200.pf_step: obs/aux scalars in (kernel arguments), Stats(ESS) read back per step"},
+                "note": "genpf_b200.pf_step / ShardedFilter.step: obs/aux scalars in (kernel arguments), "
+                        "Stats(ESS) read back per step"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic_of(dom_name), "peak_source": peak_src,
                      "algo_bytes_per_launch": algo_b, "ms_per_launch": per_launch_ms,
                      "share_of_step": dom_ms / prof_total,
                      "step_frac": (STEP_ALGO_BYTES * n / (ms_max / K * 1e-3) / 1e9) / peak,
