@@ -127,7 +127,7 @@ int32_t ensure_stats(genpf_filter_t pf, double *tile_off, double ess_frac, doubl
         GENPF_TRY(launch_reduce(pf->stream, src, pf->n, pf->nf, pf->sc.partials(0)));
         pf->part_valid = true;
     }
-    return launch_finalize(pf->stream, pf->sc.partials(0), pf->n, pf->nf, pf->sc.st(0, pf->nf), tile_off, ess_frac,
+    return launch_finalize(pf->stream, pf->sc, pf->sc.partials(0), pf->n, pf->nf, pf->sc.st(0, pf->nf), tile_off, ess_frac,
                            lml_accum);
 }
 
@@ -295,7 +295,7 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     GENPF_TRY(ensure_stats(pf, has_prio ? nullptr : sc.tile_off.as<double>(), ess_frac, lml_now));
     if (has_prio) {
         GENPF_TRY(launch_reduce(s, sel, n, nf, sc.partials(1)));
-        GENPF_TRY(launch_finalize(s, sc.partials(1), n, nf, st_sel, sc.tile_off.as<double>(), -1.0, nullptr));
+        GENPF_TRY(launch_finalize(s, sc, sc.partials(1), n, nf, st_sel, sc.tile_off.as<double>(), -1.0, nullptr));
     }
     if (want_host_check) {
         GENPF_TRY(read_stats(pf, has_prio ? 1 : 0));
@@ -308,7 +308,7 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
         }
         if ((flags & GENPF_CHECK) && any_invalid) return fail(GENPF_ERR_INVALID_WEIGHTS, "Invalid weights.");
         if (!substate) {  // update_lml_est! (resample.jl:178-182), after the check like the reference
-            GENPF_TRY(launch_finalize(s, sc.partials(0), n, nf, st_lw, nullptr, ess_frac, pf->lml));
+            GENPF_TRY(launch_finalize(s, sc, sc.partials(0), n, nf, st_lw, nullptr, ess_frac, pf->lml));
         }
         if (any_nan && nf == 1) return GENPF_OK;
     }
@@ -331,7 +331,7 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
                      (int64_t)0, n, n_out, pf->lw_alt);
         LwSrc dsrc{pf->lw_alt, 1.0};
         GENPF_TRY(launch_reduce(s, dsrc, n_out, nf, sc.partials(2)));
-        GENPF_TRY(launch_finalize(s, sc.partials(2), n_out, nf, st_d, nullptr, -1.0, nullptr));
+        GENPF_TRY(launch_finalize(s, sc, sc.partials(2), n_out, nf, st_d, nullptr, -1.0, nullptr));
         GENPF_LAUNCH(k_prio_shift, dim3(grid_1d(n_out), (unsigned)nf), 256, s, pf->lw_alt, n_out, st_d, st_lw, substate ? 1 : 0);
     }
     // update_refs!: swap (utils.jl:10-15)
@@ -414,8 +414,9 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, (unsigned)nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
-                 (const double *)sc.tile_off.as<double>(), (double *)nullptr, sc.O.as<int32_t>(),
-                 sc.tile_last.as<int32_t>(), strat, 0);
+                 (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr}, sc.O.as<int32_t>(),
+                 sc.tile_last.as<int32_t>(), strat, 0, (const double *)nullptr, (int64_t)0, sc.chunk_info_ptr(n),
+                 Scratch::kChunkTiles);
     int32_t st;
     switch (pf->model) {
         case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a); break;

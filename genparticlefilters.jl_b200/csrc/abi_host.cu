@@ -88,7 +88,7 @@ static int32_t reduce_to_host(HostWs &ws, const double *d_lw, int64_t n, Stats *
     GENPF_TRY(ws.sc.ensure(n, 1));
     LwSrc src{d_lw, 1.0};
     GENPF_TRY(launch_reduce(ws.stream, src, n, 1, ws.sc.partials(0)));
-    GENPF_TRY(launch_finalize(ws.stream, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), nullptr, -1.0, nullptr));
+    GENPF_TRY(launch_finalize(ws.stream, ws.sc, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), nullptr, -1.0, nullptr));
     GENPF_CUDA_TRY(cudaMemcpyAsync(ws.h_stats, ws.sc.st(0, 1), sizeof(Stats), cudaMemcpyDeviceToHost, ws.stream));
     GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
     *out = ws.h_stats[0];
@@ -231,10 +231,10 @@ static int32_t resample_one(HostWs &ws, int32_t method, const double *d_lw, cons
     LwSrc sel = d_lp ? LwSrc{d_lp, 1.0} : lw_src;
     Stats *st_lw = sc.st(0, 1), *st_sel = d_lp ? sc.st(1, 1) : st_lw, *st_d = sc.st(2, 1);
     GENPF_TRY(launch_reduce(s, lw_src, n_in, 1, sc.partials(0)));
-    GENPF_TRY(launch_finalize(s, sc.partials(0), n_in, 1, st_lw, d_lp ? nullptr : sc.tile_off.as<double>(), -1.0, nullptr));
+    GENPF_TRY(launch_finalize(s, sc, sc.partials(0), n_in, 1, st_lw, d_lp ? nullptr : sc.tile_off.as<double>(), -1.0, nullptr));
     if (d_lp) {
         GENPF_TRY(launch_reduce(s, sel, n_in, 1, sc.partials(1)));
-        GENPF_TRY(launch_finalize(s, sc.partials(1), n_in, 1, st_sel, sc.tile_off.as<double>(), -1.0, nullptr));
+        GENPF_TRY(launch_finalize(s, sc, sc.partials(1), n_in, 1, st_sel, sc.tile_off.as<double>(), -1.0, nullptr));
     }
     GENPF_CUDA_TRY(cudaMemcpyAsync(ws.h_stats, sc.stats.p, sizeof(Stats) * 2, cudaMemcpyDeviceToHost, s));
     GENPF_CUDA_TRY(cudaStreamSynchronize(s));
@@ -259,7 +259,7 @@ static int32_t resample_one(HostWs &ws, int32_t method, const double *d_lw, cons
                      reinterpret_cast<const long long *>(d_parents), base, n_in, n_out, d_lw_out);
         LwSrc dsrc{d_lw_out, 1.0};
         GENPF_TRY(launch_reduce(s, dsrc, n_out, 1, sc.partials(2)));
-        GENPF_TRY(launch_finalize(s, sc.partials(2), n_out, 1, st_d, nullptr, -1.0, nullptr));
+        GENPF_TRY(launch_finalize(s, sc, sc.partials(2), n_out, 1, st_d, nullptr, -1.0, nullptr));
         GENPF_LAUNCH(k_prio_shift, dim3(grid_1d(n_out), 1), 256, s, d_lw_out, n_out, st_d, st_lw, substate ? 1 : 0);
     }
     return GENPF_OK;
@@ -349,7 +349,7 @@ int32_t genpf_weighted_mean_var(const double *lw, const double *x, int64_t n, ui
     GENPF_TRY(ws.sc.ensure(n, 1));
     LwSrc src{d_lw, 1.0};
     GENPF_TRY(launch_reduce(ws.stream, src, n, 1, ws.sc.partials(0)));
-    GENPF_TRY(launch_finalize(ws.stream, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), nullptr, -1.0, nullptr));
+    GENPF_TRY(launch_finalize(ws.stream, ws.sc, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), nullptr, -1.0, nullptr));
     XSrc xs{d_x, nullptr};
     GENPF_TRY(launch_mean_var(ws.stream, ws.sc, d_lw, xs, n, 1, ws.sc.st(0, 1)));
     GENPF_CUDA_TRY(cudaMemcpyAsync(ws.h_scalars, ws.sc.moment_out.p, 16, cudaMemcpyDeviceToHost, ws.stream));
@@ -435,11 +435,12 @@ int32_t genpf_debug_cumweights(const double *lw, int64_t n, uint32_t flags, doub
     LwSrc src{d_lw, 1.0};
     const int64_t tpf = ceil_div(n, kTile);
     GENPF_TRY(launch_reduce(ws.stream, src, n, 1, ws.sc.partials(0)));
-    GENPF_TRY(launch_finalize(ws.stream, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), ws.sc.tile_off.as<double>(), -1.0, nullptr));
+    GENPF_TRY(launch_finalize(ws.stream, ws.sc, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), ws.sc.tile_off.as<double>(), -1.0, nullptr));
     UniSrc uni{nullptr, 0, 0, 0};
     StratArgs none = make_strat(uni, n);
     GENPF_LAUNCH((k_scan<int32_t>), (unsigned)tpf, kScanThreads, ws.stream, src, n, tpf, ws.sc.st(0, 1),
-                 ws.sc.tile_off.as<double>(), d_W, (int32_t *)nullptr, (int32_t *)nullptr, none, 0);
+                 ws.sc.tile_off.as<double>(), WTables{d_W, nullptr, nullptr}, (int32_t *)nullptr, (int32_t *)nullptr, none, 0,
+                 (const double *)nullptr, (int64_t)0, ws.sc.chunk_info_ptr(n), Scratch::kChunkTiles);
     GENPF_TRY(copy_out(ws, d_W, W_out, n, dp));
     GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
     return GENPF_OK;

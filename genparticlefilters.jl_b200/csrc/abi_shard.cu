@@ -197,9 +197,9 @@ int32_t genpf_shard_scan(genpf_filter_t pf) {
     StratArgs strat = make_strat(uni, sh->n_total);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, pf->stream, lw_src, n, tpf,
-                 (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), (double *)nullptr,
+                 (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr},
                  sc.O.as<int32_t>(), sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info,
-                 (int64_t)sh->rank * n);
+                 (int64_t)sh->rank * n, sc.chunk_info_ptr(n), Scratch::kChunkTiles);
     GENPF_LAUNCH(k_shard_oend, 1, 32, pf->stream, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->oend_local);
     return GENPF_OK;
 }

@@ -11,11 +11,14 @@ namespace genpf {
 struct Scratch {
     DevBuf part[3][4];  // three partial sets (lw, selection source, ratio d): m, s, s2, flags
     DevBuf stats;       // Stats[4 * nf]: [0] lw  [1] selection  [2] ratio d  [3] sorted selection
-    DevBuf tile_off, W, O, tile_last;
+    DevBuf tile_off, W, W16, W_tile_last, O, tile_last;
     DevBuf resid_c, resid_r, resid_coff, resid_roff, resid_rtot;
     DevBuf sort_tmp, sorted_keys, order, prio_col;
     DevBuf moment_partial, moment_out;
-    DevBuf misc;
+    DevBuf misc, chunk_stats, chunk_info;
+    static constexpr int64_t kChunkTiles = 8192;  // tiles finalised by one block (2^24 particles)
+    // {prefix, scale} pairs of the last finalize of a filter with more than kChunkTiles tiles (else null)
+    const double *chunk_info_ptr(int64_t n) const { return ceil_div(n, kTile) > kChunkTiles ? chunk_info.as<double>() : nullptr; }
     int64_t cap_n = -1, cap_nf = -1;
 
     int32_t ensure(int64_t n, int64_t nf) {
@@ -37,26 +40,34 @@ struct Scratch {
     Stats *st(int k, int64_t nf) { return stats.as<Stats>() + (size_t)k * nf; }
     void release() {
         for (auto &a : part) for (auto &b : a) b.release();
-        for (DevBuf *b : {&stats, &tile_off, &W, &O, &tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
-                          &sort_tmp, &sorted_keys, &order, &prio_col, &moment_partial, &moment_out, &misc})
+        for (DevBuf *b : {&stats, &tile_off, &W, &W16, &W_tile_last, &O, &tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
+                          &sort_tmp, &sorted_keys, &order, &prio_col, &moment_partial, &moment_out, &misc, &chunk_stats, &chunk_info})
             b->release();
     }
 };
 
 inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, Partials part) {
     const int64_t tpf = ceil_div(n, kTile);
-    GENPF_LAUNCH(k_reduce, dim3((unsigned)tpf, (unsigned)nf), kThreads, s, src, n, tpf, part);
+    GENPF_LAUNCH(k_reduce, dim3((unsigned)tpf, (unsigned)nf), kReduceThreads, s, src, n, tpf, part);
     return GENPF_OK;
 }
-inline int32_t launch_finalize(cudaStream_t s, Partials part, int64_t n, int64_t nf, Stats *st, double *tile_off,
-                               double ess_frac, double *lml_accum) {
+inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64_t n, int64_t nf, Stats *st,
+                               double *tile_off, double ess_frac, double *lml_accum) {
     const int64_t tpf = ceil_div(n, kTile);
     if (tpf <= 8 * 64) {
-        GENPF_LAUNCH((k_finalize_fast<64>), (unsigned)nf, 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
-    } else if (tpf <= 8 * 1024) {
-        GENPF_LAUNCH((k_finalize_fast<1024>), (unsigned)nf, 1024, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+        GENPF_LAUNCH((k_finalize_fast<64>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf);
+    } else if (tpf <= Scratch::kChunkTiles) {
+        GENPF_LAUNCH((k_finalize_fast<1024>), dim3(1, (unsigned)nf), 1024, s, part, n, tpf, st, tile_off, ess_frac,
+                     lml_accum, tpf);
     } else {
-        GENPF_LAUNCH(k_finalize, (unsigned)nf, kThreads, s, part, n, tpf, st, tile_off, ess_frac, lml_accum);
+        // large filter: per-chunk finalize, then combine (statistics, validity, lml, chunk {prefix, scale})
+        const int64_t nchunks = ceil_div(tpf, Scratch::kChunkTiles);
+        GENPF_TRY(sc.chunk_stats.ensure(sizeof(Stats) * (size_t)(nchunks * nf)));
+        GENPF_TRY(sc.chunk_info.ensure(16 * (size_t)(nchunks * nf)));
+        GENPF_LAUNCH((k_finalize_fast<1024>), dim3((unsigned)nchunks, (unsigned)nf), 1024, s, part, n, tpf,
+                     sc.chunk_stats.as<Stats>(), tile_off, -1.0, (double *)nullptr, Scratch::kChunkTiles);
+        GENPF_LAUNCH(k_chunk_combine, (unsigned)nf, 32, s, (const Stats *)sc.chunk_stats.as<Stats>(), (int)nchunks, n,
+                     Scratch::kChunkTiles * (int64_t)kTile, st, sc.chunk_info.as<double>(), ess_frac, lml_accum);
     }
     return GENPF_OK;
 }
@@ -101,27 +112,35 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
             LwSrc sorted{sc.sorted_keys.as<double>(), 1.0};
             Stats *st_sorted = sc.st(3, nf);
             GENPF_TRY(launch_reduce(s, sorted, n_in, nf, sc.partials(1)));
-            GENPF_TRY(launch_finalize(s, sc.partials(1), n_in, nf, st_sorted, tile_off, -1.0, nullptr));
+            GENPF_TRY(launch_finalize(s, sc, sc.partials(1), n_in, nf, st_sorted, tile_off, -1.0, nullptr));
             sel = sorted;
             st_sel = st_sorted;
             order = sc.order.as<int32_t>();
         }
         StratArgs strat = make_strat(uni, n_in);
         GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     (double *)nullptr, O, tile_last, strat, gate);
+                     WTables{nullptr, nullptr, nullptr}, O, tile_last, strat, gate, (const double *)nullptr, (int64_t)0,
+                     sc.chunk_info_ptr(n_in), Scratch::kChunkTiles);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0);
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
+        GENPF_TRY(sc.W16.ensure((size_t)(((n_in + 15) >> 4) * nf) * 8));
+        GENPF_TRY(sc.W_tile_last.ensure((size_t)(tpf_in * nf) * 8));
+        WTables wt{sc.W.as<double>(), sc.W16.as<double>(), sc.W_tile_last.as<double>()};
         StratArgs none = make_strat(uni, n_in);
         GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     sc.W.as<double>(), (IdxT *)nullptr, (IdxT *)nullptr, none, gate);
-        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
+                     wt, (IdxT *)nullptr, (IdxT *)nullptr, none, gate, (const double *)nullptr, (int64_t)0,
+                     sc.chunk_info_ptr(n_in), Scratch::kChunkTiles);
+        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, wt, n_in, n_out,
                      tpf_out, uni, (const IdxT *)nullptr, parents, out_base, st_sel, gate);
     } else if (method == GENPF_RESIDUAL) {
         if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated residual resample is not supported");
         const size_t np = (size_t)(tpf_in * nf);
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
+        GENPF_TRY(sc.W16.ensure((size_t)(((n_in + 15) >> 4) * nf) * 8));
+        GENPF_TRY(sc.W_tile_last.ensure((size_t)(tpf_in * nf) * 8));
+        WTables rt{sc.W.as<double>(), sc.W16.as<double>(), sc.W_tile_last.as<double>()};
         GENPF_TRY(sc.resid_c.ensure(np * 8));
         GENPF_TRY(sc.resid_r.ensure(np * 8));
         GENPF_TRY(sc.resid_coff.ensure(np * 8));
@@ -129,14 +148,14 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         GENPF_TRY(sc.resid_rtot.ensure((size_t)nf * 8));
         ResidPartials rp{sc.resid_c.as<long long>(), sc.resid_r.as<double>()};
         GENPF_LAUNCH(k_resid_partials, dim3((unsigned)tpf_in, (unsigned)nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel, rp);
-        GENPF_LAUNCH(k_resid_finalize, (unsigned)nf, kThreads, s, rp, tpf_in, sc.resid_rtot.as<double>(),
+        GENPF_LAUNCH(k_resid_finalize, (unsigned)nf, 1024, s, rp, tpf_in, sc.resid_rtot.as<double>(),
                      sc.resid_coff.as<long long>(), sc.resid_roff.as<double>());
         GENPF_LAUNCH((k_resid_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel,
                      sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
-                     tile_last, sc.W.as<double>());
+                     tile_last, rt);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
                      (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1);
-        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, sc.W.as<double>(), n_in, n_out,
+        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, rt, n_in, n_out,
                      tpf_out, uni, (const IdxT *)O, parents, out_base, st_sel, 0);
     } else {
         return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");

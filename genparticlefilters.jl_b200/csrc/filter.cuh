@@ -94,73 +94,6 @@ __device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_
     }
 }
 
-// tile epilogue shared by every kernel that produces log-weights: the K1 partials of the tile.
-// sm: 2*(T/32) doubles, smi: T/32 ints.  Cross-warp combines run in one warp (fixed shuffle tree:
-// deterministic), not redundantly in every thread.
-template <int T = kThreads>
-__device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, double *sm,
-                                              int *smi) {
-    constexpr int NW = T / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int fl = 0;
-    double m = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < kTile / T; ++k) {
-        fl |= isnan(v[k]) ? 1 : 0;
-        m = fmax(m, v[k]);
-    }
-    m = warp_max(m);
-    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
-    __syncthreads();
-    if (lane == 0) {
-        sm[warp] = m;
-        smi[warp] = fl;
-    }
-    __syncthreads();
-    // every thread needs the block max: lane l reads cell l mod NW, butterfly over NW lanes
-    m = sm[lane & (NW - 1)];
-    fl = smi[lane & (NW - 1)];
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) {
-        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        fl |= __shfl_xor_sync(0xffffffffu, fl, o);
-    }
-    double s = 0.0, s2 = 0.0;
-    if (m == INFINITY) {
-        fl |= 2;
-    } else if (m > -INFINITY) {
-#pragma unroll
-        for (int k = 0; k < kTile / T; ++k) {
-            double e = exp_nonpos(v[k] - m);
-            s += e;
-            s2 += e * e;
-        }
-    }
-    s = warp_sum(s);
-    s2 = warp_sum(s2);
-    __syncthreads();
-    if (lane == 0) {
-        sm[warp] = s;
-        sm[NW + warp] = s2;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        s = sm[lane & (NW - 1)];
-        s2 = sm[NW + (lane & (NW - 1))];
-#pragma unroll
-        for (int o = NW / 2; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        if (lane == 0) {
-            out.m[blockIdx.y * gridDim.x + blockIdx.x] = m;
-            out.s[blockIdx.y * gridDim.x + blockIdx.x] = s;
-            out.s2[blockIdx.y * gridDim.x + blockIdx.x] = s2;
-            out.flags[blockIdx.y * gridDim.x + blockIdx.x] = fl;
-        }
-    }
-}
-
 // ------------------------------------------------------------------ K10 propagate + weight (+ K1 partials)
 // INIT: pf_initialize (initialize.jl:39-41): slice_1 = transition(initial), lw = obs_logpdf
 // else: pf_update!    (update.jl:15-21):     slice_t = transition(slice_{t-1}), lw += obs_logpdf

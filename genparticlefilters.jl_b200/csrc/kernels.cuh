@@ -26,46 +26,89 @@ __device__ __forceinline__ void blk_to_tile(int64_t, int64_t &f, int64_t &tile) 
     tile = blockIdx.x;
 }
 
-// ------------------------------------------------------------------ K1/K2 reduce
-// Replaces: Gen.logsumexp, lognorm/softmax (utils.jl:100-107), safe_softmax's validity scan
-// (utils.jl:119-137), effective_sample_size (utils.jl:163-164).
-static __global__ void __launch_bounds__(kThreads) k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out) {
-    __shared__ double sm[kWarps];
-    __shared__ int smi[kWarps];
-    int64_t f, tile;
-    blk_to_tile(tpf, f, tile);
-    const int64_t start = tile * kTile;
-    const int64_t valid = min((int64_t)kTile, n - start);
-    double v[kItems];
-    load_tile(src, f * n + start, valid, v, -INFINITY);
+// tile epilogue shared by every kernel that produces log-weights: the K1 partials of the tile.
+// sm: 2*(T/32) doubles, smi: T/32 ints.  Cross-warp combines run in one warp (fixed shuffle tree:
+// deterministic), not redundantly in every thread.
+template <int T = kThreads>
+__device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, double *sm,
+                                              int *smi) {
+    constexpr int NW = T / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int fl = 0;
     double m = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
+    for (int k = 0; k < kTile / T; ++k) {
         fl |= isnan(v[k]) ? 1 : 0;
         m = fmax(m, v[k]);
     }
-    m = block_max(m, sm);
-    fl = block_or(fl, smi);
+    m = warp_max(m);
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    __syncthreads();
+    if (lane == 0) {
+        sm[warp] = m;
+        smi[warp] = fl;
+    }
+    __syncthreads();
+    // every thread needs the block max: lane l reads cell l mod NW, butterfly over NW lanes
+    m = sm[lane & (NW - 1)];
+    fl = smi[lane & (NW - 1)];
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+    }
     double s = 0.0, s2 = 0.0;
     if (m == INFINITY) {
         fl |= 2;
     } else if (m > -INFINITY) {
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
+        for (int k = 0; k < kTile / T; ++k) {
             double e = exp_nonpos(v[k] - m);
             s += e;
             s2 += e * e;
         }
     }
-    s = block_sum(s, sm);
-    s2 = block_sum(s2, sm);
-    if (threadIdx.x == 0) {
-        out.m[blockIdx.y * gridDim.x + blockIdx.x] = m;
-        out.s[blockIdx.y * gridDim.x + blockIdx.x] = s;
-        out.s2[blockIdx.y * gridDim.x + blockIdx.x] = s2;
-        out.flags[blockIdx.y * gridDim.x + blockIdx.x] = fl;
+    s = warp_sum(s);
+    s2 = warp_sum(s2);
+    __syncthreads();
+    if (lane == 0) {
+        sm[warp] = s;
+        sm[NW + warp] = s2;
     }
+    __syncthreads();
+    if (warp == 0) {
+        s = sm[lane & (NW - 1)];
+        s2 = sm[NW + (lane & (NW - 1))];
+#pragma unroll
+        for (int o = NW / 2; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            out.m[blockIdx.y * gridDim.x + blockIdx.x] = m;
+            out.s[blockIdx.y * gridDim.x + blockIdx.x] = s;
+            out.s2[blockIdx.y * gridDim.x + blockIdx.x] = s2;
+            out.flags[blockIdx.y * gridDim.x + blockIdx.x] = fl;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K1/K2 reduce
+// Replaces: Gen.logsumexp, lognorm/softmax (utils.jl:100-107), safe_softmax's validity scan
+// (utils.jl:119-137), effective_sample_size (utils.jl:163-164).  Same block size and epilogue as the
+// state-producing kernels, so the partials are bit-identical to theirs.
+constexpr int kReduceThreads = 512;
+static __global__ void __launch_bounds__(kReduceThreads) k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out) {
+    constexpr int T = kReduceThreads;
+    __shared__ double sm[2 * (T / 32)];
+    __shared__ int smi[T / 32];
+    int64_t f, tile;
+    blk_to_tile(tpf, f, tile);
+    const int64_t start = tile * kTile;
+    const int64_t valid = min((int64_t)kTile, n - start);
+    double v[kTile / T];
+    load_tile<T>(src, f * n + start, valid, v, -INFINITY);
+    emit_partials<T>(v, out, sm, smi);
 }
 
 // One block per filter.  Combines tile partials, classifies validity (utils.jl:119-137) and writes the
@@ -167,14 +210,27 @@ static __global__ void __launch_bounds__(kThreads)
 // need only a handful of block-level combines.  Same outputs as k_finalize.
 template <int THREADS>
 static __global__ void __launch_bounds__(THREADS)
-    k_finalize_fast(Partials in, int64_t n, int64_t tpf, Stats *stats, double *tile_off, double ess_frac,
-                    double *lml_accum) {
+    k_finalize_fast(Partials in, int64_t n_all, int64_t tpf_all, Stats *stats, double *tile_off, double ess_frac,
+                    double *lml_accum, int64_t chunk_tiles) {
+    // grid = (chunks, filters).  chunk_tiles == tpf_all: the block finalises a whole filter.  Otherwise it
+    // finalises one CHUNK of a large filter as if it were a filter of its own (Stats at [f*chunks + c], tile
+    // offsets normalised within the chunk); k_chunk_combine then produces the filter's statistics and each
+    // chunk's {prefix, scale}, which k_scan composes -- the same mechanism as a multi-GPU shard.
     constexpr int C = 8, NW = THREADS / 32;
     __shared__ double sm[3][NW];
     __shared__ int smi[NW];
     __shared__ double row_cell[C][NW];  // inclusive warp totals per row -> exclusive offsets
     __shared__ double row_total[C];
-    const int64_t f = blockIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * chunk_tiles;
+    const int64_t tpf = min(chunk_tiles, tpf_all - tile0);
+    const int64_t n = min(n_all - tile0 * kTile, tpf * (int64_t)kTile);
+    const int64_t f = blockIdx.y;
+    in.m += f * tpf_all + tile0 - f * tpf;  // so that in.X[f*tpf + b] addresses tile (tile0 + b) of filter f
+    in.s += f * tpf_all + tile0 - f * tpf;
+    in.s2 += f * tpf_all + tile0 - f * tpf;
+    in.flags += f * tpf_all + tile0 - f * tpf;
+    if (tile_off) tile_off += f * tpf_all + tile0 - f * tpf;
+    stats += (int64_t)blockIdx.y * gridDim.x + blockIdx.x - f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double pm[C], ps[C], ps2[C];
     int fl = 0;
@@ -289,6 +345,60 @@ static __global__ void __launch_bounds__(THREADS)
     }
 }
 
+// Large filters (more than 8192 tiles): combine the per-chunk statistics into the filter's, and give every
+// chunk its {prefix, scale} (exclusive normalised mass before the chunk, the chunk's share).  One warp per filter.
+static __global__ void k_chunk_combine(const Stats *chunk_stats, int nchunks, int64_t n, int64_t chunk_particles,
+                                       Stats *stats, double *chunk_info, double ess_frac, double *lml_accum) {
+    const int64_t f = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const Stats *cs = chunk_stats + f * nchunks;
+    double M = -INFINITY;
+    int kind = 0;
+    bool all_neginf = true, nan_in = false, nan_tot = false;
+    for (int c = 0; c < nchunks; ++c) {
+        M = fmax(M, cs[c].M);
+        if (cs[c].invalid_kind == 1) nan_in = true;
+        if (cs[c].invalid_kind == 4) nan_tot = true;
+        if (cs[c].invalid_kind != 2) all_neginf = false;
+    }
+    double S = 0.0, S2 = 0.0;
+    const bool finite = M > -INFINITY && M < INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+        const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
+        S += cs[c].S * sc;
+        S2 += cs[c].S2 * (sc * sc);
+    }
+    if (nan_in) kind = 1;
+    else if (all_neginf) kind = 2;
+    else if (nan_tot || isnan(S)) kind = 4;
+    else if (S == 0.0) kind = 3;
+    double prefix = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        double share;
+        if (kind == 2 || kind == 3) {
+            const int64_t cnt = min(chunk_particles, n - (int64_t)c * chunk_particles);
+            share = (double)cnt / (double)n;
+        } else {
+            const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
+            share = cs[c].S * sc / S;
+        }
+        chunk_info[2 * (f * nchunks + c)] = prefix;
+        chunk_info[2 * (f * nchunks + c) + 1] = share;
+        prefix += share;
+    }
+    Stats st;
+    st.M = M; st.S = S; st.S2 = S2;
+    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    st.ess = S * S / S2;
+    st.invalid_kind = kind;
+    int do_rs = 1;
+    if (ess_frac >= 0.0) do_rs = (st.ess < ess_frac * (double)n) ? 1 : 0;
+    if (kind == 1 || kind == 4) do_rs = 0;
+    st.do_resample = do_rs;
+    stats[f] = st;
+    if (lml_accum && do_rs) lml_accum[f] += st.lse - log((double)n);
+}
+
 // ------------------------------------------------------------------ stratified thresholds
 // u_i = r_i*(1/n) + lower_i with two roundings and no FMA (resample.jl:162); lower_i = element i of
 // 0.0:1/n:1.0-1/n, i.e. (i-1)/n (exact for power-of-two n).
@@ -345,11 +455,28 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t f, double W
 // Replaces safe_softmax line utils.jl:139 and the running accum_weight of resample.jl:163-166.
 // Writes W (normalised inclusive cumulative weights) and/or O (cumulative offspring counts, stratified).
 constexpr int kScanThreads = 512;  // every launch of k_scan uses this block size (fixed summation order)
+// cumulative-weight outputs for the inverse-CDF search: W[n], W16[ceil(n/16)] = W at the end of every
+// 16-particle group, tile_last[n/2048] = W at the end of every tile (three-level search index)
+struct WTables {
+    double *W, *W16, *tile_last;
+};
+template <int T>
+__device__ __forceinline__ void store_w_tables(const WTables &wt, int64_t fbase, int64_t n, int64_t tpf, int64_t f,
+                                               int64_t tile, int64_t start, int valid, const double (&W)[kTile / T]) {
+    store_tile<double, T>(wt.W, fbase + start, valid, W);
+    const int64_t n16 = (n + 15) >> 4;
+#pragma unroll
+    for (int k = 0; k < kTile / T; ++k) {
+        const int e = tile_elem<T>(k);
+        if (e < valid && ((e & 15) == 15 || e == valid - 1)) wt.W16[f * n16 + ((start + e) >> 4)] = W[k];
+        if (e == valid - 1) wt.tile_last[f * tpf + tile] = W[k];
+    }
+}
 template <typename IdxT>
 static __global__ void __launch_bounds__(kScanThreads, 2)
-    k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, double *W_out, IdxT *O_out,
+    k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, WTables wt, IdxT *O_out,
            IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info = nullptr,
-           int64_t global_base = 0) {
+           int64_t global_base = 0, const double *chunk_info = nullptr, int64_t chunk_tiles = 0) {
     // shard_info (multi-GPU particle sharding): {prefix, scale}: this shard's cumulative weights are
     // prefix + scale * (locally normalised tile offsets) + in-tile sums of globally normalised weights.
     constexpr int T = kScanThreads, I = kTile / T;
@@ -375,10 +502,18 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
     }
     tile_scan<double, T>(w, W, sm);
     double off = tile_off[f * tpf + tile];
+    if (chunk_info) {  // large filter: offsets were normalised per chunk of chunk_tiles tiles
+        const int64_t nchunks = (tpf + chunk_tiles - 1) / chunk_tiles;
+        const double *ci = chunk_info + 2 * (f * nchunks + tile / chunk_tiles);
+        off = ci[0] + ci[1] * off;
+    }
     if (shard_info) off = shard_info[0] + shard_info[1] * off;
 #pragma unroll
     for (int k = 0; k < I; ++k) W[k] = off + W[k];
-    if (W_out) store_tile<double, T>(W_out, f * n + start, valid, W);
+    if (wt.W) {
+        if (wt.W16) store_w_tables<T>(wt, f * n, n, tpf, f, tile, start, (int)valid, W);
+        else store_tile<double, T>(wt.W, f * n + start, valid, W);
+    }
     if (O_out) {
         IdxT O[I];
 #pragma unroll
@@ -587,15 +722,18 @@ static __global__ void __launch_bounds__(kThreads)
 
 // K5 inverse-CDF search for arbitrary (unsorted) uniforms: parent_j = min{k : W_k > u_j}, capped at n
 // (Distributions' single-draw rule, resize.jl:284).  Slots below first_slot (residual: the
-// deterministic copies) are left alone.  A coarse table of every 256-th W lives in shared memory so
-// only the last 8 steps touch global/L2.
-constexpr int kCoarseStride = 256;
-constexpr int kCoarseCap = 4096;  // covers n <= 2^20 fully in smem; larger n search the coarse table in global
+// deterministic copies) are left alone.  Random lookups are a gather workload, so the index is layered to
+// keep everything but the last cache line out of HBM:
+//   A. <= 4096 samples of the per-tile closing weights in shared memory      (12 steps, smem)
+//   B. the per-tile closing weights themselves                                (log2(stride) steps, L2)
+//   C. W16: the closing weight of every 16-particle group of the tile         (7 steps in 1 KB, L2)
+//   D. the 16 weights of the group                                            (4 steps in one 128-B line)
+constexpr int kCoarseCap = 4096;
 template <typename IdxT, typename OutT>
 static __global__ void __launch_bounds__(kThreads)
-    k_search(const double *W, int64_t n_src, int64_t n_out, int64_t bpf, UniSrc uni, const IdxT *first_slot_O,
+    k_search(WTables wt, int64_t n_src, int64_t n_out, int64_t bpf, UniSrc uni, const IdxT *first_slot_O,
              OutT *parents, int64_t out_base, const Stats *stats, int gate) {
-    __shared__ double sW[kCoarseCap];
+    __shared__ double sA[kCoarseCap];
     int64_t f = blockIdx.y;
     int64_t blk = blockIdx.x;
     (void)bpf;
@@ -604,29 +742,27 @@ static __global__ void __launch_bounds__(kThreads)
         if (kind == 1 || kind == 4) return;
         if (gate && !stats[f].do_resample) return;
     }
-    const double *Wf = W + f * n_src;
-    const int64_t n_coarse = (n_src + kCoarseStride - 1) / kCoarseStride;  // coarse[c] = W[min((c+1)*stride, n) - 1]
-    const bool coarse_in_smem = n_coarse <= kCoarseCap;
-    if (coarse_in_smem) {
-        for (int64_t c = threadIdx.x; c < n_coarse; c += kThreads)
-            sW[c] = Wf[min((c + 1) * (int64_t)kCoarseStride, n_src) - 1];
-        __syncthreads();
-    }
+    const int64_t tpf = (n_src + kTile - 1) / kTile;
+    const int64_t n16 = (n_src + 15) >> 4;
+    const double *Wf = wt.W + f * n_src;
+    const double *W16 = wt.W16 + f * n16;
+    const double *TL = wt.tile_last + f * tpf;
+    const int64_t strideA = (tpf + kCoarseCap - 1) / kCoarseCap;
+    const int64_t nA = (tpf + strideA - 1) / strideA;
+    for (int64_t c = threadIdx.x; c < nA; c += kThreads) sA[c] = TL[min((c + 1) * strideA, tpf) - 1];
+    __syncthreads();
     const int64_t first = first_slot_O ? (int64_t)first_slot_O[f * n_src + n_src - 1] : 0;
     for (int64_t j = blk * (int64_t)kTile + threadIdx.x; j < min(n_out, (blk + 1) * (int64_t)kTile); j += kThreads) {
         if (j < first) continue;
         const double u = uni(f * n_out + j);
-        int64_t lo = 0, hi = n_src - 1;
-        if (coarse_in_smem) {
-            int64_t c = upper_bound_clamped<double, double>(sW, n_coarse, u);
-            lo = c * kCoarseStride;
-            hi = min(lo + kCoarseStride, n_src) - 1;
-        }
-        while (lo < hi) {
-            int64_t mid = lo + ((hi - lo) >> 1);
-            if (Wf[mid] > u) hi = mid; else lo = mid + 1;
-        }
-        parents[f * n_out + j] = (OutT)(lo + out_base);
+        const int64_t a = upper_bound_clamped<double, double>(sA, nA, u);
+        const int64_t t0 = a * strideA, t1 = min(t0 + strideA, tpf);
+        const int64_t b = t0 + upper_bound_clamped<double, double>(TL + t0, t1 - t0, u);
+        const int64_t g0 = b * (kTile / 16), g1 = min(g0 + kTile / 16, n16);
+        const int64_t g = g0 + upper_bound_clamped<double, double>(W16 + g0, g1 - g0, u);
+        const int64_t k0 = g * 16, k1 = min(k0 + 16, n_src);
+        const int64_t k = k0 + upper_bound_clamped<double, double>(Wf + k0, k1 - k0, u);
+        parents[f * n_out + j] = (OutT)(k + out_base);
     }
 }
 
@@ -673,30 +809,100 @@ static __global__ void __launch_bounds__(kThreads)
         out.r[blockIdx.y * gridDim.x + blockIdx.x] = rs;
     }
 }
-// one block per filter: total residual mass, exclusive tile offsets for counts and normalised residuals
-static __global__ void __launch_bounds__(kThreads)
+// one block per filter: total residual mass, exclusive tile offsets for counts and normalised residuals.
+// 1024 threads x 8 consecutive tiles per round, running carry across rounds.
+static __global__ void __launch_bounds__(1024)
     k_resid_finalize(ResidPartials in, int64_t tpf, double *r_total, long long *c_off, double *r_off) {
-    __shared__ double sm[kWarps];
+    constexpr int T = 1024, C = 8, NW = T / 32;
+    __shared__ double smd[NW];
+    __shared__ long long sml[NW];
+    __shared__ double carry_r;
+    __shared__ long long carry_c;
     const int64_t f = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double rs = 0.0;
-    for (int64_t b = threadIdx.x; b < tpf; b += kThreads) rs += in.r[f * tpf + b];
-    const double R = block_sum(rs, sm);
+    for (int64_t b = threadIdx.x; b < tpf; b += T) rs += in.r[f * tpf + b];
+    rs = warp_sum(rs);
+    if (lane == 0) smd[warp] = rs;
+    __syncthreads();
+    double R = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) R += smd[w];
     if (threadIdx.x == 0) {
         r_total[f] = R;
-        long long c = 0;
-        double r = 0.0;
-        for (int64_t b = 0; b < tpf; ++b) {  // tpf <= n/2048: short serial carry chain
-            c_off[f * tpf + b] = c;
-            r_off[f * tpf + b] = r;
-            c += in.c[f * tpf + b];
-            r += (R > 0.0) ? in.r[f * tpf + b] / R : 0.0;
+        carry_r = 0.0;
+        carry_c = 0;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < tpf; base += (int64_t)T * C) {
+        double rv[C], rrun = 0.0;
+        long long cv[C], crun = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int64_t b = base + (int64_t)threadIdx.x * C + c;
+            rv[c] = rrun;
+            cv[c] = crun;
+            if (b < tpf) {
+                rrun += (R > 0.0) ? in.r[f * tpf + b] / R : 0.0;
+                crun += in.c[f * tpf + b];
+            }
         }
+        double rinc = rrun;
+        long long cinc = crun;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double ur = __shfl_up_sync(0xffffffffu, rinc, o);
+            long long uc = __shfl_up_sync(0xffffffffu, cinc, o);
+            if (lane >= o) {
+                rinc += ur;
+                cinc += uc;
+            }
+        }
+        double rex = __shfl_up_sync(0xffffffffu, rinc, 1);
+        long long cex = __shfl_up_sync(0xffffffffu, cinc, 1);
+        if (lane == 0) {
+            rex = 0.0;
+            cex = 0;
+        }
+        __syncthreads();
+        if (lane == 31) {
+            smd[warp] = rinc;
+            sml[warp] = cinc;
+        }
+        __syncthreads();
+        double rw = 0.0, rtot = 0.0;
+        long long cw = 0, ctot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (w < warp) {
+                rw += smd[w];
+                cw += sml[w];
+            }
+            rtot += smd[w];
+            ctot += sml[w];
+        }
+        const double cr = carry_r;
+        const long long cc = carry_c;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int64_t b = base + (int64_t)threadIdx.x * C + c;
+            if (b < tpf) {
+                r_off[f * tpf + b] = cr + ((rw + rex) + rv[c]);
+                c_off[f * tpf + b] = cc + cw + cex + cv[c];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry_r = cr + rtot;
+            carry_c = cc + ctot;
+        }
+        __syncthreads();
     }
 }
 template <typename IdxT>
 static __global__ void __launch_bounds__(kThreads)
     k_resid_scan(LwSrc src, int64_t n, int64_t n_out, int64_t tpf, const Stats *stats, const double *r_total,
-                 const long long *c_off, const double *r_off, IdxT *O_out, IdxT *tile_last_O, double *R_out) {
+                 const long long *c_off, const double *r_off, IdxT *O_out, IdxT *tile_last_O, WTables rt) {
     __shared__ double sm[32];
     __shared__ long long smi[32];
     int64_t f, tile;
@@ -728,7 +934,7 @@ static __global__ void __launch_bounds__(kThreads)
         if (tile_elem(k) == valid - 1) tile_last_O[f * tpf + tile] = O[k];
     }
     store_tile<IdxT>(O_out, f * n + start, valid, O);
-    store_tile<double>(R_out, f * n + start, valid, R);
+    store_w_tables<kThreads>(rt, f * n, n, tpf, f, tile, start, (int)valid, R);
 }
 
 // ------------------------------------------------------------------ K9 reweight after resample

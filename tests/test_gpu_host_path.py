@@ -396,3 +396,31 @@ def test_large_properties(g):
     # idempotence: resampling equal weights is the identity
     st, p2, *_ = raw_resample(g, "stratified", lw_out, None, seed=4)
     np.testing.assert_array_equal(p2, np.arange(n))
+
+
+def test_chunked_large_filter(g, orc):
+    """n > 2^24 particles: the finalize runs per 2^24-particle chunk + combine (same maths as a multi-GPU shard)."""
+    n = (1 << 25) + 12345
+    rng = np.random.default_rng(123)
+    lw = rng.normal(0, 1.5, n)
+    assert g.logsumexp_host(lw) == pytest.approx(orc.logsumexp(lw), rel=RTOL)
+
+    class S:
+        log_weights = lw
+    assert g.effective_sample_size(S) == pytest.approx(orc.ess(lw), rel=RTOL)
+    r = rng.random(n)
+    st, p, lw_out, inc, kind = raw_resample(g, "stratified", lw, r)
+    assert st == 0 and kind == 0
+    p_ref, _, inc_ref, _ = orc.resample("stratified", lw, r)
+    W_ref = orc.cumweights(orc.softmax(lw))
+    nm, gap = check_parents(p, p_ref, W_ref, strat_u(r, n))
+    assert inc == pytest.approx(inc_ref, rel=RTOL)
+    W = gpu_cumweights(g, lw)
+    assert abs(W[-1] - 1) < 1e-11 and np.max(np.abs(W - W_ref)) < tie_tolerance(n)
+    u = rng.random(1 << 20)
+    st, p, *_ = raw_resample(g, "multinomial", lw, u, n_out=u.size)
+    np.testing.assert_array_equal(p, np.minimum(np.searchsorted(W, u, side="right"), n - 1))
+    # all -Inf over several chunks: uniform fallback is still the identity for stratified
+    st, p, lw_out, inc, kind = raw_resample(g, "stratified", np.full(n, -np.inf), r)
+    assert kind == 2 and inc == -np.inf
+    assert np.mean(p == np.arange(n)) > 0.999999
