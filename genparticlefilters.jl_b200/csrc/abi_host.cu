@@ -276,6 +276,8 @@ int32_t genpf_resample(int32_t method, const double *lw, const double *log_prio,
         return fail(GENPF_ERR_INVALID_ARG, "stratified resampling cannot resize (resize.jl:16-27)");
     if ((flags & GENPF_SUBSTATE) && n_out != n_in)
         return fail(GENPF_ERR_INVALID_ARG, "a sub-state cannot be resized");
+    if (method != GENPF_STRATIFIED && n_in > (1ll << 29))
+        return fail(GENPF_ERR_UNSUPPORTED, "multinomial/residual search index supports up to 2^29 particles");
     HostWs &ws = g_ws;
     GENPF_TRY(ws.init());
     const bool dp = flags & GENPF_DEVICE_PTRS;

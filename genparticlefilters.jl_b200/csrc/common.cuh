@@ -112,6 +112,27 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// Exact fp64 maximum in the order-preserving integer domain.  fmax(double) is a 5-6 instruction sequence and
+// a 64-bit shuffle is two SHFLs; REDUX reduces a 32-bit integer across the warp in ONE instruction, so the
+// warp maximum is taken as: REDUX.MAX of the high words, then REDUX.MAX of the low words among the lanes that
+// hold the winning high word.  NaN never wins (callers flag NaN separately; fmax semantics).
+__device__ __forceinline__ long long f64_key(double v) {  // monotone double -> int64, NaN -> minimum
+    long long b = __double_as_longlong(v);
+    b ^= (b >> 63) & 0x7FFFFFFFFFFFFFFFll;
+    return v != v ? (long long)0x8000000000000000ull : b;
+}
+__device__ __forceinline__ double f64_from_key(long long k) {
+    k ^= (k >> 63) & 0x7FFFFFFFFFFFFFFFll;
+    return __longlong_as_double(k);
+}
+__device__ __forceinline__ long long warp_max_key(long long k) {
+    const int hi = (int)(k >> 32);
+    const int hmax = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo = hi == hmax ? (unsigned)k : 0u;
+    const unsigned lmax = __reduce_max_sync(0xffffffffu, lo);
+    return ((long long)hmax << 32) | (long long)lmax;
+}
+
 // all threads get the result; smem must hold T/32 values; deterministic order
 template <int T = kThreads>
 __device__ __forceinline__ double block_sum(double v, double *smem) {

@@ -2,6 +2,8 @@
 // ABI (abi_host.cu) and the device-resident filter (abi_filter.cu).  Everything here takes DEVICE
 // pointers and a stream and never synchronises.
 #pragma once
+#include <algorithm>
+
 #include "filter.cuh"
 #include "host.hpp"
 

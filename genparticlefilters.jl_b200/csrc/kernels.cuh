@@ -27,36 +27,35 @@ __device__ __forceinline__ void blk_to_tile(int64_t, int64_t &f, int64_t &tile) 
 }
 
 // tile epilogue shared by every kernel that produces log-weights: the K1 partials of the tile.
-// sm: 2*(T/32) doubles, smi: T/32 ints.  Cross-warp combines run in one warp (fixed shuffle tree:
-// deterministic), not redundantly in every thread.
+// sm: 2*(T/32) doubles, smi: T/32 ints.  The maximum is reduced exactly in the integer key domain (REDUX),
+// the sums with fixed shuffle trees in one warp: deterministic.
 template <int T = kThreads>
 __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, double *sm,
-                                              int *smi) {
+                                              int *smi, int64_t slot = -1) {
+    if (slot < 0) slot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;  // grid = (tiles, filters)
     constexpr int NW = T / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int fl = 0;
-    double m = -INFINITY;
+    long long key = f64_key(v[0]);
+    int fl = (v[0] != v[0]) ? 1 : 0;
 #pragma unroll
-    for (int k = 0; k < kTile / T; ++k) {
-        fl |= isnan(v[k]) ? 1 : 0;
-        m = fmax(m, v[k]);
+    for (int k = 1; k < kTile / T; ++k) {
+        fl |= (v[k] != v[k]) ? 1 : 0;
+        key = max(key, f64_key(v[k]));
     }
-    m = warp_max(m);
+    key = warp_max_key(key);
     fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    long long *smk = reinterpret_cast<long long *>(sm);
     __syncthreads();
     if (lane == 0) {
-        sm[warp] = m;
+        smk[warp] = key;
         smi[warp] = fl;
     }
     __syncthreads();
-    // every thread needs the block max: lane l reads cell l mod NW, butterfly over NW lanes
-    m = sm[lane & (NW - 1)];
-    fl = smi[lane & (NW - 1)];
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) {
-        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        fl |= __shfl_xor_sync(0xffffffffu, fl, o);
-    }
+    // every thread needs the block max: lane l reads cell l mod NW, REDUX over the warp
+    key = warp_max_key(smk[lane & (NW - 1)]);
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)smi[lane & (NW - 1)]);
+    // all NaN / empty maps to the minimum key: treat as -Inf (the NaN flag carries the diagnosis)
+    const double m = key == (long long)0x8000000000000000ull ? -INFINITY : f64_from_key(key);
     double s = 0.0, s2 = 0.0;
     if (m == INFINITY) {
         fl |= 2;
@@ -85,10 +84,10 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
         if (lane == 0) {
-            out.m[blockIdx.y * gridDim.x + blockIdx.x] = m;
-            out.s[blockIdx.y * gridDim.x + blockIdx.x] = s;
-            out.s2[blockIdx.y * gridDim.x + blockIdx.x] = s2;
-            out.flags[blockIdx.y * gridDim.x + blockIdx.x] = fl;
+            out.m[slot] = m;
+            out.s[slot] = s;
+            out.s2[slot] = s2;
+            out.flags[slot] = fl;
         }
     }
 }
@@ -97,7 +96,7 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
 // Replaces: Gen.logsumexp, lognorm/softmax (utils.jl:100-107), safe_softmax's validity scan
 // (utils.jl:119-137), effective_sample_size (utils.jl:163-164).  Same block size and epilogue as the
 // state-producing kernels, so the partials are bit-identical to theirs.
-constexpr int kReduceThreads = 512;
+constexpr int kReduceThreads = 256;  // 8 particles per thread: four 16-byte loads in flight each, reductions amortised
 static __global__ void __launch_bounds__(kReduceThreads) k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out) {
     constexpr int T = kReduceThreads;
     __shared__ double sm[2 * (T / 32)];
@@ -729,10 +728,37 @@ static __global__ void __launch_bounds__(kThreads)
 //   C. W16: the closing weight of every 16-particle group of the tile         (7 steps in 1 KB, L2)
 //   D. the 16 weights of the group                                            (4 steps in one 128-B line)
 constexpr int kCoarseCap = 4096;
+constexpr int kSearchItems = 8;  // lookups advanced in lockstep per thread: 8 independent load chains
+
+// count of leading elements <= u in the monotone array a[0..cnt), cnt <= M = 2^k, branch-free, then clamped
+// to cnt-1: "first index with a[idx] > u, capped at the last".  All K lookups advance together so their
+// (dependent) loads overlap.
+template <int M, int K, typename Ptr>
+__device__ __forceinline__ void ub_lockstep(Ptr (&a)[K], const int (&cnt)[K], const double (&u)[K], int (&pos)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) pos[k] = 0;
+#pragma unroll
+    for (int half = M / 2; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int idx = pos[k] + half - 1;
+            const bool le = idx < cnt[k] && a[k][idx] <= u[k];
+            pos[k] += le ? half : 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const bool le = pos[k] < cnt[k] && a[k][pos[k]] <= u[k];
+        pos[k] += le ? 1 : 0;
+        pos[k] = min(pos[k], cnt[k] - 1);
+    }
+}
+
 template <typename IdxT, typename OutT>
 static __global__ void __launch_bounds__(kThreads)
     k_search(WTables wt, int64_t n_src, int64_t n_out, int64_t bpf, UniSrc uni, const IdxT *first_slot_O,
              OutT *parents, int64_t out_base, const Stats *stats, int gate) {
+    constexpr int K = kSearchItems;
     __shared__ double sA[kCoarseCap];
     int64_t f = blockIdx.y;
     int64_t blk = blockIdx.x;
@@ -747,22 +773,63 @@ static __global__ void __launch_bounds__(kThreads)
     const double *Wf = wt.W + f * n_src;
     const double *W16 = wt.W16 + f * n16;
     const double *TL = wt.tile_last + f * tpf;
-    const int64_t strideA = (tpf + kCoarseCap - 1) / kCoarseCap;
-    const int64_t nA = (tpf + strideA - 1) / strideA;
-    for (int64_t c = threadIdx.x; c < nA; c += kThreads) sA[c] = TL[min((c + 1) * strideA, tpf) - 1];
+    const int64_t strideA = (tpf + kCoarseCap - 1) / kCoarseCap;  // <= 64 up to 2^29 particles (host checks)
+    const int nA = (int)((tpf + strideA - 1) / strideA);
+    for (int c = threadIdx.x; c < nA; c += kThreads) sA[c] = TL[min((c + 1) * strideA, tpf) - 1];
     __syncthreads();
     const int64_t first = first_slot_O ? (int64_t)first_slot_O[f * n_src + n_src - 1] : 0;
-    for (int64_t j = blk * (int64_t)kTile + threadIdx.x; j < min(n_out, (blk + 1) * (int64_t)kTile); j += kThreads) {
-        if (j < first) continue;
-        const double u = uni(f * n_out + j);
-        const int64_t a = upper_bound_clamped<double, double>(sA, nA, u);
-        const int64_t t0 = a * strideA, t1 = min(t0 + strideA, tpf);
-        const int64_t b = t0 + upper_bound_clamped<double, double>(TL + t0, t1 - t0, u);
-        const int64_t g0 = b * (kTile / 16), g1 = min(g0 + kTile / 16, n16);
-        const int64_t g = g0 + upper_bound_clamped<double, double>(W16 + g0, g1 - g0, u);
-        const int64_t k0 = g * 16, k1 = min(k0 + 16, n_src);
-        const int64_t k = k0 + upper_bound_clamped<double, double>(Wf + k0, k1 - k0, u);
-        parents[f * n_out + j] = (OutT)(k + out_base);
+    const int64_t j0 = blk * (int64_t)kTile;
+    double u[K];
+    bool live[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t j = j0 + k * kThreads + threadIdx.x;
+        live[k] = j < n_out && j >= first;
+        u[k] = live[k] ? uni(f * n_out + j) : 0.0;
+    }
+    // A: shared-memory sample
+    const double *pa[K];
+    int cnt[K], pos[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pa[k] = sA;
+        cnt[k] = nA;
+    }
+    ub_lockstep<kCoarseCap, K>(pa, cnt, u, pos);
+    // B: tile closing weights inside the sampled stride
+    int64_t tile[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t t0 = (int64_t)pos[k] * strideA;
+        pa[k] = TL + t0;
+        cnt[k] = (int)(min(t0 + strideA, tpf) - t0);
+        tile[k] = t0;
+    }
+    ub_lockstep<64, K>(pa, cnt, u, pos);  // strideA <= 64: up to 2^29 particles
+    // C: 16-particle group closing weights of the tile (128 per tile)
+    int64_t grp[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        tile[k] += pos[k];
+        const int64_t g0 = tile[k] * (kTile / 16);
+        pa[k] = W16 + g0;
+        cnt[k] = (int)(min(g0 + kTile / 16, n16) - g0);
+        grp[k] = g0;
+    }
+    ub_lockstep<kTile / 16, K>(pa, cnt, u, pos);
+    // D: the 16 weights of the group
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        grp[k] += pos[k];
+        const int64_t k0 = grp[k] * 16;
+        pa[k] = Wf + k0;
+        cnt[k] = (int)(min(k0 + 16, n_src) - k0);
+    }
+    ub_lockstep<16, K>(pa, cnt, u, pos);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t j = j0 + k * kThreads + threadIdx.x;
+        if (live[k]) parents[f * n_out + j] = (OutT)(grp[k] * 16 + pos[k] + out_base);
     }
 }
 
