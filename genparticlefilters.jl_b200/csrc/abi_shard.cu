@@ -25,7 +25,7 @@ struct ShardCtx {
     std::vector<void *> opened;
 };
 
-static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3; }
+static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3 + 4; }
 
 // fixed export order: for buf in {0,1}: for slot in {0,1}: f64 fields, u8 fields; then lw[buf 0], lw[buf 1], parents
 static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
@@ -37,6 +37,7 @@ static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
     out.push_back(pf->lw_by_buf[0]);
     out.push_back(pf->lw_by_buf[1]);
     out.push_back(pf->parents);
+    for (int k = 0; k < 4; ++k) out.push_back(pf->sc.part[0][k].p);  // K1 partial arrays (m, s, s2, flags)
 }
 
 template <class Model, class Noise>
@@ -55,11 +56,11 @@ static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, N
     if (a.mh_iters == 1) {
         GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, 1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), d, (const ShardRange *)sh->range, pf->n, tpf, sh->rank, noise);
+                     pf->slice(t - 2), pf->slice(t - 1), d, sh->oend_all, sh->world, pf->n, tpf, sh->rank, noise);
     } else {
         GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, -1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), d, (const ShardRange *)sh->range, pf->n, tpf, sh->rank, noise);
+                     pf->slice(t - 2), pf->slice(t - 1), d, sh->oend_all, sh->world, pf->n, tpf, sh->rank, noise);
     }
     return GENPF_OK;
 }
@@ -143,6 +144,9 @@ int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const
         sh->peer[0].lw[g] = (double *)ptrs[k++];
         sh->peer[1].lw[g] = (double *)ptrs[k++];
         sh->peer[0].parents[g] = sh->peer[1].parents[g] = (int32_t *)ptrs[k++];
+        Partials pp{(double *)ptrs[k], (double *)ptrs[k + 1], (double *)ptrs[k + 2], (int *)ptrs[k + 3]};
+        k += 4;
+        sh->peer[0].part[g] = sh->peer[1].part[g] = pp;
     }
     GENPF_TRY(pf->dalloc(&sh->shard_info, 2));
     GENPF_TRY(pf->dalloc(&sh->range, 1));
@@ -226,7 +230,6 @@ int32_t genpf_shard_push(genpf_filter_t pf, int64_t t, const double *obs_prev, c
     a.obs_prev_dev = a.obs_t_dev = nullptr;
     a.obs_prev = obs_prev[0];
     a.obs_t = obs_t[0];
-    GENPF_LAUNCH(k_shard_ranges, 1, 32, pf->stream, sh->oend_all, sh->world, sh->rank, (long long)sh->n_total, sh->range);
     int32_t st;
     switch (pf->model) {
         case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a); break;
@@ -244,9 +247,11 @@ int32_t genpf_shard_finish(genpf_filter_t pf) {
     pf->buf ^= 1;
     std::swap(pf->lw, pf->lw_alt);
     pf->n_resamples += 1;
-    // the received population's K1 partials (its tiles may have been written by two different ranks)
+    // full tiles arrived with their K1 partials; only tiles split between two producers are reduced here
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
     LwSrc src{pf->lw, 1.0};
-    GENPF_TRY(launch_reduce(pf->stream, src, pf->n, 1, pf->sc.partials(0)));
+    GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, pf->stream, src, sh->oend_all, sh->world,
+                 sh->rank, pf->n, pf->sc.partials(0));
     pf->part_valid = true;
     return GENPF_OK;
 }

@@ -102,8 +102,8 @@ static __global__ void __launch_bounds__(kStateThreads)
     k_propagate(ModelParams P, int64_t t, Cols prev, Cols next, double *lw, const double *obs_dev, double obs_val,
                 int64_t n, int64_t tpf, Noise noise, Partials partials) {
     constexpr int T = kStateThreads, I = kTile / T;
-    __shared__ double sm[2 * (T / 32)];
-    __shared__ int smi[T / 32];
+    __shared__ PartialSmem ps;
+    partial_smem_init(ps);
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t start = tile * kTile;
@@ -132,7 +132,7 @@ static __global__ void __launch_bounds__(kStateThreads)
     }
     store_slices<Model, T>(next, base, valid, sn);
     store_tile<double, T>(lw, base, valid, v);
-    emit_partials<T>(v, partials, sm, smi);
+    emit_partials<T>(v, partials, ps);
 }
 
 // ------------------------------------------------------------------ K11 MH rejuvenation (move-accept)

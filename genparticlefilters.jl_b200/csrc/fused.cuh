@@ -45,8 +45,9 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
-    __shared__ double smd[2 * (T / 32)];
-    __shared__ int smi[T / 32];
+    __shared__ PartialSmem ps;
+    __shared__ double smd[T / 32];
+    partial_smem_init(ps);  // ordered before the epilogue by block_expand's barriers
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t i0 = tile * kTile;
@@ -122,7 +123,7 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
         cnt = block_sum<T>(cnt, smd);
         if (threadIdx.x == 0 && cnt > 0.0) atomicAdd(&n_accept[f], (unsigned long long)cnt);
     }
-    emit_partials<T>(v, partials, smd, smi);
+    emit_partials<T>(v, partials, ps);
 }
 
 // ------------------------------------------------------------------ multi-GPU: source-side push
@@ -138,7 +139,17 @@ struct PeerDst {
     Cols dst_cur[kMaxPeers], dst_new[kMaxPeers];
     double *lw[kMaxPeers];
     int32_t *parents[kMaxPeers];
+    Partials part[kMaxPeers];  // the owner's K1 partial arrays (full tiles are reduced by their producer)
 };
+// [begin, end) of the global outputs rank `rank` parents, from the all-gathered closing counts (monotone by
+// construction: exact cover of [0, n_total), mirrored on the host in sharded.py::exchange_plan)
+__device__ __forceinline__ void shard_range(const long long *oend_all, int world, int rank, long long n_total,
+                                            long long &begin, long long &end) {
+    begin = 0;
+    for (int g = 0; g < rank; ++g) begin = max(begin, oend_all[g]);
+    end = max(begin, oend_all[rank]);
+    if (rank == world - 1) end = n_total;
+}
 struct ShardRange {  // device resident: written by k_shard_ranges
     long long out_begin, out_end;
 };
@@ -146,14 +157,17 @@ struct ShardRange {  // device resident: written by k_shard_ranges
 template <class Model, class Noise, typename IdxT, int MH>
 static __global__ void __launch_bounds__(kStateThreads, 2)
     k_step_push(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, PeerDst peer,
-                const ShardRange *range, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise) {
+                const long long *oend_all, int world, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
-    const int64_t out_begin = range->out_begin, out_end = range->out_end;
+    __shared__ PartialSmem ps;
+    partial_smem_init(ps);  // ordered before the epilogue by block_expand's barriers
+    long long out_begin, out_end;
+    shard_range(oend_all, world, rank, (long long)world * n_loc, out_begin, out_end);
     const int64_t tile = out_begin / kTile + blockIdx.x;  // global output tile
     const int64_t t0 = tile * kTile;
-    const int64_t i0 = max(t0, out_begin);
-    const int64_t i1 = min(t0 + (int64_t)kTile, out_end);
+    const int64_t i0 = max(t0, (int64_t)out_begin);
+    const int64_t i1 = min(t0 + (int64_t)kTile, (int64_t)out_end);
     if (i1 <= i0) return;  // uniform: beyond this rank's range
     const int valid = (int)(i1 - i0);
     const int owner = (int)(t0 / n_loc);
@@ -169,6 +183,7 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
     double *lw_dst = peer.lw[owner];
     int32_t *par_dst = peer.parents[owner];
     const int64_t gsrc = (int64_t)rank * n_loc + s0;  // global index of local source s0
+    double vall[I];
 #pragma unroll
     for (int j = 0; j < I / 2; ++j) {
         typename Model::Slice sc[2], sn[2];
@@ -219,7 +234,35 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
             store_pair<uint8_t>(dst_new.b[c] + lbase, e0, valid, fast, sn[0].b[c], sn[1].b[c]);
         }
         store_pair<double>(lw_dst + lbase, e0, valid, fast, v[0], v[1]);
+        vall[2 * j] = v[0];
+        vall[2 * j + 1] = v[1];
     }
+    // a full tile is reduced here and its K1 partial stored into the owner's arrays; the (at most world+1)
+    // tiles split between two producers are reduced by their owner after the barrier (k_reduce_boundary)
+    if (fast) emit_partials<T>(vall, peer.part[owner], ps, (t0 - (int64_t)owner * n_loc) / kTile);
+}
+
+// owner side: K1 partials of the tiles that two producers shared (global tile index = a range boundary)
+static __global__ void __launch_bounds__(kReduceThreads)
+    k_reduce_boundary(LwSrc src, const long long *oend_all, int world, int rank, int64_t n_loc, Partials out) {
+    constexpr int T = kReduceThreads;
+    __shared__ PartialSmem ps;
+    partial_smem_init(ps);
+    __syncthreads();
+    long long b, e;
+    shard_range(oend_all, world, (int)blockIdx.x, (long long)world * n_loc, b, e);
+    if (b % kTile == 0) return;                       // boundary on a tile edge: nothing was split
+    const int64_t gt = b / kTile;                     // the split tile
+    if (gt / (n_loc / kTile) != rank) return;         // not mine
+    for (int g = 0; g < (int)blockIdx.x; ++g) {       // several boundaries can fall into one tile: reduce it once
+        long long bg, eg;
+        shard_range(oend_all, world, g, (long long)world * n_loc, bg, eg);
+        if (bg % kTile != 0 && bg / kTile == gt) return;
+    }
+    const int64_t lt = gt - (int64_t)rank * (n_loc / kTile);
+    double v[kTile / T];
+    load_tile<T>(src, lt * kTile, kTile, v, -INFINITY);
+    emit_partials<T>(v, out, ps, lt);
 }
 
 // global statistics from the all-gathered per-shard (max, sum e, sum e^2); one thread (world <= 8)
@@ -269,17 +312,6 @@ static __global__ void k_shard_combine(const double *gathered, int world, int ra
     if (lml_accum && st.do_resample) lml_accum[0] += st.lse - log((double)n_total);
 }
 
-// output range [begin, end) this rank parents, from the all-gathered closing counts (monotone by construction)
-static __global__ void k_shard_ranges(const long long *oend_all, int world, int rank, long long n_total,
-                                      ShardRange *range) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    long long begin = 0;
-    for (int g = 0; g < rank; ++g) begin = max(begin, oend_all[g]);
-    long long end = max(begin, oend_all[rank]);
-    if (rank == world - 1) end = n_total;
-    range->out_begin = begin;
-    range->out_end = end;
-}
 static __global__ void k_shard_oend(const int32_t *tile_last_O, int64_t tpf, long long *oend_local) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *oend_local = (long long)tile_last_O[tpf - 1];
 }

@@ -27,13 +27,21 @@ __device__ __forceinline__ void blk_to_tile(int64_t, int64_t &f, int64_t &tile) 
 }
 
 // tile epilogue shared by every kernel that produces log-weights: the K1 partials of the tile.
-// sm: 2*(T/32) doubles, smi: T/32 ints.  The maximum is reduced exactly in the integer key domain (REDUX),
-// the sums with fixed shuffle trees in one warp: deterministic.
+// The maximum is reduced exactly in the integer key domain (REDUX), the sums with fixed shuffle trees in one
+// warp: deterministic.  (A barrier-free variant -- per-warp maxima, last-arriving warp combines -- was
+// measured and is slightly slower: the kernels are instruction-issue bound, not barrier bound.)
+struct PartialSmem {
+    double m[32], s[32], s2[32];
+    int fl[32];
+    unsigned count;
+};
+__device__ __forceinline__ void partial_smem_init(PartialSmem &) {}
 template <int T = kThreads>
-__device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, double *sm,
-                                              int *smi, int64_t slot = -1) {
+__device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, PartialSmem &ps,
+                                              int64_t slot = -1) {
     if (slot < 0) slot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;  // grid = (tiles, filters)
     constexpr int NW = T / 32;
+    constexpr long long kMinKey = (long long)0x8000000000000000ull;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long key = f64_key(v[0]);
     int fl = (v[0] != v[0]) ? 1 : 0;
@@ -44,18 +52,18 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
     }
     key = warp_max_key(key);
     fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
-    long long *smk = reinterpret_cast<long long *>(sm);
+    long long *smk = reinterpret_cast<long long *>(ps.m);
     __syncthreads();
     if (lane == 0) {
         smk[warp] = key;
-        smi[warp] = fl;
+        ps.fl[warp] = fl;
     }
     __syncthreads();
     // every thread needs the block max: lane l reads cell l mod NW, REDUX over the warp
     key = warp_max_key(smk[lane & (NW - 1)]);
-    fl = __reduce_or_sync(0xffffffffu, (unsigned)smi[lane & (NW - 1)]);
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)ps.fl[lane & (NW - 1)]);
     // all NaN / empty maps to the minimum key: treat as -Inf (the NaN flag carries the diagnosis)
-    const double m = key == (long long)0x8000000000000000ull ? -INFINITY : f64_from_key(key);
+    const double m = key == kMinKey ? -INFINITY : f64_from_key(key);
     double s = 0.0, s2 = 0.0;
     if (m == INFINITY) {
         fl |= 2;
@@ -69,15 +77,14 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
     }
     s = warp_sum(s);
     s2 = warp_sum(s2);
-    __syncthreads();
     if (lane == 0) {
-        sm[warp] = s;
-        sm[NW + warp] = s2;
+        ps.s[warp] = s;
+        ps.s2[warp] = s2;
     }
     __syncthreads();
     if (warp == 0) {
-        s = sm[lane & (NW - 1)];
-        s2 = sm[NW + (lane & (NW - 1))];
+        s = ps.s[lane & (NW - 1)];
+        s2 = ps.s2[lane & (NW - 1)];
 #pragma unroll
         for (int o = NW / 2; o > 0; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -99,15 +106,15 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
 constexpr int kReduceThreads = 256;  // 8 particles per thread: four 16-byte loads in flight each, reductions amortised
 static __global__ void __launch_bounds__(kReduceThreads) k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out) {
     constexpr int T = kReduceThreads;
-    __shared__ double sm[2 * (T / 32)];
-    __shared__ int smi[T / 32];
+    __shared__ PartialSmem ps;
+    partial_smem_init(ps);
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t start = tile * kTile;
     const int64_t valid = min((int64_t)kTile, n - start);
     double v[kTile / T];
     load_tile<T>(src, f * n + start, valid, v, -INFINITY);
-    emit_partials<T>(v, out, sm, smi);
+    emit_partials<T>(v, out, ps);
 }
 
 // One block per filter.  Combines tile partials, classifies validity (utils.jl:119-137) and writes the
