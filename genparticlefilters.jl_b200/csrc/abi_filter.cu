@@ -360,6 +360,14 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
                      pf->sc.partials(0));
         return GENPF_OK;
     }
+    if (a.mh_iters == 0) {
+        GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 0>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads,
+                     pf->stream, a, (const int32_t *)pf->sc.O.as<int32_t>(),
+                     (const int32_t *)pf->sc.tile_last.as<int32_t>(), pf->slice(t - 2), pf->slice(t - 1),
+                     pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt, pf->n, tpf, noise,
+                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
+        return GENPF_OK;
+    }
     GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
                  (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                  pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,

@@ -75,7 +75,7 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
             const bool live = e < valid;
             const int64_t s = sbase + rel[k];  // rel is 0 for dead slots: always a valid address
             typename Model::Slice pp, cur;
-            if (first) {
+            if (MH == 0 || first) {
                 Model::initial(a.P_prev, pp);
             } else {
 #pragma unroll
@@ -87,8 +87,9 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
             for (int c = 0; c < Model::NF; ++c) cur.f[c] = __ldg(src_cur.f[c] + s);
 #pragma unroll
             for (int c = 0; c < Model::NB; ++c) cur.b[c] = __ldg(src_cur.b[c] + s);
-            double U_mh, Z_mh, U_acc, U_up, Z_up;
-            noise.both(obase + e, U_mh, Z_mh, U_acc, U_up, Z_up);  // dead slots draw too: no divergence
+            double U_mh = 0.5, Z_mh = 0.0, U_acc = 1.0, U_up, Z_up;
+            if (MH == 0) noise.up(obase + e, U_up, Z_up);  // no mh move: only the update's draws
+            else noise.both(obase + e, U_mh, Z_mh, U_acc, U_up, Z_up);  // dead slots draw too: no divergence
             bool ok = false;
             for (int it = 0; it < iters; ++it) {
                 if (MH < 0 && it > 0) noise.mh(obase + e, it, U_mh, Z_mh, U_acc);

@@ -32,3 +32,13 @@ def test_shard_world2():
     out = run_workers(2, 1 << 16, 29612)
     assert "cross_shard_fraction" in out
     run_workers(2, (1 << 20) + 2048 * 3, 29613)
+
+
+def test_shard_world_all_gpus():
+    """Every GPU of the box (4 or 8): CUDA-IPC peer tables, ranges and the P2P push with more than two ranks."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 3:
+        pytest.skip("needs >= 3 GPUs (gpurun --gpus 4|8)")
+    out = run_workers(ng, 1 << 16, 29614)
+    assert "cross_shard_fraction" in out
