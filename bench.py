@@ -266,7 +266,8 @@ def main():
         ranges, frac = sf.exchange_summary()
         shard_info = {"cross_shard_offspring_fraction": frac,
                       "nvlink_bytes_per_step_per_gpu": frac * n * 30.0,  # parents 4 + two slices 18 + lw 8
-                      "collectives_per_step": "2 all_gather (3 f64, 1 i64) + 1 barrier, NCCL on the filter stream"}
+                      "exchange_per_step": "24 B + 8 B + barrier per rank as NVLink P2P stores + epoch flags polled "
+                                           "in-kernel (no NCCL inside the step)"}
     # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
     L.check(lib.genpf_profile_begin())
     for _ in range(K):

@@ -92,6 +92,8 @@ SIGNATURES = {
     "genpf_shard_scan": (i32, [_vp]),
     "genpf_shard_push": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32]),
     "genpf_shard_finish": (i32, [_vp]),
+    "genpf_shard_step_p2p": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32]),
+    "genpf_shard_oend": (i32, [_vp, _vp, _i32p]),
     "genpf_shard_stats": (i32, [_vp, _dp, _dp, _i32p]),
     "genpf_profile_begin": (i32, []),
     "genpf_profile_end": (i32, [C.c_char_p, i64]),

@@ -22,10 +22,12 @@ struct ShardCtx {
     const long long *oend_all = nullptr;
     double *shard_info = nullptr;
     ShardRange *range = nullptr;
+    XchgPeers xp;                   // peer-mapped exchange blocks (xp.x[rank] is mine)
+    long long *oend_p2p = nullptr;  // oend_all for the p2p protocol (local copy filled by k_xchg_oend)
     std::vector<void *> opened;
 };
 
-static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3 + 4; }
+static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3 + 4 + 1; }
 
 // fixed export order: for buf in {0,1}: for slot in {0,1}: f64 fields, u8 fields; then lw[buf 0], lw[buf 1], parents
 static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
@@ -38,15 +40,15 @@ static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
     out.push_back(pf->lw_by_buf[1]);
     out.push_back(pf->parents);
     for (int k = 0; k < 4; ++k) out.push_back(pf->sc.part[0][k].p);  // K1 partial arrays (m, s, s2, flags)
+    out.push_back(pf->shard_xchg);                                   // exchange block (flags + payload)
 }
 
 template <class Model, class Noise>
-static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, Noise noise) {
+static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, Noise noise, const long long *oend_all) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     const int64_t t = a.t;
-    // upper bound on the tiles this rank can parent is unknown on the host (device-resident range): launch
-    // enough blocks for the whole population; blocks beyond the range exit immediately
-    const unsigned grid = (unsigned)(ceil_div(sh->n_total, kTile) + 1);
+    // the range is device resident: one block per local tile (+2 for the split tiles); blocks stride
+    const unsigned grid = (unsigned)(tpf + 2);
     const PeerDst &pd = sh->peer[pf->buf ^ 1];
     PeerDst d = pd;
     // the owner's spare set holds slice t-1 at parity (t-1)&1 and receives slice t at parity t&1
@@ -56,22 +58,45 @@ static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, N
     if (a.mh_iters == 1) {
         GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, 1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), d, sh->oend_all, sh->world, pf->n, tpf, sh->rank, noise);
+                     pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise);
     } else {
         GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, -1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), d, sh->oend_all, sh->world, pf->n, tpf, sh->rank, noise);
+                     pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise);
     }
     return GENPF_OK;
 }
 template <class Model>
-static int32_t push_model(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a) {
+static int32_t push_model(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, const long long *oend_all) {
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)a.t, 0};
-        return launch_push<Model, NoisePhilox53>(pf, sh, a, nz);
+        return launch_push<Model, NoisePhilox53>(pf, sh, a, nz, oend_all);
     }
     NoiseLean nz{pf->seed, (uint64_t)a.t, 0};
-    return launch_push<Model, NoiseLean>(pf, sh, a, nz);
+    return launch_push<Model, NoiseLean>(pf, sh, a, nz, oend_all);
+}
+
+static int32_t make_step_args(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                              const double *obs_t, const double *aux_t, int32_t mh_iters, StepArgs *out) {
+    if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "the sharded step must advance to t_cur + 1");
+    if (!obs_prev || !obs_t) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
+    if (mh_iters < 0 || mh_iters > 255) return fail(GENPF_ERR_INVALID_ARG, "mh_iters out of range");
+    const ModelInfo &mi = kModels[pf->model];
+    if (mi.naux > 0 && (!aux_prev || !aux_t)) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL");
+    StepArgs a;
+    a.P_prev = pf->P;
+    a.P_t = pf->P;
+    for (int i = 0; i < mi.naux; ++i) {
+        a.P_prev.aux[i] = aux_prev[i];
+        a.P_t.aux[i] = aux_t[i];
+    }
+    a.t = t;
+    a.mh_iters = mh_iters;
+    a.obs_prev_dev = a.obs_t_dev = nullptr;
+    a.obs_prev = obs_prev[0];
+    a.obs_t = obs_t[0];
+    *out = a;
+    return GENPF_OK;
 }
 
 }  // namespace genpf
@@ -85,6 +110,13 @@ int32_t genpf_shard_ipc_export(genpf_filter_t pf, void *handles, int64_t *n_bufs
     if (!n_bufs) return fail(GENPF_ERR_INVALID_ARG, "n_bufs is NULL");
     *n_bufs = n_export_bufs(pf);
     if (!handles) return GENPF_OK;
+    if (!pf->shard_xchg) {
+        Xchg *x = nullptr;
+        GENPF_TRY(pf->dalloc(&x, 1));
+        GENPF_CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(Xchg), pf->stream));
+        GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+        pf->shard_xchg = x;
+    }
     std::vector<void *> bufs;
     list_bufs(pf, bufs);
     cudaIpcMemHandle_t *h = reinterpret_cast<cudaIpcMemHandle_t *>(handles);
@@ -102,8 +134,7 @@ int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const
     if (pf->n % kTile != 0) return fail(GENPF_ERR_INVALID_ARG, "particles per shard must be a multiple of 2048");
     if (pf->flags & GENPF_KEEP_HISTORY) return fail(GENPF_ERR_UNSUPPORTED, "sharding with GENPF_KEEP_HISTORY");
     if ((int64_t)world * pf->n >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "total population must be < 2^31");
-    if (!stats_local_dev || !stats_all_dev || !oend_local_dev || !oend_all_dev)
-        return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_attach: NULL exchange buffer");
+    if (!pf->shard_xchg) return fail(GENPF_ERR_STATE, "call genpf_shard_ipc_export before genpf_shard_attach");
     if (world > 1 && !all_handles) return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_attach: NULL handles");
     ShardCtx *sh = new ShardCtx();
     sh->rank = rank;
@@ -147,7 +178,9 @@ int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const
         Partials pp{(double *)ptrs[k], (double *)ptrs[k + 1], (double *)ptrs[k + 2], (int *)ptrs[k + 3]};
         k += 4;
         sh->peer[0].part[g] = sh->peer[1].part[g] = pp;
+        sh->xp.x[g] = (Xchg *)ptrs[k++];
     }
+    GENPF_TRY(pf->dalloc(&sh->oend_p2p, kMaxPeers));
     GENPF_TRY(pf->dalloc(&sh->shard_info, 2));
     GENPF_TRY(pf->dalloc(&sh->range, 1));
     pf->rng_offset = 0;  // Philox counters are GLOBAL particle slots
@@ -180,6 +213,8 @@ int32_t genpf_shard_begin_step(genpf_filter_t pf) {
     if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
     ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    if (!sh->stats_local || !sh->stats_all || !sh->oend_local || !sh->oend_all)
+        return fail(GENPF_ERR_STATE, "no exchange buffers were attached (use genpf_shard_step_p2p)");
     // local statistics + locally normalised tile offsets; Stats starts with the three doubles (M, S, S2)
     GENPF_TRY(ensure_stats(pf, pf->sc.tile_off.as<double>(), -1.0, nullptr));
     GENPF_CUDA_TRY(cudaMemcpyAsync(sh->stats_local, pf->sc.st(0, 1), 3 * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -212,32 +247,82 @@ int32_t genpf_shard_push(genpf_filter_t pf, int64_t t, const double *obs_prev, c
                          const double *obs_t, const double *aux_t, int32_t mh_iters) {
     GENPF_TRY(check_filter(pf));
     if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
-    if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_push must advance to t_cur + 1");
-    if (!obs_prev || !obs_t) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
-    if (mh_iters < 0 || mh_iters > 255) return fail(GENPF_ERR_INVALID_ARG, "mh_iters out of range");
     ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
-    const ModelInfo &mi = kModels[pf->model];
-    if (mi.naux > 0 && (!aux_prev || !aux_t)) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL");
+    if (!sh->oend_all) return fail(GENPF_ERR_STATE, "no exchange buffers were attached (use genpf_shard_step_p2p)");
     StepArgs a;
-    a.P_prev = pf->P;
-    a.P_t = pf->P;
-    for (int i = 0; i < mi.naux; ++i) {
-        a.P_prev.aux[i] = aux_prev[i];
-        a.P_t.aux[i] = aux_t[i];
-    }
-    a.t = t;
-    a.mh_iters = mh_iters;
-    a.obs_prev_dev = a.obs_t_dev = nullptr;
-    a.obs_prev = obs_prev[0];
-    a.obs_t = obs_t[0];
+    GENPF_TRY(make_step_args(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, &a));
     int32_t st;
     switch (pf->model) {
-        case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a); break;
-        case kModelLinGauss1D: st = push_model<LinGauss1D>(pf, sh, a); break;
+        case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a, sh->oend_all); break;
+        case kModelLinGauss1D: st = push_model<LinGauss1D>(pf, sh, a, sh->oend_all); break;
         default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
     }
     GENPF_TRY(st);
     pf->t_cur = t;  // slices now live in the spare buffer set; genpf_shard_finish swaps after the barrier
+    return GENPF_OK;
+}
+
+// The whole sharded README iteration with the peer-memory exchange: no NCCL, no host synchronisation.
+int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                             const double *obs_t, const double *aux_t, int32_t mh_iters) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    StepArgs a;
+    GENPF_TRY(make_step_args(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, &a));
+    const int64_t n = pf->n, tpf = ceil_div(n, kTile);
+    Scratch &sc = pf->sc;
+    cudaStream_t s = pf->stream;
+    const unsigned long long epoch = (unsigned long long)pf->n_resamples + 1;
+    GENPF_TRY(sc.O.ensure((size_t)n * 4));
+    GENPF_TRY(sc.tile_last.ensure((size_t)tpf * 4));
+    // 1. local statistics (locally normalised tile offsets), post + gather + combine
+    GENPF_TRY(ensure_stats(pf, sc.tile_off.as<double>(), -1.0, nullptr));
+    GENPF_LAUNCH(k_xchg_stats_combine, 1, 32, s, (const Stats *)sc.st(0, 1), sh->xp, sh->world, sh->rank, epoch,
+                 sh->n_total, sc.st(0, 1), sh->shard_info, pf->lml);
+    // 2. shard-aware scan, closing counts exchanged
+    UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, epoch), 0};
+    StratArgs strat = make_strat(uni, sh->n_total);
+    LwSrc lw_src{pf->lw, 1.0};
+    GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, 1),
+                 (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr}, sc.O.as<int32_t>(),
+                 sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info, (int64_t)sh->rank * n,
+                 sc.chunk_info_ptr(n), Scratch::kChunkTiles);
+    GENPF_LAUNCH(k_xchg_oend, 1, 32, s, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->xp, sh->world, sh->rank,
+                 epoch, sh->oend_p2p);
+    // 3. offspring to their owners over NVLink, then the barrier
+    int32_t st;
+    switch (pf->model) {
+        case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a, sh->oend_p2p); break;
+        case kModelLinGauss1D: st = push_model<LinGauss1D>(pf, sh, a, sh->oend_p2p); break;
+        default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+    }
+    GENPF_TRY(st);
+    GENPF_LAUNCH(k_xchg_done, 1, 32, s, sh->xp, sh->world, sh->rank, epoch);
+    // 4. swap, K1 partials of the tiles two producers shared
+    pf->t_cur = t;
+    pf->buf ^= 1;
+    std::swap(pf->lw, pf->lw_alt);
+    pf->n_resamples += 1;
+    LwSrc src{pf->lw, 1.0};
+    GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, s, src, (const long long *)sh->oend_p2p,
+                 sh->world, sh->rank, n, sc.partials(0));
+    pf->part_valid = true;
+    return GENPF_OK;
+}
+
+// closing counts of the last step (host copy; synchronises) + the exchange error word
+int32_t genpf_shard_oend(genpf_filter_t pf, long long *oend_all_host, int32_t *error) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, sh->oend_p2p, sizeof(long long) * kMaxPeers, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned + kMaxPeers, &sh->xp.x[sh->rank]->error, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    if (oend_all_host)
+        for (int g = 0; g < sh->world; ++g) oend_all_host[g] = reinterpret_cast<long long *>(pf->h_pinned)[g];
+    if (error) *error = *reinterpret_cast<int *>(pf->h_pinned + kMaxPeers);
     return GENPF_OK;
 }
 

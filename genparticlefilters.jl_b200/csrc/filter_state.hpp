@@ -57,6 +57,7 @@ struct genpf_filter_s {
     double *lw = nullptr, *lw_alt = nullptr;
     double *lw_by_buf[2] = {nullptr, nullptr};  // identity of the two weight buffers (lw == lw_by_buf[buf])
     void *shard = nullptr;                      // ShardCtx (abi_shard.cu)
+    void *shard_xchg = nullptr;                 // peer-mapped exchange block (abi_shard.cu)
     int32_t *parents = nullptr;
     uint8_t *accepts = nullptr;
     unsigned long long *n_accept = nullptr;

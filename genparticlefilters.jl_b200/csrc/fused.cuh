@@ -165,11 +165,13 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
     partial_smem_init(ps);  // ordered before the epilogue by block_expand's barriers
     long long out_begin, out_end;
     shard_range(oend_all, world, rank, (long long)world * n_loc, out_begin, out_end);
-    const int64_t tile = out_begin / kTile + blockIdx.x;  // global output tile
+    // grid ~ one block per local tile (+2): balanced shards do one tile per block, a shard that parents more
+    // than its share loops (block-uniform trip count)
+    for (int64_t tile = out_begin / kTile + blockIdx.x; tile * kTile < out_end; tile += gridDim.x) {
     const int64_t t0 = tile * kTile;
     const int64_t i0 = max(t0, (int64_t)out_begin);
     const int64_t i1 = min(t0 + (int64_t)kTile, (int64_t)out_end);
-    if (i1 <= i0) return;  // uniform: beyond this rank's range
+    if (i1 <= i0) continue;
     const int valid = (int)(i1 - i0);
     const int owner = (int)(t0 / n_loc);
     const int64_t lbase = i0 - (int64_t)owner * n_loc;  // slot of output i0 inside the owner's shard
@@ -241,6 +243,123 @@ static __global__ void __launch_bounds__(kStateThreads, 2)
     // a full tile is reduced here and its K1 partial stored into the owner's arrays; the (at most world+1)
     // tiles split between two producers are reduced by their owner after the barrier (k_reduce_boundary)
     if (fast) emit_partials<T>(vall, peer.part[owner], ps, (t0 - (int64_t)owner * n_loc) / kTile);
+    __syncthreads();  // shared staging is reused by the next tile of this block
+    }
+}
+
+// ------------------------------------------------------------------ peer-memory exchange (replaces NCCL)
+// The three per-step exchanges move 24, 8 and 0 bytes per rank: NCCL's launch + protocol latency (tens of
+// microseconds each at 8 ranks) dwarfs the payload.  Every rank instead owns an Xchg block that all peers
+// have mapped (CUDA IPC); a rank posts its value into slot [rank] of EVERY peer's block with plain NVLink
+// stores, fences, then stores the step's epoch into the matching flag; readers spin on their local flags.
+// Epochs only grow, so nothing is ever reset.  A bounded spin (about 4 s) turns a lost peer into an error
+// code instead of a hang.
+struct Xchg {
+    double stats[kMaxPeers][3];
+    long long oend[kMaxPeers];
+    unsigned long long flag_stats[kMaxPeers], flag_oend[kMaxPeers], flag_done[kMaxPeers];
+    int error;
+};
+struct XchgPeers {
+    Xchg *x[kMaxPeers];
+};
+__device__ __forceinline__ void xchg_wait(volatile unsigned long long *flag, unsigned long long epoch, int *error) {
+    const long long t0 = clock64();
+    while (*flag < epoch) {
+        if (clock64() - t0 > 8000000000ll) {  // ~4 s at 2 GHz
+            *error = 1;
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+// post the local (M, S, S2), wait for everybody's, combine (k_shard_combine's arithmetic)
+static __global__ void k_xchg_stats_combine(const Stats *local, XchgPeers peers, int world, int rank,
+                                            unsigned long long epoch, int64_t n_total, Stats *stats,
+                                            double *shard_info, double *lml_accum) {
+    const int g = threadIdx.x;
+    Xchg *mine = peers.x[rank];
+    if (g < world) {
+        Xchg *dst = peers.x[g];
+        dst->stats[rank][0] = local->M;
+        dst->stats[rank][1] = local->S;
+        dst->stats[rank][2] = local->S2;
+        __threadfence_system();
+        *(volatile unsigned long long *)&dst->flag_stats[rank] = epoch;
+        xchg_wait(&mine->flag_stats[g], epoch, &mine->error);
+    }
+    __syncthreads();
+    if (g != 0) return;
+    const volatile double *gathered = &mine->stats[0][0];
+    double M = -INFINITY;
+    bool nan = false;
+    for (int r = 0; r < world; ++r) {
+        double m = gathered[3 * r];
+        if (isnan(m) || isnan(gathered[3 * r + 1])) nan = true;
+        M = fmax(M, m);
+    }
+    double S = 0.0, S2 = 0.0, prefix = 0.0, share_mine = 0.0;
+    const bool finite = M > -INFINITY && M < INFINITY;
+    for (int r = 0; r < world; ++r) {
+        double m = gathered[3 * r];
+        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
+        S += gathered[3 * r + 1] * sc;
+        S2 += gathered[3 * r + 2] * (sc * sc);
+    }
+    for (int r = 0; r < world; ++r) {
+        double m = gathered[3 * r];
+        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
+        double share = gathered[3 * r + 1] * sc / S;
+        if (r < rank) prefix += share;
+        if (r == rank) share_mine = share;
+    }
+    int kind = 0;
+    if (nan) kind = 1;
+    else if (M == -INFINITY) kind = 2;
+    else if (M == INFINITY || isnan(S)) kind = 4;
+    else if (S == 0.0) kind = 3;
+    Stats st;
+    st.M = M; st.S = S; st.S2 = S2;
+    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    st.ess = S * S / S2;
+    st.invalid_kind = kind;
+    st.do_resample = (kind == 1 || kind == 4) ? 0 : 1;
+    stats[0] = st;
+    if (kind == 2 || kind == 3) {
+        prefix = (double)rank / (double)world;
+        share_mine = 1.0 / (double)world;
+    }
+    shard_info[0] = prefix;
+    shard_info[1] = share_mine;
+    if (lml_accum && st.do_resample) lml_accum[0] += st.lse - log((double)n_total);
+}
+
+// post the shard's closing offspring count, wait for everybody's; oend_out[world] is what k_step_push reads
+static __global__ void k_xchg_oend(const int32_t *tile_last_O, int64_t tpf, XchgPeers peers, int world, int rank,
+                                   unsigned long long epoch, long long *oend_out) {
+    const int g = threadIdx.x;
+    Xchg *mine = peers.x[rank];
+    if (g < world) {
+        Xchg *dst = peers.x[g];
+        dst->oend[rank] = (long long)tile_last_O[tpf - 1];
+        __threadfence_system();
+        *(volatile unsigned long long *)&dst->flag_oend[rank] = epoch;
+        xchg_wait(&mine->flag_oend[g], epoch, &mine->error);
+        oend_out[g] = *(volatile long long *)&mine->oend[g];
+    }
+}
+
+// barrier after the push kernel (stream order makes its P2P stores precede this kernel's flag stores)
+static __global__ void k_xchg_done(XchgPeers peers, int world, int rank, unsigned long long epoch) {
+    const int g = threadIdx.x;
+    Xchg *mine = peers.x[rank];
+    if (g < world) {
+        __threadfence_system();
+        *(volatile unsigned long long *)&peers.x[g]->flag_done[rank] = epoch;
+        xchg_wait(&mine->flag_done[g], epoch, &mine->error);
+    }
 }
 
 // owner side: K1 partials of the tiles that two producers shared (global tile index = a range boundary)

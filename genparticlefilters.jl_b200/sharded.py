@@ -75,8 +75,11 @@ class ShardExchange:
 class ShardedFilter:
     """One device-plugin particle filter sharded over the ranks of the default process group."""
 
-    def __init__(self, model, n_local, seed=0, noise="lean"):
+    def __init__(self, model, n_local, seed=0, noise="lean", exchange="p2p"):
+        """exchange="p2p": the library's own peer-memory flag protocol (NVLink stores + epoch flags, no NCCL in
+        the step); exchange="nccl": torch.distributed collectives issued on the filter's stream."""
         import torch
+        self.exchange = exchange
         from .api import DevicePFState
         self.torch = torch
         self.lib = L.load()
@@ -113,6 +116,11 @@ class ShardedFilter:
         """ESS -> stratified resample -> mh(t-1) -> update(t) over the whole sharded population; asynchronous."""
         h = self.state._h
         op, ot = np.array([float(obs_prev)]), np.array([float(obs_t)])
+        if self.exchange == "p2p":
+            L.check(self.lib.genpf_shard_step_p2p(h, int(t), L.ptr(op), L.ptr(self._aux(t - 1)), L.ptr(ot),
+                                                  L.ptr(self._aux(t)), int(mh_iters)))
+            self.state.t = self.t = int(t)
+            return
         with self.torch.cuda.stream(self.stream):
             L.check(self.lib.genpf_shard_begin_step(h))
             self.ex.gather_stats()
@@ -132,8 +140,17 @@ class ShardedFilter:
 
     def exchange_summary(self):
         """Output ranges per rank and the cross-shard offspring fraction of the last step (synchronises)."""
-        self.state.sync()
-        ranges = exchange_plan(self.ex.oend_all.cpu().numpy(), self.n_total)
+        if self.exchange == "p2p":
+            oend = (C.c_longlong * 8)()
+            err = C.c_int32()
+            L.check(self.lib.genpf_shard_oend(self.state._h, oend, C.byref(err)))
+            if err.value:
+                raise L.GenPFError(L.ERR_STATE, "a peer timed out in the shard exchange")
+            oend_all = np.array(list(oend)[: self.world])
+        else:
+            self.state.sync()
+            oend_all = self.ex.oend_all.cpu().numpy()
+        ranges = exchange_plan(oend_all, self.n_total)
         return ranges, cross_shard_fraction(ranges, self.n_local)
 
     def log_ml_estimate(self):

@@ -235,6 +235,14 @@ int32_t genpf_shard_scan(genpf_filter_t pf);
 int32_t genpf_shard_push(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
                          const double *obs_t, const double *aux_t, int32_t mh_iters);
 int32_t genpf_shard_finish(genpf_filter_t pf);
+/* The whole sharded iteration with the library's own peer-memory exchange instead of host-issued collectives:
+ * the 24-byte / 8-byte / barrier exchanges are NVLink P2P stores + epoch flags polled inside tiny kernels
+ * (tens of microseconds faster per step than NCCL at 8 ranks).  Asynchronous; every rank must call it with
+ * the same t.  stats/oend buffers passed to genpf_shard_attach may be NULL when only this entry point is used. */
+int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                             const double *obs_t, const double *aux_t, int32_t mh_iters);
+/* closing offspring counts of the last p2p step + the exchange error word (1 = a peer timed out); synchronises */
+int32_t genpf_shard_oend(genpf_filter_t pf, long long *oend_all_host, int32_t *error);
 /* global ESS / accumulated log_ml_est / validity as of the last genpf_shard_scan (synchronises) */
 int32_t genpf_shard_stats(genpf_filter_t pf, double *ess, double *lml_est, int32_t *invalid_kind);
 

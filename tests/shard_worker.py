@@ -31,7 +31,7 @@ def main():
         y = y + (math.sin(t) if t > 3 else 0.0) + 0.01 * rng.normal()
         obs.append(y + 0.25 * rng.normal())
     model = g.DeviceModel("object_motion")
-    sf = ShardedFilter(model, n_local, seed=77)
+    sf = ShardedFilter(model, n_local, seed=77, exchange=os.environ.get("SHARD_EXCHANGE", "p2p"))
     sf.initialize(obs[0])
     ref = None
     if rank == 0:

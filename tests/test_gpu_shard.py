@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_workers(nproc, n_local, port):
-    env = dict(os.environ, SHARD_N_LOCAL=str(n_local))
+def run_workers(nproc, n_local, port, exchange="p2p"):
+    env = dict(os.environ, SHARD_N_LOCAL=str(n_local), SHARD_EXCHANGE=exchange)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "shard_worker.py")]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
@@ -32,6 +32,7 @@ def test_shard_world2():
     out = run_workers(2, 1 << 16, 29612)
     assert "cross_shard_fraction" in out
     run_workers(2, (1 << 20) + 2048 * 3, 29613)
+    run_workers(2, 1 << 16, 29615, exchange="nccl")  # host-issued NCCL collectives on the filter stream
 
 
 def test_shard_world_all_gpus():
