@@ -424,3 +424,25 @@ def test_chunked_large_filter(g, orc):
     st, p, lw_out, inc, kind = raw_resample(g, "stratified", np.full(n, -np.inf), r)
     assert kind == 2 and inc == -np.inf
     assert np.mean(p == np.arange(n)) > 0.999999
+
+
+@pytest.mark.parametrize("n", [1000, 2048, 70_001, 1 << 20])
+def test_sort_particles_ties_and_signed_zero(g, orc, n):
+    """sortperm(lp, rev=true) semantics of the hand-written radix sort: stable (ties keep ascending index),
+    Julia isless order (0.0 before -0.0 under rev), negative and positive keys, -Inf weights."""
+    rng = np.random.default_rng(n)
+    vals = np.array([0.0, -0.0, 1.5, -2.25, -2.25, 3.0, -np.inf, 1e-300, -1e-300])
+    lw = vals[rng.integers(0, len(vals), n)]
+    lw[rng.integers(0, n)] = 7.0  # a unique maximum
+    r = rng.random(n)
+    st, p, lw_out, inc, kind = raw_resample(g, "stratified", lw, r, flags=g._lib.SORT_PARTICLES)
+    assert st == 0 and kind == 0
+    # thousands of identical addends make the SEQUENTIAL fp64 cumulative sum drift linearly (~n*eps/2), so the
+    # reference here is the exact-cumsum oracle (long double), which the blocked GPU scan must match (SURVEY 8c)
+    p_ref, _, inc_ref, _ = orc.resample("stratified", lw, r, sort=True, exact=True)
+    order = orc.sortperm_desc(lw)
+    W_ref = orc.cumweights(orc.softmax(lw), order, exact=True)
+    check_parents(p, p_ref, W_ref, strat_u(r, n), order)
+    assert inc == pytest.approx(inc_ref, rel=RTOL)
+    # the permutation itself: ancestors of distinct weight classes appear in descending weight order
+    assert np.all(np.diff(lw[p]) <= 0)
