@@ -359,3 +359,32 @@ def test_device_priorities_and_check(g, orc):
     assert np.all(pf.log_weights == 0.0)
     with pytest.raises(g.GenPFErrorException, match="not recognized"):
         g.pf_resample(pf, "systematic")
+
+
+def test_baseline_size_step_properties(g):
+    """BASELINE size (2^24 particles): size-independent properties of the fused README iteration, and
+    equality with the separately issued calls."""
+    obs = readme_observations()
+    n = 1 << 24
+    model = g.DeviceModel("object_motion")
+    a = g.pf_initialize(model, (1,), obs[0], n, seed=5)
+    b = g.pf_initialize(model, (1,), obs[0], n, seed=5)
+    for t in range(2, 5):
+        ess = g.pf_step(a, t, obs[t - 2], obs[t - 1], method="stratified", ess_thresh=1.0)
+        assert 1.0 <= ess[0] <= n
+        p = a.parents
+        assert p[0] >= 0 and p[-1] < n and np.all(np.diff(p) >= 0)  # stratified ancestors are sorted
+        counts = np.bincount(p, minlength=n)
+        assert counts.sum() == n
+        lw = a.log_weights
+        assert np.all(np.isfinite(lw))
+        g.pf_resample(b, "stratified", sort_particles=False)
+        g.pf_rejuvenate(b, g.mh, (t - 1, obs[t - 2]))
+        g.pf_update(b, (t,), None, obs[t - 1])
+        np.testing.assert_array_equal(p, b.parents)
+        np.testing.assert_array_equal(lw, b.log_weights)
+        np.testing.assert_array_equal(a.field("y", t), b.field("y", t))
+    assert g.log_ml_estimate(a) == g.log_ml_estimate(b)
+    # moving flag is a Bool column: mean in [0,1], var = m(1-m)
+    m, v = g.mean(a, (4, "moving")), g.var(a, (4, "moving"))
+    assert 0.0 <= m <= 1.0 and v == pytest.approx(m * (1 - m), abs=1e-9)
