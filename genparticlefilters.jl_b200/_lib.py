@@ -15,7 +15,7 @@ OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_INVALID_WEIGHTS, ERR_UNKNOWN_METHOD = -1, -2, -3, -4
 ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = -5, -6, -7
 MULTINOMIAL, RESIDUAL, STRATIFIED = 0, 1, 2
-SORT_PARTICLES, SUBSTATE, INDEX_BASE1, DEVICE_PTRS, CHECK = 1, 2, 4, 8, 16
+SORT_PARTICLES, SUBSTATE, INDEX_BASE1, DEVICE_PTRS, CHECK, UNIFORMS_STRATA = 1, 2, 4, 8, 16, 32
 VALID, INV_NAN_INPUT, INV_ALL_NEGINF, INV_ZERO_TOTAL, INV_NAN_TOTAL = 0, 1, 2, 3, 4
 LAYOUT_CONTIGUOUS, LAYOUT_INTERLEAVED = 0, 1
 KEEPFIRST, SAMPLE = 0, 1

@@ -418,7 +418,7 @@ int32_t genpf_uniforms(uint64_t seed, uint64_t stream, int64_t n, uint32_t flags
     double *d_out;
     GENPF_TRY(stage_out(ws.aux1, out, n, dp, &d_out));
     UniSrc uni{nullptr, seed, stream, 0};
-    GENPF_LAUNCH(k_uniforms, grid_1d(n), 256, ws.stream, uni, n, d_out);
+    GENPF_LAUNCH(k_uniforms, grid_1d(n), 256, ws.stream, uni, n, d_out, (flags & GENPF_UNIFORMS_STRATA) ? 1 : 0);
     GENPF_TRY(copy_out(ws, d_out, out, n, dp));
     GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
     return GENPF_OK;

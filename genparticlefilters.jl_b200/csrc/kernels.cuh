@@ -419,42 +419,53 @@ __device__ __forceinline__ double strat_lower(const StratArgs &a, int64_t i1) {
     return a.pow2 ? im1 * a.step : im1 / (double)a.n;
 }
 __device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t i1) {
-    double r = a.uni(f * a.n + i1 - 1);
+    const int64_t slot = f * a.n + i1 - 1;
+    double r;
+    if (a.uni.col) r = a.uni.col[slot];
+    else r = strata_word(philox_at(a.uni.seed, a.uni.stream, (uint64_t)(slot + a.uni.offset) >> 2), slot + a.uni.offset);
     return __dadd_rn(__dmul_rn(r, a.step), strat_lower(a, i1));
 }
 // C(W) = #{i in 1..n : u_i <= W}.  Because u is non-decreasing in i this is a prefix count, and
 // parent_i = min{k : W_k >= u_i} (resample.jl:163-168) == min{k : C(W_k) >= i}.
 // J = int32 when n < 2^31 (single-instruction fp64<->int conversions), else int64.
-// Deliberately ONE out-of-line copy per J: inlined at every unrolled item (Philox rounds, the
-// non-power-of-two division, two fix-up loops) k_scan grew past 100 KB of SASS and thrashed the I-cache.
+// The Philox rounds live in ONE out-of-line function (inlined at every call site k_scan had grown past
+// 100 KB of SASS and thrashed the I-cache); a per-thread cache of the last block lets the four consecutive
+// particles of a thread share draws.
+static __device__ __noinline__ uint4 strata_block(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    return philox_at(seed, stream, ctr);
+}
+struct StrataCache {
+    uint64_t ctr;
+    uint4 blk;
+};
 template <typename J>
-static __device__ __noinline__ J strat_count_impl(const double *col, uint64_t seed, uint64_t stream, int64_t slot0,
-                                                  double step, J n, int pow2, double W) {
-    const double nd = (double)n;
+__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, double W, StrataCache &cache) {
+    const J n = (J)a.n;
+    const double nd = (double)a.n;
     const double x = W * nd;
     J j = x >= nd ? n : (x <= 0.0 ? (J)0 : (J)x);
     const bool near_edge = (x - (double)j) < 1e-6;
-    auto lower_of = [&](J i1) { return pow2 ? (double)(i1 - 1) * step : (double)(i1 - 1) / nd; };
+    auto lower_of = [&](J i1) { return a.pow2 ? (double)(i1 - 1) * a.step : (double)(i1 - 1) / nd; };
     auto u_of = [&](J i1) {
+        const int64_t slot = slot0 + (int64_t)i1 - 1;
         double r;
-        if (col) {
-            r = col[slot0 + (int64_t)i1 - 1];
+        if (a.uni.col) {
+            r = a.uni.col[slot];
         } else {
-            const uint4 o = philox_at(seed, stream, (uint64_t)(slot0 + (int64_t)i1 - 1));
-            r = u53(o.x, o.y);
+            const uint64_t ctr = (uint64_t)(slot + a.uni.offset) >> 2;
+            if (ctr != cache.ctr) {
+                cache.blk = strata_block(a.uni.seed, a.uni.stream, ctr);
+                cache.ctr = ctr;
+            }
+            r = strata_word(cache.blk, slot + a.uni.offset);
         }
-        return __dadd_rn(__dmul_rn(r, step), lower_of(i1));
+        return __dadd_rn(__dmul_rn(r, a.step), lower_of(i1));
     };
     // u_i >= lower_i, so a stratum whose lower bound already exceeds W needs no draw
     while (j < n && lower_of(j + 1) <= W && u_of(j + 1) <= W) ++j;
     if (near_edge)
         while (j > 0 && u_of(j) > W) --j;
     return j;
-}
-template <typename J>
-__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t f, double W) {
-    return strat_count_impl<J>(a.uni.col, a.uni.seed, a.uni.stream, f * a.n + (a.uni.col ? 0 : a.uni.offset), a.step,
-                               (J)a.n, a.pow2, W);
 }
 
 // ------------------------------------------------------------------ K3 normalise + scan
@@ -478,6 +489,11 @@ __device__ __forceinline__ void store_w_tables(const WTables &wt, int64_t fbase,
         if (e == valid - 1) wt.tile_last[f * tpf + tile] = W[k];
     }
 }
+
+// k_scan uses a BLOCKED layout: thread t owns the four consecutive particles 4t..4t+3 of the tile (two adjacent
+// 16-byte loads, one 16-byte store of the counts).  One sequential 4-add chain + one warp scan per thread
+// instead of two pair scans, and neighbouring particles query neighbouring strata, so a thread's four
+// threshold draws usually come from one cached Philox block.
 template <typename IdxT>
 static __global__ void __launch_bounds__(kScanThreads, 2)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, WTables wt, IdxT *O_out,
@@ -485,28 +501,68 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
            int64_t global_base = 0, const double *chunk_info = nullptr, int64_t chunk_tiles = 0) {
     // shard_info (multi-GPU particle sharding): {prefix, scale}: this shard's cumulative weights are
     // prefix + scale * (locally normalised tile offsets) + in-tile sums of globally normalised weights.
-    constexpr int T = kScanThreads, I = kTile / T;
-    __shared__ double sm[32];
+    constexpr int T = kScanThreads, I = 4, NW = T / 32;
+    static_assert(T * I == kTile, "blocked scan layout");
+    __shared__ double sm[NW];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const Stats st = stats[f];
     if (st.invalid_kind == 1 || st.invalid_kind == 4) return;
     if (gate && !st.do_resample) return;
     const int64_t start = tile * kTile;
-    const int64_t valid = min((int64_t)kTile, n - start);
-    double v[I], w[I], W[I];
-    load_tile<T>(src, f * n + start, valid, v, -INFINITY);
+    const int valid = (int)min((int64_t)kTile, n - start);
+    const int e0 = 4 * (int)threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[I];
+    {
+        const double *p = src.p + f * n + start;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && e0 + 3 < valid;
+        if (vec_ok) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(p + e0));
+            const double2 b = __ldg(reinterpret_cast<const double2 *>(p + e0 + 2));
+            v[0] = src.fix(a.x); v[1] = src.fix(a.y); v[2] = src.fix(b.x); v[3] = src.fix(b.y);
+        } else {
+#pragma unroll
+            for (int k = 0; k < I; ++k) v[k] = e0 + k < valid ? src.fix(__ldg(p + e0 + k)) : -INFINITY;
+        }
+    }
     const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
     const double inv_n = 1.0 / (double)strat.n;  // == n except for a shard of a multi-GPU population
     // w_i = e_i / S evaluated as e_i * (1/S): at most 1 ulp from the reference's division, far inside the
     // sequential-vs-parallel cumulative-sum noise that defines the documented tie class
     const double inv_S = 1.0 / st.S;
+    double W[I];
+    {
+        double run = 0.0;
 #pragma unroll
-    for (int k = 0; k < I; ++k) {
-        if (uniform) w[k] = tile_elem<T>(k) < valid ? inv_n : 0.0;
-        else w[k] = exp_nonpos(v[k] - st.M) * inv_S;
+        for (int k = 0; k < I; ++k) {
+            const double w = uniform ? (e0 + k < valid ? inv_n : 0.0) : exp_nonpos(v[k] - st.M) * inv_S;
+            run += w;
+            W[k] = run;  // inclusive within the thread
+        }
     }
-    tile_scan<double, T>(w, W, sm);
+    double inc = W[I - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    double lane_excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) lane_excl = 0.0;
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 16 warp totals
+        double t = lane < NW ? sm[lane] : 0.0;
+        double s = t;
+#pragma unroll
+        for (int o = 1; o < NW; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        const double ex = __shfl_up_sync(0xffffffffu, s, 1);
+        if (lane < NW) sm[lane] = lane == 0 ? 0.0 : ex;
+    }
+    __syncthreads();
     double off = tile_off[f * tpf + tile];
     if (chunk_info) {  // large filter: offsets were normalised per chunk of chunk_tiles tiles
         const int64_t nchunks = (tpf + chunk_tiles - 1) / chunk_tiles;
@@ -514,23 +570,45 @@ static __global__ void __launch_bounds__(kScanThreads, 2)
         off = ci[0] + ci[1] * off;
     }
     if (shard_info) off = shard_info[0] + shard_info[1] * off;
+    const double base_w = off + (sm[warp] + lane_excl);
 #pragma unroll
-    for (int k = 0; k < I; ++k) W[k] = off + W[k];
+    for (int k = 0; k < I; ++k) W[k] = base_w + W[k];
     if (wt.W) {
-        if (wt.W16) store_w_tables<T>(wt, f * n, n, tpf, f, tile, start, (int)valid, W);
-        else store_tile<double, T>(wt.W, f * n + start, valid, W);
+        double *pw = wt.W + f * n + start;
+#pragma unroll
+        for (int k = 0; k < I; ++k)
+            if (e0 + k < valid) pw[e0 + k] = W[k];
+        if (wt.W16) {
+            const int64_t n16 = (n + 15) >> 4;
+#pragma unroll
+            for (int k = 0; k < I; ++k) {
+                const int e = e0 + k;
+                if (e < valid && ((e & 15) == 15 || e == valid - 1)) wt.W16[f * n16 + ((start + e) >> 4)] = W[k];
+                if (e == valid - 1) wt.tile_last[f * tpf + tile] = W[k];
+            }
+        }
     }
     if (O_out) {
         IdxT O[I];
+        StrataCache cache;
+        cache.ctr = ~0ull;
+        const int64_t slot0 = f * strat.n;  // stratum slot of this filter's first stratum (nf > 1: n == strat.n)
 #pragma unroll
         for (int k = 0; k < I; ++k) {
-            const int e = tile_elem<T>(k);
-            O[k] = e < valid ? strat_count<IdxT>(strat, f, W[k]) : (IdxT)0;
+            const int e = e0 + k;
+            O[k] = e < valid ? strat_count<IdxT>(strat, slot0, W[k], cache) : (IdxT)0;
             // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
             if (global_base + start + e == strat.n - 1) O[k] = (IdxT)strat.n;
             if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];
         }
-        store_tile<IdxT, T>(O_out, f * n + start, valid, O);
+        IdxT *po = O_out + f * n + start;
+        if (sizeof(IdxT) == 4 && ((reinterpret_cast<uintptr_t>(po) & 15) == 0) && e0 + 3 < valid) {
+            *reinterpret_cast<int4 *>(po + e0) = make_int4((int)O[0], (int)O[1], (int)O[2], (int)O[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < I; ++k)
+                if (e0 + k < valid) po[e0 + k] = O[k];
+        }
     }
 }
 
@@ -1142,9 +1220,10 @@ static __global__ void k_materialize(LwSrc src, int64_t n, double *out) {
         out[i] = src.fix(src.p[i]);
 }
 
-static __global__ void k_uniforms(UniSrc uni, int64_t n, double *out) {
+static __global__ void k_uniforms(UniSrc uni, int64_t n, double *out, int strata) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = uni(i);
+        out[i] = strata ? strata_word(philox_at(uni.seed, uni.stream, (uint64_t)(i + uni.offset) >> 2), i + uni.offset)
+                        : uni(i);
 }
 
 template <typename A, typename B>

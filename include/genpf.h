@@ -51,6 +51,7 @@ extern "C" {
 #define GENPF_INDEX_BASE1 4u    /* parents written 1-based (Vector{Int}, view.jl:21) */
 #define GENPF_DEVICE_PTRS 8u    /* array arguments are device pointers (CUDA.jl CuArray) */
 #define GENPF_CHECK 16u         /* check=true: invalid weights => GENPF_ERR_INVALID_WEIGHTS */
+#define GENPF_UNIFORMS_STRATA 32u /* genpf_uniforms: the stratum-uniform convention (see genpf_resample) */
 
 /* invalid_kind: which branch of safe_softmax fired, utils.jl:119-137 */
 #define GENPF_VALID 0
@@ -102,7 +103,9 @@ int32_t genpf_normalize(const double *lw, int64_t n, uint32_t flags, double *log
  *   epilogue  update_weights! into lw_out[n_out]              resample.jl:190-218, resize.jl:424-438
  * log_prio == NULL  <=>  `log_priorities === state.log_weights` (resample.jl:193).
  * uniforms: n_out doubles in [0,1) (stratified: one per stratum; residual: slot j uses uniforms[j]);
- *           NULL => Philox4x32-10(seed, stream 0, counter = slot), 53-bit.
+ *           NULL => Philox4x32-10(seed, stream 0): multinomial/residual draw 53 bits with counter = slot;
+ *           stratified draws 32-bit stratum uniforms, four strata per counter:
+ *           r_i = (word[i & 3] of Philox(counter = i >> 2) + 0.5) * 2^-32  (genpf_uniforms reproduces both).
  * lml_increment = logsumexp(lw) - log(n_in)  (0 for GENPF_SUBSTATE); caller adds it to state.log_ml_est.
  * NaN weights (kinds 1, 4) leave parents_out / lw_out untouched (the reference crashes there). */
 int32_t genpf_resample(int32_t method, const double *lw, const double *log_prio, int64_t n_in, int64_t n_out,

@@ -52,6 +52,17 @@ double orc_uniform53(uint64_t seed, uint64_t stream, uint64_t idx) {
     return (double)(x >> 11) * 0x1.0p-53;
 }
 
+/* stratum uniforms as the CUDA library generates them: 32-bit, four strata per Philox block */
+double orc_uniform_strata(uint64_t seed, uint64_t stream, uint64_t idx) {
+    uint32_t o[4];
+    philox_at(seed, stream, idx >> 2, o);
+    return ((double)o[idx & 3] + 0.5) * 0x1.0p-32;
+}
+void orc_fill_uniform_strata(uint64_t seed, uint64_t stream, int64_t n, double *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) out[i] = orc_uniform_strata(seed, stream, (uint64_t)i);
+}
+
 void orc_fill_uniform53(uint64_t seed, uint64_t stream, int64_t n, double *out) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) out[i] = orc_uniform53(seed, stream, (uint64_t)i);
@@ -620,7 +631,7 @@ double orc_om_filter_step(orc_om_filter *f, const orc_om_params *p, int64_t t, d
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         f->w[i] = f->w[i] / s;
-        f->r[i] = orc_uniform53(f->seed, ORC_STREAM(1, t), (uint64_t)i);
+        f->r[i] = orc_uniform_strata(f->seed, ORC_STREAM(1, t), (uint64_t)i);
     }
     /* stratified merge loop (sequential, resample.jl:159-170) */
     orc_select_stratified(f->w, NULL, n, f->r, 0, f->parents);

@@ -36,6 +36,8 @@ enum { ORC_VALID = 0, ORC_INV_NAN_INPUT = 1, ORC_INV_ALL_NEGINF = 2, ORC_INV_ZER
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double orc_uniform53(uint64_t seed, uint64_t stream, uint64_t idx);
 void orc_fill_uniform53(uint64_t seed, uint64_t stream, int64_t n, double *out);
+double orc_uniform_strata(uint64_t seed, uint64_t stream, uint64_t idx);
+void orc_fill_uniform_strata(uint64_t seed, uint64_t stream, int64_t n, double *out);
 
 /* ---- Julia Base / Gen one-liners ---- */
 double orc_sum_pairwise(const double *a, int64_t n);      /* Base.sum: pairwise, 1024 block */

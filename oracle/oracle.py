@@ -36,6 +36,7 @@ def load(omp=False):
     sig = {
         "orc_uniform53": (d, [u64, u64, u64]),
         "orc_fill_uniform53": (None, [u64, u64, i64, _vp]),
+        "orc_fill_uniform_strata": (None, [u64, u64, i64, _vp]),
         "orc_sum_pairwise": (d, [_vp, i64]),
         "orc_logsumexp": (d, [_vp, i64]),
         "orc_lognorm": (None, [_vp, i64, _vp]),
@@ -86,6 +87,13 @@ def _f(a):
 def uniforms(seed, stream, n):
     out = np.empty(n)
     load().orc_fill_uniform53(seed, stream, n, _p(out))
+    return out
+
+
+def uniforms_strata(seed, stream, n):
+    """Stratum uniforms as the CUDA library generates them (32-bit, four strata per Philox block)."""
+    out = np.empty(n)
+    load().orc_fill_uniform_strata(seed, stream, n, _p(out))
     return out
 
 

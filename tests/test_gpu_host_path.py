@@ -82,6 +82,9 @@ def test_philox_uniforms_bit_exact(g, orc):
         out = np.empty(n)
         L.check(lib.genpf_uniforms(seed, stream, n, 0, L.ptr(out)))
         np.testing.assert_array_equal(out, orc.uniforms(seed, stream, n))
+        L.check(lib.genpf_uniforms(seed, stream, n, L.UNIFORMS_STRATA, L.ptr(out)))
+        np.testing.assert_array_equal(out, orc.uniforms_strata(seed, stream, n))
+        assert out.min() > 0.0 and out.max() < 1.0
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -254,8 +257,9 @@ def test_seeded_uniforms_match_supplied(g, orc):
     rng = np.random.default_rng(5)
     n = 30_000
     lw = rng.normal(0, 1, n)
-    u = orc.uniforms(42, 0, n)
     for method in ("multinomial", "residual", "stratified"):
+        # stratified draws 32-bit stratum uniforms (4 per Philox block), the others 53-bit per slot
+        u = orc.uniforms_strata(42, 0, n) if method == "stratified" else orc.uniforms(42, 0, n)
         a = raw_resample(g, method, lw, None, seed=42)[1]
         b = raw_resample(g, method, lw, u)[1]
         np.testing.assert_array_equal(a, b)
