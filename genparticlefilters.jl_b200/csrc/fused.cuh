@@ -39,7 +39,7 @@ __device__ __forceinline__ void store_pair(X *p, int e, int valid, bool fast, X 
 
 // MH: number of mh iterations known at compile time (1 = the README configuration) or -1 = a.mh_iters
 template <class Model, class Noise, typename IdxT, int MH>
-static __global__ void __launch_bounds__(kStateThreads, 2)
+static __global__ void __launch_bounds__(kStateThreads, 4)
     k_step_fused(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, Cols dst_cur,
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials) {
@@ -156,7 +156,7 @@ struct ShardRange {  // device resident: written by k_shard_ranges
 };
 
 template <class Model, class Noise, typename IdxT, int MH>
-static __global__ void __launch_bounds__(kStateThreads, 2)
+static __global__ void __launch_bounds__(kStateThreads, 4)
     k_step_push(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, PeerDst peer,
                 const long long *oend_all, int world, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise) {
     constexpr int T = kStateThreads, I = kTile / T;

@@ -495,7 +495,7 @@ __device__ __forceinline__ void store_w_tables(const WTables &wt, int64_t fbase,
 // instead of two pair scans, and neighbouring particles query neighbouring strata, so a thread's four
 // threshold draws usually come from one cached Philox block.
 template <typename IdxT>
-static __global__ void __launch_bounds__(kScanThreads, 2)
+static __global__ void __launch_bounds__(kScanThreads, 4)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, WTables wt, IdxT *O_out,
            IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info = nullptr,
            int64_t global_base = 0, const double *chunk_info = nullptr, int64_t chunk_tiles = 0) {
