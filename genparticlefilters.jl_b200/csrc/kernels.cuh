@@ -434,12 +434,16 @@ __device__ __forceinline__ double strat_u(const StratArgs &a, int64_t f, int64_t
 static __device__ __noinline__ uint4 strata_block(uint64_t seed, uint64_t stream, uint64_t ctr) {
     return philox_at(seed, stream, ctr);
 }
-struct StrataCache {
-    uint64_t ctr;
-    uint4 blk;
+// Warp-cooperative stratum draws: the 128 consecutive particles of a warp query ~128 consecutive strata, so
+// each lane draws the Philox blocks of 8 strata of a 256-stratum window (2 calls per lane instead of one per
+// particle, and no divergence); a query outside the window falls back to a direct draw.
+constexpr int kStrataWindow = 256;
+struct StrataWindow {
+    const uint32_t *words;  // shared memory, kStrataWindow words of this warp
+    int64_t base;           // global stratum slot of words[0]; < 0: no window (column uniforms)
 };
 template <typename J>
-__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, double W, StrataCache &cache) {
+__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, double W, const StrataWindow &win) {
     const J n = (J)a.n;
     const double nd = (double)a.n;
     const double x = W * nd;
@@ -452,12 +456,13 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
         if (a.uni.col) {
             r = a.uni.col[slot];
         } else {
-            const uint64_t ctr = (uint64_t)(slot + a.uni.offset) >> 2;
-            if (ctr != cache.ctr) {
-                cache.blk = strata_block(a.uni.seed, a.uni.stream, ctr);
-                cache.ctr = ctr;
+            const int64_t gs = slot + a.uni.offset;
+            const uint64_t rel = (uint64_t)(gs - win.base);
+            if (rel < (uint64_t)kStrataWindow) {
+                r = ((double)win.words[rel] + 0.5) * 0x1.0p-32;
+            } else {
+                r = strata_word(strata_block(a.uni.seed, a.uni.stream, (uint64_t)gs >> 2), gs);
             }
-            r = strata_word(cache.blk, slot + a.uni.offset);
         }
         return __dadd_rn(__dmul_rn(r, a.step), lower_of(i1));
     };
@@ -504,6 +509,7 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     constexpr int T = kScanThreads, I = 4, NW = T / 32;
     static_assert(T * I == kTile, "blocked scan layout");
     __shared__ double sm[NW];
+    __shared__ alignas(16) uint32_t swin[NW][kStrataWindow];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const Stats st = stats[f];
@@ -590,13 +596,25 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     }
     if (O_out) {
         IdxT O[I];
-        StrataCache cache;
-        cache.ctr = ~0ull;
         const int64_t slot0 = f * strat.n;  // stratum slot of this filter's first stratum (nf > 1: n == strat.n)
+        StrataWindow win{swin[warp], -1};
+        if (!strat.uni.col) {
+            // the warp's first query is at stratum floor(n * W_excl(lane 0)) + 1 or later
+            const double w_first = __shfl_sync(0xffffffffu, base_w, 0);
+            const double xf = w_first * (double)strat.n;
+            const int64_t jf = xf <= 0.0 ? 0 : (xf >= (double)strat.n ? strat.n : (int64_t)xf);
+            win.base = ((slot0 + jf + strat.uni.offset) >> 2) << 2;
+#pragma unroll
+            for (int h = 0; h < kStrataWindow / 128; ++h) {
+                const uint4 b = strata_block(strat.uni.seed, strat.uni.stream, (uint64_t)(win.base >> 2) + h * 32 + lane);
+                *reinterpret_cast<uint4 *>(&swin[warp][(h * 32 + lane) * 4]) = b;
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int k = 0; k < I; ++k) {
             const int e = e0 + k;
-            O[k] = e < valid ? strat_count<IdxT>(strat, slot0, W[k], cache) : (IdxT)0;
+            O[k] = e < valid ? strat_count<IdxT>(strat, slot0, W[k], win) : (IdxT)0;
             // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
             if (global_base + start + e == strat.n - 1) O[k] = (IdxT)strat.n;
             if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];

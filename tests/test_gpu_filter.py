@@ -239,10 +239,11 @@ def test_step_equals_separate_calls(g):
         assert g.log_ml_estimate(a) == g.log_ml_estimate(b)
 
 
-def test_batched_filters_match_single(g, orc):
-    """n_filters independent filters (views, view.jl:16-48; config 5) == each filter run alone."""
+@pytest.mark.parametrize("nf,n", [(7, 3000), (3, 3001), (5, 2049), (2, 1)])
+def test_batched_filters_match_single(g, orc, nf, n):
+    """n_filters independent filters (views, view.jl:16-48; config 5) == each filter run alone.
+    Odd n exercises the unaligned (scalar) load/store paths of every tile kernel."""
     rng = np.random.default_rng(13)
-    nf, n = 7, 3000
     model = g.DeviceModel("object_motion")
     batch = g.DevicePFState(model, n, n_filters=nf)
     obs1, obs2 = rng.normal(0, 0.3, nf), rng.normal(0, 0.3, nf)
@@ -250,11 +251,11 @@ def test_batched_filters_match_single(g, orc):
     U2, Z2 = rng.random(nf * n), rng.normal(size=nf * n)
     r = rng.random(nf * n)
     noisy_init(g, batch, obs1, U, Z)
-    ess = g.effective_sample_size(batch)
+    ess = np.atleast_1d(g.effective_sample_size(batch))
     g.pf_resample(batch, "stratified", sort_particles=False, uniforms=r)
     noisy_update(g, batch, 2, obs2, U2, Z2)
-    lml = g.log_ml_estimate(batch)
-    mean_b = g.mean(batch, (2, "y"))
+    lml = np.atleast_1d(g.log_ml_estimate(batch))
+    mean_b = np.atleast_1d(g.mean(batch, (2, "y")))
     for f in range(nf):
         sl = slice(f * n, (f + 1) * n)
         one = g.DevicePFState(model, n)
@@ -267,6 +268,17 @@ def test_batched_filters_match_single(g, orc):
         np.testing.assert_array_equal(batch.field("y", 2)[sl], one.field("y", 2))
         assert g.log_ml_estimate(one) == lml[f]
         assert g.mean(one, (2, "y")) == mean_b[f]
+    # the fused step on the batch (Philox noise keyed by the global slot f*n + i) == separate calls on the batch
+    a = g.pf_initialize(model, (1,), obs1, n, n_filters=nf, seed=3)
+    b = g.pf_initialize(model, (1,), obs1, n, n_filters=nf, seed=3)
+    g.pf_step(a, 2, obs1, obs2, method="stratified", ess_thresh=1.0)
+    g.pf_resample(b, "stratified", sort_particles=False)
+    g.pf_rejuvenate(b, g.mh, (1, obs1))
+    g.pf_update(b, (2,), None, obs2)
+    np.testing.assert_array_equal(a.parents, b.parents)
+    np.testing.assert_array_equal(a.log_weights, b.log_weights)
+    np.testing.assert_array_equal(a.field("y", 2), b.field("y", 2))
+    np.testing.assert_array_equal(a.field("moving", 1), b.field("moving", 1))
 
 
 def test_device_resizing(g, orc):
