@@ -252,7 +252,7 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
 // microseconds each at 8 ranks) dwarfs the payload.  Every rank instead owns an Xchg block that all peers
 // have mapped (CUDA IPC); a rank posts its value into slot [rank] of EVERY peer's block with plain NVLink
 // stores, fences, then stores the step's epoch into the matching flag; readers spin on their local flags.
-// Epochs only grow, so nothing is ever reset.  A bounded spin (about 4 s) turns a lost peer into an error
+// Epochs only grow, so nothing is ever reset.  A bounded spin (about 20 s) turns a lost peer into an error
 // code instead of a hang.
 struct Xchg {
     double stats[kMaxPeers][3];
@@ -266,7 +266,7 @@ struct XchgPeers {
 __device__ __forceinline__ void xchg_wait(volatile unsigned long long *flag, unsigned long long epoch, int *error) {
     const long long t0 = clock64();
     while (*flag < epoch) {
-        if (clock64() - t0 > 8000000000ll) {  // ~4 s at 2 GHz
+        if (clock64() - t0 > 40000000000ll) {  // ~20 s at 2 GHz
             *error = 1;
             break;
         }

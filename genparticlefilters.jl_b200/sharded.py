@@ -111,6 +111,10 @@ class ShardedFilter:
         o = np.array([float(obs1)])
         L.check(self.lib.genpf_shard_initialize(self.state._h, L.ptr(o), L.ptr(self._aux(1))))
         self.state.t = self.t = 1
+        # line the ranks up before the first step: the in-kernel exchange spins (bounded) on peers' flags
+        self.state.sync()
+        if self.world > 1:
+            self.ex.dist.barrier()
 
     def step(self, t, obs_prev, obs_t, mh_iters=1):
         """ESS -> stratified resample -> mh(t-1) -> update(t) over the whole sharded population; asynchronous."""
