@@ -52,10 +52,10 @@ static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const d
     const dim3 grid((unsigned)tpf, (unsigned)pf->nf);
     if (init) {
         GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
-                     pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
+                     pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew);
     } else {
         GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(t - 1),
-                     pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0));
+                     pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew);
     }
     return GENPF_OK;
 }
@@ -124,7 +124,7 @@ static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const doubl
 int32_t ensure_stats(genpf_filter_t pf, double *tile_off, double ess_frac, double *lml_accum) {
     if (!pf->part_valid) {
         LwSrc src{pf->lw, 1.0};
-        GENPF_TRY(launch_reduce(pf->stream, src, pf->n, pf->nf, pf->sc.partials(0)));
+        GENPF_TRY(launch_reduce(pf->stream, src, pf->n, pf->nf, pf->sc.partials(0), pf->ew));
         pf->part_valid = true;
     }
     return launch_finalize(pf->stream, pf->sc, pf->sc.partials(0), pf->n, pf->nf, pf->sc.st(0, pf->nf), tile_off, ess_frac,
@@ -238,6 +238,8 @@ static int32_t resize_spare(genpf_filter_t pf, int64_t n_new) {
     GENPF_TRY(pf->dalloc(&pf->lw_alt, (size_t)total));
     pf->dfree(pf->accepts);
     GENPF_TRY(pf->dalloc(&pf->accepts, (size_t)total));
+    pf->dfree(pf->ew);
+    GENPF_TRY(pf->dalloc(&pf->ew, (size_t)total));
     return GENPF_OK;
 }
 
@@ -320,7 +322,8 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
         d_u = pf->uni_buf.as<double>();
     }
     UniSrc uni{d_u, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
-    GENPF_TRY(select_ancestors<int32_t>(s, sc, method, sel, n, n_out, nf, st_sel, uni, flags, pf->parents, 0, gate));
+    GENPF_TRY(select_ancestors<int32_t>(s, sc, method, sel, n, n_out, nf, st_sel, uni, flags, pf->parents, 0, gate,
+                                        has_prio ? nullptr : (const double *)pf->ew));
     // gather the window into the other buffer; no-priority reweight fused in
     const int64_t tpf_out = ceil_div(n_out, kTile);
     GatherCols g = window_gather_cols(pf);
@@ -357,7 +360,7 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                      pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents,
                      pf->lw_alt, pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr,
-                     pf->sc.partials(0));
+                     pf->sc.partials(0), pf->ew);
         return GENPF_OK;
     }
     if (a.mh_iters == 0) {
@@ -365,13 +368,13 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
                      pf->stream, a, (const int32_t *)pf->sc.O.as<int32_t>(),
                      (const int32_t *)pf->sc.tile_last.as<int32_t>(), pf->slice(t - 2), pf->slice(t - 1),
                      pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt, pf->n, tpf, noise,
-                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
+                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew);
         return GENPF_OK;
     }
     GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
                  (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                  pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
-                 pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0));
+                 pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew);
     return GENPF_OK;
 }
 template <class Model>
@@ -424,7 +427,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, (unsigned)nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
                  (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr}, sc.O.as<int32_t>(),
                  sc.tile_last.as<int32_t>(), strat, 0, (const double *)nullptr, (int64_t)0, sc.chunk_info_ptr(n),
-                 Scratch::kChunkTiles);
+                 Scratch::kChunkTiles, (const double *)pf->ew, (const double *)sc.tile_scale.as<double>());
     int32_t st;
     switch (pf->model) {
         case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a); break;

@@ -27,7 +27,7 @@ struct ShardCtx {
     std::vector<void *> opened;
 };
 
-static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3 + 4 + 1; }
+static int n_export_bufs(genpf_filter_t pf) { return 4 * (pf->NF + pf->NB) + 3 + 4 + 1 + 1; }
 
 // fixed export order: for buf in {0,1}: for slot in {0,1}: f64 fields, u8 fields; then lw[buf 0], lw[buf 1], parents
 static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
@@ -41,6 +41,7 @@ static void list_bufs(genpf_filter_t pf, std::vector<void *> &out) {
     out.push_back(pf->parents);
     for (int k = 0; k < 4; ++k) out.push_back(pf->sc.part[0][k].p);  // K1 partial arrays (m, s, s2, flags)
     out.push_back(pf->shard_xchg);                                   // exchange block (flags + payload)
+    out.push_back(pf->ew);                                           // e_i column
 }
 
 template <class Model, class Noise>
@@ -179,6 +180,7 @@ int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const
         k += 4;
         sh->peer[0].part[g] = sh->peer[1].part[g] = pp;
         sh->xp.x[g] = (Xchg *)ptrs[k++];
+        sh->peer[0].ew[g] = sh->peer[1].ew[g] = (double *)ptrs[k++];
     }
     GENPF_TRY(pf->dalloc(&sh->oend_p2p, kMaxPeers));
     GENPF_TRY(pf->dalloc(&sh->shard_info, 2));
@@ -238,7 +240,8 @@ int32_t genpf_shard_scan(genpf_filter_t pf) {
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, pf->stream, lw_src, n, tpf,
                  (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr},
                  sc.O.as<int32_t>(), sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info,
-                 (int64_t)sh->rank * n, sc.chunk_info_ptr(n), Scratch::kChunkTiles);
+                 (int64_t)sh->rank * n, sc.chunk_info_ptr(n), Scratch::kChunkTiles, (const double *)pf->ew,
+                 (const double *)sc.tile_scale.as<double>());
     GENPF_LAUNCH(k_shard_oend, 1, 32, pf->stream, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->oend_local);
     return GENPF_OK;
 }
@@ -288,7 +291,8 @@ int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pre
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, 1),
                  (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr}, sc.O.as<int32_t>(),
                  sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info, (int64_t)sh->rank * n,
-                 sc.chunk_info_ptr(n), Scratch::kChunkTiles);
+                 sc.chunk_info_ptr(n), Scratch::kChunkTiles, (const double *)pf->ew,
+                 (const double *)sc.tile_scale.as<double>());
     GENPF_LAUNCH(k_xchg_oend, 1, 32, s, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->xp, sh->world, sh->rank,
                  epoch, sh->oend_p2p);
     // 3. offspring to their owners over NVLink, then the barrier
@@ -307,7 +311,7 @@ int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pre
     pf->n_resamples += 1;
     LwSrc src{pf->lw, 1.0};
     GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, s, src, (const long long *)sh->oend_p2p,
-                 sh->world, sh->rank, n, sc.partials(0));
+                 sh->world, sh->rank, n, sc.partials(0), pf->ew);
     pf->part_valid = true;
     return GENPF_OK;
 }
@@ -336,7 +340,7 @@ int32_t genpf_shard_finish(genpf_filter_t pf) {
     ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
     LwSrc src{pf->lw, 1.0};
     GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, pf->stream, src, sh->oend_all, sh->world,
-                 sh->rank, pf->n, pf->sc.partials(0));
+                 sh->rank, pf->n, pf->sc.partials(0), pf->ew);
     pf->part_valid = true;
     return GENPF_OK;
 }

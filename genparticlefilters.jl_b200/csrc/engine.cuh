@@ -13,7 +13,7 @@ namespace genpf {
 struct Scratch {
     DevBuf part[3][4];  // three partial sets (lw, selection source, ratio d): m, s, s2, flags
     DevBuf stats;       // Stats[4 * nf]: [0] lw  [1] selection  [2] ratio d  [3] sorted selection
-    DevBuf tile_off, W, W16, W_tile_last, O, tile_last;
+    DevBuf tile_off, tile_scale, W, W16, W_tile_last, O, tile_last;
     DevBuf resid_c, resid_r, resid_coff, resid_roff, resid_rtot;
     DevBuf sort_tmp, sorted_keys, order, prio_col;
     DevBuf moment_partial, moment_out;
@@ -34,6 +34,7 @@ struct Scratch {
         }
         GENPF_TRY(stats.ensure(sizeof(Stats) * 4 * (size_t)nf));
         GENPF_TRY(tile_off.ensure(np * 8));
+        GENPF_TRY(tile_scale.ensure(np * 8));
         GENPF_TRY(moment_partial.ensure(np * 8));
         GENPF_TRY(moment_out.ensure((size_t)nf * 8 * 2));
         return GENPF_OK;
@@ -42,32 +43,34 @@ struct Scratch {
     Stats *st(int k, int64_t nf) { return stats.as<Stats>() + (size_t)k * nf; }
     void release() {
         for (auto &a : part) for (auto &b : a) b.release();
-        for (DevBuf *b : {&stats, &tile_off, &W, &W16, &W_tile_last, &O, &tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
+        for (DevBuf *b : {&stats, &tile_off, &tile_scale, &W, &W16, &W_tile_last, &O, &tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
                           &sort_tmp, &sorted_keys, &order, &prio_col, &moment_partial, &moment_out, &misc, &chunk_stats, &chunk_info})
             b->release();
     }
 };
 
-inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, Partials part) {
+inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, Partials part, double *ew = nullptr) {
     const int64_t tpf = ceil_div(n, kTile);
-    GENPF_LAUNCH(k_reduce, dim3((unsigned)tpf, (unsigned)nf), kReduceThreads, s, src, n, tpf, part);
+    GENPF_LAUNCH(k_reduce, dim3((unsigned)tpf, (unsigned)nf), kReduceThreads, s, src, n, tpf, part, ew);
     return GENPF_OK;
 }
 inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64_t n, int64_t nf, Stats *st,
                                double *tile_off, double ess_frac, double *lml_accum) {
     const int64_t tpf = ceil_div(n, kTile);
     if (tpf <= 8 * 64) {
-        GENPF_LAUNCH((k_finalize_fast<64>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf);
+        GENPF_LAUNCH((k_finalize_fast<64>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf,
+                     sc.tile_scale.as<double>());
     } else if (tpf <= Scratch::kChunkTiles) {
         GENPF_LAUNCH((k_finalize_fast<1024>), dim3(1, (unsigned)nf), 1024, s, part, n, tpf, st, tile_off, ess_frac,
-                     lml_accum, tpf);
+                     lml_accum, tpf, sc.tile_scale.as<double>());
     } else {
         // large filter: per-chunk finalize, then combine (statistics, validity, lml, chunk {prefix, scale})
         const int64_t nchunks = ceil_div(tpf, Scratch::kChunkTiles);
         GENPF_TRY(sc.chunk_stats.ensure(sizeof(Stats) * (size_t)(nchunks * nf)));
         GENPF_TRY(sc.chunk_info.ensure(16 * (size_t)(nchunks * nf)));
         GENPF_LAUNCH((k_finalize_fast<1024>), dim3((unsigned)nchunks, (unsigned)nf), 1024, s, part, n, tpf,
-                     sc.chunk_stats.as<Stats>(), tile_off, -1.0, (double *)nullptr, Scratch::kChunkTiles);
+                     sc.chunk_stats.as<Stats>(), tile_off, -1.0, (double *)nullptr, Scratch::kChunkTiles,
+                     sc.tile_scale.as<double>());
         GENPF_LAUNCH(k_chunk_combine, (unsigned)nf, 32, s, (const Stats *)sc.chunk_stats.as<Stats>(), (int)nchunks, n,
                      Scratch::kChunkTiles * (int64_t)kTile, st, sc.chunk_info.as<double>(), ess_frac, lml_accum);
     }
@@ -91,7 +94,7 @@ inline StratArgs make_strat(UniSrc uni, int64_t n) {
 template <typename IdxT, typename OutT>
 int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, int64_t n_in, int64_t n_out,
                            int64_t nf, Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base,
-                           int gate) {
+                           int gate, const double *ew = nullptr) {
     const int64_t tpf_in = ceil_div(n_in, kTile), tpf_out = ceil_div(n_out, kTile);
     GENPF_TRY(sc.O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
     GENPF_TRY(sc.tile_last.ensure((size_t)(tpf_in * nf) * sizeof(IdxT)));
@@ -120,9 +123,10 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
             order = sc.order.as<int32_t>();
         }
         StratArgs strat = make_strat(uni, n_in);
+        const double *ew_use = order ? nullptr : ew;  // e_i is stored in particle order
         GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
                      WTables{nullptr, nullptr, nullptr}, O, tile_last, strat, gate, (const double *)nullptr, (int64_t)0,
-                     sc.chunk_info_ptr(n_in), Scratch::kChunkTiles);
+                     sc.chunk_info_ptr(n_in), Scratch::kChunkTiles, ew_use, (const double *)sc.tile_scale.as<double>());
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0);
     } else if (method == GENPF_MULTINOMIAL) {
@@ -167,12 +171,13 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
 
 template <typename OutT>
 int32_t select_ancestors(cudaStream_t s, Scratch &sc, int method, LwSrc sel, int64_t n_in, int64_t n_out, int64_t nf,
-                         Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base, int gate) {
+                         Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base, int gate,
+                         const double *ew = nullptr) {
     if (n_in < 0x7FFFFFF0ll && n_out < 0x7FFFFFF0ll)
         return select_ancestors_t<int32_t, OutT>(s, sc, method, sel, n_in, n_out, nf, st_sel, uni, flags, parents,
-                                                 out_base, gate);
+                                                 out_base, gate, ew);
     return select_ancestors_t<long long, OutT>(s, sc, method, sel, n_in, n_out, nf, st_sel, uni, flags, parents,
-                                               out_base, gate);
+                                               out_base, gate, ew);
 }
 
 // mean / var of column x under softmax(lw) (statistics.jl:13-17,48-54); results in sc.moment_out[0..nf) and [nf..2nf)

@@ -100,7 +100,7 @@ __device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_
 template <class Model, class Noise, bool INIT>
 static __global__ void __launch_bounds__(kStateThreads)
     k_propagate(ModelParams P, int64_t t, Cols prev, Cols next, double *lw, const double *obs_dev, double obs_val,
-                int64_t n, int64_t tpf, Noise noise, Partials partials) {
+                int64_t n, int64_t tpf, Noise noise, Partials partials, double *ew) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ PartialSmem ps;
     partial_smem_init(ps);
@@ -132,7 +132,7 @@ static __global__ void __launch_bounds__(kStateThreads)
     }
     store_slices<Model, T>(next, base, valid, sn);
     store_tile<double, T>(lw, base, valid, v);
-    emit_partials<T>(v, partials, ps);
+    emit_partials<T>(v, partials, ps, -1, ew ? ew + base : nullptr, (int)valid);
 }
 
 // ------------------------------------------------------------------ K11 MH rejuvenation (move-accept)

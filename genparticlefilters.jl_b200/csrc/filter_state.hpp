@@ -55,6 +55,7 @@ struct genpf_filter_s {
     Cols win[2][2];  // [buffer][slot parity]
     int buf = 0;
     double *lw = nullptr, *lw_alt = nullptr;
+    double *ew = nullptr;  // e_i = exp(lw_i - m_tile), valid whenever part_valid (written with the K1 partials)
     double *lw_by_buf[2] = {nullptr, nullptr};  // identity of the two weight buffers (lw == lw_by_buf[buf])
     void *shard = nullptr;                      // ShardCtx (abi_shard.cu)
     void *shard_xchg = nullptr;                 // peer-mapped exchange block (abi_shard.cu)
@@ -112,6 +113,7 @@ struct genpf_filter_s {
         GENPF_TRY(dalloc(&lw_alt, (size_t)total));
         lw_by_buf[0] = lw;
         lw_by_buf[1] = lw_alt;
+        GENPF_TRY(dalloc(&ew, (size_t)total));
         GENPF_TRY(dalloc(&parents, (size_t)total));
         GENPF_TRY(dalloc(&accepts, (size_t)total));
         GENPF_TRY(sc.ensure(n_new, nf));
@@ -120,7 +122,8 @@ struct genpf_filter_s {
     void free_population() {
         for (int b = 0; b < 2; ++b)
             for (int sl = 0; sl < 2; ++sl) free_cols(win[b][sl]);
-        dfree(lw); dfree(lw_alt); dfree(parents); dfree(accepts);
+        dfree(lw); dfree(lw_alt); dfree(parents); dfree(accepts); dfree(ew);
+        ew = nullptr;
         lw = lw_alt = nullptr; parents = nullptr; accepts = nullptr;
     }
     Cols &slice(int64_t tau) { return win[buf][tau & 1]; }

@@ -42,7 +42,7 @@ template <class Model, class Noise, typename IdxT, int MH>
 static __global__ void __launch_bounds__(kStateThreads, 4)
     k_step_fused(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, Cols dst_cur,
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
-                 uint8_t *accepts, unsigned long long *n_accept, Partials partials) {
+                 uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
@@ -124,7 +124,7 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
         cnt = block_sum<T>(cnt, smd);
         if (threadIdx.x == 0 && cnt > 0.0) atomicAdd(&n_accept[f], (unsigned long long)cnt);
     }
-    emit_partials<T>(v, partials, ps);
+    emit_partials<T>(v, partials, ps, -1, ew ? ew + obase : nullptr, valid);
 }
 
 // ------------------------------------------------------------------ multi-GPU: source-side push
@@ -141,6 +141,7 @@ struct PeerDst {
     double *lw[kMaxPeers];
     int32_t *parents[kMaxPeers];
     Partials part[kMaxPeers];  // the owner's K1 partial arrays (full tiles are reduced by their producer)
+    double *ew[kMaxPeers];     // the owner's e_i = exp(lw_i - m_tile) column
 };
 // [begin, end) of the global outputs rank `rank` parents, from the all-gathered closing counts (monotone by
 // construction: exact cover of [0, n_total), mirrored on the host in sharded.py::exchange_plan)
@@ -242,7 +243,8 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
     }
     // a full tile is reduced here and its K1 partial stored into the owner's arrays; the (at most world+1)
     // tiles split between two producers are reduced by their owner after the barrier (k_reduce_boundary)
-    if (fast) emit_partials<T>(vall, peer.part[owner], ps, (t0 - (int64_t)owner * n_loc) / kTile);
+    if (fast) emit_partials<T>(vall, peer.part[owner], ps, (t0 - (int64_t)owner * n_loc) / kTile,
+                               peer.ew[owner] + (t0 - (int64_t)owner * n_loc), kTile);
     __syncthreads();  // shared staging is reused by the next tile of this block
     }
 }
@@ -364,7 +366,8 @@ static __global__ void k_xchg_done(XchgPeers peers, int world, int rank, unsigne
 
 // owner side: K1 partials of the tiles that two producers shared (global tile index = a range boundary)
 static __global__ void __launch_bounds__(kReduceThreads)
-    k_reduce_boundary(LwSrc src, const long long *oend_all, int world, int rank, int64_t n_loc, Partials out) {
+    k_reduce_boundary(LwSrc src, const long long *oend_all, int world, int rank, int64_t n_loc, Partials out,
+                      double *ew) {
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
     partial_smem_init(ps);
@@ -382,7 +385,7 @@ static __global__ void __launch_bounds__(kReduceThreads)
     const int64_t lt = gt - (int64_t)rank * (n_loc / kTile);
     double v[kTile / T];
     load_tile<T>(src, lt * kTile, kTile, v, -INFINITY);
-    emit_partials<T>(v, out, ps, lt);
+    emit_partials<T>(v, out, ps, lt, ew + lt * kTile, kTile);
 }
 
 // global statistics from the all-gathered per-shard (max, sum e, sum e^2); one thread (world <= 8)

@@ -38,7 +38,9 @@ struct PartialSmem {
 __device__ __forceinline__ void partial_smem_init(PartialSmem &) {}
 template <int T = kThreads>
 __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, PartialSmem &ps,
-                                              int64_t slot = -1) {
+                                              int64_t slot = -1, double *e_tile = nullptr, int e_valid = kTile) {
+    // e_tile (optional): this tile's slice of the filter's `ew` column; receives e_i = exp(v_i - m_tile), so the
+    // next scan forms w_i = e_i * (exp(m_tile - M) / S) with one multiply instead of a second fp64 exp
     if (slot < 0) slot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;  // grid = (tiles, filters)
     constexpr int NW = T / 32;
     constexpr long long kMinKey = (long long)0x8000000000000000ull;
@@ -65,16 +67,20 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
     // all NaN / empty maps to the minimum key: treat as -Inf (the NaN flag carries the diagnosis)
     const double m = key == kMinKey ? -INFINITY : f64_from_key(key);
     double s = 0.0, s2 = 0.0;
+    double ev[kTile / T];
+#pragma unroll
+    for (int k = 0; k < kTile / T; ++k) ev[k] = 0.0;
     if (m == INFINITY) {
         fl |= 2;
     } else if (m > -INFINITY) {
 #pragma unroll
         for (int k = 0; k < kTile / T; ++k) {
-            double e = exp_nonpos(v[k] - m);
-            s += e;
-            s2 += e * e;
+            ev[k] = exp_nonpos(v[k] - m);
+            s += ev[k];
+            s2 += ev[k] * ev[k];
         }
     }
+    if (e_tile) store_tile<double, T>(e_tile, 0, e_valid, ev);
     s = warp_sum(s);
     s2 = warp_sum(s2);
     if (lane == 0) {
@@ -104,7 +110,8 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
 // (utils.jl:119-137), effective_sample_size (utils.jl:163-164).  Same block size and epilogue as the
 // state-producing kernels, so the partials are bit-identical to theirs.
 constexpr int kReduceThreads = 256;  // 8 particles per thread: four 16-byte loads in flight each, reductions amortised
-static __global__ void __launch_bounds__(kReduceThreads) k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out) {
+static __global__ void __launch_bounds__(kReduceThreads)
+    k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out, double *ew = nullptr) {
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
     partial_smem_init(ps);
@@ -114,7 +121,7 @@ static __global__ void __launch_bounds__(kReduceThreads) k_reduce(LwSrc src, int
     const int64_t valid = min((int64_t)kTile, n - start);
     double v[kTile / T];
     load_tile<T>(src, f * n + start, valid, v, -INFINITY);
-    emit_partials<T>(v, out, ps);
+    emit_partials<T>(v, out, ps, -1, ew ? ew + f * n + start : nullptr, (int)valid);
 }
 
 // One block per filter.  Combines tile partials, classifies validity (utils.jl:119-137) and writes the
@@ -217,7 +224,7 @@ static __global__ void __launch_bounds__(kThreads)
 template <int THREADS>
 static __global__ void __launch_bounds__(THREADS)
     k_finalize_fast(Partials in, int64_t n_all, int64_t tpf_all, Stats *stats, double *tile_off, double ess_frac,
-                    double *lml_accum, int64_t chunk_tiles) {
+                    double *lml_accum, int64_t chunk_tiles, double *tile_scale = nullptr) {
     // grid = (chunks, filters).  chunk_tiles == tpf_all: the block finalises a whole filter.  Otherwise it
     // finalises one CHUNK of a large filter as if it were a filter of its own (Stats at [f*chunks + c], tile
     // offsets normalised within the chunk); k_chunk_combine then produces the filter's statistics and each
@@ -236,6 +243,7 @@ static __global__ void __launch_bounds__(THREADS)
     in.s2 += f * tpf_all + tile0 - f * tpf;
     in.flags += f * tpf_all + tile0 - f * tpf;
     if (tile_off) tile_off += f * tpf_all + tile0 - f * tpf;
+    if (tile_scale) tile_scale += f * tpf_all + tile0 - f * tpf;
     stats += (int64_t)blockIdx.y * gridDim.x + blockIdx.x - f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double pm[C], ps[C], ps2[C];
@@ -317,6 +325,8 @@ static __global__ void __launch_bounds__(THREADS)
         if (b < tpf) {
             if (uniform) v = (double)min((int64_t)kTile, n - b * kTile) * inv_n;
             else if (kind == 0) v = ps[c] * sc[c] / S;
+            // per-tile factor turning e_i = exp(lw_i - m_tile) into the normalised weight
+            if (tile_scale) tile_scale[f * tpf + b] = kind == 0 ? sc[c] / S : 0.0;
         }
         double inc = v;
 #pragma unroll
@@ -503,7 +513,10 @@ template <typename IdxT>
 static __global__ void __launch_bounds__(kScanThreads, 4)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, WTables wt, IdxT *O_out,
            IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info = nullptr,
-           int64_t global_base = 0, const double *chunk_info = nullptr, int64_t chunk_tiles = 0) {
+           int64_t global_base = 0, const double *chunk_info = nullptr, int64_t chunk_tiles = 0,
+           const double *ew = nullptr, const double *tile_scale = nullptr) {
+    // ew / tile_scale (device filters): e_i = exp(lw_i - m_tile) stored by the kernel that produced lw and the
+    // per-tile factor exp(m_tile - M)/S from the finalize: w_i = e_i * factor, no exp in this kernel.
     // shard_info (multi-GPU particle sharding): {prefix, scale}: this shard's cumulative weights are
     // prefix + scale * (locally normalised tile offsets) + in-tile sums of globally normalised weights.
     constexpr int T = kScanThreads, I = 4, NW = T / 32;
@@ -520,16 +533,21 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     const int e0 = 4 * (int)threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double v[I];
+    const bool use_e = ew != nullptr;
     {
-        const double *p = src.p + f * n + start;
+        const double *p = (use_e ? ew : src.p) + f * n + start;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && e0 + 3 < valid;
         if (vec_ok) {
             const double2 a = __ldg(reinterpret_cast<const double2 *>(p + e0));
             const double2 b = __ldg(reinterpret_cast<const double2 *>(p + e0 + 2));
-            v[0] = src.fix(a.x); v[1] = src.fix(a.y); v[2] = src.fix(b.x); v[3] = src.fix(b.y);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
         } else {
 #pragma unroll
-            for (int k = 0; k < I; ++k) v[k] = e0 + k < valid ? src.fix(__ldg(p + e0 + k)) : -INFINITY;
+            for (int k = 0; k < I; ++k) v[k] = e0 + k < valid ? __ldg(p + e0 + k) : (use_e ? 0.0 : -INFINITY);
+        }
+        if (!use_e) {
+#pragma unroll
+            for (int k = 0; k < I; ++k) v[k] = src.fix(v[k]);
         }
     }
     const bool uniform = (st.invalid_kind == 2 || st.invalid_kind == 3);
@@ -537,12 +555,21 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     // w_i = e_i / S evaluated as e_i * (1/S): at most 1 ulp from the reference's division, far inside the
     // sequential-vs-parallel cumulative-sum noise that defines the documented tie class
     const double inv_S = 1.0 / st.S;
+    double escale = 0.0;
+    if (use_e) {
+        escale = tile_scale[f * tpf + tile];
+        if (chunk_info) escale *= chunk_info[2 * (f * ((tpf + chunk_tiles - 1) / chunk_tiles) + tile / chunk_tiles) + 1];
+        if (shard_info) escale *= shard_info[1];
+    }
     double W[I];
     {
         double run = 0.0;
 #pragma unroll
         for (int k = 0; k < I; ++k) {
-            const double w = uniform ? (e0 + k < valid ? inv_n : 0.0) : exp_nonpos(v[k] - st.M) * inv_S;
+            double w;
+            if (uniform) w = e0 + k < valid ? inv_n : 0.0;
+            else if (use_e) w = v[k] * escale;
+            else w = exp_nonpos(v[k] - st.M) * inv_S;
             run += w;
             W[k] = run;  // inclusive within the thread
         }
