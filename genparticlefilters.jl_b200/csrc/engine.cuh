@@ -13,7 +13,7 @@ namespace genpf {
 struct Scratch {
     DevBuf part[3][4];  // three partial sets (lw, selection source, ratio d): m, s, s2, flags
     DevBuf stats;       // Stats[4 * nf]: [0] lw  [1] selection  [2] ratio d  [3] sorted selection
-    DevBuf tile_off, tile_scale, W, W16, W_tile_last, O, tile_last;
+    DevBuf tile_off, tile_scale, W, O, tile_last, guide, guide_O, guide_tile_last;
     DevBuf resid_c, resid_r, resid_coff, resid_roff, resid_rtot;
     DevBuf sort_tmp, sorted_keys, order, prio_col;
     DevBuf moment_partial, moment_out;
@@ -43,7 +43,7 @@ struct Scratch {
     Stats *st(int k, int64_t nf) { return stats.as<Stats>() + (size_t)k * nf; }
     void release() {
         for (auto &a : part) for (auto &b : a) b.release();
-        for (DevBuf *b : {&stats, &tile_off, &tile_scale, &W, &W16, &W_tile_last, &O, &tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
+        for (DevBuf *b : {&stats, &tile_off, &tile_scale, &W, &O, &tile_last, &guide, &guide_O, &guide_tile_last, &resid_c, &resid_r, &resid_coff, &resid_roff, &resid_rtot,
                           &sort_tmp, &sorted_keys, &order, &prio_col, &moment_partial, &moment_out, &misc, &chunk_stats, &chunk_info})
             b->release();
     }
@@ -83,7 +83,19 @@ inline StratArgs make_strat(UniSrc uni, int64_t n) {
     a.step = 1.0 / (double)n;
     a.n = n;
     a.pow2 = (n & (n - 1)) == 0;
+    a.guide = 0;
     return a;
+}
+
+// guide-table size for the inverse-CDF lookups: two particles per bucket measured best (2^24: shift 0..5 within 15 %); the table stays L2 resident next to a
+// DRAM-sized W and the bracket inside one 32-byte sector of W (GENPF_GUIDE_SHIFT overrides, for tuning)
+inline int64_t guide_buckets(int64_t n) {
+    static const int shift = [] {
+        const char *e = getenv("GENPF_GUIDE_SHIFT");
+        return e ? atoi(e) : 1;
+    }();
+    const int64_t b = n >> shift;
+    return b > 0 ? b : 1;
 }
 
 // Ancestor selection given selection statistics `st_sel` + `tile_off` already computed for `sel`
@@ -131,22 +143,30 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      parents, out_base, st_sel, gate, 0);
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
-        GENPF_TRY(sc.W16.ensure((size_t)(((n_in + 15) >> 4) * nf) * 8));
-        GENPF_TRY(sc.W_tile_last.ensure((size_t)(tpf_in * nf) * 8));
-        WTables wt{sc.W.as<double>(), sc.W16.as<double>(), sc.W_tile_last.as<double>()};
-        StratArgs none = make_strat(uni, n_in);
+        const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
+        GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * sizeof(IdxT)));
+        WTables wt{sc.W.as<double>(), nullptr, nullptr};
+        StratArgs gs = make_strat(uni, n_in);
+        gs.guide = B;  // O = guide-table counts of the weight CDF
+        IdxT *G = sc.guide.as<IdxT>();
         GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     wt, (IdxT *)nullptr, (IdxT *)nullptr, none, gate, (const double *)nullptr, (int64_t)0,
+                     wt, O, tile_last, gs, gate, (const double *)nullptr, (int64_t)0,
                      sc.chunk_info_ptr(n_in), Scratch::kChunkTiles);
-        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, wt, n_in, n_out,
-                     tpf_out, uni, (const IdxT *)nullptr, parents, out_base, st_sel, gate);
+        GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, O, tile_last, n_in, B, tpf_b,
+                     (const int32_t *)nullptr, G, (int64_t)0, st_sel, gate, 0);
+        GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
+                     kThreads, s, (const double *)wt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)nullptr, parents,
+                     out_base, st_sel, gate);
     } else if (method == GENPF_RESIDUAL) {
         if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated residual resample is not supported");
         const size_t np = (size_t)(tpf_in * nf);
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
-        GENPF_TRY(sc.W16.ensure((size_t)(((n_in + 15) >> 4) * nf) * 8));
-        GENPF_TRY(sc.W_tile_last.ensure((size_t)(tpf_in * nf) * 8));
-        WTables rt{sc.W.as<double>(), sc.W16.as<double>(), sc.W_tile_last.as<double>()};
+        const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
+        GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * sizeof(IdxT)));
+        GENPF_TRY(sc.guide_O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
+        GENPF_TRY(sc.guide_tile_last.ensure((size_t)(tpf_in * nf) * sizeof(IdxT)));
+        WTables rt{sc.W.as<double>(), nullptr, nullptr};
+        IdxT *G = sc.guide.as<IdxT>(), *GO = sc.guide_O.as<IdxT>(), *GTL = sc.guide_tile_last.as<IdxT>();
         GENPF_TRY(sc.resid_c.ensure(np * 8));
         GENPF_TRY(sc.resid_r.ensure(np * 8));
         GENPF_TRY(sc.resid_coff.ensure(np * 8));
@@ -158,11 +178,14 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      sc.resid_coff.as<long long>(), sc.resid_roff.as<double>());
         GENPF_LAUNCH((k_resid_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kThreads, s, sel, n_in, n_out, tpf_in, st_sel,
                      sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
-                     tile_last, rt);
+                     tile_last, rt, GO, GTL, B);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
                      (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1);
-        GENPF_LAUNCH((k_search<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, rt, n_in, n_out,
-                     tpf_out, uni, (const IdxT *)O, parents, out_base, st_sel, 0);
+        GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, GO, GTL, n_in, B, tpf_b,
+                     (const int32_t *)nullptr, G, (int64_t)0, st_sel, 0, 0);
+        GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
+                     kThreads, s, (const double *)rt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)O, parents,
+                     out_base, st_sel, 0);
     } else {
         return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
     }

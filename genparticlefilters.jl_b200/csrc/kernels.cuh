@@ -423,7 +423,17 @@ struct StratArgs {
     double step;  // 1/n
     int64_t n;
     int pow2;
+    int64_t guide;  // B > 0: no strata; O_k = guide-table counts ceil(B * W_k) for the inverse-CDF lookup (k_lookup)
 };
+// Guide table for the inverse-CDF draws (multinomial, residual tail): bucket b of B covers u in [b/B, (b+1)/B);
+// G[b] = min{k : ceil(fl(B*W_k)) > b} is where a lookup with floor(fl(B*u)) == b starts.  The counts only need
+// to be monotone: k_lookup verifies every answer against W itself.
+template <typename J>
+__device__ __forceinline__ J guide_count(double W, int64_t B) {
+    const double nd = (double)B;
+    const double c = ceil(W * nd);
+    return c >= nd ? (J)B : (c <= 0.0 ? (J)0 : (J)c);
+}
 __device__ __forceinline__ double strat_lower(const StratArgs &a, int64_t i1) {
     const double im1 = a.n < 0x7FFFFFFFll ? (double)(int)(i1 - 1) : (double)(i1 - 1);
     return a.pow2 ? im1 * a.step : im1 / (double)a.n;
@@ -625,7 +635,7 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
         IdxT O[I];
         const int64_t slot0 = f * strat.n;  // stratum slot of this filter's first stratum (nf > 1: n == strat.n)
         StrataWindow win{swin[warp], -1};
-        if (!strat.uni.col) {
+        if (!strat.uni.col && !strat.guide) {
             // the warp's first query is at stratum floor(n * W_excl(lane 0)) + 1 or later
             const double w_first = __shfl_sync(0xffffffffu, base_w, 0);
             const double xf = w_first * (double)strat.n;
@@ -641,9 +651,11 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
 #pragma unroll
         for (int k = 0; k < I; ++k) {
             const int e = e0 + k;
-            O[k] = e < valid ? strat_count<IdxT>(strat, slot0, W[k], win) : (IdxT)0;
+            if (e >= valid) O[k] = (IdxT)0;
+            else if (strat.guide) O[k] = guide_count<IdxT>(W[k], strat.guide);
+            else O[k] = strat_count<IdxT>(strat, slot0, W[k], win);
             // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
-            if (global_base + start + e == strat.n - 1) O[k] = (IdxT)strat.n;
+            if (global_base + start + e == strat.n - 1) O[k] = (IdxT)(strat.guide ? strat.guide : strat.n);
             if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];
         }
         IdxT *po = O_out + f * n + start;
@@ -963,6 +975,77 @@ static __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Guide-table inverse CDF: parent_j = min{k : W_k > u_j} clamped to n_src-1 (rand(Categorical(w)),
+// resample.jl:59,113; resize.jl:61,117).  b = floor(n*u) picks the bucket, G[b] .. G[b+1] brackets the answer
+// (expected bracket length 1), and the answer is always re-checked against W: two or three scattered
+// sector reads per draw instead of a ~20-probe multi-level binary search.
+constexpr int kLookupItems = 4;
+template <typename IdxT, typename OutT>
+static __global__ void __launch_bounds__(kThreads)
+    k_lookup(const double *W, const IdxT *G, int64_t B, int64_t n_src, int64_t n_out, UniSrc uni,
+             const IdxT *first_slot_O, OutT *parents, int64_t out_base, const Stats *stats, int gate) {
+    constexpr int K = kLookupItems;
+    const int64_t f = blockIdx.y;
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+        if (gate && !stats[f].do_resample) return;
+    }
+    const double *Wf = W + f * n_src;
+    const IdxT *Gf = G + f * B;
+    const int64_t first = first_slot_O ? (int64_t)first_slot_O[f * n_src + n_src - 1] : 0;
+    const int64_t j0 = (int64_t)blockIdx.x * (kThreads * K);
+    const double nd = (double)B;
+    double u[K], wk[K];
+    int64_t lo[K], hi[K];
+    bool live[K], exact[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t j = j0 + k * kThreads + threadIdx.x;
+        live[k] = j < n_out && j >= first;
+        u[k] = live[k] ? uni(f * n_out + j) : 0.0;
+        const double x = u[k] * nd;
+        int64_t b = x >= nd ? B - 1 : (x <= 0.0 ? 0 : (int64_t)x);
+        // the bracket's lower end can only be wrong when n*u rounded onto the bucket boundary (or was clamped)
+        exact[k] = !(x > (double)b && x < nd);
+        lo[k] = b;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t b = lo[k];
+        lo[k] = (int64_t)__ldg(Gf + b);
+        hi[k] = b + 1 < B ? (int64_t)__ldg(Gf + b + 1) : n_src - 1;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) wk[k] = __ldg(Wf + lo[k]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (!live[k]) continue;
+        int64_t kk = lo[k];
+        double w = wk[k];
+        bool below_known = false;  // W[kk-1] <= u established by the search itself
+        if (hi[k] - kk > 8) {
+            int64_t a = kk, c = hi[k];
+            while (a < c) {
+                const int64_t mid = a + ((c - a) >> 1);
+                if (__ldg(Wf + mid) > u[k]) c = mid; else a = mid + 1;
+            }
+            below_known = a > kk;
+            kk = a;
+            w = __ldg(Wf + kk);
+        }
+        while (w <= u[k] && kk < n_src - 1) {
+            ++kk;
+            w = __ldg(Wf + kk);
+            below_known = true;
+        }
+        if (exact[k] && !below_known)
+            while (kk > 0 && __ldg(Wf + kk - 1) > u[k]) --kk;
+        const int64_t j = j0 + k * kThreads + threadIdx.x;
+        parents[f * n_out + j] = (OutT)(kk + out_base);
+    }
+}
+
 // ------------------------------------------------------------------ K6 residual
 // c_i = floor(n_out * w_i) literally (resample.jl:99, resize.jl:103); r_i = n_out*w_i - floor(n_out*w_i).
 struct ResidPartials {
@@ -1099,7 +1182,8 @@ static __global__ void __launch_bounds__(1024)
 template <typename IdxT>
 static __global__ void __launch_bounds__(kThreads)
     k_resid_scan(LwSrc src, int64_t n, int64_t n_out, int64_t tpf, const Stats *stats, const double *r_total,
-                 const long long *c_off, const double *r_off, IdxT *O_out, IdxT *tile_last_O, WTables rt) {
+                 const long long *c_off, const double *r_off, IdxT *O_out, IdxT *tile_last_O, WTables rt,
+                 IdxT *GO_out, IdxT *G_tile_last, int64_t B) {
     __shared__ double sm[32];
     __shared__ long long smi[32];
     int64_t f, tile;
@@ -1131,7 +1215,16 @@ static __global__ void __launch_bounds__(kThreads)
         if (tile_elem(k) == valid - 1) tile_last_O[f * tpf + tile] = O[k];
     }
     store_tile<IdxT>(O_out, f * n + start, valid, O);
-    store_w_tables<kThreads>(rt, f * n, n, tpf, f, tile, start, (int)valid, R);
+    store_tile<double, kThreads>(rt.W, f * n + start, valid, R);
+    // guide-table counts of the residual CDF (k_lookup)
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        const int e = tile_elem(k);
+        O[k] = e < valid ? guide_count<IdxT>(R[k], B) : (IdxT)0;
+        if (start + e == n - 1) O[k] = (IdxT)B;
+        if (e == valid - 1) G_tile_last[f * tpf + tile] = O[k];
+    }
+    store_tile<IdxT>(GO_out, f * n + start, valid, O);
 }
 
 // ------------------------------------------------------------------ K9 reweight after resample
