@@ -425,7 +425,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, (unsigned)nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
-                 (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr}, sc.O.as<int32_t>(),
+                 (const double *)sc.tile_off.as<double>(), WTables{nullptr}, sc.O.as<int32_t>(),
                  sc.tile_last.as<int32_t>(), strat, 0, (const double *)nullptr, (int64_t)0, sc.chunk_info_ptr(n),
                  Scratch::kChunkTiles, (const double *)pf->ew, (const double *)sc.tile_scale.as<double>());
     int32_t st;

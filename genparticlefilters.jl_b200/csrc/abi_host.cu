@@ -441,7 +441,7 @@ int32_t genpf_debug_cumweights(const double *lw, int64_t n, uint32_t flags, doub
     UniSrc uni{nullptr, 0, 0, 0};
     StratArgs none = make_strat(uni, n);
     GENPF_LAUNCH((k_scan<int32_t>), (unsigned)tpf, kScanThreads, ws.stream, src, n, tpf, ws.sc.st(0, 1),
-                 ws.sc.tile_off.as<double>(), WTables{d_W, nullptr, nullptr}, (int32_t *)nullptr, (int32_t *)nullptr, none, 0,
+                 ws.sc.tile_off.as<double>(), WTables{d_W}, (int32_t *)nullptr, (int32_t *)nullptr, none, 0,
                  (const double *)nullptr, (int64_t)0, ws.sc.chunk_info_ptr(n), Scratch::kChunkTiles);
     GENPF_TRY(copy_out(ws, d_W, W_out, n, dp));
     GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));

@@ -21,7 +21,6 @@ struct ShardCtx {
     long long *oend_local = nullptr;
     const long long *oend_all = nullptr;
     double *shard_info = nullptr;
-    ShardRange *range = nullptr;
     XchgPeers xp;                   // peer-mapped exchange blocks (xp.x[rank] is mine)
     long long *oend_p2p = nullptr;  // oend_all for the p2p protocol (local copy filled by k_xchg_oend)
     std::vector<void *> opened;
@@ -184,7 +183,6 @@ int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const
     }
     GENPF_TRY(pf->dalloc(&sh->oend_p2p, kMaxPeers));
     GENPF_TRY(pf->dalloc(&sh->shard_info, 2));
-    GENPF_TRY(pf->dalloc(&sh->range, 1));
     pf->rng_offset = 0;  // Philox counters are GLOBAL particle slots
     pf->shard = sh;
     return GENPF_OK;
@@ -238,7 +236,7 @@ int32_t genpf_shard_scan(genpf_filter_t pf) {
     StratArgs strat = make_strat(uni, sh->n_total);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, pf->stream, lw_src, n, tpf,
-                 (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr},
+                 (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), WTables{nullptr},
                  sc.O.as<int32_t>(), sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info,
                  (int64_t)sh->rank * n, sc.chunk_info_ptr(n), Scratch::kChunkTiles, (const double *)pf->ew,
                  (const double *)sc.tile_scale.as<double>());
@@ -289,7 +287,7 @@ int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pre
     StratArgs strat = make_strat(uni, sh->n_total);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, 1),
-                 (const double *)sc.tile_off.as<double>(), WTables{nullptr, nullptr, nullptr}, sc.O.as<int32_t>(),
+                 (const double *)sc.tile_off.as<double>(), WTables{nullptr}, sc.O.as<int32_t>(),
                  sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info, (int64_t)sh->rank * n,
                  sc.chunk_info_ptr(n), Scratch::kChunkTiles, (const double *)pf->ew,
                  (const double *)sc.tile_scale.as<double>());

@@ -137,7 +137,7 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         StratArgs strat = make_strat(uni, n_in);
         const double *ew_use = order ? nullptr : ew;  // e_i is stored in particle order
         GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     WTables{nullptr, nullptr, nullptr}, O, tile_last, strat, gate, (const double *)nullptr, (int64_t)0,
+                     WTables{nullptr}, O, tile_last, strat, gate, (const double *)nullptr, (int64_t)0,
                      sc.chunk_info_ptr(n_in), Scratch::kChunkTiles, ew_use, (const double *)sc.tile_scale.as<double>());
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0);
@@ -145,7 +145,7 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
         GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * sizeof(IdxT)));
-        WTables wt{sc.W.as<double>(), nullptr, nullptr};
+        WTables wt{sc.W.as<double>()};
         StratArgs gs = make_strat(uni, n_in);
         gs.guide = B;  // O = guide-table counts of the weight CDF
         IdxT *G = sc.guide.as<IdxT>();
@@ -165,7 +165,7 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * sizeof(IdxT)));
         GENPF_TRY(sc.guide_O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
         GENPF_TRY(sc.guide_tile_last.ensure((size_t)(tpf_in * nf) * sizeof(IdxT)));
-        WTables rt{sc.W.as<double>(), nullptr, nullptr};
+        WTables rt{sc.W.as<double>()};
         IdxT *G = sc.guide.as<IdxT>(), *GO = sc.guide_O.as<IdxT>(), *GTL = sc.guide_tile_last.as<IdxT>();
         GENPF_TRY(sc.resid_c.ensure(np * 8));
         GENPF_TRY(sc.resid_r.ensure(np * 8));

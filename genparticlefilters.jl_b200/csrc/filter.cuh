@@ -103,7 +103,6 @@ static __global__ void __launch_bounds__(kStateThreads)
                 int64_t n, int64_t tpf, Noise noise, Partials partials, double *ew) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ PartialSmem ps;
-    partial_smem_init(ps);
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t start = tile * kTile;

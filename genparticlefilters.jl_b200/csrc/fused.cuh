@@ -47,7 +47,6 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
     __shared__ double smd[T / 32];
-    partial_smem_init(ps);  // ordered before the epilogue by block_expand's barriers
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t i0 = tile * kTile;
@@ -152,10 +151,6 @@ __device__ __forceinline__ void shard_range(const long long *oend_all, int world
     end = max(begin, oend_all[rank]);
     if (rank == world - 1) end = n_total;
 }
-struct ShardRange {  // device resident: written by k_shard_ranges
-    long long out_begin, out_end;
-};
-
 template <class Model, class Noise, typename IdxT, int MH>
 static __global__ void __launch_bounds__(kStateThreads, 4)
     k_step_push(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, PeerDst peer,
@@ -163,7 +158,6 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
-    partial_smem_init(ps);  // ordered before the epilogue by block_expand's barriers
     long long out_begin, out_end;
     shard_range(oend_all, world, rank, (long long)world * n_loc, out_begin, out_end);
     // grid ~ one block per local tile (+2): balanced shards do one tile per block, a shard that parents more
@@ -370,7 +364,6 @@ static __global__ void __launch_bounds__(kReduceThreads)
                       double *ew) {
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
-    partial_smem_init(ps);
     __syncthreads();
     long long b, e;
     shard_range(oend_all, world, (int)blockIdx.x, (long long)world * n_loc, b, e);

@@ -55,11 +55,12 @@ inline cudaEvent_t prof_mark(cudaStream_t s) {
 }
 
 // kernel launch + count (bench.py's gpu_launches) + launch-error check
-#define GENPF_LAUNCH(kernel, grid, block, stream, ...)                       \
+#define GENPF_LAUNCH(kernel, grid, block, stream, ...) GENPF_LAUNCH_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)
+#define GENPF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)            \
     do {                                                                     \
         cudaEvent_t _e0 = nullptr;                                           \
         if (::genpf::g_prof_on) _e0 = ::genpf::prof_mark(stream);            \
-        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);               \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
         if (::genpf::g_prof_on) ::genpf::g_prof.push_back({#kernel, _e0, ::genpf::prof_mark(stream)}); \
         ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed);         \
         GENPF_CUDA_TRY(cudaGetLastError());                                  \

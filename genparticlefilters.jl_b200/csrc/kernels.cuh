@@ -2,11 +2,11 @@
 //
 // Pipeline of one resample over n particles (per filter f; tile = 2048 particles):
 //   k_reduce    : tile partials (max, sum e^{v-max}, sum e^{2(v-max)}, NaN/+Inf flags)     [R 8 B/particle]
-//   k_finalize  : per filter M, S, S2, lse, ESS, invalid kind, exclusive tile offsets      [tiny]
+//   k_finalize_fast: per filter M, S, S2, lse, ESS, invalid kind, exclusive tile offsets      [tiny]
 //   k_scan      : w_i = e^{v_i-M}/S, in-tile fp64 inclusive scan + tile offset -> W_k,
 //                 and/or cumulative offspring counts O_k = #{i : u_i <= W_k}                [R 8, W 8 or 4]
 //   k_expand    : parent_i = min{k : O_k > i}  (load-balanced search, output centric)       [R ~4, W 4|8]
-//   k_search    : parent_j = min{k : W_k > u_j} (multinomial, residual tail)                [R 8 + search, W 4|8]
+//   k_lookup    : parent_j = min{k : W_k > u_j} (multinomial, residual tail), guide table   [R ~3 sectors, W 4|8]
 // The normalisation needs the global (M, S) before any cumulative weight exists, so a reduce pass is
 // unavoidable; given that pass, "reduce-then-scan" with a shared tile partition gives every tile its
 // exclusive prefix without the spinning of a decoupled look-back and is bit-deterministic.
@@ -35,7 +35,6 @@ struct PartialSmem {
     int fl[32];
     unsigned count;
 };
-__device__ __forceinline__ void partial_smem_init(PartialSmem &) {}
 template <int T = kThreads>
 __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], const Partials &out, PartialSmem &ps,
                                               int64_t slot = -1, double *e_tile = nullptr, int e_valid = kTile) {
@@ -114,7 +113,6 @@ static __global__ void __launch_bounds__(kReduceThreads)
     k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out, double *ew = nullptr) {
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
-    partial_smem_init(ps);
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
     const int64_t start = tile * kTile;
@@ -124,103 +122,13 @@ static __global__ void __launch_bounds__(kReduceThreads)
     emit_partials<T>(v, out, ps, -1, ew ? ew + f * n + start : nullptr, (int)valid);
 }
 
-// One block per filter.  Combines tile partials, classifies validity (utils.jl:119-137) and writes the
-// exclusive tile offsets of the NORMALISED weights (the scan's carry-in).
+// Finalize: one block per filter (or per chunk of a large filter).  Combines tile partials, classifies validity
+// (utils.jl:119-137) and writes the exclusive tile offsets of the NORMALISED weights (the scan's carry-in).
 //   lml_accum != null: log_ml_est[f] += lse - log(n)  (update_lml_est!, resample.jl:178-182), gated by do_resample
 //   ess_frac < 0 => do_resample = 1, else do_resample = (ess < ess_frac * n)   (README.md:68)
-static __global__ void __launch_bounds__(kThreads)
-    k_finalize(Partials in, int64_t n, int64_t tpf, Stats *stats, double *tile_off, double ess_frac,
-               double *lml_accum) {
-    __shared__ double sm[kWarps];
-    __shared__ int smi[kWarps];
-    __shared__ double carry_s;
-    const int64_t f = blockIdx.x;
-    const double *pm = in.m + f * tpf, *ps = in.s + f * tpf, *ps2 = in.s2 + f * tpf;
-    const int *pf = in.flags + f * tpf;
-    double m = -INFINITY;
-    int fl = 0;
-    for (int64_t b = threadIdx.x; b < tpf; b += kThreads) {
-        m = fmax(m, pm[b]);
-        fl |= pf[b];
-    }
-    const double M = block_max(m, sm);
-    fl = block_or(fl, smi);
-    double s = 0.0, s2 = 0.0;
-    if (M > -INFINITY && M < INFINITY) {
-        for (int64_t b = threadIdx.x; b < tpf; b += kThreads) {
-            double mb = pm[b];
-            if (mb > -INFINITY) {
-                double sc = exp(mb - M);
-                s += ps[b] * sc;
-                s2 += ps2[b] * (sc * sc);
-            }
-        }
-    }
-    const double S = block_sum(s, sm);
-    const double S2 = block_sum(s2, sm);
-    int kind = 0;
-    if (fl & 1) kind = 1;                        // NaN in input
-    else if (M == -INFINITY) kind = 2;           // all -Inf
-    else if ((fl & 2) || isnan(S)) kind = 4;     // +Inf entry => Inf-Inf = NaN total
-    else if (S == 0.0) kind = 3;                 // zero total (unreachable: e_max = 1)
-    const double lse = (M == -INFINITY) ? -INFINITY : M + log(S);
-    const double ess = S * S / S2;
-    int do_rs = 1;
-    if (ess_frac >= 0.0) do_rs = (ess < ess_frac * (double)n) ? 1 : 0;
-    if (kind == 1 || kind == 4) do_rs = 0;
-    if (threadIdx.x == 0) {
-        Stats st;
-        st.M = M; st.S = S; st.S2 = S2; st.lse = lse; st.ess = ess;
-        st.invalid_kind = kind; st.do_resample = do_rs;
-        stats[f] = st;
-        if (lml_accum && do_rs) lml_accum[f] += lse - log((double)n);
-        carry_s = 0.0;
-    }
-    if (!tile_off) return;
-    __syncthreads();
-    // exclusive scan of the normalised tile totals, 256 tiles per round, sequential carry
-    const bool uniform = (kind == 2 || kind == 3);
-    const double inv_n = 1.0 / (double)n;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t b0 = 0; b0 < tpf; b0 += kThreads) {
-        int64_t b = b0 + threadIdx.x;
-        double t = 0.0;
-        if (b < tpf) {
-            if (uniform) {
-                int64_t cnt = min((int64_t)kTile, n - b * kTile);
-                t = (double)cnt * inv_n;
-            } else if (kind == 0 && pm[b] > -INFINITY) {
-                t = ps[b] * exp(pm[b] - M) / S;
-            }
-        }
-        double inc = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        double ex = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) ex = 0.0;
-        __syncthreads();
-        if (lane == 31) sm[warp] = inc;
-        __syncthreads();
-        double woff = 0.0, tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            if (w < warp) woff += sm[w];
-            tot += sm[w];
-        }
-        const double c = carry_s;
-        if (b < tpf) tile_off[f * tpf + b] = c + (woff + ex);
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = c + tot;
-        __syncthreads();
-    }
-}
-
 // Register-resident finalize for tpf <= 8*THREADS tiles per filter: thread t owns tiles {c*THREADS + t}
 // (coalesced loads, all in flight together); the three phases (max, rescaled sums, exclusive tile offsets)
-// need only a handful of block-level combines.  Same outputs as k_finalize.
+// need only a handful of block-level combines.
 template <int THREADS>
 static __global__ void __launch_bounds__(THREADS)
     k_finalize_fast(Partials in, int64_t n_all, int64_t tpf_all, Stats *stats, double *tile_off, double ess_frac,
@@ -497,23 +405,10 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
 // Replaces safe_softmax line utils.jl:139 and the running accum_weight of resample.jl:163-166.
 // Writes W (normalised inclusive cumulative weights) and/or O (cumulative offspring counts, stratified).
 constexpr int kScanThreads = 512;  // every launch of k_scan uses this block size (fixed summation order)
-// cumulative-weight outputs for the inverse-CDF search: W[n], W16[ceil(n/16)] = W at the end of every
-// 16-particle group, tile_last[n/2048] = W at the end of every tile (three-level search index)
+// cumulative-weight output of the scan (inverse-CDF draws, genpf_debug_cumweights)
 struct WTables {
-    double *W, *W16, *tile_last;
+    double *W;
 };
-template <int T>
-__device__ __forceinline__ void store_w_tables(const WTables &wt, int64_t fbase, int64_t n, int64_t tpf, int64_t f,
-                                               int64_t tile, int64_t start, int valid, const double (&W)[kTile / T]) {
-    store_tile<double, T>(wt.W, fbase + start, valid, W);
-    const int64_t n16 = (n + 15) >> 4;
-#pragma unroll
-    for (int k = 0; k < kTile / T; ++k) {
-        const int e = tile_elem<T>(k);
-        if (e < valid && ((e & 15) == 15 || e == valid - 1)) wt.W16[f * n16 + ((start + e) >> 4)] = W[k];
-        if (e == valid - 1) wt.tile_last[f * tpf + tile] = W[k];
-    }
-}
 
 // k_scan uses a BLOCKED layout: thread t owns the four consecutive particles 4t..4t+3 of the tile (two adjacent
 // 16-byte loads, one 16-byte store of the counts).  One sequential 4-add chain + one warp scan per thread
@@ -621,15 +516,6 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
 #pragma unroll
         for (int k = 0; k < I; ++k)
             if (e0 + k < valid) pw[e0 + k] = W[k];
-        if (wt.W16) {
-            const int64_t n16 = (n + 15) >> 4;
-#pragma unroll
-            for (int k = 0; k < I; ++k) {
-                const int e = e0 + k;
-                if (e < valid && ((e & 15) == 15 || e == valid - 1)) wt.W16[f * n16 + ((start + e) >> 4)] = W[k];
-                if (e == valid - 1) wt.tile_last[f * tpf + tile] = W[k];
-            }
-        }
     }
     if (O_out) {
         IdxT O[I];
@@ -861,120 +747,9 @@ static __global__ void __launch_bounds__(kThreads)
     parents[i] = (OutT)((order ? order[lo] : lo) + out_base);
 }
 
-// K5 inverse-CDF search for arbitrary (unsorted) uniforms: parent_j = min{k : W_k > u_j}, capped at n
+// K5 inverse-CDF draws for arbitrary (unsorted) uniforms: parent_j = min{k : W_k > u_j}, capped at n
 // (Distributions' single-draw rule, resize.jl:284).  Slots below first_slot (residual: the
-// deterministic copies) are left alone.  Random lookups are a gather workload, so the index is layered to
-// keep everything but the last cache line out of HBM:
-//   A. <= 4096 samples of the per-tile closing weights in shared memory      (12 steps, smem)
-//   B. the per-tile closing weights themselves                                (log2(stride) steps, L2)
-//   C. W16: the closing weight of every 16-particle group of the tile         (7 steps in 1 KB, L2)
-//   D. the 16 weights of the group                                            (4 steps in one 128-B line)
-constexpr int kCoarseCap = 4096;
-constexpr int kSearchItems = 8;  // lookups advanced in lockstep per thread: 8 independent load chains
-
-// count of leading elements <= u in the monotone array a[0..cnt), cnt <= M = 2^k, branch-free, then clamped
-// to cnt-1: "first index with a[idx] > u, capped at the last".  All K lookups advance together so their
-// (dependent) loads overlap.
-template <int M, int K, typename Ptr>
-__device__ __forceinline__ void ub_lockstep(Ptr (&a)[K], const int (&cnt)[K], const double (&u)[K], int (&pos)[K]) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) pos[k] = 0;
-#pragma unroll
-    for (int half = M / 2; half >= 1; half >>= 1) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int idx = pos[k] + half - 1;
-            const bool le = idx < cnt[k] && a[k][idx] <= u[k];
-            pos[k] += le ? half : 0;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const bool le = pos[k] < cnt[k] && a[k][pos[k]] <= u[k];
-        pos[k] += le ? 1 : 0;
-        pos[k] = min(pos[k], cnt[k] - 1);
-    }
-}
-
-template <typename IdxT, typename OutT>
-static __global__ void __launch_bounds__(kThreads)
-    k_search(WTables wt, int64_t n_src, int64_t n_out, int64_t bpf, UniSrc uni, const IdxT *first_slot_O,
-             OutT *parents, int64_t out_base, const Stats *stats, int gate) {
-    constexpr int K = kSearchItems;
-    __shared__ double sA[kCoarseCap];
-    int64_t f = blockIdx.y;
-    int64_t blk = blockIdx.x;
-    (void)bpf;
-    if (stats) {
-        const int kind = stats[f].invalid_kind;
-        if (kind == 1 || kind == 4) return;
-        if (gate && !stats[f].do_resample) return;
-    }
-    const int64_t tpf = (n_src + kTile - 1) / kTile;
-    const int64_t n16 = (n_src + 15) >> 4;
-    const double *Wf = wt.W + f * n_src;
-    const double *W16 = wt.W16 + f * n16;
-    const double *TL = wt.tile_last + f * tpf;
-    const int64_t strideA = (tpf + kCoarseCap - 1) / kCoarseCap;  // <= 64 up to 2^29 particles (host checks)
-    const int nA = (int)((tpf + strideA - 1) / strideA);
-    for (int c = threadIdx.x; c < nA; c += kThreads) sA[c] = TL[min((c + 1) * strideA, tpf) - 1];
-    __syncthreads();
-    const int64_t first = first_slot_O ? (int64_t)first_slot_O[f * n_src + n_src - 1] : 0;
-    const int64_t j0 = blk * (int64_t)kTile;
-    double u[K];
-    bool live[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int64_t j = j0 + k * kThreads + threadIdx.x;
-        live[k] = j < n_out && j >= first;
-        u[k] = live[k] ? uni(f * n_out + j) : 0.0;
-    }
-    // A: shared-memory sample
-    const double *pa[K];
-    int cnt[K], pos[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        pa[k] = sA;
-        cnt[k] = nA;
-    }
-    ub_lockstep<kCoarseCap, K>(pa, cnt, u, pos);
-    // B: tile closing weights inside the sampled stride
-    int64_t tile[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int64_t t0 = (int64_t)pos[k] * strideA;
-        pa[k] = TL + t0;
-        cnt[k] = (int)(min(t0 + strideA, tpf) - t0);
-        tile[k] = t0;
-    }
-    ub_lockstep<64, K>(pa, cnt, u, pos);  // strideA <= 64: up to 2^29 particles
-    // C: 16-particle group closing weights of the tile (128 per tile)
-    int64_t grp[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        tile[k] += pos[k];
-        const int64_t g0 = tile[k] * (kTile / 16);
-        pa[k] = W16 + g0;
-        cnt[k] = (int)(min(g0 + kTile / 16, n16) - g0);
-        grp[k] = g0;
-    }
-    ub_lockstep<kTile / 16, K>(pa, cnt, u, pos);
-    // D: the 16 weights of the group
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        grp[k] += pos[k];
-        const int64_t k0 = grp[k] * 16;
-        pa[k] = Wf + k0;
-        cnt[k] = (int)(min(k0 + 16, n_src) - k0);
-    }
-    ub_lockstep<16, K>(pa, cnt, u, pos);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int64_t j = j0 + k * kThreads + threadIdx.x;
-        if (live[k]) parents[f * n_out + j] = (OutT)(grp[k] * 16 + pos[k] + out_base);
-    }
-}
-
+// deterministic copies) are left alone.
 // Guide-table inverse CDF: parent_j = min{k : W_k > u_j} clamped to n_src-1 (rand(Categorical(w)),
 // resample.jl:59,113; resize.jl:61,117).  b = floor(n*u) picks the bucket, G[b] .. G[b+1] brackets the answer
 // (expected bracket length 1), and the answer is always re-checked against W: two or three scattered

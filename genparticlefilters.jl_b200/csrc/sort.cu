@@ -1,21 +1,27 @@
 // sort.cu -- K7: stable descending argsort of fp64 keys (sortperm(log_priorities, rev=true),
 // reference src/resample.jl:156-157) and the key sort behind pf_coalesce! (resize.jl:309-334).
 //
-// Hand-written LSD radix sort, 8 passes of 8 bits over order-preserving 64-bit keys with a 32-bit index
-// payload.  Per pass (tile = 2048 keys, the same tile as everywhere else):
-//   k_radix_hist    per-tile 256-bin digit histogram            -> hist[digit][tile]   (digit-major)
-//   k_radix_scan*   exclusive scan of the flattened histogram   -> global offset of every (digit, tile)
-//   k_radix_scatter stable in-tile ranks (each warp owns a contiguous 256-key run; __match_any_sync ranks
-//                   a 32-key chunk, per-warp digit counters carry the order across chunks and warps)
-// Stability across tiles comes from the digit-major scan, inside a tile from the in-order walk, so equal keys
-// keep ascending original index -- Julia's sortperm tie rule.  The key transform reproduces Julia's `isless`
-// total order (-0.0 < 0.0).
+// Hand-written LSD radix sort ("onesweep" organisation), 8 digits of 8 bits over order-preserving 64-bit keys
+// with a 32-bit index payload:
+//   k_radix_prepare  key transform + index payload + ALL eight global digit histograms in one read of the keys
+//   k_radix_plan     exclusive scan of each histogram; a digit on which every key agrees is marked "skip"
+//                    (equal weights after a resample: all eight are skipped and the sort is one read)
+//   k_radix_onesweep one kernel per remaining digit: stable in-tile ranks (each warp owns a contiguous
+//                    256-key run; __match_any_sync ranks a 32-key chunk, per-warp digit counters carry the
+//                    order across chunks and warps), the tile's global offsets come from a decoupled look-back
+//                    over the per-tile digit counts (tiles take tickets, so every predecessor is resident), and
+//                    the tile leaves in digit order through shared memory
+//   k_sort_finish    inverse key transform, order -> caller's buffers (the ping-pong parity is device resident)
+// Stability across tiles comes from the ticket order, inside a tile from the in-order walk, so equal keys keep
+// ascending original index -- Julia's sortperm tie rule.  The key transform reproduces Julia's `isless` total
+// order (-0.0 < 0.0).  Counts are integers, so the look-back changes no result: bit-deterministic.
 #include "host.hpp"
 
 namespace genpf {
 
-constexpr int kSortTile = 2048;
 constexpr int kSortThreads = 256;
+constexpr int kSortPasses = 8;
+constexpr uint32_t kFlagAgg = 0x40000000u, kFlagPrefix = 0x80000000u, kCountMask = 0x3FFFFFFFu;
 
 __device__ __forceinline__ uint64_t order_bits(double x) {
     uint64_t b = (uint64_t)__double_as_longlong(x);
@@ -25,154 +31,118 @@ __device__ __forceinline__ double order_bits_inv(uint64_t t) {
     uint64_t b = (t >> 63) ? (t & 0x7FFFFFFFFFFFFFFFull) : ~t;
     return __longlong_as_double((long long)b);
 }
-static __global__ void k_sort_prepare(const double *keys, int64_t n, uint64_t *k_out, int32_t *idx) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        k_out[i] = ~order_bits(keys[i]);  // ascending radix order == descending key order
-        idx[i] = (int32_t)i;
-    }
-}
-static __global__ void k_sort_finish(const uint64_t *k_sorted, int64_t n, double *keys_sorted) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        keys_sorted[i] = order_bits_inv(~k_sorted[i]);
-}
-static __global__ void k_sort_prepare_i64(const int64_t *keys, int64_t n, uint64_t *k_out, int32_t *idx) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        k_out[i] = (uint64_t)keys[i] ^ 0x8000000000000000ull;
-        idx[i] = (int32_t)i;
-    }
-}
-static __global__ void k_sort_finish_i64(const uint64_t *k_sorted, int64_t n, int64_t *keys_sorted) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        keys_sorted[i] = (int64_t)(k_sorted[i] ^ 0x8000000000000000ull);
+// MODE 0: fp64 keys, descending (ascending radix order of the complemented key); MODE 1: int64 keys, ascending
+template <int MODE>
+__device__ __forceinline__ uint64_t key_encode(const void *keys, int64_t i) {
+    if (MODE == 0) return ~order_bits(reinterpret_cast<const double *>(keys)[i]);
+    return (uint64_t)reinterpret_cast<const int64_t *>(keys)[i] ^ 0x8000000000000000ull;
 }
 
-// ---- pass kernels
+struct SortCtrl {
+    uint32_t hist[kSortPasses][256];   // global digit histograms, then their exclusive scans
+    uint32_t ticket[kSortPasses];      // next tile of each pass
+    uint32_t skip[kSortPasses];        // every key has the same digit: the pass would be the identity
+    uint32_t src_parity[kSortPasses];  // which ping-pong buffer holds the input of the pass
+    uint32_t final_parity;
+};
+
+template <int MODE>
 static __global__ void __launch_bounds__(kSortThreads)
-    k_radix_hist(const uint64_t *keys, int64_t n, int shift, int64_t ntiles, uint32_t *hist) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+    k_radix_prepare(const void *keys, int64_t n, uint64_t *k_out, int32_t *idx, SortCtrl *ctrl) {
+    __shared__ uint32_t h[kSortPasses][256];
+    for (int d = threadIdx.x; d < kSortPasses * 256; d += kSortThreads) (&h[0][0])[d] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-    // plain shared-memory atomics: measured 2.3x faster than warp-aggregating with __match_any_sync
-    // (MATCH costs ~18 issue slots on sm_100a)
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * kSortThreads; base < n; base += (int64_t)gridDim.x * kSortThreads) {
+        const int64_t i = base + threadIdx.x;
+        const bool ok = i < n;
+        uint64_t k = 0;
+        if (ok) {
+            k = key_encode<MODE>(keys, i);
+            k_out[i] = k;
+            idx[i] = (int32_t)i;
+        }
+        // a warp whose keys all agree (equal weights) adds once per digit instead of 32 colliding atomics
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (act == 0xffffffffu && __all_sync(0xffffffffu, k == __shfl_sync(0xffffffffu, k, 0))) {
+            if (lane < kSortPasses) atomicAdd(&h[lane][(k >> (8 * lane)) & 255u], 32u);
+        } else if (ok) {
 #pragma unroll
-    for (int c = 0; c < kSortTile / kSortThreads; ++c) {
-        const int64_t i = base + c * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+            for (int p = 0; p < kSortPasses; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+        }
     }
     __syncthreads();
-    hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+    for (int d = threadIdx.x; d < kSortPasses * 256; d += kSortThreads) {
+        const uint32_t c = (&h[0][0])[d];
+        if (c) atomicAdd(&ctrl->hist[0][0] + d, c);
+    }
 }
 
-// exclusive scan of m uint32 values in three phases (2048 per block)
-static __global__ void __launch_bounds__(kSortThreads) k_radix_scan_sums(const uint32_t *a, int64_t m, uint32_t *sums) {
-    __shared__ uint32_t sw[kSortThreads / 32];
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-    uint32_t s = 0;
-#pragma unroll
-    for (int c = 0; c < kSortTile / kSortThreads; ++c) {
-        const int64_t i = base + c * kSortThreads + threadIdx.x;
-        if (i < m) s += a[i];
-    }
-    s = __reduce_add_sync(0xffffffffu, s);
-    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+static __global__ void __launch_bounds__(256) k_radix_plan(SortCtrl *ctrl, int64_t n) {
+    __shared__ uint32_t sw[8];
+    __shared__ uint32_t s_skip[kSortPasses];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    if (d < kSortPasses) s_skip[d] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kSortThreads / 32; ++w) t += sw[w];
-        sums[blockIdx.x] = t;
-    }
-}
-static __global__ void __launch_bounds__(1024) k_radix_scan_offsets(uint32_t *sums, int64_t nb) {
-    // one block, 1024 threads, 8 consecutive entries each per round, running carry
-    __shared__ uint32_t sw[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < nb; base += 1024 * 8) {
-        uint32_t v[8], run = 0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int64_t i = base + (int64_t)threadIdx.x * 8 + c;
-            v[c] = run;
-            run += i < nb ? sums[i] : 0u;
-        }
-        uint32_t inc = run;
+    for (int p = 0; p < kSortPasses; ++p) {
+        const uint32_t c = ctrl->hist[p][d];
+        if ((int64_t)c == n) s_skip[p] = 1;
+        uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += u;
         }
-        uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) ex = 0;
-        __syncthreads();
         if (lane == 31) sw[warp] = inc;
         __syncthreads();
-        uint32_t woff = 0, tot = 0;
+        uint32_t woff = 0;
 #pragma unroll
-        for (int w = 0; w < 32; ++w) {
+        for (int w = 0; w < 8; ++w)
             if (w < warp) woff += sw[w];
-            tot += sw[w];
-        }
-        const uint32_t cr = carry;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int64_t i = base + (int64_t)threadIdx.x * 8 + c;
-            if (i < nb) sums[i] = cr + woff + ex + v[c];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry = cr + tot;
+        ctrl->hist[p][d] = woff + inc - c;
         __syncthreads();
     }
-}
-static __global__ void __launch_bounds__(kSortThreads)
-    k_radix_scan_apply(uint32_t *a, int64_t m, const uint32_t *offsets) {
-    // in-place exclusive scan of one 2048-entry block: thread t owns 8 consecutive entries
-    __shared__ uint32_t sw[kSortThreads / 32];
-    const int64_t base = (int64_t)blockIdx.x * kSortTile + (int64_t)threadIdx.x * 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t v[8], run = 0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        v[c] = run;
-        run += base + c < m ? a[base + c] : 0u;
+    if (d == 0) {
+        uint32_t parity = 0;
+        for (int p = 0; p < kSortPasses; ++p) {
+            ctrl->skip[p] = s_skip[p];
+            ctrl->src_parity[p] = parity;
+            if (!s_skip[p]) parity ^= 1u;
+        }
+        ctrl->final_parity = parity;
     }
-    uint32_t inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
-    }
-    uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) ex = 0;
-    if (lane == 31) sw[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0;
-#pragma unroll
-    for (int w = 0; w < kSortThreads / 32; ++w)
-        if (w < warp) woff += sw[w];
-    const uint32_t off = offsets[blockIdx.x] + woff + ex;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        if (base + c < m) a[base + c] = off + v[c];
 }
 
-static __global__ void __launch_bounds__(kSortThreads)
-    k_radix_scatter(const uint64_t *keys, const int32_t *vals, int64_t n, int shift, int64_t ntiles,
-                    const uint32_t *offsets, uint64_t *keys_out, int32_t *vals_out) {
-    constexpr int NW = kSortThreads / 32, CH = kSortTile / kSortThreads;  // 8 warps, 8 chunks of 32 per warp
-    __shared__ uint32_t whist[NW][256];   // per-warp digit counts -> tile-local start of (warp, digit)
-    __shared__ uint32_t gdelta[256];      // global offset of (digit, tile) minus the digit's tile-local start
-    __shared__ uint32_t scan_tmp[NW];
-    __shared__ uint64_t skey[kSortTile];  // the tile in digit order: runs of equal digit leave coalesced
-    __shared__ int32_t sval[kSortTile];
+// THREADS = 256 (tile 2048) or 512 (tile 4096): larger tiles halve the look-back work per key and space the
+// tiles further apart in time, which is what keeps the look-back window short.
+template <int THREADS, int MINB>
+static __global__ void __launch_bounds__(THREADS, MINB)
+    k_radix_onesweep(SortCtrl *ctrl, int pass, uint64_t *kA, uint64_t *kB, int32_t *vA, int32_t *vB, int64_t n,
+                     uint32_t *state) {
+    constexpr int NW = THREADS / 32, CH = 8, TILE = THREADS * CH;  // each warp owns a contiguous run of 256 keys
+    if (ctrl->skip[pass]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *skey = reinterpret_cast<uint64_t *>(smem_raw);           // [TILE] the tile in digit order
+    int32_t *sval = reinterpret_cast<int32_t *>(skey + TILE);           // [TILE]
+    uint32_t(*whist)[256] = reinterpret_cast<uint32_t(*)[256]>(sval + TILE);  // [NW][256] per-warp digit counts
+    uint32_t *gdelta = &whist[NW][0];                                   // [256] global offset - tile-local start
+    uint32_t *scan_tmp = gdelta + 256;                                  // [8]
+    uint32_t *s_tile = scan_tmp + 8;
+    const bool from_b = ctrl->src_parity[pass] != 0;
+    const uint64_t *keys = from_b ? kB : kA;
+    const int32_t *vals = from_b ? vB : vA;
+    uint64_t *keys_out = from_b ? kA : kB;
+    int32_t *vals_out = from_b ? vA : vB;
+    const int shift = 8 * pass;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int d = threadIdx.x; d < NW * 256; d += kSortThreads) (&whist[0][0])[d] = 0;
-    const int64_t tile_base = (int64_t)blockIdx.x * kSortTile;
+    if (threadIdx.x == 0) *s_tile = atomicAdd(&ctrl->ticket[pass], 1u);
+    for (int d = threadIdx.x; d < NW * 256; d += THREADS) (&whist[0][0])[d] = 0;
+    __syncthreads();
+    const uint32_t tile = *s_tile;
+    const int64_t tile_base = (int64_t)tile * TILE;
     const int64_t base = tile_base + (int64_t)warp * (32 * CH);
-    const int valid = (int)min((int64_t)kSortTile, n - tile_base);
+    const int valid = (int)min((int64_t)TILE, n - tile_base);
     uint64_t k[CH];
     int32_t v[CH];
     int dgt[CH];
@@ -184,7 +154,6 @@ static __global__ void __launch_bounds__(kSortThreads)
         v[c] = ok ? vals[i] : 0;
         dgt[c] = ok ? (int)((k[c] >> shift) & 255u) : 256;  // 256 = out of range: ranked among themselves, dropped
     }
-    __syncthreads();
     // 1. per-warp digit counts of its contiguous 256-key run (the peer masks are kept for step 3: MATCH is
     //    the expensive instruction here)
     unsigned peers[CH];
@@ -195,31 +164,60 @@ static __global__ void __launch_bounds__(kSortThreads)
         __syncwarp();
     }
     __syncthreads();
-    // 2. thread d owns digit d: tile count, exclusive scan over digits (tile-local start), then over warps
+    // 2. thread d < 256 owns digit d: tile count, exclusive scan over digits (tile-local start), then over
+    //    warps; publish the count, look back over the preceding tiles for the digit's global offset
     {
-        const int d = threadIdx.x;  // kSortThreads == 256 digits
+        const int d = threadIdx.x;
+        const bool own = d < 256;
         uint32_t cnt = 0;
+        if (own) {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) cnt += whist[w][d];
+            for (int w = 0; w < NW; ++w) cnt += whist[w][d];
+            *(volatile uint32_t *)(state + (size_t)tile * 256 + d) = (tile == 0 ? kFlagPrefix : kFlagAgg) | cnt;
+        }
         uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += u;
         }
-        if (lane == 31) scan_tmp[warp] = inc;
+        if (own && lane == 31) scan_tmp[warp] = inc;
         __syncthreads();
-        uint32_t woff = 0;
+        if (own) {
+            uint32_t woff = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w)
-            if (w < warp) woff += scan_tmp[w];
-        uint32_t b = woff + inc - cnt;  // tile-local start of digit d
-        gdelta[d] = offsets[(int64_t)d * ntiles + blockIdx.x] - b;
+            for (int w = 0; w < 8; ++w)
+                if (w < warp) woff += scan_tmp[w];
+            uint32_t b = woff + inc - cnt;  // tile-local start of digit d
+            // look-back, LB predecessors per round trip (independent loads); an unpublished entry restarts there
+            uint32_t excl = 0;
+            constexpr int LB = 8;
+            int64_t t = (int64_t)tile - 1;
+            bool done = t < 0;
+            while (!done) {
+                uint32_t pv[LB];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t t = whist[w][d];
-            whist[w][d] = b;
-            b += t;
+                for (int i = 0; i < LB; ++i)
+                    pv[i] = t - i >= 0 ? *(volatile uint32_t *)(state + (size_t)(t - i) * 256 + d) : (uint32_t)0x80000000u;
+                int used = 0;
+#pragma unroll
+                for (int i = 0; i < LB; ++i) {
+                    if (done || used != i) continue;
+                    if (pv[i] == 0u) continue;  // not published yet: re-read from t - i
+                    excl += pv[i] & kCountMask;
+                    used = i + 1;
+                    if (pv[i] & kFlagPrefix) done = true;
+                }
+                t -= used;
+            }
+            if (tile != 0) *(volatile uint32_t *)(state + (size_t)tile * 256 + d) = kFlagPrefix | (excl + cnt);
+            gdelta[d] = ctrl->hist[pass][d] + excl - b;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t t2 = whist[w][d];
+                whist[w][d] = b;
+                b += t2;
+            }
         }
     }
     __syncthreads();
@@ -238,74 +236,84 @@ static __global__ void __launch_bounds__(kSortThreads)
     }
     __syncthreads();
     // 4. stream the tile out in digit order: slot s of digit d goes to gdelta[d] + s
-    for (int s = threadIdx.x; s < valid; s += kSortThreads) {
+    for (int s = threadIdx.x; s < valid; s += THREADS) {
         const uint64_t kk = skey[s];
         const uint32_t pos = gdelta[(kk >> shift) & 255u] + (uint32_t)s;
         keys_out[pos] = kk;
         vals_out[pos] = sval[s];
     }
 }
-
-// sorts (kA, vA) ascending by key, stably; kB/vB are ping-pong buffers; the result ends in (kA, vA)
-static int32_t radix_sort_pairs(uint64_t *kA, uint64_t *kB, int32_t *vA, int32_t *vB, int64_t n, uint32_t *hist,
-                                uint32_t *sums, cudaStream_t stream) {
-    const int64_t ntiles = ceil_div(n, kSortTile);
-    const int64_t m = 256 * ntiles, nb = ceil_div(m, kSortTile);
-    uint64_t *ki = kA, *ko = kB;
-    int32_t *vi = vA, *vo = vB;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 8 * pass;
-        GENPF_LAUNCH(k_radix_hist, (unsigned)ntiles, kSortThreads, stream, (const uint64_t *)ki, n, shift, ntiles, hist);
-        GENPF_LAUNCH(k_radix_scan_sums, (unsigned)nb, kSortThreads, stream, (const uint32_t *)hist, m, sums);
-        GENPF_LAUNCH(k_radix_scan_offsets, 1, 1024, stream, sums, nb);
-        GENPF_LAUNCH(k_radix_scan_apply, (unsigned)nb, kSortThreads, stream, hist, m, (const uint32_t *)sums);
-        GENPF_LAUNCH(k_radix_scatter, (unsigned)ntiles, kSortThreads, stream, (const uint64_t *)ki,
-                     (const int32_t *)vi, n, shift, ntiles, (const uint32_t *)hist, ko, vo);
-        std::swap(ki, ko);
-        std::swap(vi, vo);
-    }
-    return GENPF_OK;  // 8 passes: back in (kA, vA)
+template <int THREADS>
+constexpr size_t onesweep_smem() {
+    return (size_t)THREADS * 8 * 12 + (size_t)(THREADS / 32) * 1024 + 1024 + 64;
 }
 
-static int32_t layout_tmp(int64_t n, DevBuf &tmp, uint64_t *&kA, uint64_t *&kB, int32_t *&vB, uint32_t *&hist,
-                          uint32_t *&sums) {
-    if (n > 0x7FFFFFFFll) return fail(GENPF_ERR_UNSUPPORTED, "sort: n must be < 2^31");
-    const int64_t ntiles = ceil_div(n, kSortTile);
-    const int64_t m = 256 * ntiles, nb = ceil_div(m, kSortTile);
+template <int MODE>
+static __global__ void k_sort_finish(const SortCtrl *ctrl, const uint64_t *kA, const uint64_t *kB, const int32_t *vA,
+                                     const int32_t *vB, int64_t n, void *keys_sorted, int32_t *order32) {
+    const bool in_b = ctrl->final_parity != 0;
+    const uint64_t *ks = in_b ? kB : kA;
+    const int32_t *vs = in_b ? vB : vA;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (keys_sorted) {
+            if (MODE == 0) reinterpret_cast<double *>(keys_sorted)[i] = order_bits_inv(~ks[i]);
+            else reinterpret_cast<int64_t *>(keys_sorted)[i] = (int64_t)(ks[i] ^ 0x8000000000000000ull);
+        }
+        order32[i] = vs[i];
+    }
+}
+
+template <int MODE>
+static int32_t radix_sort(const void *keys, int64_t n, void *keys_sorted, int32_t *order32, DevBuf &tmp,
+                          cudaStream_t stream) {
+    if (n >= 0x40000000ll) return fail(GENPF_ERR_UNSUPPORTED, "sort: n must be < 2^30");
+    // measured (2^22 / 2^24 / 2^26 keys): 2048-key tiles 0.49 / 1.66 / 6.66 ms, 4096-key tiles 0.53 / 1.63 / 5.92 ms
+    const bool use_big = n >= (1 << 25);
+    const int64_t tile_keys = use_big ? 4096 : 2048;
+    const int64_t ntiles = ceil_div(n, tile_keys);
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t a = al((size_t)n * 8), b = al((size_t)n * 4), h = al((size_t)m * 4), s = al((size_t)nb * 4);
-    GENPF_TRY(tmp.ensure(2 * a + b + h + s + 256));
+    const size_t a = al((size_t)n * 8), b = al((size_t)n * 4), c = al(sizeof(SortCtrl)),
+                 st = al((size_t)ntiles * 256 * 4);
+    GENPF_TRY(tmp.ensure(2 * a + 2 * b + c + kSortPasses * st + 256));
     char *base = tmp.as<char>();
-    kA = (uint64_t *)base;
-    kB = (uint64_t *)(base + a);
-    vB = (int32_t *)(base + 2 * a);
-    hist = (uint32_t *)(base + 2 * a + b);
-    sums = (uint32_t *)(base + 2 * a + b + h);
+    uint64_t *kA = (uint64_t *)base, *kB = (uint64_t *)(base + a);
+    int32_t *vA = (int32_t *)(base + 2 * a), *vB = (int32_t *)(base + 2 * a + b);
+    SortCtrl *ctrl = (SortCtrl *)(base + 2 * a + 2 * b);
+    uint32_t *state = (uint32_t *)(base + 2 * a + 2 * b + c);
+    GENPF_CUDA_TRY(cudaMemsetAsync(ctrl, 0, c + kSortPasses * st, stream));
+    const unsigned gprep = (unsigned)std::min<int64_t>(ceil_div(n, kSortThreads), 148 * 16);
+    GENPF_LAUNCH((k_radix_prepare<MODE>), gprep, kSortThreads, stream, keys, n, kA, vA, ctrl);
+    GENPF_LAUNCH(k_radix_plan, 1, 256, stream, ctrl, n);
+    static const bool attr_set = [] {
+        cudaFuncSetAttribute(k_radix_onesweep<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)onesweep_smem<512>());
+        cudaFuncSetAttribute(k_radix_onesweep<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)onesweep_smem<256>());
+        return true;
+    }();
+    (void)attr_set;
+    for (int pass = 0; pass < kSortPasses; ++pass) {
+        uint32_t *stp = state + (size_t)pass * (st / 4);
+        if (use_big)
+            GENPF_LAUNCH_SMEM((k_radix_onesweep<512, 3>), (unsigned)ntiles, 512, onesweep_smem<512>(), stream, ctrl, pass, kA,
+                              kB, vA, vB, n, stp);
+        else
+            GENPF_LAUNCH_SMEM((k_radix_onesweep<256, 4>), (unsigned)ntiles, 256, onesweep_smem<256>(), stream, ctrl, pass, kA,
+                              kB, vA, vB, n, stp);
+    }
+    GENPF_LAUNCH((k_sort_finish<MODE>), grid_1d(n), 256, stream, (const SortCtrl *)ctrl, (const uint64_t *)kA,
+                 (const uint64_t *)kB, (const int32_t *)vA, (const int32_t *)vB, n, keys_sorted, order32);
     return GENPF_OK;
 }
 
 int32_t sort_desc_stable(const double *keys, int64_t n, double *keys_sorted, int32_t *order32, DevBuf &tmp,
                          cudaStream_t stream) {
-    uint64_t *kA, *kB;
-    int32_t *vB;
-    uint32_t *hist, *sums;
-    GENPF_TRY(layout_tmp(n, tmp, kA, kB, vB, hist, sums));
-    GENPF_LAUNCH(k_sort_prepare, grid_1d(n), 256, stream, keys, n, kA, order32);
-    GENPF_TRY(radix_sort_pairs(kA, kB, order32, vB, n, hist, sums, stream));
-    if (keys_sorted) GENPF_LAUNCH(k_sort_finish, grid_1d(n), 256, stream, (const uint64_t *)kA, n, keys_sorted);
-    return GENPF_OK;
+    return radix_sort<0>(keys, n, keys_sorted, order32, tmp, stream);
 }
 
 int32_t sort_keys_i64(const int64_t *keys, int64_t n, int64_t *keys_sorted, int32_t *order32, DevBuf &tmp,
                       cudaStream_t stream) {
-    uint64_t *kA, *kB;
-    int32_t *vB;
-    uint32_t *hist, *sums;
-    GENPF_TRY(layout_tmp(n, tmp, kA, kB, vB, hist, sums));
-    GENPF_LAUNCH(k_sort_prepare_i64, grid_1d(n), 256, stream, keys, n, kA, order32);
-    GENPF_TRY(radix_sort_pairs(kA, kB, order32, vB, n, hist, sums, stream));
-    if (keys_sorted) GENPF_LAUNCH(k_sort_finish_i64, grid_1d(n), 256, stream, (const uint64_t *)kA, n, keys_sorted);
-    return GENPF_OK;
+    return radix_sort<1>(keys, n, keys_sorted, order32, tmp, stream);
 }
 
 }  // namespace genpf
