@@ -34,8 +34,10 @@ KERNEL_ALGO_BYTES = {
     "k_expand": 4,      # W parents (int32)
     "k_gather": 44,     # R window 18 + W window 18 + W lw 8
     "k_mh": 27,         # R window 18 + W slice 9
-    "k_step_fused": 117 - 8,  # the whole step but the scan's read of lw
-    "k_step_push": 117 - 8,   # the same arithmetic, stores routed to the owning GPU (multi-GPU)
+    # fused kernels: what is left of the 117 B once gather -> MH -> update stay in registers:
+    # R window 18 + W window 18 + W lw 8 + W parents 4 (the scan's 8 B read is k_scan's)
+    "k_step_fused": 48,
+    "k_step_push": 48,   # the same arithmetic, stores routed to the owning GPU (multi-GPU)
     "k_reduce": 8,
 }
 STEP_ALGO_BYTES = 117
@@ -305,13 +307,29 @@ def main():
     total_updates = float(n) * world * K
     value = total_updates / (ms_max * 1e-3)
     peak, peak_src = measured_peak_gbs()
-    # dominant kernel by device time
+    # SURVEY 8(d)'s 117 B/particle-update describes the whole step, so the roofline figure is formed over the
+    # step's launches together (k_scan + k_finalize_fast + k_step_fused, or their sharded counterparts): fusion
+    # removed the gather->MH->update round trips, so apportioning the 117 B to the fused kernel alone would
+    # credit it with bytes it never moves.  The dominant kernel's own numbers are reported next to it.
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     dom_name, (dom_cnt, dom_ms) = dom
     per_launch_ms = dom_ms / dom_cnt
-    algo_b = KERNEL_ALGO_BYTES.get(dom_name, 0) * n
-    achieved = algo_b / (per_launch_ms * 1e-3) / 1e9
     prof_total = sum(v[1] for v in prof.values())
+    step_kernel_ms = prof_total / K
+    algo_b = STEP_ALGO_BYTES * n
+    achieved = algo_b / (step_kernel_ms * 1e-3) / 1e9
+    dom_traffic = traffic_of(dom_name)
+    step_traffic = None
+    if all(traffic_of(k) is not None for k in prof if k in ("k_scan", "k_step_fused")) and "k_step_fused" in prof:
+        step_traffic = sum(traffic_of(k) or 0.0 for k in prof)
+    dominant = {
+        "name": dom_name, "ms_per_launch": per_launch_ms, "share_of_step": dom_ms / prof_total,
+        "dram_bytes_per_launch": dom_traffic,
+        "dram_gbs": (dom_traffic / (per_launch_ms * 1e-3) / 1e9) if dom_traffic else None,
+        "dram_frac_of_peak": (dom_traffic / (per_launch_ms * 1e-3) / 1e9 / peak) if dom_traffic else None,
+        "own_algo_bytes_per_update": KERNEL_ALGO_BYTES.get(dom_name),
+        "bound": "instruction issue (ncu: ~75 % issue-slot utilisation, profiles/r1_k_ncu_summary.md)",
+    }
     line = {
         "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,11 +347,14 @@ def main():
                 "note": "genpf_b200.pf_step / ShardedFilter.step: obs/aux scalars in (kernel arguments), "
                         "Stats(ESS) read back per step"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic_of(dom_name), "peak_source": peak_src,
-                     "algo_bytes_per_launch": algo_b, "ms_per_launch": per_launch_ms,
-                     "share_of_step": dom_ms / prof_total,
-                     "step_frac": (STEP_ALGO_BYTES * n / (ms_max / K * 1e-3) / 1e9) / peak,
+        "roofline": {"bound": "hbm", "kernel": dom_name,
+                     "scope": "the step's launches together (" + " + ".join(sorted(prof)) + "); SURVEY 8(d): "
+                              "117 B/particle-update is defined on the whole step",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": step_traffic, "peak_source": peak_src,
+                     "algo_bytes_per_launch": algo_b, "ms_per_launch": step_kernel_ms,
+                     "wall_frac": (STEP_ALGO_BYTES * n / (ms_max / K * 1e-3) / 1e9) / peak,
+                     "dominant_kernel": dominant,
                      "kernels_ms_per_step": {k: v[1] / K for k, v in sorted(prof.items())}},
     }
     if world == 1 and not args.no_cpu:
