@@ -84,6 +84,7 @@ inline StratArgs make_strat(UniSrc uni, int64_t n) {
     a.n = n;
     a.pow2 = (n & (n - 1)) == 0;
     a.guide = 0;
+    a.tol = (double)n * 0x1.0p-50;
     return a;
 }
 

@@ -331,6 +331,7 @@ struct StratArgs {
     double step;  // 1/n
     int64_t n;
     int pow2;
+    double tol;     // rounding slack of the stratum-count fast path, in stratum units
     int64_t guide;  // B > 0: no strata; O_k = guide-table counts ceil(B * W_k) for the inverse-CDF lookup (k_lookup)
 };
 // Guide table for the inverse-CDF draws (multinomial, residual tail): bucket b of B covers u in [b/B, (b+1)/B);
@@ -370,8 +371,10 @@ struct StrataWindow {
     const uint32_t *words;  // shared memory, kStrataWindow words of this warp
     int64_t base;           // global stratum slot of words[0]; < 0: no window (column uniforms)
 };
+// General path: exact for every input (column uniforms, window misses, W within rounding of a stratum edge).
 template <typename J>
-__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, double W, const StrataWindow &win) {
+static __device__ __noinline__ J strat_count_slow(const StratArgs &a, int64_t slot0, double W, const uint32_t *words,
+                                                  int64_t win_base) {
     const J n = (J)a.n;
     const double nd = (double)a.n;
     const double x = W * nd;
@@ -385,9 +388,9 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
             r = a.uni.col[slot];
         } else {
             const int64_t gs = slot + a.uni.offset;
-            const uint64_t rel = (uint64_t)(gs - win.base);
-            if (rel < (uint64_t)kStrataWindow) {
-                r = ((double)win.words[rel] + 0.5) * 0x1.0p-32;
+            const uint64_t rel = (uint64_t)(gs - win_base);
+            if (win_base >= 0 && rel < (uint64_t)kStrataWindow) {
+                r = ((double)words[rel] + 0.5) * 0x1.0p-32;
             } else {
                 r = strata_word(strata_block(a.uni.seed, a.uni.stream, (uint64_t)gs >> 2), gs);
             }
@@ -399,6 +402,26 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
     if (near_edge)
         while (j > 0 && u_of(j) > W) --j;
     return j;
+}
+// Fast path (library-drawn strata inside the warp's window): with x = n*W, j = floor(x) and frac = x - j well
+// inside (0, 1), strata 1..j lie below W, stratum j+2 above, and stratum j+1 counts iff r_{j+1} < frac -- decided
+// without forming u when |frac - r| exceeds the rounding slack a.tol (4 x the worst-case error of n*W and of u);
+// anything closer goes to the exact general path, so the count is identical to it in every case.
+template <typename J>
+__device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, double W, const StrataWindow &win) {
+    const double nd = (double)a.n;
+    const double x = W * nd;
+    if (win.base >= 0 && x > 0.0 && x < nd) {
+        const J j = (J)x;
+        const double frac = x - (double)j;
+        const uint64_t rel = (uint64_t)(slot0 + (int64_t)j + a.uni.offset - win.base);
+        if (rel < (uint64_t)kStrataWindow && frac > 1e-6 && frac < 1.0 - 1e-6) {
+            const double r = fma((double)win.words[rel], 0x1.0p-32, 0x1.0p-33);  // (word + 0.5) * 2^-32, exact
+            const double d = frac - r;
+            if (fabs(d) > a.tol) return j + (J)(d > 0.0 ? 1 : 0);
+        }
+    }
+    return strat_count_slow<J>(a, slot0, W, win.words, win.base);
 }
 
 // ------------------------------------------------------------------ K3 normalise + scan

@@ -162,6 +162,42 @@ def test_selection_exact_given_gpu_cumweights(g, orc, n, kind):
     np.testing.assert_array_equal(p, expect)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 4097, 100_003, 1 << 18])
+@pytest.mark.parametrize("kind", ["A", "B", "C", "spike"])
+def test_inverse_cdf_adversarial_uniforms(g, n, kind):
+    """The guide-table lookup (k_lookup) must return min{k : W_k > u} for uniforms sitting exactly on bucket
+    boundaries, on cumulative weights themselves, at 0 and just below 1, and across long runs of zero-weight
+    particles (bracket longer than the linear-scan limit)."""
+    rng = np.random.default_rng(7 * n + len(kind))
+    if kind == "spike":  # a few carriers, long runs of -inf and of negligible weights between them
+        lw = np.full(n, -np.inf)
+        lw[rng.integers(0, n, max(1, n // 1000))] = 0.0
+        tiny = rng.integers(0, n, max(1, n // 3))
+        lw[tiny] = np.where(np.isinf(lw[tiny]), -60.0, lw[tiny])
+        lw[rng.integers(0, n)] = 3.0
+    else:
+        lw = weights(rng, n, kind)
+    W = gpu_cumweights(g, lw)
+    B = max(1, n >> 1)
+    one_m = np.nextafter(1.0, 0.0)
+    pieces = [rng.random(257), np.array([0.0, one_m, 0.5]), np.arange(min(B, 4096)) / B,
+              rng.integers(0, B, 512) / B, np.nextafter(rng.integers(1, B + 1, 512) / B, 0.0),
+              W[rng.integers(0, n, 1024)], np.nextafter(W[rng.integers(0, n, 1024)], 0.0),
+              np.nextafter(W[rng.integers(0, n, 1024)], 1.0)]
+    u = np.clip(np.concatenate(pieces), 0.0, one_m)
+    for n_out in {u.size, max(1, u.size // 3)}:
+        uu = np.ascontiguousarray(u[:n_out])
+        st, p, *_ = raw_resample(g, "multinomial", lw, uu, n_out=n_out)
+        assert st == 0
+        # the parallel scan's W may wobble by an ulp inside a run of zero-weight particles, so min{k : W_k > u}
+        # is taken over the running maximum; a different answer is accepted only as a cumulative-sum tie
+        expect = np.minimum(np.searchsorted(np.maximum.accumulate(W), uu, side="right"), n - 1)
+        ok = (W[p] > uu) | (p == n - 1)
+        below = np.where(p > 0, W[np.maximum(p - 1, 0)] <= uu, True)
+        assert np.all(ok & below), "returned index is not a crossing of the cumulative weights"
+        check_parents(p, expect, W, uu, max_frac=0.5)  # a third of the uniforms sit exactly on W values
+
+
 @pytest.mark.parametrize("n,n_out", [(100_003, 100_003), (1 << 18, 1 << 18), (1 << 18, 150_000), (70_000, 1 << 18)])
 @pytest.mark.parametrize("kind", ["A", "B", "C"])
 def test_multinomial_residual_vs_oracle(g, orc, n, n_out, kind):
