@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libgenpf_cuda.so")
 # status codes / enums (include/genpf.h)
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_INVALID_WEIGHTS, ERR_UNKNOWN_METHOD = -1, -2, -3, -4
-ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = -5, -6, -7
+ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE, ERR_ASSERT = -5, -6, -7, -8
 MULTINOMIAL, RESIDUAL, STRATIFIED = 0, 1, 2
 SORT_PARTICLES, SUBSTATE, INDEX_BASE1, DEVICE_PTRS, CHECK, UNIFORMS_STRATA = 1, 2, 4, 8, 16, 32
 VALID, INV_NAN_INPUT, INV_ALL_NEGINF, INV_ZERO_TOTAL, INV_NAN_TOTAL = 0, 1, 2, 3, 4
@@ -54,6 +54,7 @@ SIGNATURES = {
     "genpf_replicate_host": (i32, [_vp, i64, i64, i32, u32, _vp, _vp]),
     "genpf_dereplicate_host": (i32, [_vp, i64, i64, i32, i32, _vp, u64, u32, _vp, _vp]),
     "genpf_coalesce_host": (i32, [_vp, _vp, i64, u32, _vp, _vp, _ip]),
+    "genpf_optimal_resize": (i32, [_vp, i64, i64, _dp, u64, u32, _vp, _vp, _ip, _dp, _i32p]),
     "genpf_uniforms": (i32, [u64, u64, i64, u32, _vp]),
     "genpf_debug_cumweights": (i32, [_vp, i64, u32, _vp]),
     "genpf_model_builtin": (i32, [C.c_char_p, _i32p]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "genpf_replicate": (i32, [_vp, i64, i32]),
     "genpf_dereplicate": (i32, [_vp, i64, i32, i32, _vp]),
     "genpf_coalesce": (i32, [_vp, _ip]),
+    "genpf_optimal_resize_dev": (i32, [_vp, i64, _dp, u32, _ip, _dp, _i32p]),
     "genpf_get_log_weights": (i32, [_vp, _vp]),
     "genpf_set_log_weights": (i32, [_vp, _vp]),
     "genpf_get_parents": (i32, [_vp, _vp, u32]),

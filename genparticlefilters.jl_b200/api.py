@@ -375,12 +375,42 @@ def pf_stratified_resample(state, **kw):
 def pf_resize(state, n_particles, method="multinomial", **kw):
     """pf_resize!, resize.jl:16-27 (:multinomial 46-67, :residual 87-124)."""
     if method == "optimal":
-        raise GenPFErrorException("pf_optimal_resize! is outside the accelerated path (SURVEY 8f)")
+        return pf_optimal_resize(state, n_particles, **kw)
     if method not in ("multinomial", "residual"):
         raise GenPFErrorException(f"Resampling method {method} not recognized.")  # resize.jl:25
     if isinstance(state, ParticleFilterSubState):
         raise TypeError("pf_resize! takes a full ParticleFilterState")
     return pf_resample(state, method, n_out=n_particles, **kw)
+
+
+def pf_optimal_resize(state, n_particles, *, check="warn", uniform=None, seed=0):
+    """pf_optimal_resize!, resize.jl:149-196 (Fearnhead-Clifford optimal resampling; n_particles <= current size).
+    `uniform` stands for the single rand() of resize.jl:171 (None: the library's Philox draw)."""
+    if isinstance(state, ParticleFilterSubState):
+        raise TypeError("pf_resize! takes a full ParticleFilterState")
+    u = None if uniform is None else C.byref(C.c_double(float(uniform)))
+    n_keep, inv_w = C.c_int64(), C.c_double()
+    kinds = (C.c_int32 * 2)()
+    flags = L.CHECK if check is True else 0
+    if isinstance(state, DevicePFState):
+        st = L.load().genpf_optimal_resize_dev(state._h, n_particles, u, flags, C.byref(n_keep), C.byref(inv_w), kinds)
+    else:
+        lw = _f64(state.log_weights)
+        parents = np.empty(n_particles, dtype=np.int64)
+        lw_out = np.empty(n_particles)
+        st = L.load().genpf_optimal_resize(L.ptr(lw), lw.size, n_particles, u, seed, flags, L.ptr(parents),
+                                           L.ptr(lw_out), C.byref(n_keep), C.byref(inv_w), kinds)
+    if st == L.ERR_INVALID_WEIGHTS:
+        raise GenPFErrorException("Invalid weights.")
+    if st == L.ERR_ASSERT:
+        raise AssertionError(L.load().genpf_last_error().decode("utf-8", "replace"))  # @assert, resize.jl:181,183
+    L.check(st)
+    _emit_check(kinds[0], check)
+    if kinds[1] != kinds[0]:
+        _emit_check(kinds[1], check)
+    if not isinstance(state, DevicePFState):
+        _apply_resize(state, parents, lw_out)
+    return state
 
 
 def pf_multinomial_resize(state, n_particles, **kw):

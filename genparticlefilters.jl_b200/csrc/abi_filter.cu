@@ -535,6 +535,8 @@ int32_t genpf_filter_destroy(genpf_filter_t pf) {
         if (p) cudaFree(p);
     pf->sc.release();
     pf->cb.release();
+    pf->ob.release();
+    if (pf->h_opt_ctrl) cudaFreeHost(pf->h_opt_ctrl);
     pf->key_buf.release();
     for (DevBuf *b : {&pf->noise_buf[0], &pf->noise_buf[1], &pf->noise_buf[2], &pf->uni_buf, &pf->tmp_col, &pf->tmp_idx, &pf->prio_buf})
         b->release();
@@ -864,6 +866,29 @@ int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new) {
     GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
     const int64_t n_out = (int64_t) * reinterpret_cast<long long *>(pf->h_pinned);
     if (n_new) *n_new = n_out;
+    return apply_parents_and_swap(pf, n_out);
+}
+
+int32_t genpf_optimal_resize_dev(genpf_filter_t pf, int64_t n_out, const double *uniform, uint32_t flags,
+                                 int64_t *n_keep, double *inv_w_threshold, int32_t *invalid_kinds) {
+    GENPF_TRY(check_resizable(pf));
+    if (n_out <= 0) return fail(GENPF_ERR_INVALID_ARG, "genpf_optimal_resize_dev: n_out must be positive");
+    if (n_out > pf->n) return fail(GENPF_ERR_ASSERT, "optimal resize cannot grow the filter (@assert n_particles <= n_old, resize.jl:183)");
+    GENPF_TRY(resize_target(pf, n_out));
+    OptResult res;
+    UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    if (!pf->h_opt_ctrl) GENPF_CUDA_TRY(cudaMallocHost(&pf->h_opt_ctrl, sizeof(OptCtrl)));
+    const int32_t st = optimal_resize_core<int32_t>(pf->stream, pf->sc, pf->ob, (OptCtrl *)pf->h_opt_ctrl, pf->h_stats, pf->lw,
+                                                    pf->n, n_out, uniform, uni, flags & GENPF_CHECK, pf->parents, (int64_t)0,
+                                                    pf->lw_alt, &res);
+    pf->part_valid = false;  // the core reused the partial/statistics scratch
+    if (n_keep) *n_keep = res.n_keep;
+    if (inv_w_threshold) *inv_w_threshold = res.inv_w;
+    if (invalid_kinds) {
+        invalid_kinds[0] = res.kind;
+        invalid_kinds[1] = res.kind_strat;
+    }
+    if (st != GENPF_OK) return st;
     return apply_parents_and_swap(pf, n_out);
 }
 

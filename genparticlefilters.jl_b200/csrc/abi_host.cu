@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "coalesce.cuh"
+#include "optimal.cuh"
 #include "engine.cuh"
 
 namespace genpf {
@@ -19,6 +20,8 @@ struct HostWs {
     Scratch sc;
     DevBuf lw, lp, u, parents, lw_out, x, keys, aux1, aux2, aux3;
     CoalesceBufs cb;
+    OptimalBufs ob;
+    OptCtrl *h_ctrl = nullptr;  // pinned
     Stats *h_stats = nullptr;  // pinned, 4 entries
     double *h_scalars = nullptr;  // pinned, 8 doubles
     int device = -1;
@@ -31,6 +34,7 @@ struct HostWs {
         GENPF_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         GENPF_CUDA_TRY(cudaMallocHost(&h_stats, sizeof(Stats) * 4));
         GENPF_CUDA_TRY(cudaMallocHost(&h_scalars, sizeof(double) * 8));
+        GENPF_CUDA_TRY(cudaMallocHost(&h_ctrl, sizeof(OptCtrl)));
         return GENPF_OK;
     }
     void destroy() {
@@ -38,6 +42,9 @@ struct HostWs {
         for (DevBuf *b : {&lw, &lp, &u, &parents, &lw_out, &x, &keys, &aux1, &aux2, &aux3}) b->release();
         if (h_stats) cudaFreeHost(h_stats);
         if (h_scalars) cudaFreeHost(h_scalars);
+        if (h_ctrl) cudaFreeHost(h_ctrl);
+        h_ctrl = nullptr;
+        ob.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
         h_stats = nullptr;
@@ -276,8 +283,6 @@ int32_t genpf_resample(int32_t method, const double *lw, const double *log_prio,
         return fail(GENPF_ERR_INVALID_ARG, "stratified resampling cannot resize (resize.jl:16-27)");
     if ((flags & GENPF_SUBSTATE) && n_out != n_in)
         return fail(GENPF_ERR_INVALID_ARG, "a sub-state cannot be resized");
-    if (method != GENPF_STRATIFIED && n_in > (1ll << 29))
-        return fail(GENPF_ERR_UNSUPPORTED, "multinomial/residual search index supports up to 2^29 particles");
     HostWs &ws = g_ws;
     GENPF_TRY(ws.init());
     const bool dp = flags & GENPF_DEVICE_PTRS;
@@ -406,6 +411,39 @@ int32_t genpf_dereplicate_host(const double *lw, int64_t n, int64_t k, int32_t l
                  reinterpret_cast<long long *>(d_par), (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0), d_out);
     GENPF_TRY(copy_out(ws, d_par, parents_out, n_new, dp));
     GENPF_TRY(copy_out(ws, d_out, lw_out, n_new, dp));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    return GENPF_OK;
+}
+
+int32_t genpf_optimal_resize(const double *lw, int64_t n_in, int64_t n_out, const double *uniform, uint64_t seed,
+                             uint32_t flags, int64_t *parents_out, double *lw_out, int64_t *n_keep,
+                             double *inv_w_threshold, int32_t *invalid_kinds) {
+    if (!lw || !parents_out || !lw_out) return fail(GENPF_ERR_INVALID_ARG, "genpf_optimal_resize: NULL array argument");
+    if (n_in <= 0 || n_out <= 0) return fail(GENPF_ERR_INVALID_ARG, "genpf_optimal_resize: empty particle set");
+    if (n_out > n_in) return fail(GENPF_ERR_ASSERT, "optimal resize cannot grow the filter (@assert n_particles <= n_old, resize.jl:183)");
+    HostWs &ws = g_ws;
+    GENPF_TRY(ws.init());
+    const bool dp = flags & GENPF_DEVICE_PTRS;
+    const double *d_lw;
+    GENPF_TRY(stage_in(ws, ws.lw, lw, n_in, dp, &d_lw));
+    int64_t *d_par;
+    double *d_out;
+    GENPF_TRY(stage_out(ws.parents, parents_out, n_out, dp, &d_par));
+    GENPF_TRY(stage_out(ws.lw_out, lw_out, n_out, dp, &d_out));
+    OptResult res;
+    UniSrc uni{nullptr, seed, make_stream(0, 0), 0};
+    const int32_t st = optimal_resize_core<long long>(ws.stream, ws.sc, ws.ob, ws.h_ctrl, ws.h_stats, d_lw, n_in, n_out,
+                                                      uniform, uni, flags, reinterpret_cast<long long *>(d_par),
+                                                      (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0), d_out, &res);
+    if (n_keep) *n_keep = res.n_keep;
+    if (inv_w_threshold) *inv_w_threshold = res.inv_w;
+    if (invalid_kinds) {
+        invalid_kinds[0] = res.kind;
+        invalid_kinds[1] = res.kind_strat;
+    }
+    if (st != GENPF_OK) return st;
+    GENPF_TRY(copy_out(ws, d_par, parents_out, n_out, dp));
+    GENPF_TRY(copy_out(ws, d_out, lw_out, n_out, dp));
     GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
     return GENPF_OK;
 }

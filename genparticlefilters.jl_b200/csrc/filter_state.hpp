@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "coalesce.cuh"
+#include "optimal.cuh"
 #include "engine.cuh"
 #include "fused.cuh"
 
@@ -67,6 +68,8 @@ struct genpf_filter_s {
     double *noise_cols[3] = {nullptr, nullptr, nullptr};
     DevBuf noise_buf[3], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf;
     CoalesceBufs cb;
+    OptimalBufs ob;
+    void *h_opt_ctrl = nullptr;  // pinned OptCtrl, allocated on first optimal resize
     Scratch sc;
     bool part_valid = false;
     std::vector<HistSlice> hist;

@@ -31,10 +31,12 @@ __device__ __forceinline__ double order_bits_inv(uint64_t t) {
     uint64_t b = (t >> 63) ? (t & 0x7FFFFFFFFFFFFFFFull) : ~t;
     return __longlong_as_double((long long)b);
 }
-// MODE 0: fp64 keys, descending (ascending radix order of the complemented key); MODE 1: int64 keys, ascending
+// MODE 0: fp64 keys, descending (ascending radix order of the complemented key); MODE 1: int64 keys, ascending;
+// MODE 2: fp64 keys, ascending
 template <int MODE>
 __device__ __forceinline__ uint64_t key_encode(const void *keys, int64_t i) {
     if (MODE == 0) return ~order_bits(reinterpret_cast<const double *>(keys)[i]);
+    if (MODE == 2) return order_bits(reinterpret_cast<const double *>(keys)[i]);
     return (uint64_t)reinterpret_cast<const int64_t *>(keys)[i] ^ 0x8000000000000000ull;
 }
 
@@ -257,6 +259,7 @@ static __global__ void k_sort_finish(const SortCtrl *ctrl, const uint64_t *kA, c
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (keys_sorted) {
             if (MODE == 0) reinterpret_cast<double *>(keys_sorted)[i] = order_bits_inv(~ks[i]);
+            else if (MODE == 2) reinterpret_cast<double *>(keys_sorted)[i] = order_bits_inv(ks[i]);
             else reinterpret_cast<int64_t *>(keys_sorted)[i] = (int64_t)(ks[i] ^ 0x8000000000000000ull);
         }
         order32[i] = vs[i];
@@ -309,6 +312,11 @@ static int32_t radix_sort(const void *keys, int64_t n, void *keys_sorted, int32_
 int32_t sort_desc_stable(const double *keys, int64_t n, double *keys_sorted, int32_t *order32, DevBuf &tmp,
                          cudaStream_t stream) {
     return radix_sort<0>(keys, n, keys_sorted, order32, tmp, stream);
+}
+
+int32_t sort_asc_f64(const double *keys, int64_t n, double *keys_sorted, int32_t *order32, DevBuf &tmp,
+                     cudaStream_t stream) {
+    return radix_sort<2>(keys, n, keys_sorted, order32, tmp, stream);
 }
 
 int32_t sort_keys_i64(const int64_t *keys, int64_t n, int64_t *keys_sorted, int32_t *order32, DevBuf &tmp,

@@ -40,6 +40,7 @@ extern "C" {
 #define GENPF_ERR_NOMEM (-5)
 #define GENPF_ERR_UNSUPPORTED (-6)
 #define GENPF_ERR_STATE (-7)
+#define GENPF_ERR_ASSERT (-8) /* the reference would throw AssertionError (resize.jl:181,183) */
 
 /* ---- method / option enums (mirror the reference's Symbols, SURVEY.md section 5 "config") ---- */
 #define GENPF_MULTINOMIAL 0 /* :multinomial  resample.jl:48-65,  resize.jl:46-67  */
@@ -134,6 +135,17 @@ int32_t genpf_dereplicate_host(const double *lw, int64_t n, int64_t k, int32_t l
 int32_t genpf_coalesce_host(const double *lw, const int64_t *keys, int64_t n, uint32_t flags, int64_t *parents_out,
                             double *lw_out, int64_t *n_new);
 
+/* pf_optimal_resize! (resize.jl:149-196) with find_inv_w_threshold (resize.jl:199-216): Fearnhead-Clifford optimal
+ * resampling from n_in down to n_out <= n_in particles.  parents_out / lw_out sized n_out: first *n_keep entries
+ * are the kept particles in index order (weights lw + log(n_out/n_in)), the rest the systematic draws from the
+ * remainder (weights lse(lw) - log(c) + log(n_out/n_in)).  uniform = the single rand() of resize.jl:171 (host
+ * pointer), NULL => Philox(seed, stream 0, slot 0).  invalid_kinds[0]: safe_softmax of all weights, [1]: of the
+ * remainder.  Flags: INDEX_BASE1, DEVICE_PTRS (lw, parents_out, lw_out), CHECK.  GENPF_ERR_ASSERT where the
+ * reference's @assert would fail (n_out > n_in; the systematic pass selecting != n_out - n_keep particles). */
+int32_t genpf_optimal_resize(const double *lw, int64_t n_in, int64_t n_out, const double *uniform, uint64_t seed,
+                             uint32_t flags, int64_t *parents_out, double *lw_out, int64_t *n_keep,
+                             double *inv_w_threshold, int32_t *invalid_kinds);
+
 /* Philox uniforms exactly as the library generates them (for exporting / parity) */
 int32_t genpf_uniforms(uint64_t seed, uint64_t stream, int64_t n, uint32_t flags, double *out);
 
@@ -202,6 +214,10 @@ int32_t genpf_mean_var(genpf_filter_t pf, int32_t field, int64_t tau, double *me
 int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout);
 int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms);
 int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new);
+/* pf_resize!(state, n_out, :optimal) on device state (resize.jl:149-196); uniform: host pointer or NULL (library
+ * draw on the filter's resample stream) */
+int32_t genpf_optimal_resize_dev(genpf_filter_t pf, int64_t n_out, const double *uniform, uint32_t flags,
+                                 int64_t *n_keep, double *inv_w_threshold, int32_t *invalid_kinds);
 
 /* accessors (also checkpoint I/O): out sized n_particles*n_filters */
 int32_t genpf_get_log_weights(genpf_filter_t pf, double *out);

@@ -462,6 +462,79 @@ double orc_normal_logpdf(double x, double mu, double sigma) {
     double z = (x - mu) / sigma;
     return -(z * z + log(2.0 * M_PI)) / 2.0 - log(sigma);
 }
+/* ---- pf_optimal_resize! (resize.jl:149-196) + find_inv_w_threshold (resize.jl:199-216), literal ---- */
+static int cmp_double_asc(const void *a, const void *b) {
+    double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+static double julia_eps(double x) { /* eps(x): distance to the next larger float of |x| */
+    x = fabs(x);
+    return nextafter(x, INFINITY) - x;
+}
+double orc_find_inv_w_threshold(const double *w, int64_t n, int64_t n_particles) {
+    double *s = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    memcpy(s, w, sizeof(double) * (size_t)n);
+    qsort(s, (size_t)n, sizeof(double), cmp_double_asc); /* :200 */
+    int64_t A = n;                                       /* :202 */
+    double B = 0.0;                                      /* :203 */
+    for (int64_t r = 0; r < n; ++r) {
+        double kappa = s[r];
+        A -= 1;
+        B += kappa;
+        double n_check = B / kappa + (double)A;                 /* :208 */
+        if (n_check <= (double)n_particles + julia_eps(n_check)) { /* :209 */
+            double c = ((double)n_particles - (double)A) / B;   /* :211 */
+            free(s);
+            return c;
+        }
+    }
+    free(s);
+    return (double)n_particles; /* :214 */
+}
+/* returns 0, or -3 when the loop selects a number of particles different from n_resample (the reference's
+ * @assert at resize.jl:181 would throw); *n_selected reports what the loop produced */
+int32_t orc_optimal_resize(const double *lw, int64_t n, int64_t n_out, double u_rand, int64_t *parents1,
+                           double *lw_out, int64_t *n_keep_out, double *inv_w_out, int32_t *invalid_kind,
+                           int32_t *invalid_kind_strat, int64_t *n_selected) {
+    double *w = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int32_t kind = orc_safe_softmax(lw, n, w); /* :152 */
+    if (invalid_kind) *invalid_kind = kind;
+    double c = orc_find_inv_w_threshold(w, n, n_out); /* :155 */
+    if (inv_w_out) *inv_w_out = c;
+    int64_t *strat = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    double *slw = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *sw = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int64_t n_keep = 0, n_strat = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (c * w[i] >= 1.0) parents1[n_keep++] = i + 1; /* :156,159,177 */
+        else { strat[n_strat] = i + 1; slw[n_strat++] = lw[i]; }
+    }
+    if (n_keep_out) *n_keep_out = n_keep;
+    int64_t n_res = n_out - n_keep; /* :162 */
+    int32_t kind2 = n_strat > 0 ? orc_safe_softmax(slw, n_strat, sw) : 0; /* :166-167 */
+    if (invalid_kind_strat) *invalid_kind_strat = kind2;
+    double step = 1.0 / (double)n_res; /* :170 */
+    double u = u_rand * step;          /* :171 */
+    int64_t k = 0;
+    for (int64_t i = 0; i < n_strat; ++i) { /* :172-178 */
+        u = u - sw[i];
+        if (u < 0) {
+            if (n_keep + k < n_out) parents1[n_keep + k] = strat[i];
+            ++k;
+            u += step;
+        }
+    }
+    if (n_selected) *n_selected = k;
+    double log_n_ratio = log((double)n_out) - log((double)n); /* :187 */
+    double log_tot = orc_logsumexp(lw, n);                    /* :188 */
+    double res_lw = log_tot - log(c);                         /* :190 */
+    for (int64_t j = 0; j < n_keep && j < n_out; ++j) lw_out[j] = lw[parents1[j] - 1] + log_n_ratio; /* :192 */
+    for (int64_t j = n_keep; j < n_out; ++j) lw_out[j] = res_lw + log_n_ratio;                        /* :193 */
+    free(w); free(strat); free(slw); free(sw);
+    return k == n_res ? 0 : -3;
+}
+
+
 
 /* README.md:47-49: moving ~ bernoulli(moving ? .75 : .25) [rand() < p]; y ~ normal(y + vel, 0.01) [mu + sigma*randn()] */
 void orc_om_transition(const orc_om_params *p, int64_t n, const double *y_prev, const uint8_t *m_prev, double vel,

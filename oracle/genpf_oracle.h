@@ -75,6 +75,12 @@ void orc_dereplicate(const double *lw, int64_t n, int64_t k, int32_t interleaved
                      const double *u, int64_t *parents1, double *lw_out);
 int64_t orc_coalesce(const double *lw, const int64_t *keys, int64_t n, int64_t *parents1, double *lw_out);
 
+/* ---- pf_optimal_resize! (resize.jl:149-196), find_inv_w_threshold (resize.jl:199-216) ---- */
+double orc_find_inv_w_threshold(const double *w, int64_t n, int64_t n_particles);
+int32_t orc_optimal_resize(const double *lw, int64_t n, int64_t n_out, double u_rand, int64_t *parents1,
+                           double *lw_out, int64_t *n_keep, double *inv_w, int32_t *invalid_kind,
+                           int32_t *invalid_kind_strat, int64_t *n_selected);
+
 /* ---- device-plugin models, noise supplied as columns ---- */
 typedef struct {
     double p_stay, p_start, sigma_proc, sigma_obs;

@@ -210,6 +210,32 @@ def dereplicate(lw, k, interleaved=False, sample=False, u=None):
     return parents - 1, out
 
 
+def find_inv_w_threshold(w, n_particles):
+    w = _f(w)
+    fn = load().orc_find_inv_w_threshold
+    fn.restype = C.c_double
+    fn.argtypes = [_vp, C.c_int64, C.c_int64]
+    return fn(_p(w), w.size, n_particles)
+
+
+def optimal_resize(lw, n_out, u_rand):
+    """pf_optimal_resize! (resize.jl:149-196).  Returns dict(parents0, lw_out, n_keep, inv_w, kind, kind_strat,
+    n_selected, status); status -3 = the reference's @assert (resize.jl:181) would fail."""
+    lw = _f(lw)
+    parents = np.zeros(n_out, dtype=np.int64)
+    lw_out = np.zeros(n_out)
+    n_keep, n_sel = C.c_int64(), C.c_int64()
+    inv_w = C.c_double()
+    kind, kind2 = C.c_int32(), C.c_int32()
+    fn = load().orc_optimal_resize
+    fn.restype = C.c_int32
+    fn.argtypes = [_vp, C.c_int64, C.c_int64, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    st = fn(_p(lw), lw.size, n_out, float(u_rand), _p(parents), _p(lw_out), C.byref(n_keep), C.byref(inv_w),
+            C.byref(kind), C.byref(kind2), C.byref(n_sel))
+    return dict(parents0=parents - 1, lw_out=lw_out, n_keep=n_keep.value, inv_w=inv_w.value, kind=kind.value,
+                kind_strat=kind2.value, n_selected=n_sel.value, status=st)
+
+
 def coalesce(lw, keys):
     lw = _f(lw)
     keys = np.ascontiguousarray(keys, dtype=np.int64)

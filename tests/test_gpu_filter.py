@@ -324,6 +324,28 @@ def test_device_resizing(g, orc):
             g.pf_update(pf, (2,), None, 0.0)
 
 
+def test_device_optimal_resize(g, orc):
+    """pf_resize!(state, n, :optimal) on device state == the host-array call on the same weights + a gather."""
+    model = g.DeviceModel("object_motion")
+    n = 5000
+    for n_new in (n // 5, n // 2, n):
+        pf = g.pf_initialize(model, (1,), 0.1, n, seed=21)
+        g.pf_update(pf, (2,), None, 0.3)
+        lw0, y0, m0 = pf.log_weights, pf.field("y", 2), pf.field("moving", 2)
+        ref = orc.optimal_resize(lw0, n_new, 0.61)
+        g.pf_resize(pf, n_new, "optimal", uniform=0.61)
+        assert len(pf) == n_new
+        p = pf.parents
+        assert len(set(p.tolist())) == n_new
+        np.testing.assert_array_equal(p[:ref["n_keep"]], ref["parents0"][:ref["n_keep"]])
+        assert np.mean(p == ref["parents0"]) > 0.999
+        np.testing.assert_array_equal(pf.field("y", 2), y0[p])
+        np.testing.assert_array_equal(pf.field("moving", 2), m0[p])
+        np.testing.assert_allclose(pf.log_weights, ref["lw_out"], rtol=1e-10)
+        g.pf_update(pf, (3,), None, 0.2)  # the resized population keeps working
+        assert np.isfinite(g.effective_sample_size(pf))
+
+
 def test_history_lineage(g):
     """mean(state, tau=>addr) for a slice that left the window is resolved through the ancestry log."""
     obs = readme_observations()

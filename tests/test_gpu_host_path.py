@@ -486,3 +486,83 @@ def test_sort_particles_ties_and_signed_zero(g, orc, n):
     assert inc == pytest.approx(inc_ref, rel=RTOL)
     # the permutation itself: ancestors of distinct weight classes appear in descending weight order
     assert np.all(np.diff(lw[p]) <= 0)
+
+
+def raw_optimal_resize(g, lw, n_out, u=None, flags=0, seed=0):
+    L, lib = g._lib, g.load()
+    lw = np.ascontiguousarray(lw, dtype=np.float64)
+    parents = np.full(n_out, -7, dtype=np.int64)
+    lw_out = np.full(n_out, np.nan)
+    n_keep, inv_w, kinds = C.c_int64(-1), C.c_double(np.nan), (C.c_int32 * 2)(-1, -1)
+    up = None if u is None else C.byref(C.c_double(u))
+    st = lib.genpf_optimal_resize(L.ptr(lw), lw.size, n_out, up, seed, flags, L.ptr(parents), L.ptr(lw_out),
+                                  C.byref(n_keep), C.byref(inv_w), kinds)
+    return st, parents, lw_out, n_keep.value, inv_w.value, (kinds[0], kinds[1])
+
+
+@pytest.mark.parametrize("n", [100, 1000, 4097, 100_003, 1 << 20])
+@pytest.mark.parametrize("kind", ["A", "B"])
+def test_optimal_resize_vs_oracle(g, orc, n, kind):
+    """pf_optimal_resize! (resize.jl:149-216) against the literal CPU restatement with the same rand()."""
+    rng = np.random.default_rng(n + 11)
+    lw = weights(rng, n, kind)
+    for n_out in sorted({max(1, n // 7), n // 2, n - 1, n}):
+        u = float(rng.random())
+        ref = orc.optimal_resize(lw, n_out, u)
+        st, p, lw_out, n_keep, inv_w, kinds = raw_optimal_resize(g, lw, n_out, u)
+        assert st == 0 and kinds == (0, 0) if n_out > ref["n_keep"] else st == 0
+        assert inv_w == pytest.approx(ref["inv_w"], rel=1e-9)
+        w, _ = orc.safe_softmax(lw)
+        borderline = np.any(np.abs(ref["inv_w"] * w - 1.0) < 1e-9)  # keep test c*w >= 1 decided by rounding
+        if borderline:
+            continue
+        assert n_keep == ref["n_keep"]
+        np.testing.assert_array_equal(p[:n_keep], ref["parents0"][:n_keep])
+        np.testing.assert_allclose(lw_out, ref["lw_out"], rtol=RTOL)
+        n_res = n_out - n_keep
+        if n_res == 0:
+            continue
+        assert ref["status"] == 0
+        # systematic draws over the remainder: exact except at cumulative-sum ties
+        keep = np.zeros(n, dtype=bool)
+        keep[p[:n_keep]] = True
+        strat = np.flatnonzero(~keep)
+        C_ref = orc.cumweights(orc.safe_softmax(lw[strat])[0])
+        step = 1.0 / n_res
+        thr = u * step + np.arange(n_res) * step
+        q_gpu, q_ref = np.searchsorted(strat, p[n_keep:]), np.searchsorted(strat, ref["parents0"][n_keep:])
+        assert np.all(strat[q_gpu] == p[n_keep:]) and np.all(np.diff(p[n_keep:]) > 0)
+        check_parents(q_gpu, q_ref, C_ref, thr)
+
+
+def test_optimal_resize_kats_and_errors(g):
+    """test/resize.jl:86-113 through the host mirror (pf_resize!(state, n, :optimal))."""
+    rng = np.random.default_rng(3)
+    n = 100
+    for n_particles in (25, 50):
+        traces = [object() for _ in range(n)]
+        state = g.ParticleFilterState(traces, rng.normal(-20, 1.5, n))
+        lw0, lml0 = state.log_weights.copy(), g.get_lml_est(state)
+        g.pf_resize(state, n_particles, "optimal", uniform=0.25)
+        assert len(state.traces) == n_particles
+        assert all(state.traces[j] is traces[state.parents[j]] for j in range(n_particles))
+        assert g.get_lml_est(state) == pytest.approx(lml0, rel=1e-3)
+        assert len(set(state.parents.tolist())) == n_particles  # unique parents (the point of the algorithm)
+    state = g.ParticleFilterState(list(range(n)), np.full(n, -np.inf))
+    with pytest.raises(g.GenPFErrorException):
+        g.pf_optimal_resize(state, 50, check=True)
+    g.pf_optimal_resize(state, 50, check=False, uniform=0.3)
+    assert len(state.traces) == 50 and np.all(np.isneginf(state.log_weights))
+    state = g.ParticleFilterState(list(range(n)), np.zeros(n))
+    with pytest.raises(AssertionError):
+        g.pf_optimal_resize(state, n + 1)  # @assert n_particles <= n_old, resize.jl:183
+    # library-drawn uniform: deterministic in the seed
+    lw = rng.normal(0, 1, 5000)
+    a = raw_optimal_resize(g, lw, 1000, None, seed=9)
+    b = raw_optimal_resize(g, lw, 1000, None, seed=9)
+    c = raw_optimal_resize(g, lw, 1000, None, seed=10)
+    assert a[0] == 0 and np.array_equal(a[1], b[1]) and not np.array_equal(a[1], c[1])
+    u9 = np.empty(1)
+    g._lib.check(g.load().genpf_uniforms(9, 0, 1, 0, g._lib.ptr(u9)))
+    d = raw_optimal_resize(g, lw, 1000, float(u9[0]))
+    np.testing.assert_array_equal(a[1], d[1])

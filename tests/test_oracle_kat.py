@@ -241,3 +241,44 @@ def test_kat_object_motion_pieces(orc):
     prop, _ = orc.om_transition(y, m, math.sin(2.0), U, Z)
     alpha = orc.om_obs_logpdf(prop, 5.0) - orc.om_obs_logpdf(y2, 5.0)
     np.testing.assert_array_equal(acc, math.log(1.0 - 1e-12) < alpha)
+
+
+@pytest.mark.parametrize("n_particles", [25, 50])
+def test_optimal_resize_kat(orc, n_particles):
+    """test/resize.jl:86-105: length, parents, kept weights shifted by log(N/n), lml preserved to rtol 1e-3."""
+    rng = np.random.default_rng(5)
+    n = 100
+    lw = rng.normal(-20.0, 1.5, n)  # line-model-like log-weights: lml estimate well away from zero
+    w, _ = orc.safe_softmax(lw)
+    thresh = orc.find_inv_w_threshold(w, n_particles)
+    keep = np.flatnonzero(thresh * w >= 1)
+    r = orc.optimal_resize(lw, n_particles, 0.37)
+    assert r["status"] == 0 and r["n_selected"] == n_particles - keep.size
+    assert r["n_keep"] == keep.size and r["inv_w"] == thresh
+    np.testing.assert_array_equal(r["parents0"][:keep.size], keep)
+    np.testing.assert_allclose(r["lw_out"][:keep.size], lw[keep] + np.log(n_particles) - np.log(n), rtol=1e-12)
+    drawn = r["parents0"][keep.size:]
+    assert np.all(np.diff(drawn) > 0) and not np.intersect1d(drawn, keep).size  # unique, in index order
+    old = orc.logsumexp(lw) - np.log(n)
+    new = orc.logsumexp(r["lw_out"]) - np.log(n_particles)
+    assert new == pytest.approx(old, rel=1e-3)
+
+
+def test_optimal_resize_threshold_properties(orc):
+    """find_inv_w_threshold (resize.jl:199-216): c*B + A = N at the returned threshold; identity at N = n."""
+    rng = np.random.default_rng(6)
+    w, _ = orc.safe_softmax(rng.normal(0, 2, 1000))
+    for N in (1, 10, 500, 999):
+        c = orc.find_inv_w_threshold(w, N)
+        assert np.sum(np.minimum(c * w, 1.0)) == pytest.approx(N, rel=0.02)  # expected offspring sum to ~N
+    r = orc.optimal_resize(np.log(w), 1000, 0.5)
+    assert r["n_keep"] == 1000 and r["status"] == 0
+    np.testing.assert_array_equal(r["parents0"], np.arange(1000))
+
+
+def test_optimal_resize_invalid_weights(orc):
+    """test/resize.jl:107-113: all -Inf weights fall back to uniform, every output weight is -Inf."""
+    r = orc.optimal_resize(np.full(100, -np.inf), 50, 0.3)
+    assert r["kind"] == 2 and r["kind_strat"] == 2 and r["n_keep"] == 0 and r["status"] == 0
+    assert np.all(np.isneginf(r["lw_out"]))
+    np.testing.assert_array_equal(r["parents0"], np.arange(0, 100, 2))
