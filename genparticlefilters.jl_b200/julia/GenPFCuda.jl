@@ -81,6 +81,31 @@ function gpu_resample!(state::ParticleFilterView, method::Symbol=:multinomial;
     return state
 end
 
+# ---- pf_optimal_resize! (src/resize.jl:149-196): threshold search, keep set and systematic draws on the GPU
+function gpu_optimal_resize!(state::ParticleFilterState, n_particles::Int; check_=:warn,
+                             uniform::Union{Nothing,Float64}=nothing, seed::UInt64=rand(UInt64))
+    lw = state.log_weights
+    parents = Vector{Int64}(undef, n_particles)
+    lw_out = Vector{Float64}(undef, n_particles)
+    n_keep, inv_w, kinds = Ref{Int64}(0), Ref{Cdouble}(0.0), zeros(Int32, 2)
+    u = uniform === nothing ? C_NULL : Ref{Cdouble}(uniform)
+    status = ccall((:genpf_optimal_resize, LIB), Int32,
+                   (Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, UInt64, UInt32, Ptr{Int64}, Ptr{Cdouble},
+                    Ref{Int64}, Ref{Cdouble}, Ptr{Int32}),
+                   lw, length(lw), n_particles, u, seed, INDEX_BASE1 | (check_ == true ? CHECK : UInt32(0)),
+                   parents, lw_out, n_keep, inv_w, kinds)
+    status == -8 && throw(AssertionError(last_error()))               # @assert, src/resize.jl:181,183
+    check(status)
+    kinds[1] != 0 && check_ != false && @warn(WARNINGS[Int(kinds[1])])
+    resize!(state.parents, n_particles); resize!(state.new_traces, n_particles)
+    state.parents .= parents
+    state.new_traces .= view(state.traces, parents)                   # src/resize.jl:195
+    resize!(state.log_weights, n_particles); state.log_weights .= lw_out
+    tmp = state.traces; state.traces = state.new_traces; state.new_traces = tmp
+    resize!(state.new_traces, n_particles)                            # update_refs!(state, n), src/resize.jl:441-449
+    return state
+end
+
 # ---- statistics.jl:13-17,48-54
 function gpu_mean_var(state::ParticleFilterView, addr)
     x = Float64.(getindex.(state.traces, addr))
@@ -188,5 +213,9 @@ pf_replicate!(s::DevicePFState, k::Int; layout::Symbol=:contiguous) =
 pf_dereplicate!(s::DevicePFState, k::Int; layout::Symbol=:contiguous, method::Symbol=:keepfirst) =
     (check(ccall((:genpf_dereplicate, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Cdouble}),
                  s.handle, k, layout == :contiguous ? 0 : 1, method == :keepfirst ? 0 : 1, C_NULL)); s)
+pf_optimal_resize!(s::DevicePFState, n_particles::Int; check_=:warn) =
+    (check(ccall((:genpf_optimal_resize_dev, LIB), Int32,
+                 (Ptr{Cvoid}, Int64, Ptr{Cdouble}, UInt32, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int32}),
+                 s.handle, n_particles, C_NULL, check_ == true ? CHECK : UInt32(0), C_NULL, C_NULL, C_NULL)); s)
 
 end # module
