@@ -13,7 +13,7 @@ from .api import (DeviceModel, DevicePFState, GenPFErrorException, ParticleFilte
                   pf_move_accept, pf_move_reweight, pf_multinomial_resample, pf_multinomial_resize, pf_optimal_resize,
                   pf_rejuvenate,
                   pf_replicate, pf_resample, pf_residual_resample, pf_residual_resize, pf_resize, pf_step,
-                  pf_stratified_resample, pf_update, var)
+                  pf_stratified_resample, pf_update, proportionmap, var)
 
 # SURVEY.md 8(d) algorithmic bytes, defined ONCE here (bench.py and DESIGN.md cite this)
 ALGO_BYTES = {

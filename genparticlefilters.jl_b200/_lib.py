@@ -54,6 +54,7 @@ SIGNATURES = {
     "genpf_replicate_host": (i32, [_vp, i64, i64, i32, u32, _vp, _vp]),
     "genpf_dereplicate_host": (i32, [_vp, i64, i64, i32, i32, _vp, u64, u32, _vp, _vp]),
     "genpf_coalesce_host": (i32, [_vp, _vp, i64, u32, _vp, _vp, _ip]),
+    "genpf_proportionmap_host": (i32, [_vp, _vp, i64, u32, _vp, _vp, _ip]),
     "genpf_optimal_resize": (i32, [_vp, i64, i64, _dp, u64, u32, _vp, _vp, _ip, _dp, _i32p]),
     "genpf_uniforms": (i32, [u64, u64, i64, u32, _vp]),
     "genpf_debug_cumweights": (i32, [_vp, i64, u32, _vp]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "genpf_replicate": (i32, [_vp, i64, i32]),
     "genpf_dereplicate": (i32, [_vp, i64, i32, i32, _vp]),
     "genpf_coalesce": (i32, [_vp, _ip]),
+    "genpf_proportionmap": (i32, [_vp, i32, i64, _dp, _dp, i64, _ip]),
     "genpf_optimal_resize_dev": (i32, [_vp, i64, _dp, u32, _ip, _dp, _i32p]),
     "genpf_get_log_weights": (i32, [_vp, _vp]),
     "genpf_set_log_weights": (i32, [_vp, _vp]),

@@ -92,6 +92,7 @@ class DeviceModel:
         self.n_f64, self.n_u8, self.n_params, self.n_aux = nf.value, nb.value, npar.value, naux.value
         self.params = None if params is None else _f64(params)
         self.fields = {"object_motion": {"y": 0, "moving": 1}, "lingauss1d": {"x": 0}}[name]
+        self.bool_fields = {"object_motion": ("moving",), "lingauss1d": ()}[name]
 
     def aux(self, t):
         # object_motion: vel_y = sin(t) with integer t in radians, computed by the caller (README.md:48)
@@ -557,6 +558,33 @@ def mean(state, addr):
 def var(state, addr):
     """Statistics.var(state, addr), statistics.jl:48-50 (uncorrected, two-pass)."""
     return _mean_var(state, addr)[1]
+
+
+def proportionmap(state, addr, f=None, max_values=1 << 16):
+    """StatsBase.proportionmap(state, addr) / proportionmap(f, state, addr), statistics.jl:91-130: dict mapping each
+    distinct value at `addr` to the sum of normalised weights of the particles holding it."""
+    lib = L.load()
+    n_unique = C.c_int64()
+    if isinstance(state, DevicePFState):
+        if f is not None:
+            raise GenPFErrorException("proportionmap(f, ...) on a device state: apply f to the keys of the result")
+        tau, name = addr
+        vals, props = np.empty(max_values), np.empty(max_values)
+        L.check(lib.genpf_proportionmap(state._h, state.model.fields[name], int(tau), vals.ctypes.data_as(L._dp),
+                                        props.ctypes.data_as(L._dp), max_values, C.byref(n_unique)))
+        g = min(n_unique.value, max_values)
+        is_bool = name in getattr(state.model, "bool_fields", ())
+        return {(bool(v) if is_bool else float(v)): float(p) for v, p in zip(vals[:g], props[:g])}
+    vs = [tr[addr] for tr in state.traces]
+    if f is not None:
+        vs = [f(v) for v in vs]
+    codes = {}
+    keys = np.array([codes.setdefault(v, len(codes)) for v in vs], dtype=np.int64)
+    lw = _f64(state.log_weights)
+    first, props = np.empty(lw.size, dtype=np.int64), np.empty(lw.size)
+    L.check(lib.genpf_proportionmap_host(L.ptr(lw), L.ptr(keys), lw.size, 0, L.ptr(first), L.ptr(props),
+                                         C.byref(n_unique)))
+    return {vs[i]: float(p) for i, p in zip(first[:n_unique.value], props[:n_unique.value])}
 
 
 def pf_step(state, t, obs_prev, obs_t, *, method="stratified", ess_thresh=0.5, mh_iters=1, return_ess=True):

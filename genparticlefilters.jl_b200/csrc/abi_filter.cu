@@ -869,6 +869,41 @@ int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new) {
     return apply_parents_and_swap(pf, n_out);
 }
 
+int32_t genpf_proportionmap(genpf_filter_t pf, int32_t field, int64_t tau, double *values_out, double *props_out,
+                            int64_t cap, int64_t *n_unique) {
+    GENPF_TRY(check_resizable(pf));
+    if (!values_out || !props_out || cap <= 0) return fail(GENPF_ERR_INVALID_ARG, "genpf_proportionmap: bad arguments");
+    const int64_t n = pf->n;
+    XSrc x;
+    const int32_t *idx;
+    int64_t n_src;
+    GENPF_TRY(locate_field(pf, field, tau, &x, &idx, &n_src));
+    // the value column as doubles; its bit patterns are the grouping keys (Julia's isequal on Float64 / Bool)
+    GENPF_TRY(pf->tmp_col.ensure((size_t)n * 8));
+    GENPF_LAUNCH(k_read_field, dim3(grid_1d(n), 1), 256, pf->stream, x, idx, n_src, n, pf->tmp_col.as<double>());
+    GENPF_TRY(ensure_stats(pf, nullptr, -1.0, nullptr));
+    GENPF_TRY(pf->prio_buf.ensure((size_t)n * 8));
+    GENPF_TRY(pf->uni_buf.ensure((size_t)n * 8));
+    long long *n_dev = nullptr;
+    int32_t *first = reinterpret_cast<int32_t *>(pf->prio_buf.p);
+    double *prop = pf->uni_buf.as<double>();
+    GENPF_TRY(launch_coalesce<int32_t>(pf->stream, pf->cb, pf->lw, reinterpret_cast<const int64_t *>(pf->tmp_col.p), n, first,
+                                       (int64_t)0, prop, &n_dev, (const Stats *)pf->sc.st(0, 1)));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, n_dev, 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    const int64_t g = (int64_t) * reinterpret_cast<long long *>(pf->h_pinned);
+    if (n_unique) *n_unique = g;
+    const int64_t w = g < cap ? g : cap;
+    // values at the groups' first indices
+    GENPF_TRY(pf->key_buf.ensure((size_t)w * 8));
+    GENPF_LAUNCH(k_gather_f64, dim3(grid_1d(w), 1), 256, pf->stream, (const double *)pf->tmp_col.as<double>(),
+                 (const int32_t *)first, n, w, pf->key_buf.as<double>());
+    GENPF_CUDA_TRY(cudaMemcpyAsync(values_out, pf->key_buf.p, (size_t)w * 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(props_out, prop, (size_t)w * 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
+
 int32_t genpf_optimal_resize_dev(genpf_filter_t pf, int64_t n_out, const double *uniform, uint32_t flags,
                                  int64_t *n_keep, double *inv_w_threshold, int32_t *invalid_kinds) {
     GENPF_TRY(check_resizable(pf));

@@ -415,6 +415,39 @@ int32_t genpf_dereplicate_host(const double *lw, int64_t n, int64_t k, int32_t l
     return GENPF_OK;
 }
 
+int32_t genpf_proportionmap_host(const double *lw, const int64_t *keys, int64_t n, uint32_t flags,
+                                 int64_t *first_index_out, double *prop_out, int64_t *n_unique) {
+    if (!lw || !keys || !first_index_out || !prop_out || n <= 0)
+        return fail(GENPF_ERR_INVALID_ARG, "genpf_proportionmap_host: bad arguments");
+    HostWs &ws = g_ws;
+    GENPF_TRY(ws.init());
+    const bool dp = flags & GENPF_DEVICE_PTRS;
+    const double *d_lw;
+    const int64_t *d_keys;
+    GENPF_TRY(stage_in(ws, ws.lw, lw, n, dp, &d_lw));
+    GENPF_TRY(stage_in(ws, ws.keys, keys, n, dp, &d_keys));
+    int64_t *d_first;
+    double *d_prop;
+    GENPF_TRY(stage_out(ws.parents, first_index_out, n, dp, &d_first));
+    GENPF_TRY(stage_out(ws.lw_out, prop_out, n, dp, &d_prop));
+    GENPF_TRY(ws.sc.ensure(n, 1));
+    LwSrc src{d_lw, 1.0};
+    GENPF_TRY(launch_reduce(ws.stream, src, n, 1, ws.sc.partials(0)));
+    GENPF_TRY(launch_finalize(ws.stream, ws.sc, ws.sc.partials(0), n, 1, ws.sc.st(0, 1), nullptr, -1.0, nullptr));
+    long long *n_dev = nullptr;
+    GENPF_TRY(launch_coalesce<long long>(ws.stream, ws.cb, d_lw, d_keys, n, reinterpret_cast<long long *>(d_first),
+                                         (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0), d_prop, &n_dev,
+                                         (const Stats *)ws.sc.st(0, 1)));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(ws.h_scalars, n_dev, 8, cudaMemcpyDeviceToHost, ws.stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    const int64_t g = (int64_t) * reinterpret_cast<long long *>(ws.h_scalars);
+    if (n_unique) *n_unique = g;
+    GENPF_TRY(copy_out(ws, d_first, first_index_out, g, dp));
+    GENPF_TRY(copy_out(ws, d_prop, prop_out, g, dp));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    return GENPF_OK;
+}
+
 int32_t genpf_optimal_resize(const double *lw, int64_t n_in, int64_t n_out, const double *uniform, uint64_t seed,
                              uint32_t flags, int64_t *parents_out, double *lw_out, int64_t *n_keep,
                              double *inv_w_threshold, int32_t *invalid_kinds) {

@@ -5,13 +5,24 @@
 //   output  : one particle per group in ascending first-index order,
 //             lw = log(S_first) + log(n_new) - log(n_old) (resize.jl:327)
 // The reference emits groups in (unspecified) Dict order; callers compare as sets.
+// The same grouping with NORMALISED weights summed instead is StatsBase.proportionmap (statistics.jl:91-130):
+// proportion of each distinct value = sum of get_norm_weights over the group.
 #pragma once
 #include "engine.cuh"
 
 namespace genpf {
 
 static __global__ void k_coalesce_groups(const int64_t *keys_sorted, const int32_t *order, const double *lw, int64_t n,
-                                  double *acc, int32_t *is_first) {
+                                  double *acc, int32_t *is_first, const Stats *st_norm) {
+    // st_norm != null: accumulate safe_softmax weights (proportionmap) instead of exp(lw) (coalesce)
+    Stats st;
+    bool uniform = false;
+    double inv_S = 0.0;
+    if (st_norm) {
+        st = st_norm[0];
+        uniform = st.invalid_kind == 2 || st.invalid_kind == 3;
+        inv_S = 1.0 / st.S;
+    }
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         const int64_t key = keys_sorted[s];
         int64_t lo = 0, hi = s;  // first position with keys_sorted[pos] == key
@@ -20,7 +31,8 @@ static __global__ void k_coalesce_groups(const int64_t *keys_sorted, const int32
             if (keys_sorted[mid] < key) lo = mid + 1; else hi = mid;
         }
         const int32_t first = order[lo];  // stable sort => smallest original index of the group
-        atomicAdd(&acc[first], exp(lw[order[s]]));
+        const double v = lw[order[s]];
+        atomicAdd(&acc[first], st_norm ? (uniform ? 1.0 / (double)n : exp(v - st.M) * inv_S) : exp(v));
         if (lo == s) is_first[first] = 1;
     }
 }
@@ -49,7 +61,7 @@ static __global__ void k_flag_tile_offsets(long long *tile_sum, int64_t n_tiles,
 template <typename OutT>
 static __global__ void __launch_bounds__(kThreads)
     k_coalesce_write(const int32_t *is_first, const long long *tile_off, const long long *total, const double *acc,
-                     int64_t n, OutT *parents, int64_t out_base, double *lw_out) {
+                     int64_t n, OutT *parents, int64_t out_base, double *lw_out, int proportions) {
     __shared__ long long smi[32];
     const int64_t start = (int64_t)blockIdx.x * kTile;
     const int64_t valid = min((int64_t)kTile, n - start);
@@ -68,7 +80,7 @@ static __global__ void __launch_bounds__(kThreads)
         if (e < valid && fl[k]) {
             long long pos = off + inc[k] - 1;
             parents[pos] = (OutT)(start + e + out_base);
-            lw_out[pos] = log(acc[start + e]) + log_n_ratio;
+            lw_out[pos] = proportions ? acc[start + e] : log(acc[start + e]) + log_n_ratio;
         }
     }
 }
@@ -104,7 +116,8 @@ struct CoalesceBufs {
 // device pointers in, device pointers out; *n_new_dev is a device long long
 template <typename OutT>
 int32_t launch_coalesce(cudaStream_t s, CoalesceBufs &cb, const double *lw, const int64_t *keys, int64_t n,
-                        OutT *parents, int64_t out_base, double *lw_out, long long **n_new_dev) {
+                        OutT *parents, int64_t out_base, double *lw_out, long long **n_new_dev,
+                        const Stats *st_norm = nullptr) {
     const int64_t n_tiles = ceil_div(n, kTile);
     GENPF_TRY(cb.keys_sorted.ensure((size_t)n * 8));
     GENPF_TRY(cb.order.ensure((size_t)n * 4));
@@ -116,11 +129,12 @@ int32_t launch_coalesce(cudaStream_t s, CoalesceBufs &cb, const double *lw, cons
     GENPF_CUDA_TRY(cudaMemsetAsync(cb.acc.p, 0, (size_t)n * 8, s));
     GENPF_CUDA_TRY(cudaMemsetAsync(cb.is_first.p, 0, (size_t)n * 4, s));
     GENPF_LAUNCH(k_coalesce_groups, grid_1d(n), 256, s, cb.keys_sorted.as<int64_t>(), cb.order.as<int32_t>(), lw, n,
-                 cb.acc.as<double>(), cb.is_first.as<int32_t>());
+                 cb.acc.as<double>(), cb.is_first.as<int32_t>(), st_norm);
     GENPF_LAUNCH(k_flag_tile_sums, (unsigned)n_tiles, kThreads, s, cb.is_first.as<int32_t>(), n, cb.tile_sum.as<long long>());
     GENPF_LAUNCH(k_flag_tile_offsets, 1, 32, s, cb.tile_sum.as<long long>(), n_tiles, cb.total.as<long long>());
     GENPF_LAUNCH((k_coalesce_write<OutT>), (unsigned)n_tiles, kThreads, s, cb.is_first.as<int32_t>(),
-                 cb.tile_sum.as<long long>(), cb.total.as<long long>(), cb.acc.as<double>(), n, parents, out_base, lw_out);
+                 cb.tile_sum.as<long long>(), cb.total.as<long long>(), cb.acc.as<double>(), n, parents, out_base, lw_out,
+                 st_norm ? 1 : 0);
     *n_new_dev = cb.total.as<long long>();
     return GENPF_OK;
 }

@@ -135,6 +135,12 @@ int32_t genpf_dereplicate_host(const double *lw, int64_t n, int64_t k, int32_t l
 int32_t genpf_coalesce_host(const double *lw, const int64_t *keys, int64_t n, uint32_t flags, int64_t *parents_out,
                             double *lw_out, int64_t *n_new);
 
+/* StatsBase.proportionmap(state, addr), statistics.jl:91-130, with int64 codes standing for the values at addr:
+ * group g (ascending first-index order): first_index_out[g] = smallest particle index holding the value,
+ * prop_out[g] = sum of get_norm_weights over the group.  Outputs sized n (upper bound); *n_unique groups written. */
+int32_t genpf_proportionmap_host(const double *lw, const int64_t *keys, int64_t n, uint32_t flags,
+                                 int64_t *first_index_out, double *prop_out, int64_t *n_unique);
+
 /* pf_optimal_resize! (resize.jl:149-196) with find_inv_w_threshold (resize.jl:199-216): Fearnhead-Clifford optimal
  * resampling from n_in down to n_out <= n_in particles.  parents_out / lw_out sized n_out: first *n_keep entries
  * are the kept particles in index order (weights lw + log(n_out/n_in)), the rest the systematic draws from the
@@ -214,6 +220,10 @@ int32_t genpf_mean_var(genpf_filter_t pf, int32_t field, int64_t tau, double *me
 int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout);
 int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms);
 int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new);
+/* proportionmap(state, addr) on device state (statistics.jl:91-96): distinct values of `field` at slice tau (as
+ * doubles) and their proportions, up to cap groups written, *n_unique = number of distinct values (n_filters == 1) */
+int32_t genpf_proportionmap(genpf_filter_t pf, int32_t field, int64_t tau, double *values_out, double *props_out,
+                            int64_t cap, int64_t *n_unique);
 /* pf_resize!(state, n_out, :optimal) on device state (resize.jl:149-196); uniform: host pointer or NULL (library
  * draw on the filter's resample stream) */
 int32_t genpf_optimal_resize_dev(genpf_filter_t pf, int64_t n_out, const double *uniform, uint32_t flags,

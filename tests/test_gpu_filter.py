@@ -346,6 +346,23 @@ def test_device_optimal_resize(g, orc):
         assert np.isfinite(g.effective_sample_size(pf))
 
 
+def test_device_proportionmap(g):
+    """proportionmap(state, t => :moving) on device state equals mean(state, t => :moving) for a Bool field."""
+    model = g.DeviceModel("object_motion")
+    pf = g.pf_initialize(model, (1,), 0.1, 30_000, seed=4)
+    for t in range(2, 8):
+        g.pf_update(pf, (t,), None, 0.4 * t)
+    pm = g.proportionmap(pf, (7, "moving"))
+    assert set(pm) <= {True, False} and sum(pm.values()) == pytest.approx(1.0, rel=1e-12)
+    assert pm.get(True, 0.0) == pytest.approx(g.mean(pf, (7, "moving")), rel=1e-10)
+    lw, mv = pf.log_weights, pf.field("moving", 7)
+    w = np.exp(lw - lw.max())
+    w /= w.sum()
+    assert pm.get(False, 0.0) == pytest.approx(w[mv == 0].sum(), rel=1e-10)
+    ys = g.proportionmap(pf, (7, "y"), max_values=8)  # continuous field: every particle its own value
+    assert len(ys) == 8
+
+
 def test_history_lineage(g):
     """mean(state, tau=>addr) for a slice that left the window is resolved through the ancestry log."""
     obs = readme_observations()

@@ -566,3 +566,23 @@ def test_optimal_resize_kats_and_errors(g):
     g._lib.check(g.load().genpf_uniforms(9, 0, 1, 0, g._lib.ptr(u9)))
     d = raw_optimal_resize(g, lw, 1000, float(u9[0]))
     np.testing.assert_array_equal(a[1], d[1])
+
+
+def test_proportionmap(g, orc):
+    """StatsBase.proportionmap(state, addr) (statistics.jl:91-130): sum of normalised weights per distinct value."""
+    rng = np.random.default_rng(23)
+    n = 20_000
+    vals = rng.integers(-3, 4, n)
+    lw = rng.normal(0, 2, n)
+    state = g.ParticleFilterState([{"slope": int(v)} for v in vals], lw)
+    pm = g.proportionmap(state, "slope")
+    w = orc.softmax(lw)
+    assert set(pm) == set(int(v) for v in np.unique(vals))
+    for v, p in pm.items():
+        assert p == pytest.approx(w[vals == v].sum(), rel=RTOL)
+    assert sum(pm.values()) == pytest.approx(1.0, rel=1e-12)
+    pm2 = g.proportionmap(state, "slope", f=lambda v: v > 0)
+    assert pm2[True] == pytest.approx(w[vals > 0].sum(), rel=RTOL)
+    # degenerate: one value, and all -Inf weights (uniform fallback of get_norm_weights' safe path)
+    state = g.ParticleFilterState([{"slope": 1}] * 50, np.zeros(50))
+    assert g.proportionmap(state, "slope") == {1: pytest.approx(1.0)}
