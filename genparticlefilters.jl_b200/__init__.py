@@ -9,7 +9,7 @@ from ._lib import GenPFError, load
 from .api import *  # noqa: F401,F403
 from .api import (DeviceModel, DevicePFState, GenPFErrorException, ParticleFilterState, ParticleFilterSubState,
                   effective_sample_size, get_ess, get_lml_est, get_log_norm_weights, get_norm_weights,
-                  log_ml_estimate, logsumexp_host, mean, mh, pf_coalesce, pf_dereplicate, pf_initialize,
+                  log_ml_estimate, logsumexp_host, mean, mh, move_reweight, pf_coalesce, pf_dereplicate, pf_initialize,
                   pf_move_accept, pf_move_reweight, pf_multinomial_resample, pf_multinomial_resize, pf_optimal_resize,
                   pf_rejuvenate,
                   pf_replicate, pf_resample, pf_residual_resample, pf_residual_resize, pf_resize, pf_step,

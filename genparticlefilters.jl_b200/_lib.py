@@ -72,6 +72,8 @@ SIGNATURES = {
     "genpf_resample_dev": (i32, [_vp, i32, i32, f64, _vp, i64, u32, _vp, _vp]),
     "genpf_rejuvenate_mh": (i32, [_vp, i64, _vp, _vp, i32, _vp]),
     "genpf_rejuvenate_mh_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "genpf_rejuvenate_reweight": (i32, [_vp, i64, _vp, _vp, i32]),
+    "genpf_rejuvenate_reweight_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     "genpf_step": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, f64, i32, _vp]),
     "genpf_mean_var": (i32, [_vp, i32, i64, _vp, _vp]),
     "genpf_replicate": (i32, [_vp, i64, i32]),

@@ -521,8 +521,20 @@ def pf_move_accept(state, kern, kern_args=(), n_iters=1, **kwargs):
     return state
 
 
+def move_reweight(*a, **k):
+    """Marker for move_reweight(trace, selection) on a device state: pf_move_reweight(state, move_reweight, (tau, obs))."""
+    raise TypeError("move_reweight is only a marker for device states")
+
+
 def pf_move_reweight(state, kern, kern_args=(), n_iters=1, **kwargs):
-    """pf_move_reweight!, rejuvenate.jl:74-90 (host kernels only)."""
+    """pf_move_reweight!, rejuvenate.jl:74-90; device states: the built-in regenerate-and-reweight of slice tau."""
+    if isinstance(state, DevicePFState):
+        if kern is not move_reweight:
+            raise TypeError("device states reweight with the built-in move_reweight kernel")
+        tau, obs = kern_args
+        L.check(L.load().genpf_rejuvenate_reweight(state._h, int(tau), L.ptr(state._obs(obs)),
+                                                   L.ptr(state.model.aux(tau)), n_iters))
+        return state
     src, idxs = _resolve(state)
     for i in idxs:
         trace = src.traces[i]

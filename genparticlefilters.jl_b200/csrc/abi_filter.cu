@@ -139,30 +139,37 @@ int32_t read_stats(genpf_filter_t pf, int which) {
 }
 
 template <class Model, class Noise>
-static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise) {
+static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise,
+                         bool reweight) {
     const int64_t tpf = ceil_div(pf->n, kTile);
+    if (reweight) {
+        GENPF_LAUNCH((k_mh<Model, Noise, true>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter,
+                     tau == 1 ? 1 : 0, pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise,
+                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->lw);
+        return GENPF_OK;
+    }
     GENPF_LAUNCH((k_mh<Model, Noise>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
                  pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept);
     return GENPF_OK;
 }
 template <class Model>
 static int32_t mh_model(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val,
-                        const double *U2, const double *Z2, const double *U3) {
+                        const double *U2, const double *Z2, const double *U3, bool reweight) {
     if (U2 || Z2 || U3) {
         NoiseCols nz{U2, Z2, U3};
-        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz);
+        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
     }
     // the mh move on slice tau belongs to README iteration s = tau + 1 (it runs right before pf_update!(s))
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
-        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz);
+        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
     }
     NoiseLean nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
-    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz);
+    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
 }
 
 static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
-                     const double *U2, const double *Z2, const double *U3, int64_t *n_accept) {
+                     const double *U2, const double *Z2, const double *U3, int64_t *n_accept, bool reweight = false) {
     GENPF_TRY(check_filter(pf));
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
     if (tau != pf->t_cur) return fail(GENPF_ERR_UNSUPPORTED, "mh rejuvenation is implemented for tau == newest time step");
@@ -173,12 +180,13 @@ static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const do
     GENPF_TRY(stage_noise(pf, 0, U2, &dU2));
     GENPF_TRY(stage_noise(pf, 1, Z2, &dZ2));
     GENPF_TRY(stage_noise(pf, 2, U3, &dU3));
+    if (reweight) pf->part_valid = false;  // log-weights change
     GENPF_CUDA_TRY(cudaMemsetAsync(pf->n_accept, 0, (size_t)pf->nf * 8, pf->stream));
     for (int it = 0; it < n_iters; ++it) {
         int32_t st;
         switch (pf->model) {
-            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3); break;
-            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3); break;
+            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight); break;
+            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight); break;
             default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
         }
         GENPF_TRY(st);
@@ -621,6 +629,17 @@ int32_t genpf_rejuvenate_mh_with_noise(genpf_filter_t pf, int64_t tau, const dou
     if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
     if (!U2 || !Z2 || !U3) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
     return do_mh(pf, tau, obs, aux, 1, U2, Z2, U3, n_accept);
+}
+
+int32_t genpf_rejuvenate_reweight(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    return do_mh(pf, tau, obs, aux, n_iters, nullptr, nullptr, nullptr, nullptr, true);
+}
+int32_t genpf_rejuvenate_reweight_with_noise(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
+                                             const double *U2, const double *Z2) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    if (!U2 || !Z2) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    return do_mh(pf, tau, obs, aux, 1, U2, Z2, Z2, nullptr, true);
 }
 
 int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,

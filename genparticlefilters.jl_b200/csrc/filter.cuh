@@ -138,10 +138,13 @@ static __global__ void __launch_bounds__(kStateThreads)
 // pf_move_accept! (rejuvenate.jl:40-53) with kern = Gen.mh on select(tau => latents), tau the newest
 // slice: regenerate slice tau from the prior given slice tau-1; weight = obs log-density ratio;
 // accept iff log(rand()) < weight.  Log-weights are untouched.
-template <class Model, class Noise>
+// REWEIGHT: pf_move_reweight! with move_reweight(trace, selection) (rejuvenate.jl:74-90,125-132): the regenerated
+// slice always replaces the current one and the same weight is added to the particle's log-weight.
+template <class Model, class Noise, bool REWEIGHT = false>
 static __global__ void __launch_bounds__(kStateThreads)
     k_mh(ModelParams P, int64_t tau, int iter, int first_step, Cols prevprev, Cols cur, const double *obs_dev,
-         double obs_val, int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept) {
+         double obs_val, int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept,
+         double *lw = nullptr) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ double sm[T / 32];
     int64_t f, tile;
@@ -168,7 +171,13 @@ static __global__ void __launch_bounds__(kStateThreads)
         typename Model::Slice q;
         Model::transition(P, tau, sp[k], q, U, Z);
         double alpha = Model::obs_logpdf(P, q, obs) - Model::obs_logpdf(P, sc[k], obs);
-        bool a = (e < valid) && mh_accept(U3, alpha);
+        bool a;
+        if (REWEIGHT) {
+            a = e < valid;
+            if (a) lw[base + e] += alpha;
+        } else {
+            a = (e < valid) && mh_accept(U3, alpha);
+        }
         if (a) sc[k] = q;
         acc[k] = a ? 1 : 0;
         cnt += a ? 1.0 : 0.0;

@@ -213,6 +213,10 @@ pf_replicate!(s::DevicePFState, k::Int; layout::Symbol=:contiguous) =
 pf_dereplicate!(s::DevicePFState, k::Int; layout::Symbol=:contiguous, method::Symbol=:keepfirst) =
     (check(ccall((:genpf_dereplicate, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Cdouble}),
                  s.handle, k, layout == :contiguous ? 0 : 1, method == :keepfirst ? 0 : 1, C_NULL)); s)
+# pf_move_reweight!(state, move_reweight, (select(tau => ...),), n_iters), src/rejuvenate.jl:74-90,125-132
+pf_move_reweight!(s::DevicePFState, tau::Int, y_obs::Vector{Float64}, n_iters::Int=1) =
+    (check(ccall((:genpf_rejuvenate_reweight, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int32),
+                 s.handle, tau, y_obs, aux(s, tau), n_iters)); s)
 pf_optimal_resize!(s::DevicePFState, n_particles::Int; check_=:warn) =
     (check(ccall((:genpf_optimal_resize_dev, LIB), Int32,
                  (Ptr{Cvoid}, Int64, Ptr{Cdouble}, UInt32, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int32}),

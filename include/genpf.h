@@ -203,6 +203,12 @@ int32_t genpf_rejuvenate_mh(genpf_filter_t pf, int64_t tau, const double *obs, c
                             int64_t *n_accept);
 int32_t genpf_rejuvenate_mh_with_noise(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
                                        const double *U2, const double *Z2, const double *U3, int64_t *n_accept);
+/* pf_move_reweight!(state, move_reweight, (select(tau => ...),), n_iters), rejuvenate.jl:74-90,125-132: slice tau
+ * is regenerated from the model's conditional prior for every particle and log_weights += the regenerate weight
+ * (obs log-density of the new slice minus that of the old one).  _with_noise: U2, Z2 as in genpf_rejuvenate_mh. */
+int32_t genpf_rejuvenate_reweight(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters);
+int32_t genpf_rejuvenate_reweight_with_noise(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
+                                             const double *U2, const double *Z2);
 
 /* One README loop iteration (README.md:66-77) fused on the device:
  *   ess = effective_sample_size(state); if ess < ess_frac*n: pf_resample!(method); pf_rejuvenate!(mh) end;
