@@ -256,12 +256,12 @@ static int32_t resample_one(HostWs &ws, int32_t method, const double *d_lw, cons
 
     UniSrc uni{d_u, seed, make_stream(0, 0), slot_offset};
     const int64_t base = (flags & GENPF_INDEX_BASE1) ? 1 : 0;
+    // update_weights! (resample.jl:190-218, resize.jl:424-438): without priorities the constant weight is written
+    // by the kernels that write the ancestors
     GENPF_TRY(select_ancestors<long long>(s, sc, method, sel, n_in, n_out, 1, st_sel, uni, flags,
-                                          reinterpret_cast<long long *>(d_parents), base, 0));
-    // update_weights! (resample.jl:190-218, resize.jl:424-438)
-    if (!d_lp) {
-        GENPF_LAUNCH(k_fill_weights, dim3(grid_1d(n_out), 1), 256, s, d_lw_out, n_out, st_lw, substate ? 1 : 0, n_in, 0);
-    } else {
+                                          reinterpret_cast<long long *>(d_parents), base, 0, nullptr,
+                                          LwFill{d_lp ? nullptr : d_lw_out, st_lw, substate ? 1 : 0}));
+    if (d_lp) {
         GENPF_LAUNCH((k_prio_ratio<long long>), dim3(grid_1d(n_out), 1), 256, s, d_lw, sel,
                      reinterpret_cast<const long long *>(d_parents), base, n_in, n_out, d_lw_out);
         LwSrc dsrc{d_lw_out, 1.0};

@@ -107,7 +107,7 @@ inline int64_t guide_buckets(int64_t n) {
 template <typename IdxT, typename OutT>
 int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, int64_t n_in, int64_t n_out,
                            int64_t nf, Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base,
-                           int gate, const double *ew = nullptr) {
+                           int gate, const double *ew = nullptr, LwFill fill = LwFill{nullptr, nullptr, 0}) {
     const int64_t tpf_in = ceil_div(n_in, kTile), tpf_out = ceil_div(n_out, kTile);
     GENPF_TRY(sc.O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
     GENPF_TRY(sc.tile_last.ensure((size_t)(tpf_in * nf) * sizeof(IdxT)));
@@ -141,7 +141,7 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      WTables{nullptr}, O, tile_last, strat, gate, (const double *)nullptr, (int64_t)0,
                      sc.chunk_info_ptr(n_in), Scratch::kChunkTiles, ew_use, (const double *)sc.tile_scale.as<double>());
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
-                     parents, out_base, st_sel, gate, 0);
+                     parents, out_base, st_sel, gate, 0, fill);
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
@@ -157,7 +157,7 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      (const int32_t *)nullptr, G, (int64_t)0, st_sel, gate, 0);
         GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
                      kThreads, s, (const double *)wt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)nullptr, parents,
-                     out_base, st_sel, gate);
+                     out_base, st_sel, gate, fill);
     } else if (method == GENPF_RESIDUAL) {
         if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated residual resample is not supported");
         const size_t np = (size_t)(tpf_in * nf);
@@ -181,12 +181,12 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
                      tile_last, rt, GO, GTL, B);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
-                     (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1);
+                     (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1, fill);
         GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, GO, GTL, n_in, B, tpf_b,
                      (const int32_t *)nullptr, G, (int64_t)0, st_sel, 0, 0);
         GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
                      kThreads, s, (const double *)rt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)O, parents,
-                     out_base, st_sel, 0);
+                     out_base, st_sel, 0, fill);
     } else {
         return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
     }
@@ -196,12 +196,12 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
 template <typename OutT>
 int32_t select_ancestors(cudaStream_t s, Scratch &sc, int method, LwSrc sel, int64_t n_in, int64_t n_out, int64_t nf,
                          Stats *st_sel, UniSrc uni, uint32_t flags, OutT *parents, int64_t out_base, int gate,
-                         const double *ew = nullptr) {
+                         const double *ew = nullptr, LwFill fill = LwFill{nullptr, nullptr, 0}) {
     if (n_in < 0x7FFFFFF0ll && n_out < 0x7FFFFFF0ll)
         return select_ancestors_t<int32_t, OutT>(s, sc, method, sel, n_in, n_out, nf, st_sel, uni, flags, parents,
-                                                 out_base, gate, ew);
+                                                 out_base, gate, ew, fill);
     return select_ancestors_t<long long, OutT>(s, sc, method, sel, n_in, n_out, nf, st_sel, uni, flags, parents,
-                                               out_base, gate, ew);
+                                               out_base, gate, ew, fill);
 }
 
 // mean / var of column x under softmax(lw) (statistics.jl:13-17,48-54); results in sc.moment_out[0..nf) and [nf..2nf)

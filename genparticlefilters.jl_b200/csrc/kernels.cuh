@@ -721,10 +721,22 @@ __device__ __forceinline__ int64_t block_expand(const IdxT *Of, const IdxT *tile
     return s0;
 }
 
+// update_weights! without priorities fused into the kernels that write the ancestors: full state lw .= 0.0
+// (resample.jl:193-195), sub-state lw .= logsumexp(lw) - log(n_v) (resample.jl:208-210)
+struct LwFill {
+    double *out;      // null: the caller reweights separately (priorities, device filters)
+    const Stats *st;  // statistics of the log-weights (not of the priorities / sorted keys)
+    int substate;
+    __device__ __forceinline__ double value(int64_t f, int64_t n_in) const {
+        return substate ? st[f].lse - log((double)n_in) : 0.0;
+    }
+};
+
 template <typename IdxT, typename OutT>
 static __global__ void __launch_bounds__(kThreads)
     k_expand(const IdxT *O, const IdxT *tile_last_O, int64_t n_src, int64_t n_out, int64_t tpf_out,
-             const int32_t *order, OutT *parents, int64_t out_base, const Stats *stats, int gate, int residual) {
+             const int32_t *order, OutT *parents, int64_t out_base, const Stats *stats, int gate, int residual,
+             LwFill fill = LwFill{nullptr, nullptr, 0}) {
     __shared__ ExpandSmem<IdxT> sm;
     int64_t f, tile;
     blk_to_tile(tpf_out, f, tile);
@@ -752,6 +764,13 @@ static __global__ void __launch_bounds__(kThreads)
         out[k] = (OutT)(q + out_base);
     }
     store_tile<OutT>(parents, f * n_out + i0, valid, out);
+    if (fill.out) {
+        double w[kItems];
+        const double val = fill.value(f, n_src);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) w[k] = val;
+        store_tile<double>(fill.out, f * n_out + i0, valid, w);
+    }
 }
 
 // W-based stratified selection (debug / cross-check of the O path): parent_i = min{k : W_k >= u_i}
@@ -781,7 +800,8 @@ constexpr int kLookupItems = 4;
 template <typename IdxT, typename OutT>
 static __global__ void __launch_bounds__(kThreads)
     k_lookup(const double *W, const IdxT *G, int64_t B, int64_t n_src, int64_t n_out, UniSrc uni,
-             const IdxT *first_slot_O, OutT *parents, int64_t out_base, const Stats *stats, int gate) {
+             const IdxT *first_slot_O, OutT *parents, int64_t out_base, const Stats *stats, int gate,
+             LwFill fill = LwFill{nullptr, nullptr, 0}) {
     constexpr int K = kLookupItems;
     const int64_t f = blockIdx.y;
     if (stats) {
@@ -841,6 +861,7 @@ static __global__ void __launch_bounds__(kThreads)
             while (kk > 0 && __ldg(Wf + kk - 1) > u[k]) --kk;
         const int64_t j = j0 + k * kThreads + threadIdx.x;
         parents[f * n_out + j] = (OutT)(kk + out_base);
+        if (fill.out) fill.out[f * n_out + j] = fill.value(f, n_src);
     }
 }
 
@@ -1026,19 +1047,7 @@ static __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------ K9 reweight after resample
-// update_weights! without priorities: full state lw .= 0.0 (resample.jl:193-195); sub-state
-// lw .= logsumexp(lw) - log(n_v) (resample.jl:208-210).
-static __global__ void k_fill_weights(double *lw_out, int64_t n_out, const Stats *stats, int substate, int64_t n_in, int gate) {
-    int64_t f = blockIdx.y;
-    if (stats) {
-        const int kind = stats[f].invalid_kind;
-        if (kind == 1 || kind == 4) return;
-        if (gate && !stats[f].do_resample) return;
-    }
-    const double val = substate ? stats[f].lse - log((double)n_in) : 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x)
-        lw_out[f * n_out + j] = val;
-}
+// update_weights! without priorities is LwFill above (written by k_expand / k_lookup).
 // with priorities: d_j = lw[parent_j] - lp[parent_j] (resample.jl:197,212)
 template <typename InT>
 static __global__ void k_prio_ratio(const double *lw, LwSrc lp, const InT *parents, int64_t in_base, int64_t n_in,
