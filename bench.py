@@ -170,10 +170,24 @@ def run_reference(args):
                          "sample": f"{n_sample} particles per step (1/4 of the 2^24 workload), {args.steps} steps"},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # library banners (e.g. "NCCL version ...") go to stderr: stdout carries only the JSON line
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -365,7 +379,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_sample} particles x {steps_cpu} steps of the same step "
                                           "(C/OpenMP port of the reference algorithms; Julia absent from the image)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
