@@ -352,7 +352,7 @@ def main():
                                "+ MH rejuvenation + update per step (README.md:66-77, resample forced)",
                    "particles_per_gpu": n, "l2": "inputs larger than L2 (>=1.2 GB touched per step)",
                    "parallelism": "1 GPU" if world == 1 else f"one filter of {world}x2^24 particles sharded over "
-                                  f"{world} GPUs: NCCL all-gather of shard totals + NVLink P2P push of offspring",
+                                  f"{world} GPUs: shard totals exchanged through peer memory (NVLink stores + epoch flags), offspring pushed to the owner GPU over NVLink P2P inside the step kernel",
                    "sharding": shard_info,
                    "noise": "lean Philox4x32-10 (1 call/particle/purpose)", "algo_bytes_per_update": STEP_ALGO_BYTES},
         "clocks": clocks,
