@@ -232,13 +232,32 @@ get_lml_est = log_ml_estimate  # utils.jl:186
 
 
 # --------------------------------------------------------------------------- initialize.jl / update.jl
-def pf_initialize(model, model_args, observations, n_particles, **kw):
-    """initialize.jl:31-44.  Device models: observations = y_obs_1 (one per filter)."""
+def pf_initialize(model, model_args, observations, n_particles, *, strata=None, layout="contiguous", **kw):
+    """initialize.jl:31-44; with `strata` the stratified form (initialize.jl:93-108).  Device models:
+    observations = y_obs_1 (one per filter), strata = (field_name, values); host models: strata = iterable of
+    constraint dicts merged into the observations."""
     if isinstance(model, DeviceModel):
         state = DevicePFState(model, n_particles, **kw)
-        L.check(L.load().genpf_initialize(state._h, L.ptr(state._obs(observations)), L.ptr(model.aux(1))))
+        if strata is None:
+            L.check(L.load().genpf_initialize(state._h, L.ptr(state._obs(observations)), L.ptr(model.aux(1))))
+        else:
+            name, values = strata
+            vals = _f64([float(v) for v in values])
+            lay = L.LAYOUT_CONTIGUOUS if layout == "contiguous" else L.LAYOUT_INTERLEAVED
+            L.check(L.load().genpf_initialize_stratified(state._h, L.ptr(state._obs(observations)), L.ptr(model.aux(1)),
+                                                         model.fields[name], L.ptr(vals), vals.size, lay, None, None))
         state.t = 1
         return state
+    if strata is not None:
+        strata = list(strata)
+        k_n, block = len(strata), n_particles // len(strata)
+        traces, lws = [None] * n_particles, np.empty(n_particles)
+        assign = [(i // block if layout == "contiguous" else i % k_n) for i in range(block * k_n)]
+        assign += list(np.random.randint(0, k_n, n_particles - block * k_n))  # sample(strata, n_remaining)
+        for i, k in enumerate(assign):
+            traces[i], w = model.generate(model_args, {**strata[k], **observations})
+            lws[i] = w + math.log(k_n)  # initialize.jl:104
+        return ParticleFilterState(traces, lws)
     traces, lws = [], np.empty(n_particles)
     for i in range(n_particles):
         tr, w = model.generate(model_args, observations)

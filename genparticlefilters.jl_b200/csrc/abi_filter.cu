@@ -47,12 +47,12 @@ static int32_t stage_noise(genpf_filter_t pf, int which, const double *host, con
 
 template <class Model, class Noise>
 static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
-                                Noise noise) {
+                                Noise noise, Strata strata) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     const dim3 grid((unsigned)tpf, (unsigned)pf->nf);
     if (init) {
         GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
-                     pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew);
+                     pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew, strata);
     } else {
         GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(t - 1),
                      pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew);
@@ -61,17 +61,17 @@ static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const d
 }
 template <class Model>
 static int32_t propagate_model(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
-                               const double *U, const double *Z) {
+                               const double *U, const double *Z, Strata strata) {
     if (U || Z) {
         NoiseCols nz{U, Z, nullptr};
-        return launch_propagate<Model, NoiseCols>(pf, init, t, obs_dev, obs_val, nz);
+        return launch_propagate<Model, NoiseCols>(pf, init, t, obs_dev, obs_val, nz, strata);
     }
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)t, pf->rng_offset};
-        return launch_propagate<Model, NoisePhilox53>(pf, init, t, obs_dev, obs_val, nz);
+        return launch_propagate<Model, NoisePhilox53>(pf, init, t, obs_dev, obs_val, nz, strata);
     }
     NoiseLean nz{pf->seed, (uint64_t)t, pf->rng_offset};
-    return launch_propagate<Model, NoiseLean>(pf, init, t, obs_dev, obs_val, nz);
+    return launch_propagate<Model, NoiseLean>(pf, init, t, obs_dev, obs_val, nz, strata);
 }
 
 // freeze the slice that is about to leave the 2-slot window (GENPF_KEEP_HISTORY)
@@ -87,8 +87,13 @@ static int32_t archive_slice(genpf_filter_t pf, int64_t tau) {
     return GENPF_OK;
 }
 
+struct StrataHost {
+    int32_t field;
+    const double *values;
+    int32_t K, layout;
+};
 static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const double *obs, const double *aux,
-                            const double *U, const double *Z) {
+                            const double *U, const double *Z, const StrataHost *sh = nullptr) {
     GENPF_TRY(check_filter(pf));
     if (init) {
         if (t != 1) return fail(GENPF_ERR_INVALID_ARG, "initialize must create time step 1");
@@ -108,10 +113,20 @@ static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const doubl
     } else {
         GENPF_TRY(archive_slice(pf, t - 2));
     }
+    Strata strata{};
+    if (sh) {
+        if (!init) return fail(GENPF_ERR_INVALID_ARG, "strata apply to initialisation");
+        if (!sh->values || sh->K < 1 || sh->K > pf->n) return fail(GENPF_ERR_INVALID_ARG, "bad strata (need 1 <= K <= n_particles)");
+        if (sh->field < 0 || sh->field >= pf->NF + pf->NB) return fail(GENPF_ERR_INVALID_ARG, "strata field out of range");
+        GENPF_TRY(pf->strata_buf.ensure((size_t)sh->K * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->strata_buf.p, sh->values, (size_t)sh->K * 8, cudaMemcpyHostToDevice, pf->stream));
+        strata = Strata{pf->strata_buf.as<double>(), sh->K, sh->field, sh->layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, pf->seed,
+                        make_stream(kPurposeStrata, 0)};
+    }
     int32_t st;
     switch (pf->model) {
-        case kModelObjectMotion: st = propagate_model<ObjectMotion>(pf, init, t, obs_dev, obs_val, dU, dZ); break;
-        case kModelLinGauss1D: st = propagate_model<LinGauss1D>(pf, init, t, obs_dev, obs_val, dU, dZ); break;
+        case kModelObjectMotion: st = propagate_model<ObjectMotion>(pf, init, t, obs_dev, obs_val, dU, dZ, strata); break;
+        case kModelLinGauss1D: st = propagate_model<LinGauss1D>(pf, init, t, obs_dev, obs_val, dU, dZ, strata); break;
         default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
     }
     GENPF_TRY(st);
@@ -580,6 +595,13 @@ int32_t genpf_initialize_with_noise(genpf_filter_t pf, const double *obs, const 
                                     const double *Z) {
     if (!U || !Z) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
     return do_propagate(pf, true, 1, obs, aux, U, Z);
+}
+int32_t genpf_initialize_stratified(genpf_filter_t pf, const double *obs, const double *aux, int32_t field,
+                                    const double *values, int32_t n_strata, int32_t layout, const double *U,
+                                    const double *Z) {
+    if ((U == nullptr) != (Z == nullptr)) return fail(GENPF_ERR_INVALID_ARG, "give both noise columns or neither");
+    StrataHost sh{field, values, n_strata, layout};
+    return do_propagate(pf, true, 1, obs, aux, U, Z, &sh);
 }
 int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux) {
     return do_propagate(pf, false, t, obs, aux, nullptr, nullptr);

@@ -97,10 +97,26 @@ __device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_
 // ------------------------------------------------------------------ K10 propagate + weight (+ K1 partials)
 // INIT: pf_initialize (initialize.jl:39-41): slice_1 = transition(initial), lw = obs_logpdf
 // else: pf_update!    (update.jl:15-21):     slice_t = transition(slice_{t-1}), lw += obs_logpdf
+// Stratified initialisation (initialize.jl:93-108 with stratified_map!, utils.jl:29-55): K strata constrain one
+// latent of slice 1; each gets floor(n/K) particles in contiguous blocks or interleaved, the n - K*floor(n/K)
+// left-over particles (the last indices) go to strata drawn with replacement; log-weights gain log(K).
+struct Strata {
+    const double *values;  // device, K entries; null: plain pf_initialize
+    int K, field, interleaved;
+    uint64_t seed, stream;  // Philox stream of the left-over particles' strata
+    __device__ __forceinline__ int stratum(int64_t i, int64_t n) const {
+        const int64_t B = n / K;
+        if (i < B * K) return (int)(interleaved ? i % K : i / B);
+        const uint4 o = philox_at(seed, stream, (uint64_t)i);
+        const int k = (int)(u53(o.x, o.y) * (double)K);
+        return k < K ? k : K - 1;
+    }
+};
+
 template <class Model, class Noise, bool INIT>
 static __global__ void __launch_bounds__(kStateThreads)
     k_propagate(ModelParams P, int64_t t, Cols prev, Cols next, double *lw, const double *obs_dev, double obs_val,
-                int64_t n, int64_t tpf, Noise noise, Partials partials, double *ew) {
+                int64_t n, int64_t tpf, Noise noise, Partials partials, double *ew, Strata strata = Strata{}) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ PartialSmem ps;
     int64_t f, tile;
@@ -124,8 +140,14 @@ static __global__ void __launch_bounds__(kStateThreads)
         int e = tile_elem<T>(k);
         double U = 0.5, Z = 0.0;
         if (e < valid) noise.up(base + e, U, Z);
-        Model::transition(P, t, sp[k], sn[k], U, Z);
-        double l = Model::obs_logpdf(P, sn[k], obs);
+        double l = 0.0;
+        if (INIT && strata.values) {
+            const double val = strata.values[strata.stratum(e < valid ? start + e : 0, n)];
+            l = Model::constrain(P, t, sp[k], sn[k], U, Z, strata.field, val) + log((double)strata.K);
+        } else {
+            Model::transition(P, t, sp[k], sn[k], U, Z);
+        }
+        l += Model::obs_logpdf(P, sn[k], obs);
         if (e < valid) v[k] = INIT ? l : v[k] + l;
         else v[k] = -INFINITY;
     }

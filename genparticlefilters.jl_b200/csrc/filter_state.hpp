@@ -66,7 +66,7 @@ struct genpf_filter_s {
     double *lml = nullptr;
     double *obs_dev = nullptr;
     double *noise_cols[3] = {nullptr, nullptr, nullptr};
-    DevBuf noise_buf[3], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf;
+    DevBuf noise_buf[3], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf, strata_buf;
     CoalesceBufs cb;
     OptimalBufs ob;
     void *h_opt_ctrl = nullptr;  // pinned OptCtrl, allocated on first optimal resize

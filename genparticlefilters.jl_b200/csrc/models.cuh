@@ -68,6 +68,24 @@ struct ObjectMotion {
     static __device__ __forceinline__ double obs_logpdf(const ModelParams &p, const Slice &s, double obs) {
         return normal_logpdf(obs, s.f[0], p.v[5], p.v[4]);
     }
+    // generate(model, args, merge(stratum, observations)) (initialize.jl:101-104): latent `fld` (0 = y, 1 = moving)
+    // is constrained to `val`, the other one is sampled; returns the log-density of the constraint
+    static __device__ __forceinline__ double constrain(const ModelParams &p, int64_t, const Slice &prev, Slice &nxt,
+                                                       double U, double Z, int fld, double val) {
+        const double pm = prev.b[0] ? p.v[0] : p.v[1];
+        if (fld == 1) {
+            const uint8_t m = val != 0.0;
+            const double mu = __dadd_rn(prev.f[0], m ? p.aux[0] : 0.0);
+            nxt.f[0] = __dadd_rn(mu, __dmul_rn(p.v[2], Z));
+            nxt.b[0] = m;
+            return log(m ? pm : 1.0 - pm);  // logpdf(bernoulli, m, pm)
+        }
+        const uint8_t m = U < pm;
+        const double mu = __dadd_rn(prev.f[0], m ? p.aux[0] : 0.0);
+        nxt.f[0] = val;
+        nxt.b[0] = m;
+        return normal_logpdf(val, mu, 1.0 / p.v[2], log(p.v[2]));
+    }
 };
 
 // 1-D linear-Gaussian tracker: x_0 ~ N(m0, s0) marginalised into the first transition,
@@ -88,6 +106,13 @@ struct LinGauss1D {
     }
     static __device__ __forceinline__ double obs_logpdf(const ModelParams &p, const Slice &s, double obs) {
         return normal_logpdf(obs, s.f[0], p.v[7], p.v[5]);
+    }
+    static __device__ __forceinline__ double constrain(const ModelParams &p, int64_t t, const Slice &prev, Slice &nxt,
+                                                       double, double, int, double val) {
+        const double sig = (t == 1) ? p.v[6] : p.v[1];
+        nxt.f[0] = val;
+        nxt.b[0] = 0;
+        return normal_logpdf(val, __dmul_rn(p.v[0], prev.f[0]), 1.0 / sig, log(sig));
     }
 };
 

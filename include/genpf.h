@@ -181,6 +181,13 @@ int32_t genpf_filter_size(genpf_filter_t pf, int64_t *n_particles, int64_t *n_fi
 int32_t genpf_initialize(genpf_filter_t pf, const double *obs, const double *aux);
 int32_t genpf_initialize_with_noise(genpf_filter_t pf, const double *obs, const double *aux, const double *U,
                                     const double *Z);
+/* Stratified pf_initialize (initialize.jl:93-108, stratified_map! utils.jl:29-55): latent `field` of slice 1 is
+ * constrained to values[k] for the particles of stratum k (floor(n/K) each, GENPF_LAYOUT_CONTIGUOUS blocks or
+ * GENPF_LAYOUT_INTERLEAVED; the left-over last indices take strata drawn with replacement), the other latents are
+ * sampled, log_weights = log p(constraint) + obs log-density + log(K).  U/Z: noise columns (both or neither). */
+int32_t genpf_initialize_stratified(genpf_filter_t pf, const double *obs, const double *aux, int32_t field,
+                                    const double *values, int32_t n_strata, int32_t layout, const double *U,
+                                    const double *Z);
 
 /* pf_update!(state, (t,), (UnknownChange(),), obs_t), update.jl:12-25 */
 int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux);

@@ -256,6 +256,14 @@ class LGParams(C.Structure):
 OM_DEFAULT = (0.75, 0.25, 0.01, 0.25)  # README.md:47-50
 
 
+def normal_logpdf(x, mu, sigma):
+    """Gen logpdf(normal, x, mu, sigma), vectorised over x and mu (orc_normal_logpdf per element)."""
+    fn = load().orc_normal_logpdf
+    xs, mus = np.broadcast_arrays(np.asarray(x, dtype=np.float64), np.asarray(mu, dtype=np.float64))
+    out = np.array([fn(float(a), float(b), float(sigma)) for a, b in zip(xs.ravel(), mus.ravel())])
+    return out.reshape(xs.shape) if xs.shape else float(out[0])
+
+
 def om_transition(y_prev, m_prev, vel, U, Z, params=OM_DEFAULT):
     p = OMParams(*params)
     n = len(U)

@@ -346,6 +346,53 @@ def test_device_optimal_resize(g, orc):
         assert np.isfinite(g.effective_sample_size(pf))
 
 
+@pytest.mark.parametrize("layout", ["contiguous", "interleaved"])
+def test_device_stratified_initialize(g, orc, layout):
+    """Stratified pf_initialize (initialize.jl:93-108 + stratified_map!, utils.jl:29-55; test/initialize.jl:39-64)."""
+    L = g._lib
+    lib = g.load()
+    n, K = 1000, 2
+    rng = np.random.default_rng(12)
+    model = g.DeviceModel("object_motion")
+    pf = g.DevicePFState(model, n, seed=3)
+    U, Z = rng.random(n), rng.normal(size=n)
+    vals = np.array([0.0, 1.0])
+    lay = L.LAYOUT_CONTIGUOUS if layout == "contiguous" else L.LAYOUT_INTERLEAVED
+    L.check(lib.genpf_initialize_stratified(pf._h, L.ptr(pf._obs(0.3)), L.ptr(model.aux(1)), model.fields["moving"],
+                                            L.ptr(vals), K, lay, L.ptr(U), L.ptr(Z)))
+    pf.t = 1
+    k = np.arange(n) // (n // K) if layout == "contiguous" else np.arange(n) % K
+    m = vals[k].astype(np.uint8)
+    vel = math.sin(1.0)
+    y = (0.0 + np.where(m == 1, vel, 0.0)) + 0.01 * Z
+    np.testing.assert_array_equal(pf.field("moving", 1), m)  # every particle sits in its stratum
+    np.testing.assert_array_equal(pf.field("y", 1), y)
+    lw = np.log(np.where(m == 1, 0.25, 0.75)) + orc.om_obs_logpdf(y, 0.3) + math.log(K)  # initialize.jl:104
+    np.testing.assert_allclose(pf.log_weights, lw, rtol=RTOL)
+    assert g.effective_sample_size(pf) == pytest.approx(orc.ess(lw), rel=RTOL)
+    # same target as the plain initialisation: the log marginal likelihood estimates agree
+    big = 200_000
+    a = g.pf_initialize(model, (1,), 0.3, big, seed=5)
+    b = g.pf_initialize(model, (1,), 0.3, big, seed=6, strata=("moving", [False, True]), layout=layout)
+    assert g.log_ml_estimate(b) == pytest.approx(g.log_ml_estimate(a), abs=0.02)
+    assert g.mean(b, (1, "moving")) == pytest.approx(g.mean(a, (1, "moving")), abs=0.01)
+    g.pf_update(b, (2,), None, 0.4)  # the stratified population keeps working
+    # left-over particles (n not a multiple of K) take strata drawn with replacement; a continuous latent as stratum
+    grid = np.linspace(-0.5, 0.5, 5)
+    c = g.pf_initialize(model, (1,), 0.3, 1003, seed=7, strata=("y", grid), layout=layout)
+    yy = c.field("y", 1)
+    kk = np.arange(1000) // 200 if layout == "contiguous" else np.arange(1000) % 5
+    np.testing.assert_array_equal(yy[:1000], grid[kk])
+    assert np.all(np.isin(yy[1000:], grid)) and np.isfinite(c.log_weights).all()
+    lg = g.pf_initialize(g.DeviceModel("lingauss1d", (0.9, 1.0, 1.0, 0.0, 1.0)), (1,), 0.2, 600, seed=8,
+                         strata=("x", [-1.0, 0.0, 1.0]), layout=layout)
+    x = lg.field("x", 1)
+    assert set(np.unique(x)) == {-1.0, 0.0, 1.0}
+    sig = math.sqrt(0.81 + 1.0)
+    expect = orc.normal_logpdf(x, 0.0, sig) + orc.normal_logpdf(0.2, x, 1.0) + math.log(3)
+    np.testing.assert_allclose(lg.log_weights, expect, rtol=1e-9)
+
+
 def test_device_move_reweight(g, orc):
     """pf_move_reweight!(state, move_reweight, (select(tau),)) (rejuvenate.jl:74-90,125-132) with supplied noise:
     slice tau regenerated from the conditional prior for every particle, log_weights += the regenerate weight."""
