@@ -248,7 +248,7 @@ def main():
                              return_ess=True)
     else:
         # ONE filter of world * n particles, slots sharded contiguously over the ranks:
-        # NCCL all-gathers of shard totals on the filter's stream + NVLink P2P push of offspring
+        # shard totals exchanged through peer memory inside 1-warp kernels + NVLink P2P push of offspring
         from genpf_b200.sharded import ShardedFilter
         sf = ShardedFilter(model, n, seed=1234)
         sf.initialize(obs[0])

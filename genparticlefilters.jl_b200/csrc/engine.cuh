@@ -88,14 +88,10 @@ inline StratArgs make_strat(UniSrc uni, int64_t n) {
     return a;
 }
 
-// guide-table size for the inverse-CDF lookups: two particles per bucket measured best (2^24: shift 0..5 within 15 %); the table stays L2 resident next to a
-// DRAM-sized W and the bracket inside one 32-byte sector of W (GENPF_GUIDE_SHIFT overrides, for tuning)
+// guide-table size for the inverse-CDF lookups: two particles per bucket measured best at 2^24 (bucket sizes
+// of 1..32 particles stay within 15 %: a bigger table misses L2 more often, a smaller one lengthens the bracket)
 inline int64_t guide_buckets(int64_t n) {
-    static const int shift = [] {
-        const char *e = getenv("GENPF_GUIDE_SHIFT");
-        return e ? atoi(e) : 1;
-    }();
-    const int64_t b = n >> shift;
+    const int64_t b = n >> 1;
     return b > 0 ? b : 1;
 }
 
