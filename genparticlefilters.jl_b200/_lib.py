@@ -58,6 +58,7 @@ SIGNATURES = {
     "genpf_optimal_resize": (i32, [_vp, i64, i64, _dp, u64, u32, _vp, _vp, _ip, _dp, _i32p]),
     "genpf_uniforms": (i32, [u64, u64, i64, u32, _vp]),
     "genpf_debug_cumweights": (i32, [_vp, i64, u32, _vp]),
+    "genpf_debug_sortperm": (i32, [_vp, i64, u32, _vp]),
     "genpf_model_builtin": (i32, [C.c_char_p, _i32p]),
     "genpf_model_info": (i32, [i32, _i32p, _i32p, _i32p, _i32p]),
     "genpf_filter_create": (i32, [i32, _vp, i32, i64, i64, u64, u32, C.POINTER(_vp)]),

@@ -495,6 +495,24 @@ int32_t genpf_uniforms(uint64_t seed, uint64_t stream, int64_t n, uint32_t flags
     return GENPF_OK;
 }
 
+int32_t genpf_debug_sortperm(const double *keys, int64_t n, uint32_t flags, int64_t *order_out) {
+    if (!keys || !order_out || n <= 0) return fail(GENPF_ERR_INVALID_ARG, "genpf_debug_sortperm: bad arguments");
+    HostWs &ws = g_ws;
+    GENPF_TRY(ws.init());
+    const bool dp = flags & GENPF_DEVICE_PTRS;
+    const double *d_keys;
+    GENPF_TRY(stage_in(ws, ws.lw, keys, n, dp, &d_keys));
+    int64_t *d_out;
+    GENPF_TRY(stage_out(ws.parents, order_out, n, dp, &d_out));
+    GENPF_TRY(ws.sc.order.ensure((size_t)n * 4));
+    GENPF_TRY(sort_desc_stable(d_keys, n, nullptr, ws.sc.order.as<int32_t>(), ws.sc.sort_tmp, ws.stream));
+    GENPF_LAUNCH((k_convert_idx<int32_t, long long>), grid_1d(n), 256, ws.stream, (const int32_t *)ws.sc.order.as<int32_t>(),
+                 reinterpret_cast<long long *>(d_out), n, (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0));
+    GENPF_TRY(copy_out(ws, d_out, order_out, n, dp));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(ws.stream));
+    return GENPF_OK;
+}
+
 int32_t genpf_debug_cumweights(const double *lw, int64_t n, uint32_t flags, double *W_out) {
     if (!lw || !W_out || n <= 0) return fail(GENPF_ERR_INVALID_ARG, "genpf_debug_cumweights: bad arguments");
     HostWs &ws = g_ws;

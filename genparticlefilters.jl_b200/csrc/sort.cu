@@ -11,6 +11,10 @@
 //                    order across chunks and warps), the tile's global offsets come from a decoupled look-back
 //                    over the per-tile digit counts (tiles take tickets, so every predecessor is resident), and
 //                    the tile leaves in digit order through shared memory
+//   k_fix_*          (>= 2^18 keys) only the five top digits are sorted; keys agreeing on them (within 4e-9
+//                    relative) form runs in original-index order, runs containing an inversion are insertion-sorted in
+//                    place, and a run too long for that un-gates a complete 8-digit sort whose kernels otherwise
+//                    return at once (no host round trip)
 //   k_sort_finish    inverse key transform, order -> caller's buffers (the ping-pong parity is device resident)
 // Stability across tiles comes from the ticket order, inside a tile from the in-order walk, so equal keys keep
 // ascending original index -- Julia's sortperm tie rule.  The key transform reproduces Julia's `isless` total
@@ -46,11 +50,16 @@ struct SortCtrl {
     uint32_t skip[kSortPasses];        // every key has the same digit: the pass would be the identity
     uint32_t src_parity[kSortPasses];  // which ping-pong buffer holds the input of the pass
     uint32_t final_parity;
+    uint32_t go;  // fallback sequence only: set by the fix-up when a run is too long to repair locally
+    uint32_t low_const;  // every key has the same low digits: runs cannot contain inversions, no fix-up
 };
+constexpr int kLowDigits = 3;     // the hybrid sort orders by the top 64 - 8*kLowDigits bits, then repairs runs
+constexpr int kFixWalk = 64;      // longest walk back to a run's start / longest run repaired in place: 2*kFixWalk
 
 template <int MODE>
 static __global__ void __launch_bounds__(kSortThreads)
-    k_radix_prepare(const void *keys, int64_t n, uint64_t *k_out, int32_t *idx, SortCtrl *ctrl) {
+    k_radix_prepare(const void *keys, int64_t n, uint64_t *k_out, int32_t *idx, SortCtrl *ctrl, int gated) {
+    if (gated && !ctrl->go) return;
     __shared__ uint32_t h[kSortPasses][256];
     for (int d = threadIdx.x; d < kSortPasses * 256; d += kSortThreads) (&h[0][0])[d] = 0;
     __syncthreads();
@@ -80,15 +89,18 @@ static __global__ void __launch_bounds__(kSortThreads)
     }
 }
 
-static __global__ void __launch_bounds__(256) k_radix_plan(SortCtrl *ctrl, int64_t n) {
+static __global__ void __launch_bounds__(256) k_radix_plan(SortCtrl *ctrl, int64_t n, int first_digit, int gated) {
+    if (gated && !ctrl->go) return;
     __shared__ uint32_t sw[8];
     __shared__ uint32_t s_skip[kSortPasses];
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    if (d < kSortPasses) s_skip[d] = 0;
+    __shared__ uint32_t s_const[kSortPasses];
+    if (d < kSortPasses) s_skip[d] = s_const[d] = 0;
     __syncthreads();
     for (int p = 0; p < kSortPasses; ++p) {
         const uint32_t c = ctrl->hist[p][d];
-        if ((int64_t)c == n) s_skip[p] = 1;
+        if ((int64_t)c == n) s_const[p] = 1;
+        if ((int64_t)c == n || p < first_digit) s_skip[p] = 1;
         uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -112,6 +124,9 @@ static __global__ void __launch_bounds__(256) k_radix_plan(SortCtrl *ctrl, int64
             if (!s_skip[p]) parity ^= 1u;
         }
         ctrl->final_parity = parity;
+        uint32_t lc = 1;
+        for (int p = 0; p < first_digit; ++p) lc &= s_const[p];
+        ctrl->low_const = lc;
     }
 }
 
@@ -120,8 +135,9 @@ static __global__ void __launch_bounds__(256) k_radix_plan(SortCtrl *ctrl, int64
 template <int THREADS, int MINB>
 static __global__ void __launch_bounds__(THREADS, MINB)
     k_radix_onesweep(SortCtrl *ctrl, int pass, uint64_t *kA, uint64_t *kB, int32_t *vA, int32_t *vB, int64_t n,
-                     uint32_t *state) {
+                     uint32_t *state, int gated) {
     constexpr int NW = THREADS / 32, CH = 8, TILE = THREADS * CH;  // each warp owns a contiguous run of 256 keys
+    if (gated && !ctrl->go) return;
     if (ctrl->skip[pass]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *skey = reinterpret_cast<uint64_t *>(smem_raw);           // [TILE] the tile in digit order
@@ -250,10 +266,68 @@ constexpr size_t onesweep_smem() {
     return (size_t)THREADS * 8 * 12 + (size_t)(THREADS / 32) * 1024 + 1024 + 64;
 }
 
+// ---- hybrid sort: after the passes over the top digits, keys that agree on those digits sit in one run in
+// original-index order.  An inversion (key[s] < key[s-1] inside a run) marks the run's start dirty; dirty runs are
+// insertion-sorted in place (stable).  Runs of equal keys -- replicated particles, equal weights, -Inf -- have no
+// inversion and cost nothing.  A run longer than the walk limits raises `go`, which un-gates a full 8-digit sort.
+static __global__ void k_fix_detect(const SortCtrl *ctrl, const uint64_t *kA, const uint64_t *kB, int64_t n, uint8_t *dirty,
+                                    SortCtrl *fallback) {
+    if (ctrl->low_const) return;
+    const uint64_t *ks = ctrl->final_parity ? kB : kA;
+    constexpr int sh = 8 * kLowDigits;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = ks[s - 1], b = ks[s];
+        if ((a >> sh) != (b >> sh) || b >= a) continue;
+        int64_t t = s - 1;
+        int steps = 0;
+        while (t > 0 && (ks[t - 1] >> sh) == (b >> sh)) {
+            --t;
+            if (++steps > kFixWalk) {
+                fallback->go = 1;
+                break;
+            }
+        }
+        dirty[t] = 1;
+    }
+}
+static __global__ void k_fix_sort(const SortCtrl *ctrl, uint64_t *kA, uint64_t *kB, int32_t *vA, int32_t *vB, int64_t n,
+                                  const uint8_t *dirty, SortCtrl *fallback) {
+    if (ctrl->low_const) return;
+    uint64_t *ks = ctrl->final_parity ? kB : kA;
+    int32_t *vs = ctrl->final_parity ? vB : vA;
+    constexpr int sh = 8 * kLowDigits;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        if (!dirty[s]) continue;
+        const uint64_t top = ks[s] >> sh;
+        int64_t e = s + 1;
+        while (e < n && (ks[e] >> sh) == top) {
+            ++e;
+            if (e - s > 2 * kFixWalk) break;
+        }
+        if (e - s > 2 * kFixWalk) {
+            fallback->go = 1;
+            continue;
+        }
+        for (int64_t i = s + 1; i < e; ++i) {  // stable insertion sort of the run by the full key
+            const uint64_t k = ks[i];
+            const int32_t v = vs[i];
+            int64_t j = i;
+            while (j > s && ks[j - 1] > k) {
+                ks[j] = ks[j - 1];
+                vs[j] = vs[j - 1];
+                --j;
+            }
+            ks[j] = k;
+            vs[j] = v;
+        }
+    }
+}
+
 template <int MODE>
-static __global__ void k_sort_finish(const SortCtrl *ctrl, const uint64_t *kA, const uint64_t *kB, const int32_t *vA,
-                                     const int32_t *vB, int64_t n, void *keys_sorted, int32_t *order32) {
-    const bool in_b = ctrl->final_parity != 0;
+static __global__ void k_sort_finish(const SortCtrl *ctrl, const SortCtrl *fallback, const uint64_t *kA, const uint64_t *kB,
+                                     const int32_t *vA, const int32_t *vB, int64_t n, void *keys_sorted, int32_t *order32) {
+    const SortCtrl *c = (fallback && fallback->go) ? fallback : ctrl;
+    const bool in_b = c->final_parity != 0;
     const uint64_t *ks = in_b ? kB : kA;
     const int32_t *vs = in_b ? vB : vA;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -272,21 +346,26 @@ static int32_t radix_sort(const void *keys, int64_t n, void *keys_sorted, int32_
     if (n >= 0x40000000ll) return fail(GENPF_ERR_UNSUPPORTED, "sort: n must be < 2^30");
     // measured (2^22 / 2^24 / 2^26 keys): 2048-key tiles 0.49 / 1.66 / 6.66 ms, 4096-key tiles 0.53 / 1.63 / 5.92 ms
     const bool use_big = n >= (1 << 25);
+    // hybrid (top digits + run repair, full sort only as a device-gated fallback) pays off once a pass costs more
+    // than the dozen extra (mostly empty) launches
+    const bool hybrid = n >= (1 << 18);
     const int64_t tile_keys = use_big ? 4096 : 2048;
     const int64_t ntiles = ceil_div(n, tile_keys);
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const int n_seq = hybrid ? 2 : 1;
     const size_t a = al((size_t)n * 8), b = al((size_t)n * 4), c = al(sizeof(SortCtrl)),
-                 st = al((size_t)ntiles * 256 * 4);
-    GENPF_TRY(tmp.ensure(2 * a + 2 * b + c + kSortPasses * st + 256));
+                 st = al((size_t)ntiles * 256 * 4), dz = hybrid ? al((size_t)n) : 0;
+    const size_t zero_bytes = n_seq * (c + kSortPasses * st) + dz;
+    GENPF_TRY(tmp.ensure(2 * a + 2 * b + zero_bytes + 256));
     char *base = tmp.as<char>();
     uint64_t *kA = (uint64_t *)base, *kB = (uint64_t *)(base + a);
     int32_t *vA = (int32_t *)(base + 2 * a), *vB = (int32_t *)(base + 2 * a + b);
-    SortCtrl *ctrl = (SortCtrl *)(base + 2 * a + 2 * b);
-    uint32_t *state = (uint32_t *)(base + 2 * a + 2 * b + c);
-    GENPF_CUDA_TRY(cudaMemsetAsync(ctrl, 0, c + kSortPasses * st, stream));
+    char *z = base + 2 * a + 2 * b;
+    SortCtrl *ctrl[2] = {(SortCtrl *)z, (SortCtrl *)(z + c + kSortPasses * st)};
+    uint32_t *state[2] = {(uint32_t *)(z + c), (uint32_t *)(z + c + kSortPasses * st + c)};
+    uint8_t *dirty = (uint8_t *)(z + n_seq * (c + kSortPasses * st));
+    GENPF_CUDA_TRY(cudaMemsetAsync(z, 0, zero_bytes, stream));
     const unsigned gprep = (unsigned)std::min<int64_t>(ceil_div(n, kSortThreads), 148 * 16);
-    GENPF_LAUNCH((k_radix_prepare<MODE>), gprep, kSortThreads, stream, keys, n, kA, vA, ctrl);
-    GENPF_LAUNCH(k_radix_plan, 1, 256, stream, ctrl, n);
     static const bool attr_set = [] {
         cudaFuncSetAttribute(k_radix_onesweep<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)onesweep_smem<512>());
@@ -295,17 +374,30 @@ static int32_t radix_sort(const void *keys, int64_t n, void *keys_sorted, int32_
         return true;
     }();
     (void)attr_set;
-    for (int pass = 0; pass < kSortPasses; ++pass) {
-        uint32_t *stp = state + (size_t)pass * (st / 4);
-        if (use_big)
-            GENPF_LAUNCH_SMEM((k_radix_onesweep<512, 3>), (unsigned)ntiles, 512, onesweep_smem<512>(), stream, ctrl, pass, kA,
-                              kB, vA, vB, n, stp);
-        else
-            GENPF_LAUNCH_SMEM((k_radix_onesweep<256, 4>), (unsigned)ntiles, 256, onesweep_smem<256>(), stream, ctrl, pass, kA,
-                              kB, vA, vB, n, stp);
+    for (int seq = 0; seq < n_seq; ++seq) {
+        // seq 0: the sort proper (hybrid: top digits only); seq 1: full sort, every kernel gated on ctrl[1]->go
+        const int gated = seq, first_digit = (hybrid && seq == 0) ? kLowDigits : 0;
+        GENPF_LAUNCH((k_radix_prepare<MODE>), gprep, kSortThreads, stream, keys, n, kA, vA, ctrl[seq], gated);
+        GENPF_LAUNCH(k_radix_plan, 1, 256, stream, ctrl[seq], n, first_digit, gated);
+        for (int pass = first_digit; pass < kSortPasses; ++pass) {
+            uint32_t *stp = state[seq] + (size_t)pass * (st / 4);
+            if (use_big)
+                GENPF_LAUNCH_SMEM((k_radix_onesweep<512, 3>), (unsigned)ntiles, 512, onesweep_smem<512>(), stream, ctrl[seq], pass,
+                                  kA, kB, vA, vB, n, stp, gated);
+            else
+                GENPF_LAUNCH_SMEM((k_radix_onesweep<256, 4>), (unsigned)ntiles, 256, onesweep_smem<256>(), stream, ctrl[seq], pass,
+                                  kA, kB, vA, vB, n, stp, gated);
+        }
+        if (hybrid && seq == 0) {
+            GENPF_LAUNCH(k_fix_detect, grid_1d(n), 256, stream, (const SortCtrl *)ctrl[0], (const uint64_t *)kA,
+                         (const uint64_t *)kB, n, dirty, ctrl[1]);
+            GENPF_LAUNCH(k_fix_sort, grid_1d(n), 256, stream, (const SortCtrl *)ctrl[0], kA, kB, vA, vB, n,
+                         (const uint8_t *)dirty, ctrl[1]);
+        }
     }
-    GENPF_LAUNCH((k_sort_finish<MODE>), grid_1d(n), 256, stream, (const SortCtrl *)ctrl, (const uint64_t *)kA,
-                 (const uint64_t *)kB, (const int32_t *)vA, (const int32_t *)vB, n, keys_sorted, order32);
+    GENPF_LAUNCH((k_sort_finish<MODE>), grid_1d(n), 256, stream, (const SortCtrl *)ctrl[0],
+                 (const SortCtrl *)(hybrid ? ctrl[1] : nullptr), (const uint64_t *)kA, (const uint64_t *)kB, (const int32_t *)vA,
+                 (const int32_t *)vB, n, keys_sorted, order32);
     return GENPF_OK;
 }
 

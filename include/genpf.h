@@ -155,6 +155,10 @@ int32_t genpf_optimal_resize(const double *lw, int64_t n_in, int64_t n_out, cons
 /* Philox uniforms exactly as the library generates them (for exporting / parity) */
 int32_t genpf_uniforms(uint64_t seed, uint64_t stream, int64_t n, uint32_t flags, double *out);
 
+/* debug / parity: sortperm(keys, rev=true) exactly as the sorted stratified path uses it (resample.jl:156-157):
+ * stable, Julia isless order; order_out 0-based (1-based with GENPF_INDEX_BASE1) */
+int32_t genpf_debug_sortperm(const double *keys, int64_t n, uint32_t flags, int64_t *order_out);
+
 /* debug / parity: normalised cumulative weights W_k the selection kernels search (device order) */
 int32_t genpf_debug_cumweights(const double *lw, int64_t n, uint32_t flags, double *W_out);
 

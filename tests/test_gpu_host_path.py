@@ -488,6 +488,32 @@ def test_sort_particles_ties_and_signed_zero(g, orc, n):
     assert np.all(np.diff(lw[p]) <= 0)
 
 
+@pytest.mark.parametrize("n", [1000, (1 << 18) + 5, 1 << 21])
+@pytest.mark.parametrize("kind", ["random", "equal", "small_runs", "long_runs", "one_run", "int_like"])
+def test_sortperm_exact(g, orc, n, kind):
+    """The radix sort's permutation == sortperm(keys, rev=true) (stable) on every path of the hybrid sort: plain
+    keys, all-equal keys (every digit skipped), keys agreeing on the top 40 bits in short runs (repaired in
+    place), in long runs and in a single run (device-gated full sort)."""
+    rng = np.random.default_rng(n + len(kind))
+    if kind == "random":
+        keys = rng.normal(0, 3, n)
+    elif kind == "equal":
+        keys = np.full(n, -1.25)
+    elif kind == "small_runs":  # ~8 keys per cluster, differing only in the last mantissa bits
+        keys = rng.integers(1, max(2, n // 8), n).astype(float) * (1.0 + 1e-13 * rng.integers(-50, 50, n))
+    elif kind == "long_runs":   # clusters of ~1000 keys within 4e-9 relative of each other
+        keys = rng.integers(1, max(2, n // 1000), n).astype(float) * (1.0 + 1e-13 * rng.integers(-50, 50, n))
+    elif kind == "one_run":
+        keys = 2.0 + 1e-12 * rng.normal(size=n)
+    else:                       # many exact duplicates, signed zeros, infinities
+        keys = rng.integers(-3, 4, n).astype(float)
+        keys[rng.integers(0, n, n // 50)] = -np.inf
+        keys[rng.integers(0, n, n // 50)] = -0.0
+    out = np.empty(n, dtype=np.int64)
+    g._lib.check(g.load().genpf_debug_sortperm(g._lib.ptr(keys), n, 0, g._lib.ptr(out)))
+    np.testing.assert_array_equal(out, orc.sortperm_desc(keys))
+
+
 def raw_optimal_resize(g, lw, n_out, u=None, flags=0, seed=0):
     L, lib = g._lib, g.load()
     lw = np.ascontiguousarray(lw, dtype=np.float64)
