@@ -420,6 +420,38 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
             const double d = frac - r;
             if (fabs(d) > a.tol) return j + (J)(d > 0.0 ? 1 : 0);
         }
+        // n*W within 1e-6 of an integer (equal weights put EVERY particle here): the general path's two loops,
+        // evaluated from the window with a bounded trip count; anything unusual falls through to it
+        const J n = (J)a.n;
+        auto lower_of = [&](J i1) { return a.pow2 ? (double)(i1 - 1) * a.step : (double)(i1 - 1) / nd; };
+        bool ok = true;
+        auto u_win = [&](J i1) {
+            const uint64_t rr = (uint64_t)(slot0 + (int64_t)i1 - 1 + a.uni.offset - win.base);
+            if (rr >= (uint64_t)kStrataWindow) {
+                ok = false;
+                return 0.0;
+            }
+            const double r = fma((double)win.words[rr], 0x1.0p-32, 0x1.0p-33);
+            return __dadd_rn(__dmul_rn(r, a.step), lower_of(i1));
+        };
+        J c = j;
+        int trips = 0;
+        while (ok && c < n && lower_of(c + 1) <= W) {
+            const double u = u_win(c + 1);
+            if (!ok || !(u <= W)) break;
+            ++c;
+            if (++trips > 3) ok = false;
+        }
+        if (ok && frac < 1e-6) {
+            trips = 0;
+            while (ok && c > 0) {
+                const double u = u_win(c);
+                if (!ok || !(u > W)) break;
+                --c;
+                if (++trips > 3) ok = false;
+            }
+        }
+        if (ok) return c;
     }
     return strat_count_slow<J>(a, slot0, W, win.words, win.base);
 }
