@@ -81,6 +81,8 @@ SIGNATURES = {
     "genpf_replicate": (i32, [_vp, i64, i32]),
     "genpf_dereplicate": (i32, [_vp, i64, i32, i32, _vp]),
     "genpf_coalesce": (i32, [_vp, _ip]),
+    "genpf_filter_get_progress": (i32, [_vp, _ip, _ip, _vp]),
+    "genpf_filter_set_progress": (i32, [_vp, i64, i64, _vp]),
     "genpf_proportionmap": (i32, [_vp, i32, i64, _dp, _dp, i64, _ip]),
     "genpf_optimal_resize_dev": (i32, [_vp, i64, _dp, u32, _ip, _dp, _i32p]),
     "genpf_get_log_weights": (i32, [_vp, _vp]),

@@ -113,6 +113,8 @@ class DevicePFState:
         self._h = h
         self.n_filters = n_filters
         self.t = 0
+        self._ctor = dict(n_particles=int(n_particles), n_filters=int(n_filters), seed=int(seed),
+                          keep_history=bool(keep_history), noise=noise)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -176,6 +178,43 @@ class DevicePFState:
 
     def sync(self):
         L.check(L.load().genpf_filter_sync(self._h))
+
+    # checkpoint / resume (column dump of the resident window; the reference has none)
+    def save(self, path):
+        """Writes an .npz from which `DevicePFState.load` continues bit-identically: resident window fields,
+        log-weights, accumulated log_ml_est, step / resample counters, seed and noise policy."""
+        if self._ctor["keep_history"]:
+            raise GenPFErrorException("checkpointing a filter that keeps its history is not supported")
+        t, nres = C.c_int64(), C.c_int64()
+        lml = np.empty(self.n_filters)
+        L.check(L.load().genpf_filter_get_progress(self._h, C.byref(t), C.byref(nres), L.ptr(lml)))
+        ctor = dict(self._ctor, n_particles=len(self))
+        out = dict(model=self.model.name, params=np.zeros(0) if self.model.params is None else self.model.params,
+                   t=t.value, n_resamples=nres.value, lml=lml, log_weights=self.log_weights,
+                   **{"ctor_" + k: v for k, v in ctor.items()})
+        for tau in (t.value - 1, t.value):
+            if tau >= 1:
+                for name in self.model.fields:
+                    out[f"field_{name}_{tau}"] = self.field(name, tau)
+        np.savez(path, **out)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, allow_pickle=False)
+        params = z["params"]
+        model = DeviceModel(str(z["model"]), None if params.size == 0 else params)
+        state = cls(model, int(z["ctor_n_particles"]), n_filters=int(z["ctor_n_filters"]), seed=int(z["ctor_seed"]),
+                    keep_history=False, noise=str(z["ctor_noise"]))
+        t = int(z["t"])
+        lml = _f64(z["lml"])
+        L.check(L.load().genpf_filter_set_progress(state._h, t, int(z["n_resamples"]), L.ptr(lml)))
+        state.t = t
+        for tau in (t - 1, t):
+            if tau >= 1:
+                for name in model.fields:
+                    state.set_field(name, tau, z[f"field_{name}_{tau}"])
+        state.log_weights = z["log_weights"]
+        return state
 
 
 def logsumexp_host(v):

@@ -821,6 +821,28 @@ int32_t genpf_set_field(genpf_filter_t pf, int32_t field, int64_t tau, const dou
     GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
     return GENPF_OK;
 }
+int32_t genpf_filter_get_progress(genpf_filter_t pf, int64_t *t_cur, int64_t *n_resamples, double *log_ml_accum) {
+    GENPF_TRY(check_filter(pf));
+    if (t_cur) *t_cur = pf->t_cur;
+    if (n_resamples) *n_resamples = pf->n_resamples;
+    if (log_ml_accum) {
+        GENPF_CUDA_TRY(cudaMemcpyAsync(log_ml_accum, pf->lml, (size_t)pf->nf * 8, cudaMemcpyDeviceToHost, pf->stream));
+        GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    }
+    return GENPF_OK;
+}
+int32_t genpf_filter_set_progress(genpf_filter_t pf, int64_t t_cur, int64_t n_resamples, const double *log_ml_accum) {
+    GENPF_TRY(check_filter(pf));
+    if (t_cur < 1 || n_resamples < 0 || !log_ml_accum) return fail(GENPF_ERR_INVALID_ARG, "genpf_filter_set_progress: bad arguments");
+    if (pf->flags & GENPF_KEEP_HISTORY) return fail(GENPF_ERR_UNSUPPORTED, "resume of a filter that keeps its history is not supported");
+    pf->t_cur = t_cur;
+    pf->n_resamples = n_resamples;
+    pf->part_valid = false;
+    GENPF_LAUNCH(k_iota32, grid_1d(pf->n * pf->nf), 256, pf->stream, pf->parents, pf->n, pf->n * pf->nf);
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->lml, log_ml_accum, (size_t)pf->nf * 8, cudaMemcpyHostToDevice, pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+    return GENPF_OK;
+}
 int32_t genpf_get_accepts(genpf_filter_t pf, uint8_t *out) {
     GENPF_TRY(check_filter(pf));
     if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");

@@ -246,6 +246,13 @@ int32_t genpf_proportionmap(genpf_filter_t pf, int32_t field, int64_t tau, doubl
 int32_t genpf_optimal_resize_dev(genpf_filter_t pf, int64_t n_out, const double *uniform, uint32_t flags,
                                  int64_t *n_keep, double *inv_w_threshold, int32_t *invalid_kinds);
 
+/* checkpoint / resume (absent in the reference): together with the seed, the window fields
+ * (genpf_get/set_field for t_cur-1 and t_cur) and the log-weights, these scalars determine every later step.
+ * log_ml_accum: n_filters doubles (the accumulated log_ml_est, without the current weights' term).
+ * set_progress is called on a freshly created filter of the same model, size, seed and noise flags. */
+int32_t genpf_filter_get_progress(genpf_filter_t pf, int64_t *t_cur, int64_t *n_resamples, double *log_ml_accum);
+int32_t genpf_filter_set_progress(genpf_filter_t pf, int64_t t_cur, int64_t n_resamples, const double *log_ml_accum);
+
 /* accessors (also checkpoint I/O): out sized n_particles*n_filters */
 int32_t genpf_get_log_weights(genpf_filter_t pf, double *out);
 int32_t genpf_set_log_weights(genpf_filter_t pf, const double *in);

@@ -393,6 +393,37 @@ def test_device_stratified_initialize(g, orc, layout):
     np.testing.assert_allclose(lg.log_weights, expect, rtol=1e-9)
 
 
+@pytest.mark.parametrize("noise", ["lean", "philox53"])
+def test_checkpoint_resume(g, tmp_path, noise):
+    """save -> load continues bit-identically (fields, log-weights, ancestors, log_ml_est) to the uninterrupted run."""
+    model = g.DeviceModel("object_motion")
+    obs = [0.1, 0.2, 0.0, 0.4, 1.1, 1.6, 1.4]
+
+    def advance(pf, ts):
+        for t in ts:
+            if g.effective_sample_size(pf) < 0.9 * len(pf):
+                g.pf_resample(pf, "residual" if t % 2 else "stratified", sort_particles=False)
+                g.pf_rejuvenate(pf, g.mh, (t - 1, obs[t - 2]))
+            g.pf_update(pf, (t,), None, obs[t - 1])
+
+    a = g.pf_initialize(model, (1,), obs[0], 3000, seed=31, noise=noise)
+    advance(a, range(2, 5))
+    path = str(tmp_path / "ckpt.npz")
+    a.save(path)
+    b = g.DevicePFState.load(path)
+    assert len(b) == len(a) and b.t == a.t
+    np.testing.assert_array_equal(b.log_weights, a.log_weights)
+    assert g.log_ml_estimate(b) == g.log_ml_estimate(a)
+    advance(a, range(5, 8))
+    advance(b, range(5, 8))
+    for name in ("y", "moving"):
+        np.testing.assert_array_equal(b.field(name, 7), a.field(name, 7))
+        np.testing.assert_array_equal(b.field(name, 6), a.field(name, 6))
+    np.testing.assert_array_equal(b.log_weights, a.log_weights)
+    np.testing.assert_array_equal(b.parents, a.parents)
+    assert g.log_ml_estimate(b) == g.log_ml_estimate(a)
+
+
 def test_device_move_reweight(g, orc):
     """pf_move_reweight!(state, move_reweight, (select(tau),)) (rejuvenate.jl:74-90,125-132) with supplied noise:
     slice tau regenerated from the conditional prior for every particle, log_weights += the regenerate weight."""
