@@ -419,6 +419,29 @@ def test_replicate_dereplicate_coalesce(g, orc):
     assert g.get_lml_est(state) == pytest.approx(lml0, abs=1e-6)
 
 
+def test_coalesce_large_groups_deterministic(g, orc):
+    """Groups longer than the 4096-particle chunk are summed chunk-wise in a fixed order: matches the oracle to
+    1e-10 and is bit-identical run to run (groups within one chunk are added in the reference's own order; only
+    the device exp() differs from libm's in the last bit)."""
+    rng = np.random.default_rng(77)
+    for n, n_keys in ((60_000, 3), (60_000, 40)):
+        vals = rng.integers(0, n_keys, n)
+        lw = rng.normal(0, 1, n)
+        outs = []
+        for _ in range(2):
+            state = g.ParticleFilterState([("k", int(v)) for v in vals], lw)
+            g.pf_coalesce(state, by=lambda tr: tr[1])
+            outs.append((state.parents.copy(), state.log_weights.copy()))
+        p_ref, lw_ref = orc.coalesce(lw, vals)
+        np.testing.assert_array_equal(outs[0][0], p_ref)
+        np.testing.assert_allclose(outs[0][1], lw_ref, rtol=RTOL)
+        np.testing.assert_array_equal(outs[0][1], outs[1][1])
+        pm = g.proportionmap(g.ParticleFilterState([{"k": int(v)} for v in vals], lw), "k")
+        w = orc.softmax(lw)
+        for v, p in pm.items():
+            assert p == pytest.approx(w[vals == v].sum(), rel=RTOL)
+
+
 def test_large_properties(g):
     """BASELINE-size properties that need no oracle: 2^24 particles, stratified."""
     n = 1 << 24
