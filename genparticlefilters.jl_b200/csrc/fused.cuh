@@ -8,9 +8,10 @@
 // pins it.
 //
 // Traffic per particle: R O ~4, R window 18 (gathered, monotone), W parents 4, W slice t-1 9, W slice t 9,
-// W lw 8  = 52 B against 117 B algorithmic (slice t-2 is never copied: it leaves the window at this step).
-// The kernel is instruction-issue bound, not DRAM bound (ncu, profiles/), hence 512 threads x 4 particles:
-// small per-thread footprint for occupancy, Philox + Box-Muller shared between the mh move and the update.
+// W lw 8, W e 8 = 60 B (ncu: 64 B incl. evictions) against the 109 B the unfused kernels would move (slice t-2 is
+// never copied: it leaves the window at this step).  The kernel is instruction-issue bound, not DRAM bound (ncu,
+// profiles/r1_k_ncu_summary.md), hence 512 threads x 4 particles at 32 registers (4 blocks/SM): small
+// per-thread footprint for occupancy, Philox + Box-Muller shared between the mh move and the update.
 #pragma once
 #include "filter.cuh"
 
