@@ -7,6 +7,7 @@ name carries a dot, so the repo-root shim genpf_b200.py loads it).
 from . import _lib
 from ._lib import GenPFError, load
 from .api import *  # noqa: F401,F403
+from .api import (choiceproduct, get_log_weights, get_traces, pf_introduce, sample_unweighted_traces)  # noqa: F401
 from .api import (DeviceModel, DevicePFState, GenPFErrorException, ParticleFilterState, ParticleFilterSubState,
                   effective_sample_size, get_ess, get_lml_est, get_log_norm_weights, get_norm_weights,
                   log_ml_estimate, logsumexp_host, mean, mh, move_reweight, pf_coalesce, pf_dereplicate, pf_initialize,

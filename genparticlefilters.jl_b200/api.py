@@ -535,6 +535,69 @@ def pf_coalesce(state, *, by=None):
     return state
 
 
+def pf_introduce(state, model, model_args, observations, n_particles, *, proposal=None, proposal_args=()):
+    """pf_introduce!, resize.jl:351-421 (host models): append `n_particles` freshly generated traces.  The
+    accumulated log_ml_est is folded into the existing weights first (resize.jl:362-365); `model` / `model_args`
+    None reuse those of the first trace (trace.model, trace.args).  With a proposal (callable returning
+    (choices, log_q)) the new weight is model_weight - log_q (resize.jl:410-413)."""
+    if isinstance(state, (ParticleFilterSubState, DevicePFState)):
+        raise TypeError("pf_introduce! takes a full host ParticleFilterState")
+    model = state.traces[0].model if model is None else model
+    model_args = state.traces[0].args if model_args is None else model_args
+    if state.log_ml_est != 0.0:
+        state.log_weights = state.log_weights + state.log_ml_est
+        state.log_ml_est = 0.0
+    n_old = len(state.traces)
+    new_lw = np.empty(n_particles)
+    for i in range(n_particles):
+        if proposal is None:
+            tr, w = model.generate(model_args, observations)
+        else:
+            choices, log_q = proposal(*proposal_args)
+            tr, w = model.generate(model_args, {**observations, **choices})
+            w = w - log_q
+        state.traces.append(tr)
+        new_lw[i] = w
+    state.log_weights = np.concatenate([state.log_weights, new_lw])
+    state.parents = np.concatenate([state.parents, np.zeros(n_particles, dtype=np.int64)])  # resize!: unspecified
+    state.new_traces = [None] * (n_old + n_particles)
+    return state
+
+
+def choiceproduct(*choices):
+    """choiceproduct, utils.jl:56-95: iterator over constraint dicts, the Cartesian product of (addr, values) pairs
+    (or of a dict addr -> values); the strata argument of the stratified pf_initialize."""
+    import itertools
+    if len(choices) == 1 and isinstance(choices[0], dict):
+        choices = tuple(choices[0].items())
+    return (dict(cs) for cs in itertools.product(*[[(addr, v) for v in vals] for addr, vals in choices]))
+
+
+def get_traces(state):
+    """Gen.get_traces"""
+    return list(state.traces)
+
+
+def get_log_weights(state):
+    """Gen.get_log_weights"""
+    return _f64(state.log_weights).copy()
+
+
+def sample_unweighted_traces(state, n_samples, *, uniforms=None, seed=0):
+    """Gen.sample_unweighted_traces / its sub-state method (utils.jl:189-194): n_samples traces drawn with
+    replacement in proportion to the normalised weights (inverse-CDF draws on the GPU); the state is not changed."""
+    lw = _f64(state.log_weights)
+    u = None if uniforms is None else _f64(uniforms)
+    parents = np.empty(n_samples, dtype=np.int64)
+    lw_out = np.empty(n_samples)
+    inc, kind = C.c_double(), C.c_int32()
+    L.check(L.load().genpf_resample(L.METHODS["multinomial"], L.ptr(lw), None, lw.size, n_samples, L.ptr(u), seed,
+                                    L.SUBSTATE if n_samples == lw.size else 0, L.ptr(parents), L.ptr(lw_out),
+                                    C.byref(inc), C.byref(kind)))
+    traces = state.traces
+    return [traces[p] for p in parents]
+
+
 def _apply_resize(state, parents, lw_out):
     state.new_traces = [state.traces[p] for p in parents]
     state.parents = parents

@@ -635,3 +635,21 @@ def test_proportionmap(g, orc):
     # degenerate: one value, and all -Inf weights (uniform fallback of get_norm_weights' safe path)
     state = g.ParticleFilterState([{"slope": 1}] * 50, np.zeros(50))
     assert g.proportionmap(state, "slope") == {1: pytest.approx(1.0)}
+
+
+def test_sample_unweighted_traces(g, orc):
+    """Gen.sample_unweighted_traces (sub-state method utils.jl:189-194): draws in proportion to the normalised
+    weights, state untouched; with supplied uniforms = the inverse-CDF rule of the multinomial path."""
+    rng = np.random.default_rng(5)
+    n = 10_000
+    lw = rng.normal(0, 2, n)
+    state = g.ParticleFilterState(list(range(n)), lw)
+    u = rng.random(2500)
+    out = g.sample_unweighted_traces(state, 2500, uniforms=u)
+    p_ref, *_ = orc.resample("multinomial", lw, u, n_out=2500)
+    assert out == [int(p) for p in p_ref]
+    np.testing.assert_array_equal(state.log_weights, lw)
+    sub = state[100:600]
+    out = g.sample_unweighted_traces(sub, 500, uniforms=u[:500])
+    p_ref, *_ = orc.resample("multinomial", lw[100:600], u[:500])
+    assert out == [100 + int(p) for p in p_ref]
