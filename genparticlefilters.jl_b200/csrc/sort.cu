@@ -366,14 +366,10 @@ static int32_t radix_sort(const void *keys, int64_t n, void *keys_sorted, int32_
     uint8_t *dirty = (uint8_t *)(z + n_seq * (c + kSortPasses * st));
     GENPF_CUDA_TRY(cudaMemsetAsync(z, 0, zero_bytes, stream));
     const unsigned gprep = (unsigned)std::min<int64_t>(ceil_div(n, kSortThreads), 148 * 16);
-    static const bool attr_set = [] {
-        cudaFuncSetAttribute(k_radix_onesweep<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)onesweep_smem<512>());
-        cudaFuncSetAttribute(k_radix_onesweep<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)onesweep_smem<256>());
-        return true;
-    }();
-    (void)attr_set;
+    // per device and cheap: set on every call (a process may drive several devices)
+    if (use_big)
+        GENPF_CUDA_TRY(cudaFuncSetAttribute(k_radix_onesweep<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)onesweep_smem<512>()));
     for (int seq = 0; seq < n_seq; ++seq) {
         // seq 0: the sort proper (hybrid: top digits only); seq 1: full sort, every kernel gated on ctrl[1]->go
         const int gated = seq, first_digit = (hybrid && seq == 0) ? kLowDigits : 0;
