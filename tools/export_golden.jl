@@ -52,28 +52,28 @@ function dense_uniforms(weights::Vector{Float64}, order::Vector{Int}, draws::Vec
 end
 
 arrays = Tuple{String,String,Int}[]   # (name, dtype, length)
-function dump(dir, name, x::Vector{Float64})
+function dump_array(dir, name, x::Vector{Float64})
     open(joinpath(dir, replace(name, "/" => "__") * ".bin"), "w") do io
         write(io, htol.(x))
     end
     push!(arrays, (name, "f64", length(x)))
 end
-function dump(dir, name, x::Vector{Int64})
+function dump_array(dir, name, x::Vector{Int64})
     open(joinpath(dir, replace(name, "/" => "__") * ".bin"), "w") do io
         write(io, htol.(x))
     end
     push!(arrays, (name, "i64", length(x)))
 end
-dump(dir, name, x::Real) = dump(dir, name, [Float64(x)])
+dump_array(dir, name, x::Real) = dump_array(dir, name, [Float64(x)])
 
 function export_case(dir, case, n, seed, sigma)
     Random.seed!(seed)
     lw = sigma .* randn(n)
-    dump(dir, "$case/lw", lw)
+    dump_array(dir, "$case/lw", lw)
     state = fresh_state(lw)
-    dump(dir, "$case/lse", Gen.logsumexp(lw))
-    dump(dir, "$case/ess", effective_sample_size(state))
-    dump(dir, "$case/norm_w", get_norm_weights(state))
+    dump_array(dir, "$case/lse", Gen.logsumexp(lw))
+    dump_array(dir, "$case/ess", effective_sample_size(state))
+    dump_array(dir, "$case/norm_w", get_norm_weights(state))
     for (tag, sorted) in (("strat", false), ("strat_sorted", true))
         state = fresh_state(lw)
         Random.seed!(seed + 1000)
@@ -84,22 +84,22 @@ function export_case(dir, case, n, seed, sigma)
         weights, _ = GenParticleFilters.safe_softmax(lw)
         order = sorted ? sortperm(lw, rev=true) : collect(1:n)
         r, k = dense_uniforms(weights, order, draws)
-        dump(dir, "$case/$tag/r", r)
-        dump(dir, "$case/$tag/parents", Vector{Int64}(parents))
-        dump(dir, "$case/$tag/lml", get_lml_est(state))
-        dump(dir, "$case/$tag/n_draws", k)
+        dump_array(dir, "$case/$tag/r", r)
+        dump_array(dir, "$case/$tag/parents", Vector{Int64}(parents))
+        dump_array(dir, "$case/$tag/lml", get_lml_est(state))
+        dump_array(dir, "$case/$tag/n_draws", k)
     end
     for N in (max(1, n ÷ 4), n ÷ 2)
         state = fresh_state(lw)
         w = GenParticleFilters.softmax(lw)
-        dump(dir, "$case/optimal_$N/inv_w", GenParticleFilters.find_inv_w_threshold(w, N))
+        dump_array(dir, "$case/optimal_$N/inv_w", GenParticleFilters.find_inv_w_threshold(w, N))
         Random.seed!(seed + 2000)
         u = rand()
         Random.seed!(seed + 2000)
         pf_resize!(state, N, :optimal)
-        dump(dir, "$case/optimal_$N/u", u)
-        dump(dir, "$case/optimal_$N/parents", Vector{Int64}(state.parents))
-        dump(dir, "$case/optimal_$N/lw_out", copy(state.log_weights))
+        dump_array(dir, "$case/optimal_$N/u", u)
+        dump_array(dir, "$case/optimal_$N/parents", Vector{Int64}(state.parents))
+        dump_array(dir, "$case/optimal_$N/lw_out", copy(state.log_weights))
     end
 end
 
