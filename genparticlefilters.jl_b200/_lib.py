@@ -67,6 +67,7 @@ SIGNATURES = {
     "genpf_initialize": (i32, [_vp, _vp, _vp]),
     "genpf_initialize_with_noise": (i32, [_vp, _vp, _vp, _vp, _vp]),
     "genpf_initialize_stratified": (i32, [_vp, _vp, _vp, i32, _vp, i32, i32, _vp, _vp]),
+    "genpf_update_stratified": (i32, [_vp, i64, _vp, _vp, i32, _vp, i32, i32, _vp, _vp]),
     "genpf_update": (i32, [_vp, i64, _vp, _vp]),
     "genpf_update_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     "genpf_ess_dev": (i32, [_vp, _vp]),

@@ -305,20 +305,37 @@ def pf_initialize(model, model_args, observations, n_particles, *, strata=None, 
     return ParticleFilterState(traces, lws)
 
 
-def pf_update(state, new_args, argdiffs, observations):
-    """pf_update!, update.jl:12-25."""
+def pf_update(state, new_args, argdiffs, observations, *, strata=None, layout="interleaved"):
+    """pf_update!, update.jl:12-25; with `strata` the stratified form (update.jl:193-210): device states take
+    strata = (field_name, values), host states an iterable of constraint dicts."""
     if isinstance(state, DevicePFState):
         t = int(new_args[0])
-        L.check(L.load().genpf_update(state._h, t, L.ptr(state._obs(observations)), L.ptr(state.model.aux(t))))
+        if strata is None:
+            L.check(L.load().genpf_update(state._h, t, L.ptr(state._obs(observations)), L.ptr(state.model.aux(t))))
+        else:
+            name, values = strata
+            vals = _f64([float(v) for v in values])
+            lay = L.LAYOUT_CONTIGUOUS if layout == "contiguous" else L.LAYOUT_INTERLEAVED
+            L.check(L.load().genpf_update_stratified(state._h, t, L.ptr(state._obs(observations)),
+                                                     L.ptr(state.model.aux(t)), state.model.fields[name], L.ptr(vals),
+                                                     vals.size, lay, None, None))
         state.t = t
         return state
     src, idxs = _resolve(state)
-    for i in idxs:
-        new_tr, incr, _, discard = src.traces[i].update(new_args, argdiffs, observations)
+    assign = None
+    if strata is not None:
+        strata = list(strata)
+        k_n, n_p = len(strata), len(idxs)
+        block = n_p // k_n
+        assign = [(j // block if layout == "contiguous" else j % k_n) for j in range(block * k_n)]
+        assign += list(np.random.randint(0, k_n, n_p - block * k_n))  # sample(strata, n_remaining)
+    for j, i in enumerate(idxs):
+        cons = observations if assign is None else {**strata[assign[j]], **observations}
+        new_tr, incr, _, discard = src.traces[i].update(new_args, argdiffs, cons)
         if discard:
             raise GenPFErrorException(f"Choices were updated or deleted: {discard}")  # update.jl:18-20
         src.new_traces[i] = new_tr
-        src.log_weights[i] += incr
+        src.log_weights[i] += incr + (0.0 if assign is None else math.log(len(strata)))
     _update_refs(state)
     return state
 

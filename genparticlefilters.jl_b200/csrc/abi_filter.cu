@@ -55,7 +55,7 @@ static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const d
                      pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew, strata);
     } else {
         GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(t - 1),
-                     pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew);
+                     pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew, strata);
     }
     return GENPF_OK;
 }
@@ -115,13 +115,12 @@ static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const doubl
     }
     Strata strata{};
     if (sh) {
-        if (!init) return fail(GENPF_ERR_INVALID_ARG, "strata apply to initialisation");
         if (!sh->values || sh->K < 1 || sh->K > pf->n) return fail(GENPF_ERR_INVALID_ARG, "bad strata (need 1 <= K <= n_particles)");
         if (sh->field < 0 || sh->field >= pf->NF + pf->NB) return fail(GENPF_ERR_INVALID_ARG, "strata field out of range");
         GENPF_TRY(pf->strata_buf.ensure((size_t)sh->K * 8));
         GENPF_CUDA_TRY(cudaMemcpyAsync(pf->strata_buf.p, sh->values, (size_t)sh->K * 8, cudaMemcpyHostToDevice, pf->stream));
         strata = Strata{pf->strata_buf.as<double>(), sh->K, sh->field, sh->layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, pf->seed,
-                        make_stream(kPurposeStrata, 0)};
+                        make_stream(kPurposeStrata, (uint64_t)t)};
     }
     int32_t st;
     switch (pf->model) {
@@ -602,6 +601,12 @@ int32_t genpf_initialize_stratified(genpf_filter_t pf, const double *obs, const 
     if ((U == nullptr) != (Z == nullptr)) return fail(GENPF_ERR_INVALID_ARG, "give both noise columns or neither");
     StrataHost sh{field, values, n_strata, layout};
     return do_propagate(pf, true, 1, obs, aux, U, Z, &sh);
+}
+int32_t genpf_update_stratified(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, int32_t field,
+                                const double *values, int32_t n_strata, int32_t layout, const double *U, const double *Z) {
+    if ((U == nullptr) != (Z == nullptr)) return fail(GENPF_ERR_INVALID_ARG, "give both noise columns or neither");
+    StrataHost sh{field, values, n_strata, layout};
+    return do_propagate(pf, false, t, obs, aux, U, Z, &sh);
 }
 int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux) {
     return do_propagate(pf, false, t, obs, aux, nullptr, nullptr);

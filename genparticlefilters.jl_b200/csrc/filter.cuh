@@ -97,8 +97,8 @@ __device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_
 // ------------------------------------------------------------------ K10 propagate + weight (+ K1 partials)
 // INIT: pf_initialize (initialize.jl:39-41): slice_1 = transition(initial), lw = obs_logpdf
 // else: pf_update!    (update.jl:15-21):     slice_t = transition(slice_{t-1}), lw += obs_logpdf
-// Stratified initialisation (initialize.jl:93-108 with stratified_map!, utils.jl:29-55): K strata constrain one
-// latent of slice 1; each gets floor(n/K) particles in contiguous blocks or interleaved, the n - K*floor(n/K)
+// Stratified initialisation / update (initialize.jl:93-108, update.jl:193-210 with stratified_map!,
+// utils.jl:29-55): K strata constrain one latent of the new slice; each gets floor(n/K) particles in contiguous blocks or interleaved, the n - K*floor(n/K)
 // left-over particles (the last indices) go to strata drawn with replacement; log-weights gain log(K).
 struct Strata {
     const double *values;  // device, K entries; null: plain pf_initialize
@@ -141,7 +141,7 @@ static __global__ void __launch_bounds__(kStateThreads)
         double U = 0.5, Z = 0.0;
         if (e < valid) noise.up(base + e, U, Z);
         double l = 0.0;
-        if (INIT && strata.values) {
+        if (strata.values) {  // stratified initialise / update: one latent constrained, + log p(constraint) + log K
             const double val = strata.values[strata.stratum(e < valid ? start + e : 0, n)];
             l = Model::constrain(P, t, sp[k], sn[k], U, Z, strata.field, val) + log((double)strata.K);
         } else {

@@ -192,6 +192,10 @@ int32_t genpf_initialize_with_noise(genpf_filter_t pf, const double *obs, const 
 int32_t genpf_initialize_stratified(genpf_filter_t pf, const double *obs, const double *aux, int32_t field,
                                     const double *values, int32_t n_strata, int32_t layout, const double *U,
                                     const double *Z);
+/* Stratified pf_update! (update.jl:193-210): the same constraint on the NEW slice t, log_weights += log p(constraint |
+ * previous slice) + obs log-density + log(K); the reference's default layout here is GENPF_LAYOUT_INTERLEAVED. */
+int32_t genpf_update_stratified(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, int32_t field,
+                                const double *values, int32_t n_strata, int32_t layout, const double *U, const double *Z);
 
 /* pf_update!(state, (t,), (UnknownChange(),), obs_t), update.jl:12-25 */
 int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux);

@@ -384,6 +384,26 @@ def test_device_stratified_initialize(g, orc, layout):
     kk = np.arange(1000) // 200 if layout == "contiguous" else np.arange(1000) % 5
     np.testing.assert_array_equal(yy[:1000], grid[kk])
     assert np.all(np.isin(yy[1000:], grid)) and np.isfinite(c.log_weights).all()
+    # stratified update (update.jl:193-210): the constraint applies to the new slice, weights gain
+    # log p(moving_2 | moving_1) + obs log-density + log K
+    n2 = 1000
+    pf2 = g.DevicePFState(model, n2, seed=9)
+    U, Z = rng.random(n2), rng.normal(size=n2)
+    noisy_init(g, pf2, 0.1, U, Z)
+    y1, m1 = orc.om_transition(None, None, math.sin(1.0), U, Z)
+    lw1 = orc.om_obs_logpdf(y1, 0.1)
+    U, Z = rng.random(n2), rng.normal(size=n2)
+    L.check(lib.genpf_update_stratified(pf2._h, 2, L.ptr(pf2._obs(0.5)), L.ptr(model.aux(2)), model.fields["moving"],
+                                        L.ptr(vals), K, lay, L.ptr(U), L.ptr(Z)))
+    pf2.t = 2
+    k2 = np.arange(n2) // (n2 // K) if layout == "contiguous" else np.arange(n2) % K
+    m2 = vals[k2].astype(np.uint8)
+    y2 = (y1 + np.where(m2 == 1, math.sin(2.0), 0.0)) + 0.01 * Z
+    p_move = np.where(m1 == 1, 0.75, 0.25)
+    lw2 = lw1 + np.log(np.where(m2 == 1, p_move, 1.0 - p_move)) + orc.om_obs_logpdf(y2, 0.5) + math.log(K)
+    np.testing.assert_array_equal(pf2.field("moving", 2), m2)
+    np.testing.assert_array_equal(pf2.field("y", 2), y2)
+    np.testing.assert_allclose(pf2.log_weights, lw2, rtol=RTOL)
     lg = g.pf_initialize(g.DeviceModel("lingauss1d", (0.9, 1.0, 1.0, 0.0, 1.0)), (1,), 0.2, 600, seed=8,
                          strata=("x", [-1.0, 0.0, 1.0]), layout=layout)
     x = lg.field("x", 1)
