@@ -13,6 +13,23 @@ class LineTrace:
     def __getitem__(self, addr):
         return self.choices[addr]
 
+    def update(self, new_args, argdiffs, constraints):
+        """Gen.update for the toy model: extend to new_args[0] points; constrained y's are scored, an `outlier_i`
+        flag may be constrained too (prior 0.1), nothing is ever discarded."""
+        (n_new,) = new_args
+        ch, incr = dict(self.choices), 0.0
+        slope = ch["slope"]
+        for i in range(self.args[0] + 1, n_new + 1):
+            flag = constraints.get(("outlier", i), False)
+            incr += math.log(0.1 if flag else 0.9) if ("outlier", i) in constraints else 0.0
+            ch[("outlier", i)] = flag
+            y = constraints.get(("y", i), slope * i)
+            sd = 10.0 if flag else 1.0
+            if ("y", i) in constraints:
+                incr += -0.5 * (((y - slope * i) / sd) ** 2 + math.log(2 * math.pi)) - math.log(sd)
+            ch[("y", i)] = y
+        return LineTrace(self.model, new_args, ch, self.score + incr), incr, None, {}
+
 
 class LineModel:
     """slope ~ uniform_discrete(-2, 2); y_i ~ normal(slope * i, 1): the reference tests' line_model in miniature."""
@@ -84,3 +101,19 @@ def test_pf_introduce(api):
     expect = -math.log(5.0) - 0.5 * ((0.5 - 1.0) ** 2 + math.log(2 * math.pi)) - math.log(0.5)
     np.testing.assert_allclose(state.log_weights[15:], expect)
     assert api.get_traces(state)[0] is state.traces[0] and api.get_log_weights(state).shape == (18,)
+
+
+@pytest.mark.parametrize("layout", ["interleaved", "contiguous"])
+def test_host_stratified_update(api, layout):
+    """update.jl:193-210: every particle is updated under merge(stratum, observations) and gains log(n_strata)."""
+    model = LineModel()
+    state = api.pf_initialize(model, (1,), {("y", 1): 0.0}, 100, strata=[{"slope": 1}])
+    lw0 = state.log_weights.copy()
+    strata = [{("outlier", 2): False}, {("outlier", 2): True}]
+    api.pf_update(state, (2,), None, {("y", 2): 2.5}, strata=strata, layout=layout)
+    for k, flag in enumerate((False, True)):
+        idx = list(range(50 * k, 50 * (k + 1))) if layout == "contiguous" else list(range(k, 100, 2))
+        assert all(state.traces[i][("outlier", 2)] is flag for i in idx)
+        sd = 10.0 if flag else 1.0
+        incr = math.log(0.1 if flag else 0.9) - 0.5 * (((2.5 - 2.0) / sd) ** 2 + math.log(2 * math.pi)) - math.log(sd)
+        np.testing.assert_allclose(state.log_weights[idx], lw0[idx] + incr + math.log(2))
