@@ -158,6 +158,63 @@ def mean_var(lw, x):  # statistics.jl:13-17,48-54
     return mu, jl_sum([a * ((b - mu) * (b - mu)) for a, b in zip(w, x)])
 
 
+def find_inv_w_threshold(w, n_particles):  # resize.jl:199-216, literal
+    ws = sorted(w)
+    A, B = len(ws), 0.0
+    for kappa in ws:
+        A -= 1
+        B += kappa
+        n_check = B / kappa + A if kappa != 0.0 else math.nan
+        eps = math.ulp(abs(n_check)) if n_check == n_check else math.nan
+        if n_check <= n_particles + eps:
+            return (n_particles - A) / B
+    return float(n_particles)
+
+
+def optimal_resize(lw, n_particles, u_rand):  # resize.jl:149-196, literal; 0-based parents
+    n = len(lw)
+    w, _ = safe_softmax(lw)
+    c = find_inv_w_threshold(w, n_particles)
+    keep = [i for i in range(n) if c * w[i] >= 1]
+    strat = [i for i in range(n) if not c * w[i] >= 1]
+    n_keep, n_res = len(keep), n_particles - len(keep)
+    parents = list(keep)
+    if strat:
+        sw, _ = safe_softmax([lw[i] for i in strat])
+        step = 1 / n_res if n_res else math.inf
+        u = u_rand * step
+        for q, i in enumerate(strat):
+            u = u - sw[q]
+            if u < 0:
+                parents.append(i)
+                u += step
+    assert len(parents) == n_particles  # resize.jl:181
+    log_n_ratio = math.log(n_particles) - math.log(n)
+    res_lw = logsumexp(lw) - math.log(c)
+    lw_out = [lw[i] + log_n_ratio for i in keep] + [res_lw + log_n_ratio] * n_res
+    return parents, lw_out, n_keep, c
+
+
+def main_optimal():
+    """tests/golden/golden_v2_optimal.npz: pf_optimal_resize! cases on the inputs of golden_v1 (kept in a second
+    file so that golden_v1.npz stays byte-identical)."""
+    out = {}
+    cases = [("n100_s1", 100, 1.0, 11), ("n1000_s5", 1000, 5.0, 12), ("n2048_s2", 2048, 2.0, 13),
+             ("n3000_s1", 3000, 1.0, 14)]
+    for name, n, sigma, seed in cases:
+        lw = [sigma * normal_from(seed, 7, i) for i in range(n)]
+        for N in (max(1, n // 4), n // 2, n - 1):
+            u = uniform53(seed, 3, N)
+            parents, lw_out, n_keep, c = optimal_resize(lw, N, u)
+            out[f"{name}/optimal_{N}/u"] = np.array(u)
+            out[f"{name}/optimal_{N}/parents"] = np.array(parents)
+            out[f"{name}/optimal_{N}/lw_out"] = np.array(lw_out)
+            out[f"{name}/optimal_{N}/n_keep"] = np.array(n_keep)
+            out[f"{name}/optimal_{N}/inv_w"] = np.array(c)
+    np.savez_compressed(os.path.join(HERE, "golden_v2_optimal.npz"), **out)
+    print("wrote", len(out), "arrays (optimal)")
+
+
 def main():
     out = {}
     cases = [("n100_s1", 100, 1.0, 11), ("n1000_s5", 1000, 5.0, 12), ("n2048_s2", 2048, 2.0, 13),
@@ -202,3 +259,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_optimal()

@@ -282,3 +282,22 @@ def test_optimal_resize_invalid_weights(orc):
     assert r["kind"] == 2 and r["kind_strat"] == 2 and r["n_keep"] == 0 and r["status"] == 0
     assert np.all(np.isneginf(r["lw_out"]))
     np.testing.assert_array_equal(r["parents0"], np.arange(0, 100, 2))
+
+
+def test_optimal_resize_golden(orc):
+    """The C oracle's pf_optimal_resize! reproduces the independent pure-Python restatement
+    (tests/golden/make_golden.py::optimal_resize) bit for bit: threshold, keep set, systematic draws, weights."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_optimal.npz"))
+    g1 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+    keys = sorted(k for k in z.files if k.endswith("/u"))
+    assert len(keys) == 12
+    for key in keys:
+        case, tag, _ = key.split("/")
+        N = int(tag.split("_")[1])
+        lw = g1[f"{case}/lw"]
+        r = orc.optimal_resize(lw, N, float(z[key]))
+        assert r["status"] == 0 and r["n_keep"] == int(z[f"{case}/{tag}/n_keep"])
+        assert r["inv_w"] == float(z[f"{case}/{tag}/inv_w"])
+        np.testing.assert_array_equal(r["parents0"], z[f"{case}/{tag}/parents"])
+        np.testing.assert_array_equal(r["lw_out"], z[f"{case}/{tag}/lw_out"])
