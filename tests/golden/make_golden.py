@@ -215,6 +215,68 @@ def main_optimal():
     print("wrote", len(out), "arrays (optimal)")
 
 
+def replicate(lw, k, interleaved):  # resize.jl:236-244: repeat(x; inner=k) | repeat(x, k)
+    n = len(lw)
+    parents = [i for _ in range(k) for i in range(n)] if interleaved else [i for i in range(n) for _ in range(k)]
+    return parents, [lw[i] for i in parents]
+
+
+def dereplicate(lw, k, interleaved, sample, us):  # resize.jl:267-297
+    n_old = len(lw)
+    assert n_old % k == 0
+    n_new = n_old // k
+    blocks = [list(range(b, n_old, n_new)) for b in range(n_new)] if interleaved else \
+             [list(range(b * k, (b + 1) * k)) for b in range(n_new)]
+    if not sample:
+        idxs = [blk[0] for blk in blocks]
+        return idxs, [lw[i] for i in idxs]
+    idxs, out = [], []
+    for b, blk in enumerate(blocks):
+        w = softmax([lw[i] for i in blk])
+        j, cp = 0, w[0]  # rand(Categorical(w)): inverse CDF, first cumulative > u (Distributions single draw)
+        while cp <= us[b] and j < k - 1:
+            j += 1
+            cp += w[j]
+        idxs.append(blk[j])
+        out.append(logsumexp([lw[i] for i in blk]) - math.log(k))
+    return idxs, out
+
+
+def coalesce(lw, keys):  # resize.jl:309-334; groups emitted in ascending first-index order
+    first, acc = {}, {}
+    for i, (v, w) in enumerate(zip(keys, lw)):
+        j = first.setdefault(v, i)
+        acc[j] = acc.get(j, 0.0) + math.exp(w)
+    n_new = len(first)
+    ratio = math.log(n_new) - math.log(len(lw))
+    parents = sorted(first.values())
+    return parents, [math.log(acc[j]) + ratio for j in parents]
+
+
+def main_resize():
+    """tests/golden/golden_v3_resize.npz: pf_replicate! / pf_dereplicate! / pf_coalesce! on golden_v1's inputs."""
+    out = {}
+    for name, n, sigma, seed in [("n100_s1", 100, 1.0, 11), ("n3000_s1", 3000, 1.0, 14)]:
+        lw = [sigma * normal_from(seed, 7, i) for i in range(n)]
+        for tag, inter in (("contiguous", False), ("interleaved", True)):
+            p, w = replicate(lw, 3, inter)
+            out[f"{name}/replicate3_{tag}/parents"] = np.array(p)
+            out[f"{name}/replicate3_{tag}/lw_out"] = np.array(w)
+            us = [uniform53(seed, 5, b) for b in range(n // 5)]
+            out[f"{name}/u_derep"] = np.array(us)
+            for mtag, smp in (("keepfirst", False), ("sample", True)):
+                p, w = dereplicate(lw, 5, inter, smp, us)
+                out[f"{name}/dereplicate5_{tag}_{mtag}/parents"] = np.array(p)
+                out[f"{name}/dereplicate5_{tag}_{mtag}/lw_out"] = np.array(w)
+        keys = [int(uniform53(seed, 6, i) * 7) - 3 for i in range(n)]
+        out[f"{name}/coalesce/keys"] = np.array(keys, dtype=np.int64)
+        p, w = coalesce(lw, keys)
+        out[f"{name}/coalesce/parents"] = np.array(p)
+        out[f"{name}/coalesce/lw_out"] = np.array(w)
+    np.savez_compressed(os.path.join(HERE, "golden_v3_resize.npz"), **out)
+    print("wrote", len(out), "arrays (resize)")
+
+
 def main():
     out = {}
     cases = [("n100_s1", 100, 1.0, 11), ("n1000_s5", 1000, 5.0, 12), ("n2048_s2", 2048, 2.0, 13),
@@ -260,3 +322,4 @@ def main():
 if __name__ == "__main__":
     main()
     main_optimal()
+    main_resize()

@@ -301,3 +301,24 @@ def test_optimal_resize_golden(orc):
         assert r["inv_w"] == float(z[f"{case}/{tag}/inv_w"])
         np.testing.assert_array_equal(r["parents0"], z[f"{case}/{tag}/parents"])
         np.testing.assert_array_equal(r["lw_out"], z[f"{case}/{tag}/lw_out"])
+
+
+def test_resize_golden(orc):
+    """pf_replicate! / pf_dereplicate! (keepfirst and sample) / pf_coalesce!: the C oracle reproduces the independent
+    pure-Python restatement (tests/golden/make_golden.py) bit for bit."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, g1 = np.load(os.path.join(here, "golden_v3_resize.npz")), np.load(os.path.join(here, "golden_v1.npz"))
+    for case in ("n100_s1", "n3000_s1"):
+        lw = g1[f"{case}/lw"]
+        for tag, inter in (("contiguous", False), ("interleaved", True)):
+            p, w = orc.replicate(lw, 3, inter)
+            np.testing.assert_array_equal(p, z[f"{case}/replicate3_{tag}/parents"])
+            np.testing.assert_array_equal(w, z[f"{case}/replicate3_{tag}/lw_out"])
+            for mtag, smp in (("keepfirst", False), ("sample", True)):
+                p, w = orc.dereplicate(lw, 5, inter, smp, z[f"{case}/u_derep"])
+                np.testing.assert_array_equal(p, z[f"{case}/dereplicate5_{tag}_{mtag}/parents"])
+                np.testing.assert_array_equal(w, z[f"{case}/dereplicate5_{tag}_{mtag}/lw_out"])
+        p, w = orc.coalesce(lw, z[f"{case}/coalesce/keys"])
+        np.testing.assert_array_equal(p, z[f"{case}/coalesce/parents"])
+        np.testing.assert_array_equal(w, z[f"{case}/coalesce/lw_out"])
