@@ -41,6 +41,7 @@ KERNEL_ALGO_BYTES = {
     "k_reduce": 8,
 }
 STEP_ALGO_BYTES = 117
+HEADLINE_NOISE = "philox53"  # 53-bit uniforms + fp64 Box-Muller is the production policy
 
 
 def measured_peak_gbs():
@@ -134,12 +135,13 @@ class ClockSampler:
                 "power_w_max": max(r[2] for r in self.rows)}
 
 
-def cpu_arm(steps, warmup, n_sample, omp=True):
-    """The CPU port of the reference path (oracle/) on the host cores: same step, bounded sample."""
+def cpu_arm(steps, warmup, n_sample, omp=True, threads=None):
+    """The CPU port of the reference path (oracle/) on the host cores: same step, bounded sample.
+    torchrun exports OMP_NUM_THREADS=1 to its workers, so the thread count is set explicitly."""
     from oracle import oracle as orc
     T = warmup + steps + 1
     obs = observations(T)
-    f = orc.OMFilter(n_sample, seed=0, omp=omp)
+    f = orc.OMFilter(n_sample, seed=0, omp=omp, threads=threads or os.cpu_count())
     f.init(math.sin(1.0), obs[0])
     t = 2
     for _ in range(warmup):
@@ -153,21 +155,30 @@ def cpu_arm(steps, warmup, n_sample, omp=True):
     return n_sample * steps / dt, dt / steps, f.threads()
 
 
+WORKLOAD = ("object_motion 2^24 particles/GPU: ESS + stratified resample(sort_particles=false) + MH rejuvenation "
+            "+ update per step (README.md:66-77, resample forced)")
+
+
 def run_reference(args):
+    """--impl reference: the reference's CPU path.  Julia/Gen cannot be installed here (a Julia package; no julia
+    binary in the image, no network), so the C/OpenMP port of the reference algorithms (oracle/) is timed on all
+    host cores on the SAME workload (2^24 particles per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 1 << 22
+    n_sample = args.particles
     value, sec_per_step, cores = cpu_arm(args.steps, args.warmup, n_sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "object_motion 2^24 particles: ESS + stratified resample(sort=false) + MH + update",
+        "config": {"workload": WORKLOAD, "particles_per_gpu": n_sample,
                    "note": "Julia/Gen cannot run here (no julia in the image); this is the C/OpenMP port of the "
-                           "reference algorithms (oracle/), faster than the real reference (no trace overhead)"},
+                           "reference algorithms (oracle/), faster than the real reference (no Gen trace overhead); "
+                           "at --gpus N it still times ONE 2^24-particle filter on the host cores"},
         "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} particles per step (1/4 of the 2^24 workload), {args.steps} steps"},
+                         "sample": f"{n_sample} particles per step (the full 2^24 workload), {args.steps} steps, "
+                                   f"{cores} OpenMP threads"},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -183,6 +194,88 @@ def emit(line):
     out.flush()
 
 
+def parse_profile(buf):
+    prof = {}
+    for row in buf.value.decode().strip().splitlines():
+        name, cnt, tot = row.split("\t")
+        name = name.strip("()").split("<")[0]
+        c, tt = prof.get(name, (0, 0.0))
+        prof[name] = (c + int(cnt), tt + float(tot))
+    return prof
+
+
+def resample_microbench(g, torch, peak, log2n=26, reps=5):
+    """BASELINE metric, second half: "resample HBM GB/s vs peak" (SURVEY 8d config 2).  Host-array semantics with the
+    inputs resident in HBM (GENPF_DEVICE_PTRS), n = 2^26 fp64 log-weights ~ N(0,1) (512 MB > L2, and L2 flushed
+    between repetitions); time = summed CUDA-event durations of the call's kernels, median of `reps`;
+    GB/s = algorithmic bytes (ESS 8 B, resample 24 B per particle) / time."""
+    import ctypes as C
+    L, lib = g._lib, g.load()
+    n = 1 << log2n
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    lw = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    parents = torch.empty(n, dtype=torch.int64, device="cuda")
+    lw_out = torch.empty(n, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    inc, kind, ess = C.c_double(), C.c_int32(), C.c_double()
+
+    def timed(fn):
+        ts = []
+        for _ in range(reps + 1):
+            flush.zero_()
+            torch.cuda.synchronize()
+            L.check(lib.genpf_profile_begin())
+            fn()
+            buf = C.create_string_buffer(1 << 14)
+            L.check(lib.genpf_profile_end(buf, len(buf)))
+            prof = parse_profile(buf)
+            ts.append((sum(v[1] for v in prof.values()), {k: v[1] for k, v in prof.items()}))
+        ts = sorted(ts[1:], key=lambda t: t[0])  # first repetition = warm-up (allocations)
+        return ts[len(ts) // 2]
+
+    rows = {}
+
+    def add(name, algo, fn):
+        ms, parts = timed(fn)
+        rows[name] = {"ms": ms, "GBps": algo * n / ms / 1e6, "frac": algo * n / ms / 1e6 / peak,
+                      "algo_bytes_per_particle": algo, "kernels_ms": parts}
+
+    add("ess+logsumexp", 8, lambda: L.check(lib.genpf_ess(lw.data_ptr(), n, L.DEVICE_PTRS, C.byref(ess))))
+    for name, method, flags in (("stratified(sort_particles=false)", L.STRATIFIED, 0),
+                                ("stratified(sort_particles=true)", L.STRATIFIED, L.SORT_PARTICLES),
+                                ("multinomial", L.MULTINOMIAL, 0), ("residual", L.RESIDUAL, 0)):
+        add(name, 24, lambda m=method, f=flags: L.check(lib.genpf_resample(
+            m, lw.data_ptr(), None, n, n, None, 1, f | L.DEVICE_PTRS, parents.data_ptr(), lw_out.data_ptr(),
+            C.byref(inc), C.byref(kind))))
+    del lw, parents, lw_out, flush
+    torch.cuda.empty_cache()
+    return {"n": n, "dist": "N(0,1)", "l2": "flushed between repetitions; 512 MB input > L2", "reps": reps,
+            "peak_GBps": peak, "rows": rows}
+
+
+def host_array_e2e(g, torch, n, reps=5):
+    """The drop-in call for arbitrary Gen models (north star path 1): genpf_resample with HOST buffers -- log_weights
+    in, Int64 ancestors + new log_weights out -- copies inside the timed region (pinned host memory)."""
+    import ctypes as C
+    L, lib = g._lib, g.load()
+    lw = torch.randn(n, dtype=torch.float64).pin_memory()
+    parents = torch.empty(n, dtype=torch.int64).pin_memory()
+    lw_out = torch.empty(n, dtype=torch.float64).pin_memory()
+    inc, kind = C.c_double(), C.c_int32()
+    out = {}
+    for name, method, flags in (("stratified(sort_particles=false)", L.STRATIFIED, 0), ("residual", L.RESIDUAL, 0)):
+        ts = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            L.check(lib.genpf_resample(method, lw.data_ptr(), None, n, n, None, 1, flags, parents.data_ptr(),
+                                       lw_out.data_ptr(), C.byref(inc), C.byref(kind)))
+            ts.append(time.perf_counter() - t0)
+        t = sorted(ts[1:])[len(ts[1:]) // 2]
+        out[name] = {"ms": t * 1e3, "particles_per_s": n / t, "h2d_bytes": 8 * n, "d2h_bytes": 16 * n,
+                     "pcie_GBps": 24 * n / t / 1e9}
+    return {"n": n, "call": "genpf_resample(host pointers, pinned)", "rows": out}
+
+
 def main():
     # library banners (e.g. "NCCL version ...") go to stderr: stdout carries only the JSON line
     global _OUT
@@ -195,6 +288,9 @@ def main():
     ap.add_argument("--impl", default="genpf")
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-micro", action="store_true", help="skip the resample microbench + host-array e2e objects")
+    ap.add_argument("--noise", default=HEADLINE_NOISE, choices=["lean", "philox53"],
+                    help="noise policy of the headline `value` (the other one is reported beside it at 1 GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -231,148 +327,172 @@ def main():
     auxs = [np.array([math.sin(float(t))]) for t in range(T + 2)]
     obs_arr = [np.array([o]) for o in obs]
     method = L.STRATIFIED
-    shard_info = None
-    if world == 1:
-        state = g.pf_initialize(model, (1,), obs[0], n, seed=1234)
-        sp = C.c_void_p()
-        L.check(lib.genpf_filter_stream(state._h, C.byref(sp)))
-        stream = torch.cuda.ExternalStream(sp.value)
 
-        def raw_step(t):  # asynchronous: nothing is copied back
-            L.check(lib.genpf_step(state._h, t, L.ptr(obs_arr[t - 2]), L.ptr(auxs[t - 1]), L.ptr(obs_arr[t - 1]),
-                                   L.ptr(auxs[t]), method, 1.0, 1, None))
-            state.t = t
+    def measure(noise, sampler_on):
+        """W warm-up + K timed steps (device resident) + K profiled steps + K end-to-end steps for one noise policy."""
+        shard_info = None
+        if world == 1:
+            state = g.pf_initialize(model, (1,), obs[0], n, seed=1234, noise=noise)
+            sp = C.c_void_p()
+            L.check(lib.genpf_filter_stream(state._h, C.byref(sp)))
+            stream = torch.cuda.ExternalStream(sp.value)
 
-        def e2e_step(t, pin_prev, pin_t):
-            return g.pf_step(state, t, pin_prev, pin_t, method="stratified", ess_thresh=1.0, mh_iters=1,
-                             return_ess=True)
-    else:
-        # ONE filter of world * n particles, slots sharded contiguously over the ranks:
-        # shard totals exchanged through peer memory inside 1-warp kernels + NVLink P2P push of offspring
-        from genpf_b200.sharded import ShardedFilter
-        sf = ShardedFilter(model, n, seed=1234)
-        sf.initialize(obs[0])
-        stream = sf.stream
+            def raw_step(t):  # asynchronous: nothing is copied back
+                L.check(lib.genpf_step(state._h, t, L.ptr(obs_arr[t - 2]), L.ptr(auxs[t - 1]), L.ptr(obs_arr[t - 1]),
+                                       L.ptr(auxs[t]), method, 1.0, 1, None))
+                state.t = t
 
-        def raw_step(t):
-            sf.step(t, obs[t - 2], obs[t - 1])
+            def e2e_step(t, pin_prev, pin_t):
+                return g.pf_step(state, t, pin_prev, pin_t, method="stratified", ess_thresh=1.0, mh_iters=1,
+                                 return_ess=True)
+        else:
+            # ONE filter of world * n particles, slots sharded contiguously over the ranks (SURVEY 8e):
+            # shard totals exchanged through peer memory inside 1-warp kernels + NVLink P2P push of offspring
+            from genpf_b200.sharded import ShardedFilter
+            sf = ShardedFilter(model, n, seed=1234, noise=noise)
+            sf.initialize(obs[0])
+            stream = sf.stream
 
-        def e2e_step(t, pin_prev, pin_t):
-            sf.step(t, pin_prev[0], pin_t[0])
-            return np.array([sf.stats()[0]])
+            def raw_step(t):
+                sf.step(t, obs[t - 2], obs[t - 1])
 
-    t = 2
-    for _ in range(W):
-        raw_step(t)
-        t += 1
-    # ---- timed region 1: device-resident throughput
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = lib.genpf_launch_count()
-    e0.record(stream)
-    for _ in range(K):
-        raw_step(t)
-        t += 1
-    e1.record(stream)
-    barrier()
-    launches = lib.genpf_launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        ranges, frac = sf.exchange_summary()
-        shard_info = {"cross_shard_offspring_fraction": frac,
-                      "nvlink_bytes_per_step_per_gpu": frac * n * 30.0,  # parents 4 + two slices 18 + lw 8
-                      "exchange_per_step": "24 B + 8 B + barrier per rank as NVLink P2P stores + epoch flags polled "
-                                           "in-kernel (no NCCL inside the step)"}
-    # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
-    L.check(lib.genpf_profile_begin())
-    for _ in range(K):
-        raw_step(t)
-        t += 1
-    buf = C.create_string_buffer(1 << 16)
-    L.check(lib.genpf_profile_end(buf, len(buf)))
-    prof = {}
-    for row in buf.value.decode().strip().splitlines():
-        name, cnt, tot = row.split("\t")
-        name = name.strip("()").split("<")[0]
-        c, tt = prof.get(name, (0, 0.0))
-        prof[name] = (c + int(cnt), tt + float(tot))
-    # ---- timed region 3: end to end through the public API: host obs in, ESS back, every step
-    pin_prev, pin_t = np.empty(1), np.empty(1)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(K):
-        pin_prev[0], pin_t[0] = obs[t - 2], obs[t - 1]
-        ess = e2e_step(t, pin_prev, pin_t)
-        t += 1
-    barrier()
-    e2e_s = time.perf_counter() - w0
-    assert np.isfinite(ess).all()
-    clocks = sampler.stop() if sampler else None
+            def e2e_step(t, pin_prev, pin_t):
+                sf.step(t, pin_prev[0], pin_t[0])
+                return np.array([sf.stats()[0]])
 
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = times.tolist()
+        t = 2
+        for _ in range(W):
+            raw_step(t)
+            t += 1
+        # ---- timed region 1: device-resident throughput
+        sampler = ClockSampler(local_rank) if (rank == 0 and sampler_on) else None
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.genpf_launch_count()
+        e0.record(stream)
+        for _ in range(K):
+            raw_step(t)
+            t += 1
+        e1.record(stream)
+        barrier()
+        launches = lib.genpf_launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            ranges, frac = sf.exchange_summary()
+            shard_info = {"cross_shard_offspring_fraction": frac,
+                          "nvlink_bytes_per_step_per_gpu": frac * n * 38.0,  # parents 4 + two slices 18 + lw 8 + e 8
+                          "exchange_per_step": "24 B + 8 B + barrier per rank as NVLink P2P stores + epoch flags "
+                                               "polled in-kernel (no NCCL inside the step)"}
+        # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
+        L.check(lib.genpf_profile_begin())
+        for _ in range(K):
+            raw_step(t)
+            t += 1
+        buf = C.create_string_buffer(1 << 16)
+        L.check(lib.genpf_profile_end(buf, len(buf)))
+        prof = parse_profile(buf)
+        # ---- timed region 3: end to end through the public API: host obs in, ESS back, every step
+        pin_prev, pin_t = np.empty(1), np.empty(1)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(K):
+            pin_prev[0], pin_t[0] = obs[t - 2], obs[t - 1]
+            ess = e2e_step(t, pin_prev, pin_t)
+            t += 1
+        barrier()
+        e2e_s = time.perf_counter() - w0
+        assert np.isfinite(ess).all()
+        clocks = sampler.stop() if sampler else None
+        times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+            sf.close()
+        ms_max, e2e_ms_max = times.tolist()
+        return dict(ms=ms_max, e2e_ms=e2e_ms_max, launches=int(launches), prof=prof, clocks=clocks,
+                    shard_info=shard_info)
+
+    head = measure(args.noise, True)
+    other_noise = "lean" if args.noise == "philox53" else "philox53"
+    other = measure(other_noise, False) if world == 1 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    total_updates = float(n) * world * K
-    value = total_updates / (ms_max * 1e-3)
     peak, peak_src = measured_peak_gbs()
+    total_updates = float(n) * world * K
+
+    def summarise(m):
+        v = total_updates / (m["ms"] * 1e-3)
+        step_kernel_ms = sum(x[1] for x in m["prof"].values()) / K
+        return {"value": v, "ms_per_step": m["ms"] / K, "e2e_value": total_updates / (m["e2e_ms"] * 1e-3),
+                "roofline_frac": STEP_ALGO_BYTES * n / (step_kernel_ms * 1e-3) / 1e9 / peak,
+                "kernels_ms_per_step": {k: x[1] / K for k, x in sorted(m["prof"].items())}}
+
+    hs = summarise(head)
+    prof = head["prof"]
     # SURVEY 8(d)'s 117 B/particle-update describes the whole step, so the roofline figure is formed over the
     # step's launches together (k_scan + k_finalize_fast + k_step_fused, or their sharded counterparts): fusion
     # removed the gather->MH->update round trips, so apportioning the 117 B to the fused kernel alone would
     # credit it with bytes it never moves.  The dominant kernel's own numbers are reported next to it.
-    dom = max(prof.items(), key=lambda kv: kv[1][1])
-    dom_name, (dom_cnt, dom_ms) = dom
+    dom_name, (dom_cnt, dom_ms) = max(prof.items(), key=lambda kv: kv[1][1])
     per_launch_ms = dom_ms / dom_cnt
     prof_total = sum(v[1] for v in prof.values())
     step_kernel_ms = prof_total / K
     algo_b = STEP_ALGO_BYTES * n
     achieved = algo_b / (step_kernel_ms * 1e-3) / 1e9
-    dom_traffic = traffic_of(dom_name)
+    tkey = lambda k: k + ("" if args.noise == "lean" else "@" + args.noise)  # noqa: E731
+    tr = lambda k: traffic_of(tkey(k)) if traffic_of(tkey(k)) is not None else traffic_of(k)  # noqa: E731
+    dom_traffic = tr(dom_name)
     step_traffic = None
-    if all(traffic_of(k) is not None for k in prof if k in ("k_scan", "k_step_fused")) and "k_step_fused" in prof:
-        step_traffic = sum(traffic_of(k) or 0.0 for k in prof)
+    if all(tr(k) is not None for k in prof if k in ("k_scan", "k_step_fused")) and "k_step_fused" in prof:
+        step_traffic = sum(tr(k) or 0.0 for k in prof)
     dominant = {
         "name": dom_name, "ms_per_launch": per_launch_ms, "share_of_step": dom_ms / prof_total,
         "dram_bytes_per_launch": dom_traffic,
         "dram_gbs": (dom_traffic / (per_launch_ms * 1e-3) / 1e9) if dom_traffic else None,
         "dram_frac_of_peak": (dom_traffic / (per_launch_ms * 1e-3) / 1e9 / peak) if dom_traffic else None,
         "own_algo_bytes_per_update": KERNEL_ALGO_BYTES.get(dom_name),
-        "bound": "instruction issue (ncu: ~75 % issue-slot utilisation, profiles/r1_k_ncu_summary.md)",
+        "bound": "instruction issue (ncu summary under profiles/)",
     }
+    noise_desc = {"lean": "lean: ONE Philox4x32-10 block/particle/step (24-bit Bernoulli uniforms, 32-bit accept uniform, "
+                          "fp32 Box-Muller pair)",
+                  "philox53": "philox53 (SURVEY 8c production noise): 53-bit uniforms (x>>11)*2^-53 + fp64 Box-Muller, "
+                              "three Philox4x32-10 blocks/particle/step"}
     line = {
-        "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": hs["value"], "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": hs["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "object_motion 2^24 particles/GPU: ESS + stratified resample(sort_particles=false) "
-                               "+ MH rejuvenation + update per step (README.md:66-77, resample forced)",
+        "config": {"workload": WORKLOAD,
                    "particles_per_gpu": n, "l2": "inputs larger than L2 (>=1.2 GB touched per step)",
                    "parallelism": "1 GPU" if world == 1 else f"one filter of {world}x2^24 particles sharded over "
                                   f"{world} GPUs: shard totals exchanged through peer memory (NVLink stores + epoch flags), offspring pushed to the owner GPU over NVLink P2P inside the step kernel",
-                   "sharding": shard_info,
-                   "noise": "lean Philox4x32-10 (1 call/particle/purpose)", "algo_bytes_per_update": STEP_ALGO_BYTES},
-        "clocks": clocks,
-        "e2e": {"value": total_updates / (e2e_ms_max * 1e-3), "unit": "particle-updates/s",
+                   "sharding": head["shard_info"],
+                   "noise": noise_desc[args.noise], "algo_bytes_per_update": STEP_ALGO_BYTES,
+                   "resample_note": "stratified with sort_particles=false (the reference README uses :residual and "
+                                    "the stratified default sorts; both are in resample_microbench)"},
+        "clocks": head["clocks"],
+        "e2e": {"value": hs["e2e_value"], "unit": "particle-updates/s",
                 "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 48,
                 "note": "genpf_b200.pf_step / ShardedFilter.step: obs/aux scalars in (kernel arguments), "
                         "Stats(ESS) read back per step"},
-        "gpu_launches": int(launches),
+        "gpu_launches": head["launches"],
         "roofline": {"bound": "hbm", "kernel": dom_name,
                      "scope": "the step's launches together (" + " + ".join(sorted(prof)) + "); SURVEY 8(d): "
                               "117 B/particle-update is defined on the whole step",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": step_traffic, "peak_source": peak_src,
                      "algo_bytes_per_launch": algo_b, "ms_per_launch": step_kernel_ms,
-                     "wall_frac": (STEP_ALGO_BYTES * n / (ms_max / K * 1e-3) / 1e9) / peak,
+                     "wall_frac": (STEP_ALGO_BYTES * n / (hs["ms_per_step"] * 1e-3) / 1e9) / peak,
                      "dominant_kernel": dominant,
-                     "kernels_ms_per_step": {k: v[1] / K for k, v in sorted(prof.items())}},
+                     "kernels_ms_per_step": hs["kernels_ms_per_step"]},
     }
+    if other is not None:
+        line["noise_policies"] = {args.noise: dict(hs, headline=True), other_noise: dict(summarise(other), headline=False)}
+    if world == 1 and not args.no_micro:
+        line["resample_microbench"] = resample_microbench(g, torch, peak)
+        line["e2e_host_arrays"] = host_array_e2e(g, torch, n)
     if world == 1 and not args.no_cpu:
-        n_sample = 1 << 22
+        n_sample = n
         v1, s1, cores = cpu_arm(2, 1, n_sample)
         steps_cpu = max(2, min(40, int(12.0 / max(s1, 1e-3))))
         v, s, cores = cpu_arm(steps_cpu, 1, n_sample)

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenpf_cuda.so")
+# GENPF_LIBRARY overrides the in-tree build (kernel-variant experiments); there is still no fallback
+LIB_PATH = os.environ.get("GENPF_LIBRARY") or os.path.join(_HERE, "libgenpf_cuda.so")
 
 # status codes / enums (include/genpf.h)
 OK = 0
@@ -78,6 +79,7 @@ SIGNATURES = {
     "genpf_rejuvenate_reweight": (i32, [_vp, i64, _vp, _vp, i32]),
     "genpf_rejuvenate_reweight_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     "genpf_step": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, f64, i32, _vp]),
+    "genpf_step_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "genpf_mean_var": (i32, [_vp, i32, i64, _vp, _vp]),
     "genpf_replicate": (i32, [_vp, i64, i32]),
     "genpf_dereplicate": (i32, [_vp, i64, i32, i32, _vp]),
@@ -104,6 +106,7 @@ SIGNATURES = {
     "genpf_shard_push": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32]),
     "genpf_shard_finish": (i32, [_vp]),
     "genpf_shard_step_p2p": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32]),
+    "genpf_shard_step_p2p_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "genpf_shard_oend": (i32, [_vp, _vp, _i32p]),
     "genpf_shard_stats": (i32, [_vp, _dp, _dp, _i32p]),
     "genpf_profile_begin": (i32, []),

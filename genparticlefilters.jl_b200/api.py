@@ -34,6 +34,15 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _fresh_seed(seed):
+    """The reference draws from Julia's global RNG: every call sees fresh randomness.  The C ABI is stateless
+    (Philox keyed by `seed`), so `seed=None` draws a new 64-bit key per call from numpy's global generator
+    (`np.random.seed` makes a run reproducible, like `Random.seed!`); an explicit seed pins the draw."""
+    if seed is None:
+        return int(np.random.randint(0, np.iinfo(np.int64).max, dtype=np.int64))
+    return int(seed)
+
+
 # --------------------------------------------------------------------------- states
 class ParticleFilterState:
     """Gen.ParticleFilterState restricted to what this path touches (initialize.jl:4-10,42-43)."""
@@ -196,7 +205,8 @@ class DevicePFState:
             if tau >= 1:
                 for name in self.model.fields:
                     out[f"field_{name}_{tau}"] = self.field(name, tau)
-        np.savez(path, **out)
+        with open(path, "wb") as fh:  # np.savez on a file object keeps the caller's path verbatim (no '.npz' appended)
+            np.savez(fh, **out)
 
     @classmethod
     def load(cls, path):
@@ -370,7 +380,7 @@ def _emit_check(kind, check):
 
 
 def pf_resample(state, method="multinomial", *, priority_fn=None, check="warn", sort_particles=True,
-                uniforms=None, seed=0, n_out=None):
+                uniforms=None, seed=None, n_out=None):
     """pf_resample!, resample.jl:19-30 (dispatch), 48-65 / 85-120 / 143-175.
 
     `uniforms` (optional) are the reference RNG's draws exported per output slot / stratum; without
@@ -409,7 +419,7 @@ def pf_resample(state, method="multinomial", *, priority_fn=None, check="warn", 
     parents = np.empty(n_out, dtype=np.int64)
     lw_out = np.empty(n_out)
     lml_inc, kind = C.c_double(), C.c_int32()
-    st = lib.genpf_resample(m, L.ptr(lw), L.ptr(lp), n_in, n_out, L.ptr(u), seed,
+    st = lib.genpf_resample(m, L.ptr(lw), L.ptr(lp), n_in, n_out, L.ptr(u), _fresh_seed(seed),
                             flags | (L.SUBSTATE if sub else 0) | (L.CHECK if check is True else 0),
                             L.ptr(parents), L.ptr(lw_out), C.byref(lml_inc), C.byref(kind))
     if st == L.ERR_INVALID_WEIGHTS:
@@ -459,7 +469,7 @@ def pf_resize(state, n_particles, method="multinomial", **kw):
     return pf_resample(state, method, n_out=n_particles, **kw)
 
 
-def pf_optimal_resize(state, n_particles, *, check="warn", uniform=None, seed=0):
+def pf_optimal_resize(state, n_particles, *, check="warn", uniform=None, seed=None):
     """pf_optimal_resize!, resize.jl:149-196 (Fearnhead-Clifford optimal resampling; n_particles <= current size).
     `uniform` stands for the single rand() of resize.jl:171 (None: the library's Philox draw)."""
     if isinstance(state, ParticleFilterSubState):
@@ -474,7 +484,7 @@ def pf_optimal_resize(state, n_particles, *, check="warn", uniform=None, seed=0)
         lw = _f64(state.log_weights)
         parents = np.empty(n_particles, dtype=np.int64)
         lw_out = np.empty(n_particles)
-        st = L.load().genpf_optimal_resize(L.ptr(lw), lw.size, n_particles, u, seed, flags, L.ptr(parents),
+        st = L.load().genpf_optimal_resize(L.ptr(lw), lw.size, n_particles, u, _fresh_seed(seed), flags, L.ptr(parents),
                                            L.ptr(lw_out), C.byref(n_keep), C.byref(inv_w), kinds)
     if st == L.ERR_INVALID_WEIGHTS:
         raise GenPFErrorException("Invalid weights.")
@@ -512,7 +522,7 @@ def pf_replicate(state, n_replicates, *, layout="contiguous"):
     return state
 
 
-def pf_dereplicate(state, n_replicates, *, layout="contiguous", method="keepfirst", uniforms=None, seed=0):
+def pf_dereplicate(state, n_replicates, *, layout="contiguous", method="keepfirst", uniforms=None, seed=None):
     """pf_dereplicate!, resize.jl:267-297."""
     lay = L.LAYOUT_CONTIGUOUS if layout == "contiguous" else L.LAYOUT_INTERLEAVED
     meth = L.KEEPFIRST if method == "keepfirst" else L.SAMPLE
@@ -525,7 +535,7 @@ def pf_dereplicate(state, n_replicates, *, layout="contiguous", method="keepfirs
     lw = _f64(state.log_weights)
     parents = np.empty(n // n_replicates, dtype=np.int64)
     lw_out = np.empty(n // n_replicates)
-    L.check(L.load().genpf_dereplicate_host(L.ptr(lw), n, n_replicates, lay, meth, L.ptr(u), seed, 0,
+    L.check(L.load().genpf_dereplicate_host(L.ptr(lw), n, n_replicates, lay, meth, L.ptr(u), _fresh_seed(seed), 0,
                                             L.ptr(parents), L.ptr(lw_out)))
     _apply_resize(state, parents, lw_out)
     return state
@@ -534,6 +544,9 @@ def pf_dereplicate(state, n_replicates, *, layout="contiguous", method="keepfirs
 def pf_coalesce(state, *, by=None):
     """pf_coalesce!, resize.jl:309-334.  `by(trace)` must return something hashable."""
     if isinstance(state, DevicePFState):
+        if by is not None:
+            raise GenPFErrorException("pf_coalesce!(device state): particles are grouped by their resident window "
+                                      "(all fields of slices t-1 and t); a custom `by` is not supported")
         n_new = C.c_int64()
         L.check(L.load().genpf_coalesce(state._h, C.byref(n_new)))
         return state
@@ -600,7 +613,7 @@ def get_log_weights(state):
     return _f64(state.log_weights).copy()
 
 
-def sample_unweighted_traces(state, n_samples, *, uniforms=None, seed=0):
+def sample_unweighted_traces(state, n_samples, *, uniforms=None, seed=None):
     """Gen.sample_unweighted_traces / its sub-state method (utils.jl:189-194): n_samples traces drawn with
     replacement in proportion to the normalised weights (inverse-CDF draws on the GPU); the state is not changed."""
     lw = _f64(state.log_weights)
@@ -608,7 +621,8 @@ def sample_unweighted_traces(state, n_samples, *, uniforms=None, seed=0):
     parents = np.empty(n_samples, dtype=np.int64)
     lw_out = np.empty(n_samples)
     inc, kind = C.c_double(), C.c_int32()
-    L.check(L.load().genpf_resample(L.METHODS["multinomial"], L.ptr(lw), None, lw.size, n_samples, L.ptr(u), seed,
+    L.check(L.load().genpf_resample(L.METHODS["multinomial"], L.ptr(lw), None, lw.size, n_samples, L.ptr(u),
+                                    _fresh_seed(seed),
                                     L.SUBSTATE if n_samples == lw.size else 0, L.ptr(parents), L.ptr(lw_out),
                                     C.byref(inc), C.byref(kind)))
     traces = state.traces
@@ -643,6 +657,8 @@ def pf_move_accept(state, kern, kern_args=(), n_iters=1, **kwargs):
         if kern is not mh:
             raise TypeError("device states rejuvenate with the built-in mh kernel")
         tau, obs = kern_args
+        if not 0 <= int(n_iters) <= 256:
+            raise GenPFErrorException("device mh rejuvenation supports at most 256 iterations per call")
         acc = np.zeros(state.n_filters, dtype=np.int64)
         L.check(L.load().genpf_rejuvenate_mh(state._h, int(tau), L.ptr(state._obs(obs)),
                                              L.ptr(state.model.aux(tau)), n_iters, L.ptr(acc)))
@@ -722,6 +738,8 @@ def proportionmap(state, addr, f=None, max_values=1 << 16):
         vals, props = np.empty(max_values), np.empty(max_values)
         L.check(lib.genpf_proportionmap(state._h, state.model.fields[name], int(tau), vals.ctypes.data_as(L._dp),
                                         props.ctypes.data_as(L._dp), max_values, C.byref(n_unique)))
+        if n_unique.value > max_values:
+            warnings.warn(f"proportionmap: {n_unique.value} distinct values, only the first {max_values} returned")
         g = min(n_unique.value, max_values)
         is_bool = name in getattr(state.model, "bool_fields", ())
         return {(bool(v) if is_bool else float(v)): float(p) for v, p in zip(vals[:g], props[:g])}
@@ -746,3 +764,16 @@ def pf_step(state, t, obs_prev, obs_t, *, method="stratified", ess_thresh=0.5, m
                                 int(mh_iters), L.ptr(ess)))
     state.t = int(t)
     return ess
+
+
+def pf_step_with_noise(state, t, obs_prev, obs_t, *, method="stratified", mh_iters=1, uniforms=None, U2=None, Z2=None,
+                       U3=None, U1=None, Z1=None):
+    """The README iteration in parity mode: resample taken, every draw supplied as a column indexed by
+    output particle (uniforms=None: the library's own Philox stratum / inverse-CDF draws)."""
+    m = state.model
+    cols = [None if c is None else _f64(c) for c in (uniforms, U2, Z2, U3, U1, Z1)]
+    L.check(L.load().genpf_step_with_noise(state._h, int(t), L.ptr(state._obs(obs_prev)), L.ptr(m.aux(t - 1)),
+                                           L.ptr(state._obs(obs_t)), L.ptr(m.aux(t)), L.METHODS[method], int(mh_iters),
+                                           *[L.ptr(c) for c in cols]))
+    state.t = int(t)
+    return state

@@ -33,12 +33,12 @@ static int32_t set_obs(genpf_filter_t pf, const double *obs, const double *aux, 
     return GENPF_OK;
 }
 
-static int32_t stage_noise(genpf_filter_t pf, int which, const double *host, const double **dev) {
+int32_t stage_noise(genpf_filter_t pf, int which, const double *host, const double **dev, int64_t count) {
     if (!host) {
         *dev = nullptr;
         return GENPF_OK;
     }
-    const size_t bytes = (size_t)(pf->n * pf->nf) * 8;
+    const size_t bytes = (size_t)(count > 0 ? count : pf->n * pf->nf) * 8;
     GENPF_TRY(pf->noise_buf[which].ensure(bytes));
     GENPF_CUDA_TRY(cudaMemcpyAsync(pf->noise_buf[which].p, host, bytes, cudaMemcpyHostToDevice, pf->stream));
     *dev = pf->noise_buf[which].as<double>();
@@ -63,7 +63,7 @@ template <class Model>
 static int32_t propagate_model(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
                                const double *U, const double *Z, Strata strata) {
     if (U || Z) {
-        NoiseCols nz{U, Z, nullptr};
+        NoiseCols nz{U, Z, nullptr, nullptr, nullptr};
         return launch_propagate<Model, NoiseCols>(pf, init, t, obs_dev, obs_val, nz, strata);
     }
     if (pf->flags & GENPF_NOISE_PHILOX53) {
@@ -104,8 +104,8 @@ static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const doubl
     const double *obs_dev, *dU, *dZ;
     double obs_val;
     GENPF_TRY(set_obs(pf, obs, aux, &obs_dev, &obs_val));
-    GENPF_TRY(stage_noise(pf, 0, U, &dU));
-    GENPF_TRY(stage_noise(pf, 1, Z, &dZ));
+    GENPF_TRY(stage_noise(pf, 3, U, &dU, 0));
+    GENPF_TRY(stage_noise(pf, 4, Z, &dZ, 0));
     if (init) {
         GENPF_CUDA_TRY(cudaMemsetAsync(pf->lml, 0, (size_t)pf->nf * 8, pf->stream));
         pf->n_resamples = 0;
@@ -170,7 +170,7 @@ template <class Model>
 static int32_t mh_model(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val,
                         const double *U2, const double *Z2, const double *U3, bool reweight) {
     if (U2 || Z2 || U3) {
-        NoiseCols nz{U2, Z2, U3};
+        NoiseCols nz{U2, Z2, U3, nullptr, nullptr};
         return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
     }
     // the mh move on slice tau belongs to README iteration s = tau + 1 (it runs right before pf_update!(s))
@@ -191,9 +191,9 @@ static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const do
     const double *obs_dev, *dU2, *dZ2, *dU3;
     double obs_val;
     GENPF_TRY(set_obs(pf, obs, aux, &obs_dev, &obs_val));
-    GENPF_TRY(stage_noise(pf, 0, U2, &dU2));
-    GENPF_TRY(stage_noise(pf, 1, Z2, &dZ2));
-    GENPF_TRY(stage_noise(pf, 2, U3, &dU3));
+    GENPF_TRY(stage_noise(pf, 0, U2, &dU2, 0));
+    GENPF_TRY(stage_noise(pf, 1, Z2, &dZ2, 0));
+    GENPF_TRY(stage_noise(pf, 2, U3, &dU3, 0));
     if (reweight) pf->part_valid = false;  // log-weights change
     GENPF_CUDA_TRY(cudaMemsetAsync(pf->n_accept, 0, (size_t)pf->nf * 8, pf->stream));
     for (int it = 0; it < n_iters; ++it) {
@@ -234,21 +234,61 @@ static GatherCols window_gather_cols(genpf_filter_t pf) {
     return g;
 }
 
-// grow / shrink the population buffers of the *other* buffer set + lw_alt + parents to n_out
+// grow / shrink the population buffers of the *other* buffer set + lw_alt + parents to n_out.  The old buffers
+// are parked in pf->undo until the resize commits: a call that fails validation afterwards (check=true with
+// invalid weights, the optimal resize's @assert) rolls back and leaves the filter exactly as it was.
 static int32_t resize_target(genpf_filter_t pf, int64_t n_out) {
     if (n_out == pf->n) return GENPF_OK;
     const int64_t total = n_out * pf->nf;
+    ResizeUndo &u = pf->undo;
+    u.active = true;
+    for (int sl = 0; sl < 2; ++sl) {
+        u.win[sl] = pf->win[pf->buf ^ 1][sl];
+        memset(&pf->win[pf->buf ^ 1][sl], 0, sizeof(Cols));
+    }
+    u.lw_alt = pf->lw_alt;
+    u.parents = pf->parents;
+    int32_t st = GENPF_OK;
+    for (int sl = 0; sl < 2 && st == GENPF_OK; ++sl) st = pf->alloc_cols(pf->win[pf->buf ^ 1][sl], total);
+    pf->lw_alt = nullptr;
+    pf->parents = nullptr;
+    if (st == GENPF_OK) st = pf->dalloc(&pf->lw_alt, (size_t)total);
+    if (st == GENPF_OK) st = pf->dalloc(&pf->parents, (size_t)total);
+    if (st == GENPF_OK) st = pf->sc.ensure(n_out > pf->n ? n_out : pf->n, pf->nf);
+    if (st != GENPF_OK) resize_rollback(pf);
+    return st;
+}
+void resize_rollback(genpf_filter_t pf) {
+    ResizeUndo &u = pf->undo;
+    if (!u.active) return;
+    cudaStreamSynchronize(pf->stream);
     for (int sl = 0; sl < 2; ++sl) {
         pf->free_cols(pf->win[pf->buf ^ 1][sl]);
-        GENPF_TRY(pf->alloc_cols(pf->win[pf->buf ^ 1][sl], total));
+        pf->win[pf->buf ^ 1][sl] = u.win[sl];
     }
     pf->dfree(pf->lw_alt);
-    GENPF_TRY(pf->dalloc(&pf->lw_alt, (size_t)total));
     pf->dfree(pf->parents);
-    GENPF_TRY(pf->dalloc(&pf->parents, (size_t)total));
-    GENPF_TRY(pf->sc.ensure(n_out > pf->n ? n_out : pf->n, pf->nf));
-    return GENPF_OK;
+    pf->lw_alt = u.lw_alt;
+    pf->parents = u.parents;
+    u.active = false;
 }
+// the resize went through: the parked buffers (old spare window, old lw_alt, old parents) are released
+static void resize_commit(genpf_filter_t pf) {
+    ResizeUndo &u = pf->undo;
+    if (!u.active) return;
+    for (int sl = 0; sl < 2; ++sl) pf->free_cols(u.win[sl]);
+    pf->dfree(u.lw_alt);
+    pf->dfree(u.parents);
+    u.active = false;
+}
+#define GENPF_TRY_RB(pf, expr)             \
+    do {                                   \
+        int32_t _s = (expr);               \
+        if (_s != GENPF_OK) {              \
+            ::genpf::resize_rollback(pf);  \
+            return _s;                     \
+        }                                  \
+    } while (0)
 // after the swap: make the (now spare) old buffers match the new size (update_refs!, resize.jl:441-449)
 static int32_t resize_spare(genpf_filter_t pf, int64_t n_new) {
     const int64_t total = n_new * pf->nf;
@@ -296,7 +336,6 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     Scratch &sc = pf->sc;
     const bool substate = flags & GENPF_SUBSTATE;
     const bool want_host_check = (flags & GENPF_CHECK) || invalid_kinds;
-    GENPF_TRY(resize_target(pf, n_out));
 
     // selection source
     LwSrc lw_src{pf->lw, 1.0}, sel = lw_src;
@@ -344,8 +383,10 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
         d_u = pf->uni_buf.as<double>();
     }
     UniSrc uni{d_u, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
-    GENPF_TRY(select_ancestors<int32_t>(s, sc, method, sel, n, n_out, nf, st_sel, uni, flags, pf->parents, 0, gate,
-                                        has_prio ? nullptr : (const double *)pf->ew));
+    // every validation that can refuse the call is behind us: only now are the target buffers resized
+    GENPF_TRY(resize_target(pf, n_out));
+    GENPF_TRY_RB(pf, select_ancestors<int32_t>(s, sc, method, sel, n, n_out, nf, st_sel, uni, flags, pf->parents, 0, gate,
+                                               has_prio ? nullptr : (const double *)pf->ew));
     // gather the window into the other buffer; no-priority reweight fused in
     const int64_t tpf_out = ceil_div(n_out, kTile);
     GatherCols g = window_gather_cols(pf);
@@ -363,6 +404,7 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     pf->buf ^= 1;
     std::swap(pf->lw, pf->lw_alt);
     pf->part_valid = false;
+    resize_commit(pf);
     GENPF_TRY(log_parents(pf, n, n_out));
     if (n_out != n) {
         pf->n = n_out;
@@ -400,7 +442,8 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
     return GENPF_OK;
 }
 template <class Model>
-static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a) {
+static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a, const NoiseCols *cols) {
+    if (cols) return launch_step_fused<Model, NoiseCols>(pf, a, *cols);
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)a.t, pf->rng_offset};
         return launch_step_fused<Model, NoisePhilox53>(pf, a, nz);
@@ -410,7 +453,8 @@ static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a) {
 }
 
 static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
-                             const double *obs_t, const double *aux_t, int32_t mh_iters, bool finalized) {
+                             const double *obs_t, const double *aux_t, int32_t mh_iters, bool finalized,
+                             const double *d_uniforms = nullptr, const NoiseCols *cols = nullptr) {
     const ModelInfo &mi = kModels[pf->model];
     const int64_t n = pf->n, nf = pf->nf;
     cudaStream_t s = pf->stream;
@@ -431,8 +475,8 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
         a.obs_prev = obs_prev[0];
         a.obs_t = obs_t[0];
     } else {
-        GENPF_TRY(pf->uni_buf.ensure((size_t)nf * 16));
-        double *d = pf->uni_buf.as<double>();
+        GENPF_TRY(pf->step_obs.ensure((size_t)nf * 16));
+        double *d = pf->step_obs.as<double>();
         GENPF_CUDA_TRY(cudaMemcpyAsync(d, obs_prev, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
         GENPF_CUDA_TRY(cudaMemcpyAsync(d + nf, obs_t, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
         a.obs_prev_dev = d;
@@ -443,7 +487,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     GENPF_TRY(sc.O.ensure((size_t)(n * nf) * 4));
     GENPF_TRY(sc.tile_last.ensure((size_t)(tpf * nf) * 4));
     if (!finalized) GENPF_TRY(ensure_stats(pf, sc.tile_off.as<double>(), -1.0, pf->lml));
-    UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, (unsigned)nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
@@ -452,8 +496,8 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
                  Scratch::kChunkTiles, (const double *)pf->ew, (const double *)sc.tile_scale.as<double>());
     int32_t st;
     switch (pf->model) {
-        case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a); break;
-        case kModelLinGauss1D: st = step_fused_model<LinGauss1D>(pf, a); break;
+        case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a, cols); break;
+        case kModelLinGauss1D: st = step_fused_model<LinGauss1D>(pf, a, cols); break;
         default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
     }
     GENPF_TRY(st);
@@ -560,7 +604,7 @@ int32_t genpf_filter_destroy(genpf_filter_t pf) {
     pf->ob.release();
     if (pf->h_opt_ctrl) cudaFreeHost(pf->h_opt_ctrl);
     pf->key_buf.release();
-    for (DevBuf *b : {&pf->noise_buf[0], &pf->noise_buf[1], &pf->noise_buf[2], &pf->uni_buf, &pf->tmp_col, &pf->tmp_idx, &pf->prio_buf})
+    for (DevBuf *b : {&pf->noise_buf[0], &pf->noise_buf[1], &pf->noise_buf[2], &pf->noise_buf[3], &pf->noise_buf[4], &pf->step_obs, &pf->strata_buf, &pf->uni_buf, &pf->tmp_col, &pf->tmp_idx, &pf->prio_buf})
         b->release();
     if (pf->h_pinned) cudaFreeHost(pf->h_pinned);
     if (pf->h_stats) cudaFreeHost(pf->h_stats);
@@ -704,6 +748,40 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
         GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, mh_iters, nullptr, nullptr, nullptr, nullptr));
     }
     return do_propagate(pf, false, t, obs_t, aux_t, nullptr, nullptr);
+}
+
+// One README iteration in parity mode: the resample is taken (forced), every random draw is supplied
+// by the caller -- stratum / inverse-CDF uniforms (NULL: the library's Philox draws), the mh move's [U2, Z2, U3]
+// and the update's [U1, Z1], n_particles * n_filters each, indexed by output particle.  Stratified resampling runs
+// the SAME kernels as genpf_step (k_scan + k_step_fused) with the column noise policy.
+int32_t genpf_step_with_noise(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                              const double *obs_t, const double *aux_t, int32_t method, int32_t mh_iters,
+                              const double *uniforms, const double *U2, const double *Z2, const double *U3,
+                              const double *U1, const double *Z1) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_step_with_noise must advance to t_cur + 1");
+    if (mh_iters != 0 && mh_iters != 1) return fail(GENPF_ERR_INVALID_ARG, "noise columns serve mh_iters 0 or 1");
+    if (!U1 || !Z1 || (mh_iters == 1 && (!U2 || !Z2 || !U3))) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    if (method == GENPF_STRATIFIED) {
+        const double *d_u = nullptr;
+        NoiseCols nz{nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (uniforms) {
+            GENPF_TRY(pf->uni_buf.ensure((size_t)(pf->n * pf->nf) * 8));
+            GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms, (size_t)(pf->n * pf->nf) * 8, cudaMemcpyHostToDevice, pf->stream));
+            d_u = pf->uni_buf.as<double>();
+        }
+        GENPF_TRY(stage_noise(pf, 0, U2, &nz.U, 0));
+        GENPF_TRY(stage_noise(pf, 1, Z2, &nz.Z, 0));
+        GENPF_TRY(stage_noise(pf, 2, U3, &nz.U3, 0));
+        GENPF_TRY(stage_noise(pf, 3, U1, &nz.Uup, 0));
+        GENPF_TRY(stage_noise(pf, 4, Z1, &nz.Zup, 0));
+        GENPF_TRY(pf->sc.O.ensure(4));
+        return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, false, d_u, &nz);
+    }
+    GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, uniforms, nullptr, -1.0));
+    if (mh_iters == 1) GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, 1, U2, Z2, U3, nullptr));
+    return do_propagate(pf, false, t, obs_t, aux_t, U1, Z1);
 }
 
 // resolve which column holds (tau, field) and, for archived slices, the lineage index into it
@@ -868,6 +946,7 @@ static int32_t apply_parents_and_swap(genpf_filter_t pf, int64_t n_out) {
     pf->buf ^= 1;
     std::swap(pf->lw, pf->lw_alt);
     pf->part_valid = false;
+    resize_commit(pf);
     const int64_t n_prev = pf->n;
     GENPF_TRY(log_parents(pf, n_prev, n_out));
     if (n_out != n_prev) {
@@ -991,7 +1070,10 @@ int32_t genpf_optimal_resize_dev(genpf_filter_t pf, int64_t n_out, const double 
         invalid_kinds[0] = res.kind;
         invalid_kinds[1] = res.kind_strat;
     }
-    if (st != GENPF_OK) return st;
+    if (st != GENPF_OK) {
+        resize_rollback(pf);
+        return st;
+    }
     return apply_parents_and_swap(pf, n_out);
 }
 

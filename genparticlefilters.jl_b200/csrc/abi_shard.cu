@@ -67,7 +67,9 @@ static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, N
     return GENPF_OK;
 }
 template <class Model>
-static int32_t push_model(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, const long long *oend_all) {
+static int32_t push_model(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, const long long *oend_all,
+                          const NoiseCols *cols = nullptr) {
+    if (cols) return launch_push<Model, NoiseCols>(pf, sh, a, *cols, oend_all);
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)a.t, 0};
         return launch_push<Model, NoisePhilox53>(pf, sh, a, nz, oend_all);
@@ -264,8 +266,9 @@ int32_t genpf_shard_push(genpf_filter_t pf, int64_t t, const double *obs_prev, c
 }
 
 // The whole sharded README iteration with the peer-memory exchange: no NCCL, no host synchronisation.
-int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
-                             const double *obs_t, const double *aux_t, int32_t mh_iters) {
+static int32_t shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                              const double *obs_t, const double *aux_t, int32_t mh_iters, const double *d_uniforms,
+                              const NoiseCols *cols) {
     GENPF_TRY(check_filter(pf));
     if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
@@ -283,7 +286,7 @@ int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pre
     GENPF_LAUNCH(k_xchg_stats_combine, 1, 32, s, (const Stats *)sc.st(0, 1), sh->xp, sh->world, sh->rank, epoch,
                  sh->n_total, sc.st(0, 1), sh->shard_info, pf->lml);
     // 2. shard-aware scan, closing counts exchanged
-    UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, epoch), 0};
+    UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, epoch), 0};
     StratArgs strat = make_strat(uni, sh->n_total);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, 1),
@@ -296,8 +299,8 @@ int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pre
     // 3. offspring to their owners over NVLink, then the barrier
     int32_t st;
     switch (pf->model) {
-        case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a, sh->oend_p2p); break;
-        case kModelLinGauss1D: st = push_model<LinGauss1D>(pf, sh, a, sh->oend_p2p); break;
+        case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a, sh->oend_p2p, cols); break;
+        case kModelLinGauss1D: st = push_model<LinGauss1D>(pf, sh, a, sh->oend_p2p, cols); break;
         default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
     }
     GENPF_TRY(st);
@@ -312,6 +315,39 @@ int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pre
                  sh->world, sh->rank, n, sc.partials(0), pf->ew);
     pf->part_valid = true;
     return GENPF_OK;
+}
+
+int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                             const double *obs_t, const double *aux_t, int32_t mh_iters) {
+    return shard_step_p2p(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, nullptr, nullptr);
+}
+
+// The sharded step in parity mode: every rank passes the SAME global-length host columns
+// (world * n_local entries, indexed by GLOBAL output slot / stratum): "uniforms replicated first".  Runs the same
+// kernels as genpf_shard_step_p2p (shard-aware k_scan, k_step_push, peer-memory exchange) with the column policy.
+int32_t genpf_shard_step_p2p_with_noise(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                                        const double *obs_t, const double *aux_t, int32_t mh_iters,
+                                        const double *uniforms, const double *U2, const double *Z2, const double *U3,
+                                        const double *U1, const double *Z1) {
+    GENPF_TRY(check_filter(pf));
+    if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    if (mh_iters != 0 && mh_iters != 1) return fail(GENPF_ERR_INVALID_ARG, "noise columns serve mh_iters 0 or 1");
+    if (!U1 || !Z1 || (mh_iters == 1 && (!U2 || !Z2 || !U3))) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
+    const int64_t nt = sh->n_total;
+    const double *d_u = nullptr;
+    if (uniforms) {
+        GENPF_TRY(pf->uni_buf.ensure((size_t)nt * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms, (size_t)nt * 8, cudaMemcpyHostToDevice, pf->stream));
+        d_u = pf->uni_buf.as<double>();
+    }
+    NoiseCols nz{nullptr, nullptr, nullptr, nullptr, nullptr};
+    GENPF_TRY(stage_noise(pf, 0, U2, &nz.U, nt));
+    GENPF_TRY(stage_noise(pf, 1, Z2, &nz.Z, nt));
+    GENPF_TRY(stage_noise(pf, 2, U3, &nz.U3, nt));
+    GENPF_TRY(stage_noise(pf, 3, U1, &nz.Uup, nt));
+    GENPF_TRY(stage_noise(pf, 4, Z1, &nz.Zup, nt));
+    return shard_step_p2p(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, d_u, &nz);
 }
 
 // closing counts of the last step (host copy; synchronises) + the exchange error word

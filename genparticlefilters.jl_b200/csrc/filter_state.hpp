@@ -37,6 +37,13 @@ struct ParentLog {  // ancestry of resample number `gen` (1-based): population g
     int64_t n_prev, n_cur;
 };
 
+struct ResizeUndo {  // buffers parked by a resize that has not committed yet (abi_filter.cu::resize_target)
+    bool active = false;
+    Cols win[2];
+    double *lw_alt = nullptr;
+    int32_t *parents = nullptr;
+};
+
 }  // namespace genpf
 
 using namespace genpf;
@@ -66,12 +73,13 @@ struct genpf_filter_s {
     double *lml = nullptr;
     double *obs_dev = nullptr;
     double *noise_cols[3] = {nullptr, nullptr, nullptr};
-    DevBuf noise_buf[3], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf, strata_buf;
+    DevBuf noise_buf[5], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf, strata_buf, step_obs;
     CoalesceBufs cb;
     OptimalBufs ob;
     void *h_opt_ctrl = nullptr;  // pinned OptCtrl, allocated on first optimal resize
     Scratch sc;
     bool part_valid = false;
+    ResizeUndo undo;
     std::vector<HistSlice> hist;
     std::vector<ParentLog> plog;
     std::vector<void *> owned;
@@ -139,4 +147,6 @@ int32_t check_filter(genpf_filter_t pf);
 int32_t log_parents(genpf_filter_t pf, int64_t n_prev, int64_t n_cur);
 int32_t ensure_stats(genpf_filter_t pf, double *tile_off, double ess_frac, double *lml_accum);
 int32_t read_stats(genpf_filter_t pf, int which);
+void resize_rollback(genpf_filter_t pf);
+int32_t stage_noise(genpf_filter_t pf, int which, const double *host, const double **dev, int64_t count);
 }  // namespace genpf

@@ -39,8 +39,11 @@ __device__ __forceinline__ void store_pair(X *p, int e, int valid, bool fast, X 
 }
 
 // MH: number of mh iterations known at compile time (1 = the README configuration) or -1 = a.mh_iters
+#ifndef GENPF_FUSED_MINB
+#define GENPF_FUSED_MINB 4
+#endif
 template <class Model, class Noise, typename IdxT, int MH>
-static __global__ void __launch_bounds__(kStateThreads, 4)
+static __global__ void __launch_bounds__(kStateThreads, GENPF_FUSED_MINB)
     k_step_fused(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, Cols dst_cur,
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew) {
@@ -88,11 +91,13 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
 #pragma unroll
             for (int c = 0; c < Model::NB; ++c) cur.b[c] = __ldg(src_cur.b[c] + s);
             double U_mh = 0.5, Z_mh = 0.0, U_acc = 1.0, U_up, Z_up;
-            if (MH == 0) noise.up(obase + e, U_up, Z_up);  // no mh move: only the update's draws
-            else noise.both(obase + e, U_mh, Z_mh, U_acc, U_up, Z_up);  // dead slots draw too: no divergence
+            // dead slots draw too (no divergence); noise columns are read at an in-range slot instead
+            const int64_t ni = (Noise::kIndexed && !live) ? obase : obase + e;
+            if (MH == 0) noise.up(ni, U_up, Z_up);  // no mh move: only the update's draws
+            else noise.both(ni, U_mh, Z_mh, U_acc, U_up, Z_up);
             bool ok = false;
             for (int it = 0; it < iters; ++it) {
-                if (MH < 0 && it > 0) noise.mh(obase + e, it, U_mh, Z_mh, U_acc);
+                if (MH < 0 && it > 0) noise.mh(ni, it, U_mh, Z_mh, U_acc);
                 typename Model::Slice q;
                 Model::transition(a.P_prev, a.t - 1, pp, q, U_mh, Z_mh);
                 const double alpha =
@@ -208,9 +213,10 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
 #pragma unroll
             for (int c = 0; c < Model::NB; ++c) cur.b[c] = __ldg(src_cur.b[c] + s);
             double U_mh, Z_mh, U_acc, U_up, Z_up;
-            noise.both(i0 + e, U_mh, Z_mh, U_acc, U_up, Z_up);  // GLOBAL output slot
+            const int64_t ni = (Noise::kIndexed && !live) ? i0 : i0 + e;  // GLOBAL output slot
+            noise.both(ni, U_mh, Z_mh, U_acc, U_up, Z_up);
             for (int it = 0; it < iters; ++it) {
-                if (MH < 0 && it > 0) noise.mh(i0 + e, it, U_mh, Z_mh, U_acc);
+                if (MH < 0 && it > 0) noise.mh(ni, it, U_mh, Z_mh, U_acc);
                 typename Model::Slice q;
                 Model::transition(a.P_prev, a.t - 1, pp, q, U_mh, Z_mh);
                 const double alpha =

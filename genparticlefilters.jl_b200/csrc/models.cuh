@@ -134,6 +134,7 @@ __device__ __forceinline__ float fast_bm_radius(float ua) {
 // (the two outputs of one Box-Muller transform are independent normals).  fp32 transcendental units.
 // mh iterations it >= 1 draw their own call: U = w0, radius w1, angle w2, U_acc = w3.
 struct NoiseLean {
+    static constexpr bool kIndexed = false;
     uint64_t seed;
     uint64_t step;  // s
     int64_t offset;
@@ -170,46 +171,152 @@ struct NoiseLean {
         U3 = ((double)o.w + 0.5) * 0x1.0p-32;
     }
 };
-// High-fidelity: 53-bit uniforms + fp64 Box-Muller, two Philox calls per move
+// ------------------------------------------------------------------ fp64 Box-Muller building blocks
+// The production noise of SURVEY 8(c): 53-bit uniforms (x >> 11) * 2^-53 and an fp64 Box-Muller transform.  The
+// step kernels are instruction-issue bound, so the three transcendental pieces are written for exactly the
+// arguments they get (no special cases, no denormals), ~1 ulp each (checked against long-double references):
+//   log_unit   : log(u) for u = k * 2^-53, k in [1, 2^53]  (atanh-series form, reciprocal by MUFU.RCP64H + Newton)
+//   sqrt_pos   : sqrt(x) for x in [1e-300, 1e3]            (MUFU.RSQ64H + two Goldschmidt steps + one correction)
+//   sincos_2pi : sin / cos of 2 pi a for a in [0, 1)        (exact quadrant reduction, degree-13/14 kernels)
+__device__ __forceinline__ double log_unit(double u) {
+    int hi = __double2hiint(u);
+    const int lo = __double2loint(u);
+    hi += 0x3FF00000 - 0x3FE6A09E;  // mantissa into [sqrt(1/2), sqrt(2))
+    const int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000FFFFF) + 0x3FE6A09E;
+    const double f = __hiloint2double(hi, lo) - 1.0;  // exact
+    const double d = 2.0 + f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    double sq = f * r;
+    sq = fma(fma(-sq, d, f), r, sq);  // s = f / (2 + f), correctly rounded up to the last bit
+    const double z = sq * sq, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t1 + t2;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, x), h, g);
+}
+__device__ __forceinline__ void sincos_2pi(double a, double &sn, double &cs) {
+    const double SH = 6755399441055744.0;  // 2^52 + 2^51
+    const double zq = fma(a, 4.0, SH);
+    const int q = __double2loint(zq);             // rint(4a) in 0..4
+    const double t = fma(zq - SH, -0.25, a);      // exact, |t| <= 1/8
+    const double phi = t * 6.283185307179586476925;
+    const double z = phi * phi;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sp = fma(phi * z, ps, phi);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cp = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const bool swap = q & 1;
+    double s0 = swap ? cp : sp, c0 = swap ? sp : cp;
+    // q: 0 (s, c)  1 (c, -s)  2 (-s, -c)  3 (-c, s)  4 == 0
+    const int ss = (q & 2) << 30, sc = ((q + 1) & 2) << 30;
+    sn = __hiloint2double(__double2hiint(s0) ^ ss, __double2loint(s0));
+    cs = __hiloint2double(__double2hiint(c0) ^ sc, __double2loint(c0));
+}
+// two independent standard normals from ua in (0, 1], ub in [0, 1)
+__device__ __forceinline__ void normal_pair(double ua, double ub, double &z0, double &z1) {
+    const double r = sqrt_pos(fmax(-2.0 * log_unit(ua), 1e-300));
+    double sn, cs;
+    sincos_2pi(ub, sn, cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+// High-fidelity (SURVEY 8c production noise): 53-bit uniforms + fp64 Box-Muller.  One README iteration draws
+// THREE Philox4x32-10 blocks per particle: a = {U_mh, U_up}, b = {Box-Muller radius, angle}, c = {U_acc, -};
+// the two outputs of the one transform are the two independent normals Z_mh = r cos, Z_up = r sin.  The unfused
+// kernels (k_mh iteration 0, k_propagate) derive their draws from the same three blocks, so fused == separate.
+// mh iterations it >= 1 draw two blocks of their own stream.
 struct NoisePhilox53 {
+    static constexpr bool kIndexed = false;
     uint64_t seed;
     uint64_t step;
     int64_t offset;
-    __device__ __forceinline__ void draw(uint64_t stream, int64_t i, double &U, double &Z, double &U3) const {
-        const uint4 a = philox_at(seed, stream, (uint64_t)(i + offset));
-        const uint4 b = philox_at(seed, stream ^ (1ull << 55), (uint64_t)(i + offset));
-        U = u53(a.x, a.y);
-        const double ua = 1.0 - u53(a.z, a.w);  // (0,1]
-        const double ub = u53(b.x, b.y);
-        Z = sqrt(-2.0 * log(ua)) * cospi(2.0 * ub);
-        U3 = 1.0 - u53(b.z, b.w);  // (0,1]
-    }
-    __device__ __forceinline__ void up(int64_t i, double &U, double &Z) const {
-        double u3;
-        draw(make_stream(kPurposeUpdate, step), i, U, Z, u3);
-    }
-    __device__ __forceinline__ void mh(int64_t i, int it, double &U, double &Z, double &U3) const {
-        draw(make_stream(kPurposeMH, (step << 8) | (uint64_t)(it & 0xFF)), i, U, Z, U3);
-    }
     __device__ __forceinline__ void both(int64_t i, double &U_mh, double &Z_mh, double &U_acc, double &U_up,
                                          double &Z_up) const {
-        mh(i, 0, U_mh, Z_mh, U_acc);
-        up(i, U_up, Z_up);
+        const uint64_t st = make_stream(kPurposeUpdate, step), c = (uint64_t)(i + offset);
+        const uint4 a = philox_at(seed, st, c);
+        const uint4 b = philox_at(seed, st ^ (1ull << 55), c);
+        const uint4 d = philox_at(seed, st ^ (1ull << 54), c);
+        U_mh = u53(a.x, a.y);
+        U_up = u53(a.z, a.w);
+        U_acc = 1.0 - u53(d.x, d.y);  // (0,1]
+        normal_pair(1.0 - u53(b.x, b.y), u53(b.z, b.w), Z_mh, Z_up);
+    }
+    __device__ __forceinline__ void up(int64_t i, double &U, double &Z) const {
+        const uint64_t st = make_stream(kPurposeUpdate, step), c = (uint64_t)(i + offset);
+        const uint4 a = philox_at(seed, st, c);
+        const uint4 b = philox_at(seed, st ^ (1ull << 55), c);
+        U = u53(a.z, a.w);
+        double zc;
+        normal_pair(1.0 - u53(b.x, b.y), u53(b.z, b.w), zc, Z);
+    }
+    __device__ __forceinline__ void mh(int64_t i, int it, double &U, double &Z, double &U3) const {
+        if (it == 0) {
+            double a, b;
+            both(i, U, Z, U3, a, b);
+            return;
+        }
+        const uint64_t st = make_stream(kPurposeMH, (step << 8) | (uint64_t)(it & 0xFF)), c = (uint64_t)(i + offset);
+        const uint4 a = philox_at(seed, st, c);
+        const uint4 b = philox_at(seed, st ^ (1ull << 55), c);
+        U = u53(a.x, a.y);
+        U3 = 1.0 - u53(a.z, a.w);
+        double zs;
+        normal_pair(1.0 - u53(b.x, b.y), u53(b.z, b.w), Z, zs);
     }
 };
-// parity mode: noise supplied as columns (exported from the reference's RNG)
+// parity mode: noise supplied as columns (exported from the reference's RNG), read by particle slot.
+//   mh move      : U, Z, U3        (draw order [U2, Z2, U3])
+//   update / init: Uup, Zup        (draw order [U1, Z1]); when both are null the update reads U, Z
+// kIndexed tells the fused kernels that the slot must be in range (Philox policies accept any counter).
 struct NoiseCols {
+    static constexpr bool kIndexed = true;
     const double *U, *Z, *U3;
+    const double *Uup, *Zup;
     __device__ __forceinline__ void up(int64_t i, double &u, double &z) const {
-        u = U ? U[i] : 0.0;
-        z = Z ? Z[i] : 0.0;
+        const double *pu = (Uup || Zup) ? Uup : U, *pz = (Uup || Zup) ? Zup : Z;
+        u = pu ? pu[i] : 0.0;
+        z = pz ? pz[i] : 0.0;
     }
     __device__ __forceinline__ void mh(int64_t i, int, double &u, double &z, double &u3) const {
         u = U ? U[i] : 0.0;
         z = Z ? Z[i] : 0.0;
         u3 = U3 ? U3[i] : 1.0;
     }
-    __device__ __forceinline__ void both(int64_t, double &, double &, double &, double &, double &) const {}
+    __device__ __forceinline__ void both(int64_t i, double &U_mh, double &Z_mh, double &U_acc, double &U_up,
+                                         double &Z_up) const {
+        mh(i, 0, U_mh, Z_mh, U_acc);
+        up(i, U_up, Z_up);
+    }
 };
 
 }  // namespace genpf

@@ -136,6 +136,18 @@ class ShardedFilter:
             L.check(self.lib.genpf_shard_finish(h))
         self.state.t = self.t = int(t)
 
+    def step_with_noise(self, t, obs_prev, obs_t, *, mh_iters=1, uniforms=None, U2=None, Z2=None, U3=None, U1=None,
+                        Z1=None):
+        """Parity mode of `step`: GLOBAL-length noise columns (world * n_local), identical on every rank."""
+        h = self.state._h
+        op, ot = np.array([float(obs_prev)]), np.array([float(obs_t)])
+        cols = [None if c is None else np.ascontiguousarray(c, dtype=np.float64) for c in (uniforms, U2, Z2, U3, U1, Z1)]
+        for c in cols:
+            assert c is None or c.size == self.n_total
+        L.check(self.lib.genpf_shard_step_p2p_with_noise(h, int(t), L.ptr(op), L.ptr(self._aux(t - 1)), L.ptr(ot),
+                                                         L.ptr(self._aux(t)), int(mh_iters), *[L.ptr(c) for c in cols]))
+        self.state.t = self.t = int(t)
+
     def stats(self):
         """(global ESS before the last resample, accumulated log_ml_est, invalid kind) -- synchronises."""
         ess, lml, kind = C.c_double(), C.c_double(), C.c_int32()

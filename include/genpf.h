@@ -233,6 +233,17 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
                    const double *obs_t, const double *aux_t, int32_t method, double ess_frac, int32_t mh_iters,
                    double *ess_out);
 
+/* The same iteration in parity mode (noise exported from the reference's RNG): the resample is taken
+ * and EVERY random draw is an input column of n_particles*n_filters doubles indexed by output particle --
+ * `uniforms` = the rand() of each stratum (resample.jl:162) / inverse-CDF draw (NULL: library Philox draws),
+ * [U2, Z2, U3] = the mh move's bernoulli / normal / accept draws (ignored when mh_iters == 0), [U1, Z1] = the
+ * update's bernoulli / normal draws (Gen `regenerate` / `update`, rejuvenate.jl:40-53, update.jl:12-25).
+ * method == GENPF_STRATIFIED runs exactly the kernels of genpf_step (scan + fused step). */
+int32_t genpf_step_with_noise(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                              const double *obs_t, const double *aux_t, int32_t method, int32_t mh_iters,
+                              const double *uniforms, const double *U2, const double *Z2, const double *U3,
+                              const double *U1, const double *Z1);
+
 /* mean(state, tau=>field) / var(...), statistics.jl:13-17,48-54.  field: 0..n_f64-1 are the fp64 fields,
  * n_f64.. the u8 (Bool) fields promoted to fp64 (README.md:97).  out[n_filters]. */
 int32_t genpf_mean_var(genpf_filter_t pf, int32_t field, int64_t tau, double *mean, double *var);
@@ -298,6 +309,13 @@ int32_t genpf_shard_finish(genpf_filter_t pf);
  * the same t.  stats/oend buffers passed to genpf_shard_attach may be NULL when only this entry point is used. */
 int32_t genpf_shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
                              const double *obs_t, const double *aux_t, int32_t mh_iters);
+/* parity mode of the sharded iteration (README.md:66-77 over a sharded population): every rank passes the same
+ * GLOBAL-length host columns (world*n_loc doubles, indexed by global output slot / stratum), as in
+ * genpf_step_with_noise; same kernels as genpf_shard_step_p2p. */
+int32_t genpf_shard_step_p2p_with_noise(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
+                                        const double *obs_t, const double *aux_t, int32_t mh_iters,
+                                        const double *uniforms, const double *U2, const double *Z2, const double *U3,
+                                        const double *U1, const double *Z1);
 /* closing offspring counts of the last p2p step + the exchange error word (1 = a peer timed out); synchronises */
 int32_t genpf_shard_oend(genpf_filter_t pf, long long *oend_all_host, int32_t *error);
 /* global ESS / accumulated log_ml_est / validity as of the last genpf_shard_scan (synchronises) */

@@ -744,3 +744,12 @@ int32_t orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py's reference arm sets the thread count explicitly */
+void orc_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -122,6 +122,7 @@ void orc_om_filter_init(orc_om_filter *f, const orc_om_params *p, double vel1, d
 double orc_om_filter_step(orc_om_filter *f, const orc_om_params *p, int64_t t, double vel_prev, double obs_prev,
                           double vel_t, double obs_t);
 int32_t orc_num_threads(void);
+void orc_set_num_threads(int32_t n);
 
 #ifdef __cplusplus
 }

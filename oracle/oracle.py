@@ -67,6 +67,7 @@ def load(omp=False):
         "orc_om_filter_init": (None, [_vp, _vp, d, d]),
         "orc_om_filter_step": (d, [_vp, _vp, i64, d, d, d, d]),
         "orc_num_threads": (i32, []),
+        "orc_set_num_threads": (None, [i32]),
     }
     for k, (res, args) in sig.items():
         fn = getattr(lib, k)
@@ -323,8 +324,10 @@ def lg_mh(x_pp, x_cur, obs, Z2, U3, params):
 class OMFilter:
     """CPU baseline: README loop on object_motion (bench.py only)."""
 
-    def __init__(self, n, seed=0, omp=True, params=OM_DEFAULT):
+    def __init__(self, n, seed=0, omp=True, params=OM_DEFAULT, threads=None):
         self.lib = load(omp=omp)
+        if threads:
+            self.lib.orc_set_num_threads(int(threads))
         self.p = OMParams(*params)
         self.h = self.lib.orc_om_filter_create(n, seed)
         self.n = n

@@ -31,6 +31,8 @@ def main():
         y = y + (math.sin(t) if t > 3 else 0.0) + 0.01 * rng.normal()
         obs.append(y + 0.25 * rng.normal())
     model = g.DeviceModel("object_motion")
+    if os.environ.get("SHARD_MODE", "philox") == "noise":
+        return noise_mode(g, ShardedFilter, dist, torch, model, rank, world, n_local, obs)
     sf = ShardedFilter(model, n_local, seed=77, exchange=os.environ.get("SHARD_EXCHANGE", "p2p"))
     sf.initialize(obs[0])
     ref = None
@@ -81,6 +83,57 @@ def main():
     if rank == 0:
         lml_r = g.log_ml_estimate(ref)
         assert abs(lml_s - lml_r) <= 1e-9 * max(1.0, abs(lml_r)), (lml_s, lml_r)
+        print("[shard_worker] OK", flush=True)
+    dist.barrier()
+    sf.close()
+    dist.destroy_process_group()
+
+
+def noise_mode(g, ShardedFilter, dist, torch, model, rank, world, n_local, obs):
+    """k_step_push (the kernel every multi-GPU number comes from) against the CPU ORACLE: every rank passes the
+    same global noise columns (parity mode); rank 0 gathers the shards and compares with
+    tests/util.py::oracle_readme_step -- ancestors tie-tolerant, y / moving bit-identical, log-weights 1e-10."""
+    from oracle import oracle as orc
+    from util import oracle_readme_step
+    L = g._lib
+    n = n_local * world
+    rng = np.random.default_rng(99)  # identical stream on every rank
+    sf = ShardedFilter(model, n_local, seed=77)
+    sl = slice(rank * n_local, (rank + 1) * n_local)
+    U, Z = rng.random(n), rng.normal(size=n)
+    Ul, Zl = np.ascontiguousarray(U[sl]), np.ascontiguousarray(Z[sl])
+    L.check(g.load().genpf_initialize_with_noise(sf.state._h, L.ptr(np.array([obs[0]])), L.ptr(model.aux(1)), L.ptr(Ul), L.ptr(Zl)))
+    sf.state.t = sf.t = 1
+    sf.state.sync()
+    dist.barrier()
+
+    def gather(col):
+        t_ = torch.from_numpy(np.ascontiguousarray(col)).cuda()
+        out = [torch.empty_like(t_) for _ in range(world)]
+        dist.all_gather(out, t_)
+        return np.concatenate([o.cpu().numpy() for o in out])
+
+    y1, m1 = orc.om_transition(None, None, math.sin(1.0), U, Z)
+    st = dict(y_pp=None, m_pp=None, y=y1, m=m1, lw=orc.om_obs_logpdf(y1, obs[0]))
+    ties = 0
+    for t in range(2, 5):
+        r, U2, Z2, U3, U1, Z1 = rng.random(n), rng.random(n), rng.normal(size=n), rng.random(n), rng.random(n), rng.normal(size=n)
+        ess_ref = orc.ess(st["lw"])
+        sf.step_with_noise(t, obs[t - 2], obs[t - 1], uniforms=r, U2=U2, Z2=Z2, U3=U3, U1=U1, Z1=Z1)
+        ess, lml, kind = sf.stats()
+        ranges, frac = sf.exchange_summary()
+        par = gather(sf.state.parents)
+        yt, ym = gather(sf.state.field("y", t)), gather(sf.state.field("y", t - 1))
+        mt, lw = gather(sf.state.field("moving", t)), gather(sf.state.log_weights)
+        st, p_ref, n_tie, inc, _ = oracle_readme_step(orc, st, t, obs[t - 2], obs[t - 1], r, U2, Z2, U3, U1, Z1, p_gpu=par)
+        ties += n_tie
+        if rank == 0:
+            assert kind == 0 and abs(ess - ess_ref) <= 1e-10 * ess_ref, (ess, ess_ref)
+            assert np.array_equal(yt, st["y"]) and np.array_equal(mt, st["m"]) and np.array_equal(ym, st["y_pp"])
+            np.testing.assert_allclose(lw, st["lw"], rtol=1e-10, atol=1e-12)
+            print(f"[shard_worker] noise t={t} tie_ancestors={n_tie} cross_shard_fraction={frac:.5f}", flush=True)
+    assert ties <= 4
+    if rank == 0:
         print("[shard_worker] OK", flush=True)
     dist.barrier()
     sf.close()

@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_workers(nproc, n_local, port, exchange="p2p"):
-    env = dict(os.environ, SHARD_N_LOCAL=str(n_local), SHARD_EXCHANGE=exchange)
+def run_workers(nproc, n_local, port, exchange="p2p", mode="philox"):
+    env = dict(os.environ, SHARD_N_LOCAL=str(n_local), SHARD_EXCHANGE=exchange, SHARD_MODE=mode)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "shard_worker.py")]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
@@ -23,6 +23,20 @@ def run_workers(nproc, n_local, port, exchange="p2p"):
 
 def test_shard_world1():
     run_workers(1, 1 << 16, 29611)
+
+
+@pytest.mark.parametrize("n_local", [1 << 16, 1 << 22])
+def test_shard_world1_push_kernel_vs_oracle(n_local):
+    """k_step_push + shard-aware scan + peer exchange (world 1) against the CPU oracle with supplied noise."""
+    run_workers(1, n_local, 29621, mode="noise")
+
+
+def test_shard_world2_push_kernel_vs_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    run_workers(2, 1 << 16, 29622, mode="noise")
+    run_workers(2, 1 << 23, 29623, mode="noise")  # one filter of 2^24 particles over two GPUs
 
 
 def test_shard_world2():
