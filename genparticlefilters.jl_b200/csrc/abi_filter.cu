@@ -490,10 +490,9 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
-    GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, (unsigned)nf), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, nf),
-                 (const double *)sc.tile_off.as<double>(), WTables{nullptr}, sc.O.as<int32_t>(),
-                 sc.tile_last.as<int32_t>(), strat, 0, (const double *)nullptr, (int64_t)0, sc.chunk_info_ptr(n),
-                 Scratch::kChunkTiles, (const double *)pf->ew, (const double *)sc.tile_scale.as<double>());
+    GENPF_TRY(launch_scan_counts<int32_t>(s, lw_src, n, tpf, nf, sc.st(0, nf), sc.tile_off.as<double>(), sc.O.as<int32_t>(),
+                                          sc.tile_last.as<int32_t>(), strat, 0, nullptr, 0, sc.chunk_info_ptr(n), pf->ew,
+                                          sc.tile_scale.as<double>()));
     int32_t st;
     switch (pf->model) {
         case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a, cols); break;

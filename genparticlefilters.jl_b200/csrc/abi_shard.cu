@@ -237,11 +237,9 @@ int32_t genpf_shard_scan(genpf_filter_t pf) {
     UniSrc uni{nullptr, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), 0};
     StratArgs strat = make_strat(uni, sh->n_total);
     LwSrc lw_src{pf->lw, 1.0};
-    GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, pf->stream, lw_src, n, tpf,
-                 (const Stats *)sc.st(0, 1), (const double *)sc.tile_off.as<double>(), WTables{nullptr},
-                 sc.O.as<int32_t>(), sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info,
-                 (int64_t)sh->rank * n, sc.chunk_info_ptr(n), Scratch::kChunkTiles, (const double *)pf->ew,
-                 (const double *)sc.tile_scale.as<double>());
+    GENPF_TRY(launch_scan_counts<int32_t>(pf->stream, lw_src, n, tpf, 1, sc.st(0, 1), sc.tile_off.as<double>(),
+                                          sc.O.as<int32_t>(), sc.tile_last.as<int32_t>(), strat, 0, sh->shard_info,
+                                          (int64_t)sh->rank * n, sc.chunk_info_ptr(n), pf->ew, sc.tile_scale.as<double>()));
     GENPF_LAUNCH(k_shard_oend, 1, 32, pf->stream, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->oend_local);
     return GENPF_OK;
 }
@@ -289,11 +287,9 @@ static int32_t shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pr
     UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, epoch), 0};
     StratArgs strat = make_strat(uni, sh->n_total);
     LwSrc lw_src{pf->lw, 1.0};
-    GENPF_LAUNCH((k_scan<int32_t>), dim3((unsigned)tpf, 1), kScanThreads, s, lw_src, n, tpf, (const Stats *)sc.st(0, 1),
-                 (const double *)sc.tile_off.as<double>(), WTables{nullptr}, sc.O.as<int32_t>(),
-                 sc.tile_last.as<int32_t>(), strat, 0, (const double *)sh->shard_info, (int64_t)sh->rank * n,
-                 sc.chunk_info_ptr(n), Scratch::kChunkTiles, (const double *)pf->ew,
-                 (const double *)sc.tile_scale.as<double>());
+    GENPF_TRY(launch_scan_counts<int32_t>(s, lw_src, n, tpf, 1, sc.st(0, 1), sc.tile_off.as<double>(), sc.O.as<int32_t>(),
+                                          sc.tile_last.as<int32_t>(), strat, 0, sh->shard_info, (int64_t)sh->rank * n,
+                                          sc.chunk_info_ptr(n), pf->ew, sc.tile_scale.as<double>()));
     GENPF_LAUNCH(k_xchg_oend, 1, 32, s, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->xp, sh->world, sh->rank,
                  epoch, sh->oend_p2p);
     // 3. offspring to their owners over NVLink, then the barrier

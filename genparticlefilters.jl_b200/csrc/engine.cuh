@@ -18,7 +18,7 @@ struct Scratch {
     DevBuf sort_tmp, sorted_keys, order, prio_col;
     DevBuf moment_partial, moment_out;
     DevBuf misc, chunk_stats, chunk_info;
-    static constexpr int64_t kChunkTiles = 8192;  // tiles finalised by one block (2^24 particles)
+    static constexpr int64_t kChunkTiles = genpf::kChunkTiles;  // tiles finalised by one block (2^20 particles)
     // {prefix, scale} pairs of the last finalize of a filter with more than kChunkTiles tiles (else null)
     const double *chunk_info_ptr(int64_t n) const { return ceil_div(n, kTile) > kChunkTiles ? chunk_info.as<double>() : nullptr; }
     int64_t cap_n = -1, cap_nf = -1;
@@ -57,18 +57,19 @@ inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, P
 inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64_t n, int64_t nf, Stats *st,
                                double *tile_off, double ess_frac, double *lml_accum) {
     const int64_t tpf = ceil_div(n, kTile);
-    if (tpf <= 8 * 64) {
-        GENPF_LAUNCH((k_finalize_fast<64>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf,
+    if (tpf <= 64) {
+        GENPF_LAUNCH((k_finalize_fast<64, 1>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf,
                      sc.tile_scale.as<double>());
     } else if (tpf <= Scratch::kChunkTiles) {
-        GENPF_LAUNCH((k_finalize_fast<1024>), dim3(1, (unsigned)nf), 1024, s, part, n, tpf, st, tile_off, ess_frac,
+        GENPF_LAUNCH((k_finalize_fast<512, 1>), dim3(1, (unsigned)nf), 512, s, part, n, tpf, st, tile_off, ess_frac,
                      lml_accum, tpf, sc.tile_scale.as<double>());
     } else {
-        // large filter: per-chunk finalize, then combine (statistics, validity, lml, chunk {prefix, scale})
+        // large filter: one block per chunk of 512 tiles (one tile per thread: the finalize is latency bound, so all
+        // chunks run in parallel), then a one-warp combine (statistics, validity, lml, chunk {prefix, scale})
         const int64_t nchunks = ceil_div(tpf, Scratch::kChunkTiles);
         GENPF_TRY(sc.chunk_stats.ensure(sizeof(Stats) * (size_t)(nchunks * nf)));
         GENPF_TRY(sc.chunk_info.ensure(16 * (size_t)(nchunks * nf)));
-        GENPF_LAUNCH((k_finalize_fast<1024>), dim3((unsigned)nchunks, (unsigned)nf), 1024, s, part, n, tpf,
+        GENPF_LAUNCH((k_finalize_fast<512, 1>), dim3((unsigned)nchunks, (unsigned)nf), 512, s, part, n, tpf,
                      sc.chunk_stats.as<Stats>(), tile_off, -1.0, (double *)nullptr, Scratch::kChunkTiles,
                      sc.tile_scale.as<double>());
         GENPF_LAUNCH(k_chunk_combine, (unsigned)nf, 32, s, (const Stats *)sc.chunk_stats.as<Stats>(), (int)nchunks, n,
@@ -86,6 +87,29 @@ inline StratArgs make_strat(UniSrc uni, int64_t n) {
     a.guide = 0;
     a.tol = (double)n * 0x1.0p-50;
     return a;
+}
+
+// cumulative offspring counts O_k of a stratified resample (no W output): the hot kernel when the strata are the
+// library's Philox draws, the general k_scan for supplied uniform columns
+template <typename IdxT>
+inline int32_t launch_scan_counts(cudaStream_t s, LwSrc sel, int64_t n, int64_t tpf, int64_t nf, const Stats *st,
+                                  const double *tile_off, IdxT *O, IdxT *tile_last, const StratArgs &strat, int gate,
+                                  const double *shard_info, int64_t global_base, const double *chunk_info,
+                                  const double *ew, const double *tile_scale) {
+    const dim3 grid((unsigned)tpf, (unsigned)nf);
+    if (!strat.uni.col && !strat.guide && strat.pow2) {
+        if (ew) {
+            GENPF_LAUNCH((k_scan_hot<IdxT, true>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
+                         shard_info, global_base, chunk_info, ew, tile_scale);
+        } else {
+            GENPF_LAUNCH((k_scan_hot<IdxT, false>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
+                         shard_info, global_base, chunk_info, ew, tile_scale);
+        }
+        return GENPF_OK;
+    }
+    GENPF_LAUNCH((k_scan<IdxT>), grid, kScanThreads, s, sel, n, tpf, st, tile_off, WTables{nullptr}, O, tile_last, strat, gate,
+                 shard_info, global_base, chunk_info, Scratch::kChunkTiles, ew, tile_scale);
+    return GENPF_OK;
 }
 
 // guide-table size for the inverse-CDF lookups: two particles per bucket measured best at 2^24 (bucket sizes
@@ -133,9 +157,8 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         }
         StratArgs strat = make_strat(uni, n_in);
         const double *ew_use = order ? nullptr : ew;  // e_i is stored in particle order
-        GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
-                     WTables{nullptr}, O, tile_last, strat, gate, (const double *)nullptr, (int64_t)0,
-                     sc.chunk_info_ptr(n_in), Scratch::kChunkTiles, ew_use, (const double *)sc.tile_scale.as<double>());
+        GENPF_TRY(launch_scan_counts<IdxT>(s, sel, n_in, tpf_in, nf, st_sel, tile_off, O, tile_last, strat, gate,
+                                           nullptr, 0, sc.chunk_info_ptr(n_in), ew_use, sc.tile_scale.as<double>()));
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out, order,
                      parents, out_base, st_sel, gate, 0, fill);
     } else if (method == GENPF_MULTINOMIAL) {

@@ -19,7 +19,10 @@ struct Cols {
     uint8_t *b[kMaxB];
 };
 
-constexpr int kStateThreads = 512;  // block size of every kernel that produces particle state + K1 partials
+#ifndef GENPF_STATE_THREADS
+#define GENPF_STATE_THREADS 512
+#endif
+constexpr int kStateThreads = GENPF_STATE_THREADS;  // block size of every kernel that produces particle state + K1 partials
 
 template <int T = kThreads>
 __device__ __forceinline__ void load_tile_u8(const uint8_t *col, int64_t base, int64_t valid,

@@ -129,7 +129,7 @@ static __global__ void __launch_bounds__(kReduceThreads)
 // Register-resident finalize for tpf <= 8*THREADS tiles per filter: thread t owns tiles {c*THREADS + t}
 // (coalesced loads, all in flight together); the three phases (max, rescaled sums, exclusive tile offsets)
 // need only a handful of block-level combines.
-template <int THREADS>
+template <int THREADS, int C = 8>
 static __global__ void __launch_bounds__(THREADS)
     k_finalize_fast(Partials in, int64_t n_all, int64_t tpf_all, Stats *stats, double *tile_off, double ess_frac,
                     double *lml_accum, int64_t chunk_tiles, double *tile_scale = nullptr) {
@@ -137,7 +137,7 @@ static __global__ void __launch_bounds__(THREADS)
     // finalises one CHUNK of a large filter as if it were a filter of its own (Stats at [f*chunks + c], tile
     // offsets normalised within the chunk); k_chunk_combine then produces the filter's statistics and each
     // chunk's {prefix, scale}, which k_scan composes -- the same mechanism as a multi-GPU shard.
-    constexpr int C = 8, NW = THREADS / 32;
+    constexpr int NW = THREADS / 32;
     __shared__ double sm[3][NW];
     __shared__ int smi[NW];
     __shared__ double row_cell[C][NW];  // inclusive warp totals per row -> exclusive offsets
@@ -269,47 +269,66 @@ static __global__ void __launch_bounds__(THREADS)
     }
 }
 
-// Large filters (more than 8192 tiles): combine the per-chunk statistics into the filter's, and give every
-// chunk its {prefix, scale} (exclusive normalised mass before the chunk, the chunk's share).  One warp per filter.
-static __global__ void k_chunk_combine(const Stats *chunk_stats, int nchunks, int64_t n, int64_t chunk_particles,
-                                       Stats *stats, double *chunk_info, double ess_frac, double *lml_accum) {
+// Large filters (more than kChunkTiles tiles): combine the per-chunk statistics into the filter's, and give every
+// chunk its {prefix, scale} (exclusive normalised mass before the chunk, the chunk's share).  One warp per filter;
+// lane l owns chunks l, l+32, ...; sums use fixed shuffle trees, the prefix is an ordered warp scan with a carry.
+static __global__ void __launch_bounds__(32)
+    k_chunk_combine(const Stats *chunk_stats, int nchunks, int64_t n, int64_t chunk_particles, Stats *stats,
+                    double *chunk_info, double ess_frac, double *lml_accum) {
     const int64_t f = blockIdx.x;
-    if (threadIdx.x != 0) return;
+    const int lane = threadIdx.x;
     const Stats *cs = chunk_stats + f * nchunks;
     double M = -INFINITY;
-    int kind = 0;
-    bool all_neginf = true, nan_in = false, nan_tot = false;
-    for (int c = 0; c < nchunks; ++c) {
+    int bits = 0;  // 1: NaN input somewhere, 2: NaN total somewhere, 4: some chunk is not all -Inf
+    for (int c = lane; c < nchunks; c += 32) {
         M = fmax(M, cs[c].M);
-        if (cs[c].invalid_kind == 1) nan_in = true;
-        if (cs[c].invalid_kind == 4) nan_tot = true;
-        if (cs[c].invalid_kind != 2) all_neginf = false;
+        const int k = cs[c].invalid_kind;
+        bits |= (k == 1 ? 1 : 0) | (k == 4 ? 2 : 0) | (k != 2 ? 4 : 0);
     }
-    double S = 0.0, S2 = 0.0;
+    M = warp_max(M);
+    bits = __reduce_or_sync(0xffffffffu, (unsigned)bits);
     const bool finite = M > -INFINITY && M < INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
+    double S = 0.0, S2 = 0.0;
+    for (int c = lane; c < nchunks; c += 32) {
         const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
         S += cs[c].S * sc;
         S2 += cs[c].S2 * (sc * sc);
     }
-    if (nan_in) kind = 1;
-    else if (all_neginf) kind = 2;
-    else if (nan_tot || isnan(S)) kind = 4;
+    S = warp_sum(S);
+    S2 = warp_sum(S2);
+    int kind = 0;
+    if (bits & 1) kind = 1;
+    else if (!(bits & 4)) kind = 2;
+    else if ((bits & 2) || isnan(S)) kind = 4;
     else if (S == 0.0) kind = 3;
-    double prefix = 0.0;
-    for (int c = 0; c < nchunks; ++c) {
-        double share;
-        if (kind == 2 || kind == 3) {
-            const int64_t cnt = min(chunk_particles, n - (int64_t)c * chunk_particles);
-            share = (double)cnt / (double)n;
-        } else {
-            const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
-            share = cs[c].S * sc / S;
+    double carry = 0.0;
+    for (int c0 = 0; c0 < nchunks; c0 += 32) {
+        const int c = c0 + lane;
+        double share = 0.0;
+        if (c < nchunks) {
+            if (kind == 2 || kind == 3) {
+                const int64_t cnt = min(chunk_particles, n - (int64_t)c * chunk_particles);
+                share = (double)cnt / (double)n;
+            } else {
+                const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
+                share = cs[c].S * sc / S;
+            }
         }
-        chunk_info[2 * (f * nchunks + c)] = prefix;
-        chunk_info[2 * (f * nchunks + c) + 1] = share;
-        prefix += share;
+        double inc = share;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0.0;
+        if (c < nchunks) {
+            chunk_info[2 * (f * nchunks + c)] = carry + ex;
+            chunk_info[2 * (f * nchunks + c) + 1] = share;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
+    if (lane != 0) return;
     Stats st;
     st.M = M; st.S = S; st.S2 = S2;
     st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
@@ -368,13 +387,14 @@ static __device__ __noinline__ uint4 strata_block(uint64_t seed, uint64_t stream
 // particle, and no divergence); a query outside the window falls back to a direct draw.
 constexpr int kStrataWindow = 256;
 struct StrataWindow {
-    const uint32_t *words;  // shared memory, kStrataWindow words of this warp
+    const uint32_t *words;  // shared memory: `len` stratum words (a warp's window in k_scan, the tile's in k_scan_hot)
     int64_t base;           // global stratum slot of words[0]; < 0: no window (column uniforms)
+    int len;
 };
 // General path: exact for every input (column uniforms, window misses, W within rounding of a stratum edge).
 template <typename J>
 static __device__ __noinline__ J strat_count_slow(const StratArgs &a, int64_t slot0, double W, const uint32_t *words,
-                                                  int64_t win_base) {
+                                                  int64_t win_base, int win_len) {
     const J n = (J)a.n;
     const double nd = (double)a.n;
     const double x = W * nd;
@@ -389,7 +409,7 @@ static __device__ __noinline__ J strat_count_slow(const StratArgs &a, int64_t sl
         } else {
             const int64_t gs = slot + a.uni.offset;
             const uint64_t rel = (uint64_t)(gs - win_base);
-            if (win_base >= 0 && rel < (uint64_t)kStrataWindow) {
+            if (win_base >= 0 && rel < (uint64_t)win_len) {
                 r = ((double)words[rel] + 0.5) * 0x1.0p-32;
             } else {
                 r = strata_word(strata_block(a.uni.seed, a.uni.stream, (uint64_t)gs >> 2), gs);
@@ -415,7 +435,7 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
         const J j = (J)x;
         const double frac = x - (double)j;
         const uint64_t rel = (uint64_t)(slot0 + (int64_t)j + a.uni.offset - win.base);
-        if (rel < (uint64_t)kStrataWindow && frac > 1e-6 && frac < 1.0 - 1e-6) {
+        if (rel < (uint64_t)win.len && frac > 1e-6 && frac < 1.0 - 1e-6) {
             const double r = fma((double)win.words[rel], 0x1.0p-32, 0x1.0p-33);  // (word + 0.5) * 2^-32, exact
             const double d = frac - r;
             if (fabs(d) > a.tol) return j + (J)(d > 0.0 ? 1 : 0);
@@ -427,7 +447,7 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
         bool ok = true;
         auto u_win = [&](J i1) {
             const uint64_t rr = (uint64_t)(slot0 + (int64_t)i1 - 1 + a.uni.offset - win.base);
-            if (rr >= (uint64_t)kStrataWindow) {
+            if (rr >= (uint64_t)win.len) {
                 ok = false;
                 return 0.0;
             }
@@ -453,7 +473,14 @@ __device__ __forceinline__ J strat_count(const StratArgs &a, int64_t slot0, doub
         }
         if (ok) return c;
     }
-    return strat_count_slow<J>(a, slot0, W, win.words, win.base);
+    return strat_count_slow<J>(a, slot0, W, win.words, win.base, win.len);
+}
+
+// the whole exact count behind one call: k_scan_hot keeps only the common case inline
+template <typename J>
+static __device__ __noinline__ J strat_count_outline(const StratArgs &a, int64_t slot0, double W, const uint32_t *words,
+                                                     int64_t win_base, int win_len) {
+    return strat_count<J>(a, slot0, W, StrataWindow{words, win_base, win_len});
 }
 
 // ------------------------------------------------------------------ K3 normalise + scan
@@ -518,7 +545,7 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     double escale = 0.0;
     if (use_e) {
         escale = tile_scale[f * tpf + tile];
-        if (chunk_info) escale *= chunk_info[2 * (f * ((tpf + chunk_tiles - 1) / chunk_tiles) + tile / chunk_tiles) + 1];
+        if (chunk_info) escale *= chunk_info[2 * (f * ((tpf + kChunkTiles - 1) >> kChunkLog2) + (tile >> kChunkLog2)) + 1];
         if (shard_info) escale *= shard_info[1];
     }
     double W[I];
@@ -558,8 +585,8 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     __syncthreads();
     double off = tile_off[f * tpf + tile];
     if (chunk_info) {  // large filter: offsets were normalised per chunk of chunk_tiles tiles
-        const int64_t nchunks = (tpf + chunk_tiles - 1) / chunk_tiles;
-        const double *ci = chunk_info + 2 * (f * nchunks + tile / chunk_tiles);
+        const int64_t nchunks = (tpf + kChunkTiles - 1) >> kChunkLog2;
+        const double *ci = chunk_info + 2 * (f * nchunks + (tile >> kChunkLog2));
         off = ci[0] + ci[1] * off;
     }
     if (shard_info) off = shard_info[0] + shard_info[1] * off;
@@ -575,7 +602,7 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     if (O_out) {
         IdxT O[I];
         const int64_t slot0 = f * strat.n;  // stratum slot of this filter's first stratum (nf > 1: n == strat.n)
-        StrataWindow win{swin[warp], -1};
+        StrataWindow win{swin[warp], -1, kStrataWindow};
         if (!strat.uni.col && !strat.guide) {
             // the warp's first query is at stratum floor(n * W_excl(lane 0)) + 1 or later
             const double w_first = __shfl_sync(0xffffffffu, base_w, 0);
@@ -607,6 +634,187 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
             for (int k = 0; k < I; ++k)
                 if (e0 + k < valid) po[e0 + k] = O[k];
         }
+    }
+}
+
+// ------------------------------------------------------------------ K3, hot path
+// The scan of the README step (and of every stratified resample with library-drawn strata over a power-of-two
+// population -- every BASELINE size): no W output, no guide table, Philox stratum uniforms.  Same summation order
+// and the SAME count C(W_k) = #{i : u_i <= W_k} as k_scan (the parity tests compare the two through the
+// column-uniform path), organised for instruction issue -- the kernel has no function call and no slow path:
+//   * ONE stratum window per TILE: the tile's strata are [floor(n*off), floor(n*(off+total))], ~2048 for balanced
+//     weights, so each thread draws ~1.1 Philox blocks (4 strata each); a query outside the window (a tile holding
+//     a particle with thousands of offspring) draws its block in place;
+//   * for n = 2^p the stratum lower bounds j/n are exact, so the count is evaluated literally and branch-free:
+//     j = floor(n*W) corrected by at most one so that j/n <= W < (j+1)/n, then
+//     C(W) = j + [fl(fl(r_{j+1} * (1/n)) + j/n) <= W]   (u_i of resample.jl:162 for the only stratum that can straddle W);
+//     the uniform-weight fallback of safe_softmax (W_k = k/n) and equal weights need no special case;
+//   * block-uniform conditions (validity kind, closing particle, alignment) are hoisted out of the particle loop.
+constexpr int kHotWindow = 2560;  // stratum words staged per tile (2048 + 25 % slack): 10 KB
+#ifndef GENPF_HOT_THREADS
+#define GENPF_HOT_THREADS 256
+#endif
+constexpr int kHotThreads = GENPF_HOT_THREADS;  // 256 threads x 8 particles: per-thread overheads amortised over 8
+template <typename IdxT, bool USE_E, int T = kHotThreads>
+static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
+    k_scan_hot(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, IdxT *O_out,
+               IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info, int64_t global_base,
+               const double *chunk_info, const double *ew, const double *tile_scale) {
+    constexpr int I = kTile / T, NW = T / 32;
+    __shared__ double sm[NW + 1];
+    __shared__ alignas(16) uint32_t swin[kHotWindow];
+    const int64_t f = blockIdx.y, tile = blockIdx.x;
+    const int kind = stats[f].invalid_kind;
+    if (kind == 1 || kind == 4) return;
+    if (gate && !stats[f].do_resample) return;
+    const int64_t start = tile * kTile;
+    const int valid = (int)min((int64_t)kTile, n - start);
+    const int e0 = I * (int)threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[I];
+    {
+        const double *p = (USE_E ? ew : src.p) + f * n + start;
+        if (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && e0 + I - 1 < valid) {
+#pragma unroll
+            for (int k = 0; k < I; k += 2) {
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(p + e0 + k));
+                v[k] = a.x;
+                v[k + 1] = a.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < I; ++k) v[k] = e0 + k < valid ? __ldg(p + e0 + k) : (USE_E ? 0.0 : -INFINITY);
+        }
+    }
+    const double step = strat.step;  // 1/n, exact (n is a power of two)
+    double W[I];
+    if (kind != 0) {  // uniform fallback of safe_softmax (utils.jl:123-133): block-uniform, rare
+        double run = 0.0;
+#pragma unroll
+        for (int k = 0; k < I; ++k) {
+            run += e0 + k < valid ? step : 0.0;
+            W[k] = run;
+        }
+    } else if (USE_E) {
+        double escale = tile_scale[f * tpf + tile];
+        if (chunk_info) escale *= chunk_info[2 * (f * ((tpf + kChunkTiles - 1) >> kChunkLog2) + (tile >> kChunkLog2)) + 1];
+        if (shard_info) escale *= shard_info[1];
+        double run = 0.0;
+#pragma unroll
+        for (int k = 0; k < I; ++k) {
+            run += v[k] * escale;
+            W[k] = run;
+        }
+    } else {
+        const double M = stats[f].M, inv_S = 1.0 / stats[f].S;
+        double run = 0.0;
+#pragma unroll
+        for (int k = 0; k < I; ++k) {
+            run += exp_nonpos(src.fix(v[k]) - M) * inv_S;
+            W[k] = run;
+        }
+    }
+    double inc = W[I - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    double lane_excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) lane_excl = 0.0;
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 16 warp totals (+ the tile total in sm[NW])
+        double t = lane < NW ? sm[lane] : 0.0;
+        double s = t;
+#pragma unroll
+        for (int o = 1; o < NW; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        const double ex = __shfl_up_sync(0xffffffffu, s, 1);
+        if (lane < NW) sm[lane] = lane == 0 ? 0.0 : ex;
+        if (lane == NW - 1) sm[NW] = s;
+    }
+    __syncthreads();
+    double off = tile_off[f * tpf + tile];
+    if (chunk_info) {
+        const int64_t nchunks = (tpf + kChunkTiles - 1) >> kChunkLog2;
+        const double *ci = chunk_info + 2 * (f * nchunks + (tile >> kChunkLog2));
+        off = ci[0] + ci[1] * off;
+    }
+    if (shard_info) off = shard_info[0] + shard_info[1] * off;
+    const double base_w = off + (sm[warp] + lane_excl);
+    // ---- the tile's stratum window: 0-based strata [jw, jw + 4*ncalls) of this filter
+    const double nd = (double)strat.n;
+    const IdxT nI = (IdxT)strat.n;
+    const int64_t goff = f * strat.n + strat.uni.offset;  // global Philox slot of this filter's stratum 0
+    IdxT jw;
+    int ncalls;
+    {
+        const double x0 = off * nd, x1 = (off + sm[NW]) * nd;
+        const IdxT jb = x0 <= 0.0 ? (IdxT)0 : (x0 >= nd ? nI : (IdxT)x0);
+        const IdxT je = x1 <= 0.0 ? (IdxT)0 : (x1 >= nd ? nI : (IdxT)x1);
+        const int64_t wb = ((goff + (int64_t)jb) >> 2) << 2;  // window base slot (a Philox block boundary)
+        jw = (IdxT)(wb - goff);
+        const int64_t want = (int64_t)je - (int64_t)jw + 3;  // stratum je is queried, +-1 for the floor correction
+        ncalls = (int)min((int64_t)(kHotWindow / 4), (want + 3) >> 2);
+        for (int c = threadIdx.x; c < ncalls; c += T) {
+            const uint4 b = philox_at(strat.uni.seed, strat.uni.stream, (uint64_t)(wb >> 2) + c);
+            *reinterpret_cast<uint4 *>(&swin[4 * c]) = b;
+        }
+    }
+    __syncthreads();
+    const IdxT wlen = (IdxT)(4 * ncalls);
+    IdxT O[I];
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+        const double Wk = base_w + W[k];
+        const double x = fmin(Wk * nd, nd);  // Wk >= 0
+        IdxT j = (IdxT)x;                     // floor(n*W) up to the rounding of the product
+        double lo = (double)j * step;         // exact: j/n
+        // one correction makes j/n <= W < (j+1)/n hold exactly (the product's rounding error is << 1 stratum)
+        const bool dn = Wk < lo, up = !dn && Wk >= lo + step;
+        j += (IdxT)(up ? 1 : 0) - (IdxT)(dn ? 1 : 0);
+        lo = dn ? lo - step : (up ? lo + step : lo);
+        // stratum j+1 (1-based) is the only one that can straddle W: strata <= j lie below, strata >= j+2 above
+        const IdxT rel = j - jw;
+        uint32_t word;
+        if (rel >= 0 && rel < wlen) {
+            word = swin[(int)rel];
+        } else {  // outside the staged window (a tile spanning thousands of strata): draw the block in place
+            const int64_t gs = goff + (int64_t)(j < nI ? j : nI - 1);
+            const uint4 b = philox_at(strat.uni.seed, strat.uni.stream, (uint64_t)gs >> 2);
+            const int q = (int)(gs & 3);
+            word = q == 0 ? b.x : (q == 1 ? b.y : (q == 2 ? b.z : b.w));
+        }
+        const double r = fma((double)word, 0x1.0p-32, 0x1.0p-33);          // (word + 0.5) * 2^-32, exact
+        const double u = __dadd_rn(__dmul_rn(r, step), lo);                // resample.jl:162, two roundings
+        O[k] = j >= nI ? nI : j + (IdxT)(u <= Wk ? 1 : 0);
+    }
+    if (valid < kTile) {
+#pragma unroll
+        for (int k = 0; k < I; ++k)
+            if (e0 + k >= valid) O[k] = (IdxT)0;
+    }
+    // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
+    const bool closes = (global_base + start + valid == strat.n);
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+        if (e0 + k == valid - 1) {
+            if (closes) O[k] = nI;
+            tile_last_O[f * tpf + tile] = O[k];
+        }
+    }
+    IdxT *po = O_out + f * n + start;
+    if (sizeof(IdxT) == 4 && ((reinterpret_cast<uintptr_t>(po) & 15) == 0) && e0 + I - 1 < valid) {
+#pragma unroll
+        for (int k = 0; k < I; k += 4)
+            *reinterpret_cast<int4 *>(po + e0 + k) = make_int4((int)O[k], (int)O[k + 1], (int)O[k + 2], (int)O[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < I; ++k)
+            if (e0 + k < valid) po[e0 + k] = O[k];
     }
 }
 

@@ -23,6 +23,10 @@ def check_parents(p_gpu, p_ref, W_ref, u, order=None, max_frac=1e-4, p_exact=Non
     if mism.size == 0:
         return 0, 0.0
     assert mism.size <= max(8, int(max_frac * p_ref.size)), f"{mism.size} ancestor mismatches of {p_ref.size}"
+    if p_exact is not None:
+        # the parallel fp64 scan agrees with the long-double cumulative sum almost everywhere (SURVEY 8c "exact mode")
+        n_ex = int(np.sum(p_gpu != p_exact))
+        assert n_ex <= max(4, int(2e-6 * p_ref.size)), f"{n_ex} ancestors differ from the exact-mode oracle"
     if order is not None:
         inv = np.empty(n, dtype=np.int64)
         inv[order] = np.arange(n)
