@@ -766,14 +766,15 @@ def pf_step(state, t, obs_prev, obs_t, *, method="stratified", ess_thresh=0.5, m
     return ess
 
 
-def pf_step_with_noise(state, t, obs_prev, obs_t, *, method="stratified", mh_iters=1, uniforms=None, U2=None, Z2=None,
-                       U3=None, U1=None, Z1=None):
-    """The README iteration in parity mode: resample taken, every draw supplied as a column indexed by
-    output particle (uniforms=None: the library's own Philox stratum / inverse-CDF draws)."""
+def pf_step_with_noise(state, t, obs_prev, obs_t, *, method="stratified", ess_thresh=1.0, mh_iters=1, uniforms=None,
+                       U2=None, Z2=None, U3=None, U1=None, Z1=None):
+    """The README iteration in parity mode: every draw supplied as a column indexed by output particle
+    (uniforms=None: the library's own Philox stratum / inverse-CDF draws).  ess_thresh >= 1 resamples every filter,
+    below 1 each filter of a batch decides for itself (ess < ess_thresh * n)."""
     m = state.model
     cols = [None if c is None else _f64(c) for c in (uniforms, U2, Z2, U3, U1, Z1)]
     L.check(L.load().genpf_step_with_noise(state._h, int(t), L.ptr(state._obs(obs_prev)), L.ptr(m.aux(t - 1)),
-                                           L.ptr(state._obs(obs_t)), L.ptr(m.aux(t)), L.METHODS[method], int(mh_iters),
-                                           *[L.ptr(c) for c in cols]))
+                                           L.ptr(state._obs(obs_t)), L.ptr(m.aux(t)), L.METHODS[method],
+                                           float(ess_thresh), int(mh_iters), *[L.ptr(c) for c in cols]))
     state.t = int(t)
     return state

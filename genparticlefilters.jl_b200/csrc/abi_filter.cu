@@ -154,7 +154,7 @@ int32_t read_stats(genpf_filter_t pf, int which) {
 
 template <class Model, class Noise>
 static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise,
-                         bool reweight) {
+                         bool reweight, bool gated) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     if (reweight) {
         GENPF_LAUNCH((k_mh<Model, Noise, true>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter,
@@ -163,27 +163,29 @@ static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double 
         return GENPF_OK;
     }
     GENPF_LAUNCH((k_mh<Model, Noise>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
-                 pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept);
+                 pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept,
+                 (double *)nullptr, gated ? (const Stats *)pf->sc.st(0, pf->nf) : (const Stats *)nullptr);
     return GENPF_OK;
 }
 template <class Model>
 static int32_t mh_model(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val,
-                        const double *U2, const double *Z2, const double *U3, bool reweight) {
+                        const double *U2, const double *Z2, const double *U3, bool reweight, bool gated) {
     if (U2 || Z2 || U3) {
         NoiseCols nz{U2, Z2, U3, nullptr, nullptr};
-        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
+        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated);
     }
     // the mh move on slice tau belongs to README iteration s = tau + 1 (it runs right before pf_update!(s))
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
-        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
+        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated);
     }
     NoiseLean nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
-    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz, reweight);
+    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated);
 }
 
 static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
-                     const double *U2, const double *Z2, const double *U3, int64_t *n_accept, bool reweight = false) {
+                     const double *U2, const double *Z2, const double *U3, int64_t *n_accept, bool reweight = false,
+                     bool gated = false) {
     GENPF_TRY(check_filter(pf));
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
     if (tau != pf->t_cur) return fail(GENPF_ERR_UNSUPPORTED, "mh rejuvenation is implemented for tau == newest time step");
@@ -199,8 +201,8 @@ static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const do
     for (int it = 0; it < n_iters; ++it) {
         int32_t st;
         switch (pf->model) {
-            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight); break;
-            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight); break;
+            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated); break;
+            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated); break;
             default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
         }
         GENPF_TRY(st);
@@ -329,7 +331,6 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     if (n_out <= 0) n_out = pf->n;
     if (n_out != pf->n && method == GENPF_STRATIFIED)
         return fail(GENPF_ERR_INVALID_ARG, "stratified resampling cannot resize (resize.jl:16-27)");
-    if (n_out != pf->n && pf->nf != 1) return fail(GENPF_ERR_UNSUPPORTED, "resize needs n_filters == 1");
     const int gate = ess_frac >= 0.0 ? 1 : 0;
     const int64_t n = pf->n, nf = pf->nf;
     cudaStream_t s = pf->stream;
@@ -416,15 +417,17 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
 
 // ---- fused README iteration (stratified, resample taken, Philox noise): finalize -> scan -> k_step_fused
 template <class Model, class Noise>
-static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noise) {
+static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noise, int gate) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     const int64_t t = a.t;
+    const Stats *gst = pf->sc.st(0, pf->nf);
+    const double *lw_src = pf->lw;
     if (a.mh_iters == 1) {
         GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                      pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents,
                      pf->lw_alt, pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr,
-                     pf->sc.partials(0), pf->ew);
+                     pf->sc.partials(0), pf->ew, gst, gate, lw_src);
         return GENPF_OK;
     }
     if (a.mh_iters == 0) {
@@ -432,29 +435,31 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
                      pf->stream, a, (const int32_t *)pf->sc.O.as<int32_t>(),
                      (const int32_t *)pf->sc.tile_last.as<int32_t>(), pf->slice(t - 2), pf->slice(t - 1),
                      pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt, pf->n, tpf, noise,
-                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew);
+                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew, gst, gate, lw_src);
         return GENPF_OK;
     }
     GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
                  (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                  pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
-                 pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew);
+                 pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew, gst,
+                 gate, lw_src);
     return GENPF_OK;
 }
 template <class Model>
-static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a, const NoiseCols *cols) {
-    if (cols) return launch_step_fused<Model, NoiseCols>(pf, a, *cols);
+static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a, const NoiseCols *cols, int gate) {
+    if (cols) return launch_step_fused<Model, NoiseCols>(pf, a, *cols, gate);
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)a.t, pf->rng_offset};
-        return launch_step_fused<Model, NoisePhilox53>(pf, a, nz);
+        return launch_step_fused<Model, NoisePhilox53>(pf, a, nz, gate);
     }
     NoiseLean nz{pf->seed, (uint64_t)a.t, pf->rng_offset};
-    return launch_step_fused<Model, NoiseLean>(pf, a, nz);
+    return launch_step_fused<Model, NoiseLean>(pf, a, nz, gate);
 }
 
 static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
                              const double *obs_t, const double *aux_t, int32_t mh_iters, bool finalized,
-                             const double *d_uniforms = nullptr, const NoiseCols *cols = nullptr) {
+                             const double *d_uniforms = nullptr, const NoiseCols *cols = nullptr, int gate = 0,
+                             double ess_frac = -1.0) {
     const ModelInfo &mi = kModels[pf->model];
     const int64_t n = pf->n, nf = pf->nf;
     cudaStream_t s = pf->stream;
@@ -486,17 +491,17 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     const int64_t tpf = ceil_div(n, kTile);
     GENPF_TRY(sc.O.ensure((size_t)(n * nf) * 4));
     GENPF_TRY(sc.tile_last.ensure((size_t)(tpf * nf) * 4));
-    if (!finalized) GENPF_TRY(ensure_stats(pf, sc.tile_off.as<double>(), -1.0, pf->lml));
+    if (!finalized) GENPF_TRY(ensure_stats(pf, sc.tile_off.as<double>(), ess_frac, pf->lml));
     UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
     StratArgs strat = make_strat(uni, n);
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_TRY(launch_scan_counts<int32_t>(s, lw_src, n, tpf, nf, sc.st(0, nf), sc.tile_off.as<double>(), sc.O.as<int32_t>(),
-                                          sc.tile_last.as<int32_t>(), strat, 0, nullptr, 0, sc.chunk_info_ptr(n), pf->ew,
+                                          sc.tile_last.as<int32_t>(), strat, gate, nullptr, 0, sc.chunk_info_ptr(n), pf->ew,
                                           sc.tile_scale.as<double>()));
     int32_t st;
     switch (pf->model) {
-        case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a, cols); break;
-        case kModelLinGauss1D: st = step_fused_model<LinGauss1D>(pf, a, cols); break;
+        case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a, cols, gate); break;
+        case kModelLinGauss1D: st = step_fused_model<LinGauss1D>(pf, a, cols, gate); break;
         default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
     }
     GENPF_TRY(st);
@@ -737,14 +742,15 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
             any |= r;
             every &= r;
         }
-        if (any && !every)
-            return fail(GENPF_ERR_UNSUPPORTED,
-                        "filters of one batch disagree on resampling; use the separate entry points per view");
     }
-    if (any && fusable) return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, finalized);
+    // filters of one batch may disagree (every view decides for itself, README.md:68-74): the device-side
+    // do_resample flag of each filter gates the kernels, the others are only updated
+    const int gate = (any && !every) ? 1 : 0;
+    if (any && fusable)
+        return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, finalized, nullptr, nullptr, gate);
     if (any) {
-        GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, nullptr, nullptr, -1.0));
-        GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, mh_iters, nullptr, nullptr, nullptr, nullptr));
+        GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, nullptr, nullptr, gate ? ess_frac : -1.0));
+        GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, mh_iters, nullptr, nullptr, nullptr, nullptr, false, gate != 0));
     }
     return do_propagate(pf, false, t, obs_t, aux_t, nullptr, nullptr);
 }
@@ -754,14 +760,16 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
 // and the update's [U1, Z1], n_particles * n_filters each, indexed by output particle.  Stratified resampling runs
 // the SAME kernels as genpf_step (k_scan + k_step_fused) with the column noise policy.
 int32_t genpf_step_with_noise(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
-                              const double *obs_t, const double *aux_t, int32_t method, int32_t mh_iters,
-                              const double *uniforms, const double *U2, const double *Z2, const double *U3,
-                              const double *U1, const double *Z1) {
+                              const double *obs_t, const double *aux_t, int32_t method, double ess_frac,
+                              int32_t mh_iters, const double *uniforms, const double *U2, const double *Z2,
+                              const double *U3, const double *U1, const double *Z1) {
     GENPF_TRY(check_filter(pf));
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
     if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_step_with_noise must advance to t_cur + 1");
     if (mh_iters != 0 && mh_iters != 1) return fail(GENPF_ERR_INVALID_ARG, "noise columns serve mh_iters 0 or 1");
     if (!U1 || !Z1 || (mh_iters == 1 && (!U2 || !Z2 || !U3))) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
+    // ess_frac >= 1: every filter resamples; below, each filter decides on the device (ess < ess_frac * n)
+    const int gate = ess_frac < 1.0 ? 1 : 0;
     if (method == GENPF_STRATIFIED) {
         const double *d_u = nullptr;
         NoiseCols nz{nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -776,10 +784,10 @@ int32_t genpf_step_with_noise(genpf_filter_t pf, int64_t t, const double *obs_pr
         GENPF_TRY(stage_noise(pf, 3, U1, &nz.Uup, 0));
         GENPF_TRY(stage_noise(pf, 4, Z1, &nz.Zup, 0));
         GENPF_TRY(pf->sc.O.ensure(4));
-        return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, false, d_u, &nz);
+        return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, false, d_u, &nz, gate, gate ? ess_frac : -1.0);
     }
-    GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, uniforms, nullptr, -1.0));
-    if (mh_iters == 1) GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, 1, U2, Z2, U3, nullptr));
+    GENPF_TRY(do_resample(pf, method, GENPF_PRIO_NONE, 1.0, nullptr, pf->n, 0, uniforms, nullptr, gate ? ess_frac : -1.0));
+    if (mh_iters == 1) GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, 1, U2, Z2, U3, nullptr, false, gate != 0));
     return do_propagate(pf, false, t, obs_t, aux_t, U1, Z1);
 }
 
@@ -954,10 +962,13 @@ static int32_t apply_parents_and_swap(genpf_filter_t pf, int64_t n_out) {
     }
     return GENPF_OK;
 }
-static int32_t check_resizable(genpf_filter_t pf) {
+// batched = true: the operation keeps every filter of a batch at the same size (replicate, dereplicate, resize by
+// resampling); coalesce / optimal resize / proportionmap give data-dependent sizes and need n_filters == 1
+static int32_t check_resizable(genpf_filter_t pf, bool batched = false) {
     GENPF_TRY(check_filter(pf));
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
-    if (pf->nf != 1) return fail(GENPF_ERR_UNSUPPORTED, "resizing needs n_filters == 1");
+    if (pf->nf != 1 && !batched) return fail(GENPF_ERR_UNSUPPORTED, "this resizing operation needs n_filters == 1");
+    if (pf->shard) return fail(GENPF_ERR_UNSUPPORTED, "a sharded filter cannot be resized");
     return GENPF_OK;
 }
 }  // namespace genpf
@@ -965,29 +976,29 @@ static int32_t check_resizable(genpf_filter_t pf) {
 extern "C" {
 
 int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout) {
-    GENPF_TRY(check_resizable(pf));
+    GENPF_TRY(check_resizable(pf, true));
     if (k < 1) return fail(GENPF_ERR_INVALID_ARG, "n_replicates must be >= 1");
     const int64_t n_out = pf->n * k;
     if (n_out >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "replicated population must stay < 2^31");
     GENPF_TRY(resize_target(pf, n_out));
-    GENPF_LAUNCH((k_replicate<int32_t>), grid_1d(n_out), 256, pf->stream, (const double *)pf->lw, pf->n, k,
+    GENPF_LAUNCH((k_replicate<int32_t>), dim3(grid_1d(n_out), (unsigned)pf->nf), 256, pf->stream, (const double *)pf->lw, pf->n, k,
                  layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, pf->parents, (int64_t)0, pf->lw_alt);
     return apply_parents_and_swap(pf, n_out);
 }
 
 int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms) {
-    GENPF_TRY(check_resizable(pf));
+    GENPF_TRY(check_resizable(pf, true));
     if (k < 1 || pf->n % k != 0) return fail(GENPF_ERR_INVALID_ARG, "n must be a multiple of n_replicates (resize.jl:270)");
     const int64_t n_out = pf->n / k;
     const double *d_u = nullptr;
     if (uniforms) {
-        GENPF_TRY(pf->uni_buf.ensure((size_t)n_out * 8));
-        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms, (size_t)n_out * 8, cudaMemcpyHostToDevice, pf->stream));
+        GENPF_TRY(pf->uni_buf.ensure((size_t)(n_out * pf->nf) * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms, (size_t)(n_out * pf->nf) * 8, cudaMemcpyHostToDevice, pf->stream));
         d_u = pf->uni_buf.as<double>();
     }
     GENPF_TRY(resize_target(pf, n_out));
     UniSrc uni{d_u, pf->seed, make_stream(kPurposeDerep, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
-    GENPF_LAUNCH((k_dereplicate<int32_t>), grid_1d(n_out), 256, pf->stream, (const double *)pf->lw, pf->n, k,
+    GENPF_LAUNCH((k_dereplicate<int32_t>), dim3(grid_1d(n_out), (unsigned)pf->nf), 256, pf->stream, (const double *)pf->lw, pf->n, k,
                  layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, method == GENPF_SAMPLE ? 1 : 0, uni, pf->parents,
                  (int64_t)0, pf->lw_alt);
     return apply_parents_and_swap(pf, n_out);

@@ -379,7 +379,7 @@ int32_t genpf_replicate_host(const double *lw, int64_t n, int64_t k, int32_t lay
     double *d_out;
     GENPF_TRY(stage_out(ws.parents, parents_out, n * k, dp, &d_par));
     GENPF_TRY(stage_out(ws.lw_out, lw_out, n * k, dp, &d_out));
-    GENPF_LAUNCH((k_replicate<long long>), grid_1d(n * k), 256, ws.stream, d_lw, n, k,
+    GENPF_LAUNCH((k_replicate<long long>), dim3(grid_1d(n * k), 1), 256, ws.stream, d_lw, n, k,
                  layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, reinterpret_cast<long long *>(d_par),
                  (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0), d_out);
     GENPF_TRY(copy_out(ws, d_par, parents_out, n * k, dp));
@@ -406,7 +406,7 @@ int32_t genpf_dereplicate_host(const double *lw, int64_t n, int64_t k, int32_t l
     GENPF_TRY(stage_out(ws.parents, parents_out, n_new, dp, &d_par));
     GENPF_TRY(stage_out(ws.lw_out, lw_out, n_new, dp, &d_out));
     UniSrc uni{d_u, seed, make_stream(kPurposeDerep, 0), 0};
-    GENPF_LAUNCH((k_dereplicate<long long>), grid_1d(n_new), 256, ws.stream, d_lw, n, k,
+    GENPF_LAUNCH((k_dereplicate<long long>), dim3(grid_1d(n_new), 1), 256, ws.stream, d_lw, n, k,
                  layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, method == GENPF_SAMPLE ? 1 : 0, uni,
                  reinterpret_cast<long long *>(d_par), (int64_t)((flags & GENPF_INDEX_BASE1) ? 1 : 0), d_out);
     GENPF_TRY(copy_out(ws, d_par, parents_out, n_new, dp));

@@ -144,9 +144,8 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
             if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated resample with sort_particles is not supported");
             double *keys = sc.prio_col.as<double>();
             GENPF_LAUNCH(k_materialize, grid_1d(n_in * nf), 256, s, sel, n_in * nf, keys);
-            for (int64_t f = 0; f < nf; ++f)
-                GENPF_TRY(sort_desc_stable(keys + f * n_in, n_in, sc.sorted_keys.as<double>() + f * n_in,
-                                           sc.order.as<int32_t>() + f * n_in, sc.sort_tmp, s));
+            GENPF_TRY(sort_desc_stable_batched(keys, n_in, nf, sc.sorted_keys.as<double>(), sc.order.as<int32_t>(),
+                                               sc.sort_tmp, s));
             LwSrc sorted{sc.sorted_keys.as<double>(), 1.0};
             Stats *st_sorted = sc.st(3, nf);
             GENPF_TRY(launch_reduce(s, sorted, n_in, nf, sc.partials(1)));
@@ -178,7 +177,6 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      kThreads, s, (const double *)wt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)nullptr, parents,
                      out_base, st_sel, gate, fill);
     } else if (method == GENPF_RESIDUAL) {
-        if (gate) return fail(GENPF_ERR_UNSUPPORTED, "gated residual resample is not supported");
         const size_t np = (size_t)(tpf_in * nf);
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
@@ -200,12 +198,12 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      sc.resid_rtot.as<double>(), sc.resid_coff.as<long long>(), sc.resid_roff.as<double>(), O,
                      tile_last, rt, GO, GTL, B);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
-                     (const int32_t *)nullptr, parents, out_base, st_sel, 0, 1, fill);
+                     (const int32_t *)nullptr, parents, out_base, st_sel, gate, 1, fill);
         GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, GO, GTL, n_in, B, tpf_b,
                      (const int32_t *)nullptr, G, (int64_t)0, st_sel, 0, 0);
         GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
                      kThreads, s, (const double *)rt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)O, parents,
-                     out_base, st_sel, 0, fill);
+                     out_base, st_sel, gate, fill);
     } else {
         return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
     }

@@ -20,7 +20,7 @@ struct Cols {
 };
 
 #ifndef GENPF_STATE_THREADS
-#define GENPF_STATE_THREADS 512
+#define GENPF_STATE_THREADS 256
 #endif
 constexpr int kStateThreads = GENPF_STATE_THREADS;  // block size of every kernel that produces particle state + K1 partials
 
@@ -169,11 +169,13 @@ template <class Model, class Noise, bool REWEIGHT = false>
 static __global__ void __launch_bounds__(kStateThreads)
     k_mh(ModelParams P, int64_t tau, int iter, int first_step, Cols prevprev, Cols cur, const double *obs_dev,
          double obs_val, int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept,
-         double *lw = nullptr) {
+         double *lw = nullptr, const Stats *gate_stats = nullptr) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ double sm[T / 32];
     int64_t f, tile;
     blk_to_tile(tpf, f, tile);
+    // gated batch (README.md:68-74 per view): filters that did not resample are not rejuvenated either
+    if (gate_stats && (!gate_stats[f].do_resample || gate_stats[f].invalid_kind == 1 || gate_stats[f].invalid_kind == 4)) return;
     const int64_t start = tile * kTile;
     const int64_t valid = min((int64_t)kTile, n - start);
     const int64_t base = f * n + start;

@@ -10,7 +10,7 @@
 // Traffic per particle: R O ~4, R window 18 (gathered, monotone), W parents 4, W slice t-1 9, W slice t 9,
 // W lw 8, W e 8 = 60 B (ncu: 64 B incl. evictions) against the 109 B the unfused kernels would move (slice t-2 is
 // never copied: it leaves the window at this step).  The kernel is instruction-issue bound, not DRAM bound (ncu,
-// profiles/r1_k_ncu_summary.md), hence 512 threads x 4 particles at 32 registers (4 blocks/SM): small
+// profiles/), hence 256 threads x 8 particles at 64 registers (4 blocks/SM, no spills; per-thread overheads amortised): small
 // per-thread footprint for occupancy, Philox + Box-Muller shared between the mh move and the update.
 #pragma once
 #include "filter.cuh"
@@ -46,7 +46,8 @@ template <class Model, class Noise, typename IdxT, int MH>
 static __global__ void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_FUSED_MINB : 4)
     k_step_fused(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, Cols dst_cur,
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
-                 uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew) {
+                 uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew,
+                 const Stats *stats = nullptr, int gate = 0, const double *lw_src = nullptr) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
@@ -56,14 +57,31 @@ static __global__ void __launch_bounds__(kStateThreads, kStateThreads == 512 ? G
     const int64_t i0 = tile * kTile;
     const int valid = (int)min((int64_t)kTile, n - i0);
     const int64_t obase = f * n + i0;
+    // Per-filter decision of a batch (README.md:68-74 inside every view, test/resample.jl:130-162): a filter whose
+    // ESS stayed above the threshold (or whose weights are NaN) is only updated -- identity ancestors, no mh move,
+    // lw += increment -- while its neighbours in the same launch resample.  Block-uniform.
+    bool pass = false;
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        pass = kind == 1 || kind == 4 || (gate && !stats[f].do_resample);
+    }
     int32_t rel[I];
-    const int64_t s0 = block_expand<IdxT, T>(O + f * n, tile_last_O + f * tpf, n, tpf, i0, valid, sm, rel);
+    int64_t s0 = i0;
+    if (pass) {
+#pragma unroll
+        for (int k = 0; k < I; ++k) {
+            const int e = tile_elem<T>(k);
+            rel[k] = e < valid ? e : 0;
+        }
+    } else {
+        s0 = block_expand<IdxT, T>(O + f * n, tile_last_O + f * tpf, n, tpf, i0, valid, sm, rel);
+    }
     const int64_t sbase = f * n + s0;
     const bool fast = (valid == kTile) && ((obase & 1) == 0);  // every column base is 256-B aligned
     const double obs_prev = a.obs_prev_dev ? a.obs_prev_dev[f] : a.obs_prev;
     const double obs_t = a.obs_t_dev ? a.obs_t_dev[f] : a.obs_t;
     const bool first = (a.t - 1) == 1;  // slice t-2 is the constant initial slice
-    const int iters = MH >= 0 ? MH : a.mh_iters;
+    const int iters = pass ? 0 : (MH >= 0 ? MH : a.mh_iters);
     double v[I];
     double cnt = 0.0;
 #pragma unroll
@@ -109,7 +127,9 @@ static __global__ void __launch_bounds__(kStateThreads, kStateThreads == 512 ? G
             acc[c2] = ok ? 1 : 0;  // flag of the last iteration, like k_mh launched once per iteration
             Model::transition(a.P_t, a.t, cur, sn[c2], U_up, Z_up);
             sc[c2] = cur;
-            v[k] = live ? 0.0 + Model::obs_logpdf(a.P_t, sn[c2], obs_t) : -INFINITY;
+            // update_weights! left lw = 0 on a resampled filter (resample.jl:193-195); a passing one keeps its weight
+            const double lw0 = pass ? __ldg(lw_src + s) : 0.0;
+            v[k] = live ? lw0 + Model::obs_logpdf(a.P_t, sn[c2], obs_t) : -INFINITY;
         }
         store_pair<int32_t>(parents + obase, e0, valid, fast, (int32_t)(s0 + rel[2 * j]), (int32_t)(s0 + rel[2 * j + 1]));
 #pragma unroll

@@ -106,6 +106,9 @@ inline unsigned grid_1d(int64_t n, int block = 256, int64_t max_blocks = 148 * 1
 // order32[k] = original index of the k-th largest key; ties keep ascending original index.
 int32_t sort_desc_stable(const double *keys, int64_t n, double *keys_sorted, int32_t *order32, DevBuf &tmp,
                          cudaStream_t stream);
+// the same for every filter of a batch (filter f at [f*n, (f+1)*n)): one launch for small filters (n <= 4096)
+int32_t sort_desc_stable_batched(const double *keys, int64_t n, int64_t nf, double *keys_sorted, int32_t *order32,
+                                 DevBuf &tmp, cudaStream_t stream);
 // stable ascending sort of int64 keys with index payload (coalesce)
 int32_t sort_keys_i64(const int64_t *keys, int64_t n, int64_t *keys_sorted, int32_t *order32, DevBuf &tmp,
                       cudaStream_t stream);

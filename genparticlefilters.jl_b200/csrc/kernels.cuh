@@ -1364,10 +1364,11 @@ static __global__ void __launch_bounds__(kThreads) k_sum_partials(const double *
 template <typename OutT>
 static __global__ void k_replicate(const double *lw, int64_t n, int64_t k, int interleaved, OutT *parents, int64_t out_base,
                             double *lw_out) {
+    const int64_t f = blockIdx.y;  // batches: every filter is replicated on its own (parents local to the filter)
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n * k; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t src = interleaved ? (j % n) : (j / k);
-        if (parents) parents[j] = (OutT)(src + out_base);
-        if (lw_out) lw_out[j] = lw[src];
+        if (parents) parents[f * n * k + j] = (OutT)(src + out_base);
+        if (lw_out) lw_out[f * n * k + j] = lw[f * n + src];
     }
 }
 // pf_dereplicate! resize.jl:267-297.  One thread per retained particle; the block of k replicas is walked
@@ -1376,6 +1377,11 @@ template <typename OutT>
 static __global__ void k_dereplicate(const double *lw, int64_t n, int64_t k, int interleaved, int sample, UniSrc uni,
                               OutT *parents, int64_t out_base, double *lw_out) {
     const int64_t n_new = n / k;
+    const int64_t f = blockIdx.y;  // batches: blocks of replicas never straddle two filters
+    lw += f * n;
+    lw_out += f * n_new;
+    if (parents) parents += f * n_new;
+    const int64_t uoff = f * n_new;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_new; b += (int64_t)gridDim.x * blockDim.x) {
         const int64_t first = interleaved ? b : b * k;
         const int64_t stride = interleaved ? n_new : 1;
@@ -1388,7 +1394,7 @@ static __global__ void k_dereplicate(const double *lw, int64_t n, int64_t k, int
         for (int64_t j = 0; j < k; ++j) m = fmax(m, lw[first + j * stride]);
         double s = 0.0;
         for (int64_t j = 0; j < k; ++j) s += exp(lw[first + j * stride] - m);
-        const double u = uni(b);
+        const double u = uni(uoff + b);
         int64_t i = 0;
         double cp = exp(lw[first] - m) / s;
         while (cp <= u && i < k - 1) {

@@ -397,6 +397,59 @@ static int32_t radix_sort(const void *keys, int64_t n, void *keys_sorted, int32_
     return GENPF_OK;
 }
 
+// ------------------------------------------------------------------ batches of small filters (config 5)
+// sortperm(log_priorities, rev=true) for EVERY filter of a batch in one launch: one block per filter sorts its
+// n <= kSegSortMax keys in shared memory with a bitonic network over (encoded key, index) pairs.  Comparing the
+// index on equal keys makes the network's result the stable order (Julia's sortperm tie rule) although the
+// network itself is not stable.  Padding slots carry the largest pair and stay at the end.
+constexpr int kSegSortMax = 4096;
+constexpr int kSegSortThreads = 512;
+static __global__ void __launch_bounds__(kSegSortThreads)
+    k_segsort_desc(const double *keys, int n, int N, double *keys_sorted, int32_t *order32) {
+    __shared__ uint64_t sk[kSegSortMax];
+    __shared__ uint16_t si[kSegSortMax];
+    const int64_t f = blockIdx.x;
+    keys += f * n;
+    for (int i = threadIdx.x; i < N; i += kSegSortThreads) {
+        sk[i] = i < n ? key_encode<0>(keys, i) : ~0ull;
+        si[i] = (uint16_t)(i < n ? i : 0xFFFF);
+    }
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N >> 1); t += kSegSortThreads) {
+                const int i = 2 * t - (t & (j - 1)), p = i + j;
+                const uint64_t ka = sk[i], kb = sk[p];
+                const uint16_t ia = si[i], ib = si[p];
+                const bool a_first = ka < kb || (ka == kb && ia < ib);  // (a, b) already ascending
+                const bool asc = (i & k) == 0;
+                if (a_first != asc) {
+                    sk[i] = kb; sk[p] = ka;
+                    si[i] = ib; si[p] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += kSegSortThreads) {
+        if (keys_sorted) keys_sorted[f * n + i] = order_bits_inv(~sk[i]);
+        order32[f * n + i] = (int32_t)si[i];
+    }
+}
+
+int32_t sort_desc_stable_batched(const double *keys, int64_t n, int64_t nf, double *keys_sorted, int32_t *order32,
+                                 DevBuf &tmp, cudaStream_t stream) {
+    if (nf > 1 && n <= kSegSortMax) {
+        int N = 2;
+        while (N < n) N <<= 1;
+        GENPF_LAUNCH(k_segsort_desc, (unsigned)nf, kSegSortThreads, stream, keys, (int)n, N, keys_sorted, order32);
+        return GENPF_OK;
+    }
+    for (int64_t f = 0; f < nf; ++f)
+        GENPF_TRY(sort_desc_stable(keys + f * n, n, keys_sorted ? keys_sorted + f * n : nullptr, order32 + f * n, tmp, stream));
+    return GENPF_OK;
+}
+
 int32_t sort_desc_stable(const double *keys, int64_t n, double *keys_sorted, int32_t *order32, DevBuf &tmp,
                          cudaStream_t stream) {
     return radix_sort<0>(keys, n, keys_sorted, order32, tmp, stream);

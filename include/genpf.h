@@ -238,17 +238,20 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
  * `uniforms` = the rand() of each stratum (resample.jl:162) / inverse-CDF draw (NULL: library Philox draws),
  * [U2, Z2, U3] = the mh move's bernoulli / normal / accept draws (ignored when mh_iters == 0), [U1, Z1] = the
  * update's bernoulli / normal draws (Gen `regenerate` / `update`, rejuvenate.jl:40-53, update.jl:12-25).
- * method == GENPF_STRATIFIED runs exactly the kernels of genpf_step (scan + fused step). */
+ * method == GENPF_STRATIFIED runs exactly the kernels of genpf_step (scan + fused step).  ess_frac >= 1 resamples
+ * every filter; below 1 each filter of the batch decides for itself on the device (ess < ess_frac * n, README.md:68)
+ * and a filter that keeps its population is only updated. */
 int32_t genpf_step_with_noise(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
-                              const double *obs_t, const double *aux_t, int32_t method, int32_t mh_iters,
-                              const double *uniforms, const double *U2, const double *Z2, const double *U3,
-                              const double *U1, const double *Z1);
+                              const double *obs_t, const double *aux_t, int32_t method, double ess_frac,
+                              int32_t mh_iters, const double *uniforms, const double *U2, const double *Z2,
+                              const double *U3, const double *U1, const double *Z1);
 
 /* mean(state, tau=>field) / var(...), statistics.jl:13-17,48-54.  field: 0..n_f64-1 are the fp64 fields,
  * n_f64.. the u8 (Bool) fields promoted to fp64 (README.md:97).  out[n_filters]. */
 int32_t genpf_mean_var(genpf_filter_t pf, int32_t field, int64_t tau, double *mean, double *var);
 
-/* pf_replicate! / pf_dereplicate! / pf_coalesce!, resize.jl:236-334, on device state (n_filters == 1) */
+/* pf_replicate! / pf_dereplicate! / pf_coalesce!, resize.jl:236-334, on device state.  replicate / dereplicate (and
+ * genpf_resample_dev with n_out != n, resize.jl:46-124) act on every filter of a batch; coalesce needs n_filters == 1 */
 int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout);
 int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms);
 int32_t genpf_coalesce(genpf_filter_t pf, int64_t *n_new);
