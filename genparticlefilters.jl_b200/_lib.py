@@ -62,6 +62,15 @@ SIGNATURES = {
     "genpf_debug_sortperm": (i32, [_vp, i64, u32, _vp]),
     "genpf_model_builtin": (i32, [C.c_char_p, _i32p]),
     "genpf_model_info": (i32, [i32, _i32p, _i32p, _i32p, _i32p]),
+    "genpf_model_caps": (i32, [i32, _i32p]),
+    "genpf_model_compile": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32p]),
+    "genpf_model_export": (i32, [i32, _vp, i64, _ip]),
+    "genpf_model_load_image": (i32, [_vp, i64, _i32p]),
+    "genpf_model_plugin_sources": (i32, [i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+    "genpf_initialize_proposal": (i32, [_vp, _vp, _vp, _vp, _vp]),
+    "genpf_update_proposal": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
+    "genpf_update_translate": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
+    "genpf_rejuvenate_reweight_proposal": (i32, [_vp, i64, _vp, _vp, i32, _vp, _vp]),
     "genpf_filter_create": (i32, [i32, _vp, i32, i64, i64, u64, u32, C.POINTER(_vp)]),
     "genpf_filter_destroy": (i32, [_vp]),
     "genpf_filter_size": (i32, [_vp, _ip, _ip]),

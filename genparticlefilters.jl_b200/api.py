@@ -88,24 +88,78 @@ class ParticleFilterSubState:
         return self.source.parents[self.idxs]
 
 
+_PLUGIN_META = {}  # name -> dict(fields, bool_fields, aux_fn) of models registered from source in this process
+
+
 class DeviceModel:
-    """A model registered as a device plugin of libgenpf_cuda.so (include/genpf.h)."""
+    """A model registered as a device plugin of libgenpf_cuda.so (include/genpf.h): one of the built-in ones
+    ("object_motion", "lingauss1d") or one compiled at run time from CUDA C++ source (`DeviceModel.from_source`)."""
 
     def __init__(self, name, params=None):
         lib = L.load()
         mid = C.c_int32()
         L.check(lib.genpf_model_builtin(name.encode(), C.byref(mid)))
         self.name, self.model_id = name, mid.value
-        nf, nb, npar, naux = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        nf, nb, npar, naux, caps = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         L.check(lib.genpf_model_info(mid, C.byref(nf), C.byref(nb), C.byref(npar), C.byref(naux)))
+        L.check(lib.genpf_model_caps(mid, C.byref(caps)))
         self.n_f64, self.n_u8, self.n_params, self.n_aux = nf.value, nb.value, npar.value, naux.value
+        self.has_proposal, self.has_translator = bool(caps.value & 1), bool(caps.value & 2)
         self.params = None if params is None else _f64(params)
-        self.fields = {"object_motion": {"y": 0, "moving": 1}, "lingauss1d": {"x": 0}}[name]
-        self.bool_fields = {"object_motion": ("moving",), "lingauss1d": ()}[name]
+        builtin = {"object_motion": ({"y": 0, "moving": 1}, ("moving",)), "lingauss1d": ({"x": 0}, ())}
+        if name in builtin:
+            self.fields, self.bool_fields = builtin[name]
+            self._aux_fn = (lambda t: [math.sin(float(t))]) if name == "object_motion" else None
+        else:
+            meta = _PLUGIN_META.get(name, {})
+            default = {f"f{i}": i for i in range(self.n_f64)}
+            default.update({f"b{i}": self.n_f64 + i for i in range(self.n_u8)})
+            self.fields = meta.get("fields") or default
+            self.bool_fields = meta.get("bool_fields") or tuple(k for k, v in self.fields.items() if v >= self.n_f64)
+            self._aux_fn = meta.get("aux_fn")
+
+    @classmethod
+    def from_source(cls, name, source, struct_name, *, fields=None, bool_fields=None, aux_fn=None, params=None,
+                    options=None):
+        """Compile `source` (CUDA C++ defining `struct_name` with the plugin interface of csrc/models.cuh) with NVRTC
+        for sm_100a and register it under `name` (C ABI genpf_model_compile).  fields: {"name": index}, fp64 fields
+        first; aux_fn(t) -> the model's per-step host scalars (NAUX of them) or None."""
+        mid = C.c_int32()
+        st = L.load().genpf_model_compile(name.encode(), source.encode(), struct_name.encode(),
+                                          None if options is None else options.encode(), C.byref(mid))
+        if st != L.OK:
+            raise GenPFErrorException(L.load().genpf_last_error().decode("utf-8", "replace"))
+        _PLUGIN_META[name] = dict(fields=fields, bool_fields=bool_fields, aux_fn=aux_fn)
+        return cls(name, params)
+
+    def export_image(self):
+        """The compiled plugin as bytes (kernel names + cubin); `DeviceModel.from_image` loads it without NVRTC."""
+        size = C.c_int64()
+        L.check(L.load().genpf_model_export(self.model_id, None, 0, C.byref(size)))
+        buf = C.create_string_buffer(size.value)
+        L.check(L.load().genpf_model_export(self.model_id, buf, size.value, C.byref(size)))
+        return buf.raw
+
+    @classmethod
+    def from_image(cls, image, *, fields=None, bool_fields=None, aux_fn=None, params=None):
+        mid = C.c_int32()
+        buf = C.create_string_buffer(image, len(image))
+        L.check(L.load().genpf_model_load_image(buf, len(image), C.byref(mid)))
+        # the image carries the model's name: look it up through the registry
+        name = _image_name(image)
+        _PLUGIN_META[name] = dict(fields=fields, bool_fields=bool_fields, aux_fn=aux_fn)
+        return cls(name, params)
 
     def aux(self, t):
         # object_motion: vel_y = sin(t) with integer t in radians, computed by the caller (README.md:48)
-        return _f64([math.sin(float(t))]) if self.name == "object_motion" else None
+        return None if self._aux_fn is None else _f64(self._aux_fn(t))
+
+
+def _image_name(image):
+    import struct
+    off = 8 + 4 + 24
+    (ln,) = struct.unpack_from("<I", image, off)
+    return image[off + 4: off + 4 + ln].decode()
 
 
 class DevicePFState:
@@ -281,13 +335,17 @@ get_lml_est = log_ml_estimate  # utils.jl:186
 
 
 # --------------------------------------------------------------------------- initialize.jl / update.jl
-def pf_initialize(model, model_args, observations, n_particles, *, strata=None, layout="contiguous", **kw):
+def pf_initialize(model, model_args, observations, n_particles, *, strata=None, layout="contiguous", proposal=None,
+                  proposal_args=(), **kw):
     """initialize.jl:31-44; with `strata` the stratified form (initialize.jl:93-108).  Device models:
     observations = y_obs_1 (one per filter), strata = (field_name, values); host models: strata = iterable of
     constraint dicts merged into the observations."""
     if isinstance(model, DeviceModel):
         state = DevicePFState(model, n_particles, **kw)
-        if strata is None:
+        if proposal is not None:  # initialize.jl:46-62: the plugin's own proposal; weight = model - proposal score
+            L.check(L.load().genpf_initialize_proposal(state._h, L.ptr(state._obs(observations)), L.ptr(model.aux(1)),
+                                                       None, None))
+        elif strata is None:
             L.check(L.load().genpf_initialize(state._h, L.ptr(state._obs(observations)), L.ptr(model.aux(1))))
         else:
             name, values = strata
@@ -297,6 +355,14 @@ def pf_initialize(model, model_args, observations, n_particles, *, strata=None, 
                                                          model.fields[name], L.ptr(vals), vals.size, lay, None, None))
         state.t = 1
         return state
+    if proposal is not None and strata is None:  # initialize.jl:46-62 (host models): proposal(*args) -> (choices, log q)
+        traces, lws = [], np.empty(n_particles)
+        for i in range(n_particles):
+            choices, log_q = proposal(*proposal_args)
+            tr, w = model.generate(model_args, {**observations, **choices})
+            traces.append(tr)
+            lws[i] = w - log_q
+        return ParticleFilterState(traces, lws)
     if strata is not None:
         strata = list(strata)
         k_n, block = len(strata), n_particles // len(strata)
@@ -315,12 +381,25 @@ def pf_initialize(model, model_args, observations, n_particles, *, strata=None, 
     return ParticleFilterState(traces, lws)
 
 
-def pf_update(state, new_args, argdiffs, observations, *, strata=None, layout="interleaved"):
+def pf_update(state, new_args=None, argdiffs=None, observations=None, *, strata=None, layout="interleaved",
+              proposal=None, proposal_args=(), translator=None, **translator_kw):
     """pf_update!, update.jl:12-25; with `strata` the stratified form (update.jl:193-210): device states take
-    strata = (field_name, values), host states an iterable of constraint dicts."""
+    strata = (field_name, values), host states an iterable of constraint dicts.  `proposal`: the custom-proposal
+    form (update.jl:79-96); `translator`: the generic form pf_update!(state, translator) (update.jl:35-44) -- a
+    callable trace -> (new_trace, log_weight) for host states, True for a device plugin that defines `translate`."""
+    if translator is not None and not isinstance(state, DevicePFState):
+        src, idxs = _resolve(state)
+        for i in idxs:
+            src.new_traces[i], log_weight = translator(src.traces[i], **translator_kw)
+            src.log_weights[i] += log_weight
+        _update_refs(state)
+        return state
     if isinstance(state, DevicePFState):
         t = int(new_args[0])
-        if strata is None:
+        if translator is not None or proposal is not None:
+            fn = L.load().genpf_update_translate if translator is not None else L.load().genpf_update_proposal
+            L.check(fn(state._h, t, L.ptr(state._obs(observations)), L.ptr(state.model.aux(t)), None, None))
+        elif strata is None:
             L.check(L.load().genpf_update(state._h, t, L.ptr(state._obs(observations)), L.ptr(state.model.aux(t))))
         else:
             name, values = strata
@@ -341,7 +420,12 @@ def pf_update(state, new_args, argdiffs, observations, *, strata=None, layout="i
         assign += list(np.random.randint(0, k_n, n_p - block * k_n))  # sample(strata, n_remaining)
     for j, i in enumerate(idxs):
         cons = observations if assign is None else {**strata[assign[j]], **observations}
+        prop_w = 0.0
+        if proposal is not None:  # update.jl:79-96: proposal(trace, *args) -> (choices, log q)
+            choices, prop_w = proposal(src.traces[i], *proposal_args)
+            cons = {**cons, **choices}
         new_tr, incr, _, discard = src.traces[i].update(new_args, argdiffs, cons)
+        incr = incr - prop_w
         if discard:
             raise GenPFErrorException(f"Choices were updated or deleted: {discard}")  # update.jl:18-20
         src.new_traces[i] = new_tr
@@ -681,11 +765,16 @@ def move_reweight(*a, **k):
 
 
 def pf_move_reweight(state, kern, kern_args=(), n_iters=1, **kwargs):
-    """pf_move_reweight!, rejuvenate.jl:74-90; device states: the built-in regenerate-and-reweight of slice tau."""
+    """pf_move_reweight!, rejuvenate.jl:74-90; device states: the built-in regenerate-and-reweight of slice tau
+    (`proposal=True`: move_reweight(trace, proposal, proposal_args), rejuvenate.jl:134-148, with the plugin's proposal)."""
     if isinstance(state, DevicePFState):
         if kern is not move_reweight:
             raise TypeError("device states reweight with the built-in move_reweight kernel")
         tau, obs = kern_args
+        if kwargs.get("proposal"):
+            L.check(L.load().genpf_rejuvenate_reweight_proposal(state._h, int(tau), L.ptr(state._obs(obs)),
+                                                                L.ptr(state.model.aux(tau)), n_iters, None, None))
+            return state
         L.check(L.load().genpf_rejuvenate_reweight(state._h, int(tau), L.ptr(state._obs(obs)),
                                                    L.ptr(state.model.aux(tau)), n_iters))
         return state

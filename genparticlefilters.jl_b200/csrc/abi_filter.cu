@@ -6,9 +6,28 @@
 #include <memory>
 
 
+#include <type_traits>
+
 #include "filter_state.hpp"
+#include "plugin.hpp"
 
 namespace genpf {
+
+// a model registered at run time (abi_plugin.cu): its kernels come from the plugin image, their parameter lists
+// are those of the built-in instantiations
+struct PluginTag {};
+template <class Model>
+using SigModel = typename std::conditional<std::is_same<Model, PluginTag>::value, ObjectMotion, Model>::type;
+#define GENPF_PLUGIN_OR_BUILTIN(Model, slot, builtin_fn, fn_out)                       \
+    do {                                                                               \
+        if constexpr (std::is_same<Model, PluginTag>::value) {                         \
+            PluginModel *_pm = plugin_model(pf->model);                                \
+            if (!_pm) return fail(GENPF_ERR_INVALID_ARG, "unknown model");             \
+            GENPF_TRY(plugin_kernel(_pm, (slot), &(fn_out)));                          \
+        } else {                                                                       \
+            (fn_out) = (const void *)(builtin_fn);                                     \
+        }                                                                              \
+    } while (0)
 
 int32_t check_filter(genpf_filter_t pf) {
     if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
@@ -18,7 +37,7 @@ int32_t check_filter(genpf_filter_t pf) {
 
 static int32_t set_obs(genpf_filter_t pf, const double *obs, const double *aux, const double **obs_dev,
                        double *obs_val) {
-    const ModelInfo &mi = kModels[pf->model];
+    const ModelInfo &mi = *model_info(pf->model);
     if (!obs) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
     if (mi.naux > 0 && !aux) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL but the model needs per-step scalars");
     for (int i = 0; i < mi.naux; ++i) pf->P.aux[i] = aux[i];
@@ -50,14 +69,18 @@ static int32_t launch_propagate(genpf_filter_t pf, bool init, int64_t t, const d
                                 Noise noise, Strata strata) {
     const int64_t tpf = ceil_div(pf->n, kTile);
     const dim3 grid((unsigned)tpf, (unsigned)pf->nf);
+    const void *fn = nullptr;
+    constexpr int slot = kPlugProp + NoiseIndex<Noise>::value * 2;
     if (init) {
-        GENPF_LAUNCH((k_propagate<Model, Noise, true>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(0), pf->slice(1),
-                     pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew, strata);
-    } else {
-        GENPF_LAUNCH((k_propagate<Model, Noise, false>), grid, kStateThreads, pf->stream, pf->P, t, pf->slice(t - 1),
-                     pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0), pf->ew, strata);
+        GENPF_PLUGIN_OR_BUILTIN(Model, slot + 1, (&k_propagate<SigModel<Model>, Noise, true>), fn);
+        return launch_typed("k_propagate", &k_propagate<SigModel<Model>, Noise, true>, fn, grid, dim3(kStateThreads), pf->stream,
+                            pf->P, t, pf->slice(0), pf->slice(1), pf->lw, obs_dev, obs_val, pf->n, tpf, noise,
+                            pf->sc.partials(0), pf->ew, strata);
     }
-    return GENPF_OK;
+    GENPF_PLUGIN_OR_BUILTIN(Model, slot, (&k_propagate<SigModel<Model>, Noise, false>), fn);
+    return launch_typed("k_propagate", &k_propagate<SigModel<Model>, Noise, false>, fn, grid, dim3(kStateThreads), pf->stream, pf->P,
+                        t, pf->slice(t - 1), pf->slice(t), pf->lw, obs_dev, obs_val, pf->n, tpf, noise, pf->sc.partials(0),
+                        pf->ew, strata);
 }
 template <class Model>
 static int32_t propagate_model(genpf_filter_t pf, bool init, int64_t t, const double *obs_dev, double obs_val,
@@ -93,8 +116,16 @@ struct StrataHost {
     int32_t K, layout;
 };
 static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const double *obs, const double *aux,
-                            const double *U, const double *Z, const StrataHost *sh = nullptr) {
+                            const double *U, const double *Z, const StrataHost *sh = nullptr, int mode = kPropPrior) {
     GENPF_TRY(check_filter(pf));
+    if (mode != kPropPrior) {
+        const int need = mode == kPropProposal ? 1 : 2;
+        if (!(model_info(pf->model)->caps & need))
+            return fail(GENPF_ERR_UNSUPPORTED, mode == kPropProposal
+                                                   ? "this model defines no custom proposal (propose / proposal_logpdf / transition_logpdf)"
+                                                   : "this model defines no translator (translate)");
+        if ((U == nullptr) != (Z == nullptr)) return fail(GENPF_ERR_INVALID_ARG, "give both noise columns or neither");
+    }
     if (init) {
         if (t != 1) return fail(GENPF_ERR_INVALID_ARG, "initialize must create time step 1");
     } else {
@@ -114,19 +145,20 @@ static int32_t do_propagate(genpf_filter_t pf, bool init, int64_t t, const doubl
         GENPF_TRY(archive_slice(pf, t - 2));
     }
     Strata strata{};
+    strata.mode = mode;
     if (sh) {
         if (!sh->values || sh->K < 1 || sh->K > pf->n) return fail(GENPF_ERR_INVALID_ARG, "bad strata (need 1 <= K <= n_particles)");
         if (sh->field < 0 || sh->field >= pf->NF + pf->NB) return fail(GENPF_ERR_INVALID_ARG, "strata field out of range");
         GENPF_TRY(pf->strata_buf.ensure((size_t)sh->K * 8));
         GENPF_CUDA_TRY(cudaMemcpyAsync(pf->strata_buf.p, sh->values, (size_t)sh->K * 8, cudaMemcpyHostToDevice, pf->stream));
         strata = Strata{pf->strata_buf.as<double>(), sh->K, sh->field, sh->layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, pf->seed,
-                        make_stream(kPurposeStrata, (uint64_t)t)};
+                        make_stream(kPurposeStrata, (uint64_t)t), kPropPrior};
     }
     int32_t st;
     switch (pf->model) {
         case kModelObjectMotion: st = propagate_model<ObjectMotion>(pf, init, t, obs_dev, obs_val, dU, dZ, strata); break;
         case kModelLinGauss1D: st = propagate_model<LinGauss1D>(pf, init, t, obs_dev, obs_val, dU, dZ, strata); break;
-        default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+        default: st = propagate_model<PluginTag>(pf, init, t, obs_dev, obs_val, dU, dZ, strata); break;
     }
     GENPF_TRY(st);
     pf->t_cur = t;
@@ -154,38 +186,43 @@ int32_t read_stats(genpf_filter_t pf, int which) {
 
 template <class Model, class Noise>
 static int32_t launch_mh(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val, Noise noise,
-                         bool reweight, bool gated) {
+                         bool reweight, bool gated, int use_proposal = 0) {
     const int64_t tpf = ceil_div(pf->n, kTile);
+    const dim3 grid((unsigned)tpf, (unsigned)pf->nf);
+    const void *fn = nullptr;
+    constexpr int slot = kPlugMh + NoiseIndex<Noise>::value * 2;
+    const Stats *gst = gated ? (const Stats *)pf->sc.st(0, pf->nf) : (const Stats *)nullptr;
     if (reweight) {
-        GENPF_LAUNCH((k_mh<Model, Noise, true>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter,
-                     tau == 1 ? 1 : 0, pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise,
-                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->lw);
-        return GENPF_OK;
+        GENPF_PLUGIN_OR_BUILTIN(Model, slot + 1, (&k_mh<SigModel<Model>, Noise, true>), fn);
+        return launch_typed("k_mh", &k_mh<SigModel<Model>, Noise, true>, fn, grid, dim3(kStateThreads), pf->stream, pf->P, tau, iter,
+                            tau == 1 ? 1 : 0, pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise,
+                            (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->lw, gst, use_proposal);
     }
-    GENPF_LAUNCH((k_mh<Model, Noise>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, pf->P, tau, iter, tau == 1 ? 1 : 0,
-                 pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts, pf->n_accept,
-                 (double *)nullptr, gated ? (const Stats *)pf->sc.st(0, pf->nf) : (const Stats *)nullptr);
-    return GENPF_OK;
+    GENPF_PLUGIN_OR_BUILTIN(Model, slot, (&k_mh<SigModel<Model>, Noise, false>), fn);
+    return launch_typed("k_mh", &k_mh<SigModel<Model>, Noise, false>, fn, grid, dim3(kStateThreads), pf->stream, pf->P, tau, iter,
+                        tau == 1 ? 1 : 0, pf->slice(tau - 1), pf->slice(tau), obs_dev, obs_val, pf->n, tpf, noise, pf->accepts,
+                        pf->n_accept, (double *)nullptr, gst, 0);
 }
 template <class Model>
 static int32_t mh_model(genpf_filter_t pf, int64_t tau, int iter, const double *obs_dev, double obs_val,
-                        const double *U2, const double *Z2, const double *U3, bool reweight, bool gated) {
+                        const double *U2, const double *Z2, const double *U3, bool reweight, bool gated,
+                        int use_proposal = 0) {
     if (U2 || Z2 || U3) {
         NoiseCols nz{U2, Z2, U3, nullptr, nullptr};
-        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated);
+        return launch_mh<Model, NoiseCols>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated, use_proposal);
     }
     // the mh move on slice tau belongs to README iteration s = tau + 1 (it runs right before pf_update!(s))
     if (pf->flags & GENPF_NOISE_PHILOX53) {
         NoisePhilox53 nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
-        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated);
+        return launch_mh<Model, NoisePhilox53>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated, use_proposal);
     }
     NoiseLean nz{pf->seed, (uint64_t)tau + 1, pf->rng_offset};
-    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated);
+    return launch_mh<Model, NoiseLean>(pf, tau, iter, obs_dev, obs_val, nz, reweight, gated, use_proposal);
 }
 
 static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters,
                      const double *U2, const double *Z2, const double *U3, int64_t *n_accept, bool reweight = false,
-                     bool gated = false) {
+                     bool gated = false, int use_proposal = 0) {
     GENPF_TRY(check_filter(pf));
     if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
     if (tau != pf->t_cur) return fail(GENPF_ERR_UNSUPPORTED, "mh rejuvenation is implemented for tau == newest time step");
@@ -201,9 +238,9 @@ static int32_t do_mh(genpf_filter_t pf, int64_t tau, const double *obs, const do
     for (int it = 0; it < n_iters; ++it) {
         int32_t st;
         switch (pf->model) {
-            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated); break;
-            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated); break;
-            default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+            case kModelObjectMotion: st = mh_model<ObjectMotion>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated, use_proposal); break;
+            case kModelLinGauss1D: st = mh_model<LinGauss1D>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated, use_proposal); break;
+            default: st = mh_model<PluginTag>(pf, tau, it, obs_dev, obs_val, dU2, dZ2, dU3, reweight, gated, use_proposal); break;
         }
         GENPF_TRY(st);
     }
@@ -422,28 +459,27 @@ static int32_t launch_step_fused(genpf_filter_t pf, const StepArgs &a, Noise noi
     const int64_t t = a.t;
     const Stats *gst = pf->sc.st(0, pf->nf);
     const double *lw_src = pf->lw;
+    const dim3 grid((unsigned)tpf, (unsigned)pf->nf);
+    const void *fn = nullptr;
+    constexpr int slot = kPlugFused + NoiseIndex<Noise>::value * 3;
+#define GENPF_FUSED_ARGS                                                                                                  \
+    a, (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(), pf->slice(t - 2),         \
+        pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt, pf->n, tpf, noise,             \
+        (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew, gst, gate, lw_src
     if (a.mh_iters == 1) {
-        GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
-                     (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents,
-                     pf->lw_alt, pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr,
-                     pf->sc.partials(0), pf->ew, gst, gate, lw_src);
-        return GENPF_OK;
+        GENPF_PLUGIN_OR_BUILTIN(Model, slot + 0, (&k_step_fused<SigModel<Model>, Noise, int32_t, 1>), fn);
+        return launch_typed("k_step_fused", &k_step_fused<SigModel<Model>, Noise, int32_t, 1>, fn, grid, dim3(kStateThreads),
+                            pf->stream, GENPF_FUSED_ARGS);
     }
     if (a.mh_iters == 0) {
-        GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, 0>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads,
-                     pf->stream, a, (const int32_t *)pf->sc.O.as<int32_t>(),
-                     (const int32_t *)pf->sc.tile_last.as<int32_t>(), pf->slice(t - 2), pf->slice(t - 1),
-                     pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt, pf->n, tpf, noise,
-                     (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew, gst, gate, lw_src);
-        return GENPF_OK;
+        GENPF_PLUGIN_OR_BUILTIN(Model, slot + 1, (&k_step_fused<SigModel<Model>, Noise, int32_t, 0>), fn);
+        return launch_typed("k_step_fused", &k_step_fused<SigModel<Model>, Noise, int32_t, 0>, fn, grid, dim3(kStateThreads),
+                            pf->stream, GENPF_FUSED_ARGS);
     }
-    GENPF_LAUNCH((k_step_fused<Model, Noise, int32_t, -1>), dim3((unsigned)tpf, (unsigned)pf->nf), kStateThreads, pf->stream, a,
-                 (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                 pf->slice(t - 2), pf->slice(t - 1), pf->slice_alt(t - 1), pf->slice_alt(t), pf->parents, pf->lw_alt,
-                 pf->n, tpf, noise, (uint8_t *)nullptr, (unsigned long long *)nullptr, pf->sc.partials(0), pf->ew, gst,
-                 gate, lw_src);
-    return GENPF_OK;
+    GENPF_PLUGIN_OR_BUILTIN(Model, slot + 2, (&k_step_fused<SigModel<Model>, Noise, int32_t, -1>), fn);
+    return launch_typed("k_step_fused", &k_step_fused<SigModel<Model>, Noise, int32_t, -1>, fn, grid, dim3(kStateThreads),
+                        pf->stream, GENPF_FUSED_ARGS);
+#undef GENPF_FUSED_ARGS
 }
 template <class Model>
 static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a, const NoiseCols *cols, int gate) {
@@ -460,7 +496,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
                              const double *obs_t, const double *aux_t, int32_t mh_iters, bool finalized,
                              const double *d_uniforms = nullptr, const NoiseCols *cols = nullptr, int gate = 0,
                              double ess_frac = -1.0) {
-    const ModelInfo &mi = kModels[pf->model];
+    const ModelInfo &mi = *model_info(pf->model);
     const int64_t n = pf->n, nf = pf->nf;
     cudaStream_t s = pf->stream;
     Scratch &sc = pf->sc;
@@ -502,7 +538,7 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
     switch (pf->model) {
         case kModelObjectMotion: st = step_fused_model<ObjectMotion>(pf, a, cols, gate); break;
         case kModelLinGauss1D: st = step_fused_model<LinGauss1D>(pf, a, cols, gate); break;
-        default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
+        default: st = step_fused_model<PluginTag>(pf, a, cols, gate); break;
     }
     GENPF_TRY(st);
     pf->buf ^= 1;
@@ -529,32 +565,37 @@ extern "C" {
 
 int32_t genpf_model_builtin(const char *name, int32_t *model_id) {
     if (!name || !model_id) return fail(GENPF_ERR_INVALID_ARG, "genpf_model_builtin: NULL argument");
-    for (int i = 0; i < kNumModels; ++i)
-        if (strcmp(name, kModels[i].name) == 0) {
-            *model_id = i;
-            return GENPF_OK;
-        }
-    return fail(GENPF_ERR_INVALID_ARG, std::string("unknown built-in model: ") + name);
+    const int32_t id = find_model(name);  // built-in models and plugins registered at run time
+    if (id < 0) return fail(GENPF_ERR_INVALID_ARG, std::string("unknown model: ") + name);
+    *model_id = id;
+    return GENPF_OK;
 }
 
 int32_t genpf_model_info(int32_t model_id, int32_t *n_f64_fields, int32_t *n_u8_fields, int32_t *n_params,
                          int32_t *n_aux) {
-    if (model_id < 0 || model_id >= kNumModels) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
-    if (n_f64_fields) *n_f64_fields = kModels[model_id].nf;
-    if (n_u8_fields) *n_u8_fields = kModels[model_id].nb;
-    if (n_params) *n_params = kModels[model_id].np;
-    if (n_aux) *n_aux = kModels[model_id].naux;
+    const ModelInfo *mi = model_info(model_id);
+    if (!mi) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
+    if (n_f64_fields) *n_f64_fields = mi->nf;
+    if (n_u8_fields) *n_u8_fields = mi->nb;
+    if (n_params) *n_params = mi->np;
+    if (n_aux) *n_aux = mi->naux;
+    return GENPF_OK;
+}
+int32_t genpf_model_caps(int32_t model_id, int32_t *caps) {
+    const ModelInfo *mi = model_info(model_id);
+    if (!mi || !caps) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
+    *caps = mi->caps;
     return GENPF_OK;
 }
 
 int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_params, int64_t n_particles,
                             int64_t n_filters, uint64_t seed, uint32_t flags, genpf_filter_t *out) {
     if (!out) return fail(GENPF_ERR_INVALID_ARG, "out is NULL");
-    if (model_id < 0 || model_id >= kNumModels) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
+    if (!model_info(model_id)) return fail(GENPF_ERR_INVALID_ARG, "unknown model id");
     if (n_particles <= 0 || n_filters <= 0) return fail(GENPF_ERR_INVALID_ARG, "n_particles and n_filters must be > 0");
     if (n_particles >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "n_particles per filter must be < 2^31");
     if (n_filters > 65535) return fail(GENPF_ERR_UNSUPPORTED, "n_filters must be <= 65535 (grid.y)");
-    const ModelInfo &mi = kModels[model_id];
+    const ModelInfo &mi = *model_info(model_id);
     if (params && n_params != mi.np) return fail(GENPF_ERR_INVALID_ARG, "wrong number of model parameters");
     std::unique_ptr<genpf_filter_s> pf(new genpf_filter_s());
     pf->model = model_id;
@@ -571,6 +612,8 @@ int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_pa
         for (int i = 0; i < 4; ++i) pf->P.v[i] = params ? params[i] : def[i];
         pf->P.v[4] = log(pf->P.v[3]);
         pf->P.v[5] = 1.0 / pf->P.v[3];
+    } else if (model_id >= kPluginIdBase) {
+        for (int i = 0; i < mi.np; ++i) pf->P.v[i] = params ? params[i] : 0.0;  // a plugin derives what it needs itself
     } else {
         const double def[5] = {0.9, 1.0, 1.0, 0.0, 1.0};
         for (int i = 0; i < 5; ++i) pf->P.v[i] = params ? params[i] : def[i];
@@ -665,6 +708,24 @@ int32_t genpf_update_with_noise(genpf_filter_t pf, int64_t t, const double *obs,
     return do_propagate(pf, false, t, obs, aux, U, Z);
 }
 
+// pf_initialize(model, args, obs, proposal, proposal_args, n) (initialize.jl:46-62) and
+// pf_update!(state, new_args, argdiffs, obs, proposal, proposal_args) (update.jl:79-96) for plugins that define a
+// proposal: x ~ q(. | prev, obs), log-weight (+)= log p(x | prev) + log p(obs | x) - log q(x).  U, Z: the proposal's
+// draws as columns (parity mode) or both NULL (library Philox noise).
+int32_t genpf_initialize_proposal(genpf_filter_t pf, const double *obs, const double *aux, const double *U, const double *Z) {
+    return do_propagate(pf, true, 1, obs, aux, U, Z, nullptr, kPropProposal);
+}
+int32_t genpf_update_proposal(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
+                              const double *Z) {
+    return do_propagate(pf, false, t, obs, aux, U, Z, nullptr, kPropProposal);
+}
+// pf_update!(state, translator) (update.jl:35-44): the plugin's translate(current slice) returns the new slice and the
+// log-weight increment, log_weights[i] += increment
+int32_t genpf_update_translate(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
+                               const double *Z) {
+    return do_propagate(pf, false, t, obs, aux, U, Z, nullptr, kPropTranslate);
+}
+
 int32_t genpf_ess_dev(genpf_filter_t pf, double *ess) {
     GENPF_TRY(check_filter(pf));
     if (!ess) return fail(GENPF_ERR_INVALID_ARG, "ess is NULL");
@@ -715,6 +776,18 @@ int32_t genpf_rejuvenate_reweight_with_noise(genpf_filter_t pf, int64_t tau, con
     if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
     if (!U2 || !Z2) return fail(GENPF_ERR_INVALID_ARG, "noise columns are NULL");
     return do_mh(pf, tau, obs, aux, 1, U2, Z2, Z2, nullptr, true);
+}
+
+// pf_move_reweight! with move_reweight(trace, proposal, proposal_args) (rejuvenate.jl:74-90,134-148): slice tau is
+// re-proposed from the plugin's proposal and log_weights += up_weight - fwd_weight + bwd_weight.  U2, Z2: the
+// proposal's draws (n_iters must be 1 then) or both NULL.
+int32_t genpf_rejuvenate_reweight_proposal(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
+                                           int32_t n_iters, const double *U2, const double *Z2) {
+    if (!pf) return fail(GENPF_ERR_INVALID_ARG, "filter handle is NULL");
+    if (!(model_info(pf->model)->caps & 1)) return fail(GENPF_ERR_UNSUPPORTED, "this model defines no custom proposal");
+    if ((U2 == nullptr) != (Z2 == nullptr)) return fail(GENPF_ERR_INVALID_ARG, "give both noise columns or neither");
+    if (U2 && n_iters != 1) return fail(GENPF_ERR_INVALID_ARG, "noise columns serve one iteration");
+    return do_mh(pf, tau, obs, aux, n_iters, U2, Z2, U2 ? Z2 : nullptr, nullptr, true, false, 1);
 }
 
 int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,

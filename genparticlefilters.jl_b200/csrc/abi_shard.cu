@@ -9,6 +9,7 @@
 //   genpf_shard_push         offspring of local parents -> owner's buffers over NVLink P2P       [barrier]
 //   genpf_shard_finish       swap buffers, K1 partials of the received population
 #include "filter_state.hpp"
+#include "plugin.hpp"
 
 namespace genpf {
 
@@ -83,7 +84,7 @@ static int32_t make_step_args(genpf_filter_t pf, int64_t t, const double *obs_pr
     if (t != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "the sharded step must advance to t_cur + 1");
     if (!obs_prev || !obs_t) return fail(GENPF_ERR_INVALID_ARG, "obs is NULL");
     if (mh_iters < 0 || mh_iters > 255) return fail(GENPF_ERR_INVALID_ARG, "mh_iters out of range");
-    const ModelInfo &mi = kModels[pf->model];
+    const ModelInfo &mi = *model_info(pf->model);
     if (mi.naux > 0 && (!aux_prev || !aux_t)) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL");
     StepArgs a;
     a.P_prev = pf->P;
@@ -133,6 +134,7 @@ int32_t genpf_shard_attach(genpf_filter_t pf, int32_t rank, int32_t world, const
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
         return fail(GENPF_ERR_INVALID_ARG, "genpf_shard_attach: need 1 <= world <= 8 and 0 <= rank < world");
     if (pf->nf != 1) return fail(GENPF_ERR_UNSUPPORTED, "sharding needs n_filters == 1");
+    if (pf->model >= kPluginIdBase) return fail(GENPF_ERR_UNSUPPORTED, "run-time plugins cannot be sharded yet (no push kernel in the image)");
     if (pf->n % kTile != 0) return fail(GENPF_ERR_INVALID_ARG, "particles per shard must be a multiple of 2048");
     if (pf->flags & GENPF_KEEP_HISTORY) return fail(GENPF_ERR_UNSUPPORTED, "sharding with GENPF_KEEP_HISTORY");
     if ((int64_t)world * pf->n >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "total population must be < 2^31");

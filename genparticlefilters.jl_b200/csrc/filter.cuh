@@ -103,10 +103,15 @@ __device__ __forceinline__ void store_slices(const Cols &c, int64_t base, int64_
 // Stratified initialisation / update (initialize.jl:93-108, update.jl:193-210 with stratified_map!,
 // utils.jl:29-55): K strata constrain one latent of the new slice; each gets floor(n/K) particles in contiguous blocks or interleaved, the n - K*floor(n/K)
 // left-over particles (the last indices) go to strata drawn with replacement; log-weights gain log(K).
+enum { kPropPrior = 0, kPropProposal = 1, kPropTranslate = 2 };
 struct Strata {
     const double *values;  // device, K entries; null: plain pf_initialize
     int K, field, interleaved;
     uint64_t seed, stream;  // Philox stream of the left-over particles' strata
+    // how the new slice is produced: kPropPrior = Gen `generate`/`update` from the model's prior transition;
+    // kPropProposal = custom proposal (initialize.jl:46-62, update.jl:79-96): x ~ q, lw += log p(x|prev) + log p(obs|x)
+    // - log q(x); kPropTranslate = a trace translator (update.jl:35-44): (x, increment) = translate(current slice)
+    int mode;
     __device__ __forceinline__ int stratum(int64_t i, int64_t n) const {
         const int64_t B = n / K;
         if (i < B * K) return (int)(interleaved ? i % K : i / B);
@@ -117,7 +122,7 @@ struct Strata {
 };
 
 template <class Model, class Noise, bool INIT>
-static __global__ void __launch_bounds__(kStateThreads)
+GENPF_KERNEL void __launch_bounds__(kStateThreads)
     k_propagate(ModelParams P, int64_t t, Cols prev, Cols next, double *lw, const double *obs_dev, double obs_val,
                 int64_t n, int64_t tpf, Noise noise, Partials partials, double *ew, Strata strata = Strata{}) {
     constexpr int T = kStateThreads, I = kTile / T;
@@ -144,13 +149,24 @@ static __global__ void __launch_bounds__(kStateThreads)
         double U = 0.5, Z = 0.0;
         if (e < valid) noise.up(base + e, U, Z);
         double l = 0.0;
+        bool weighted = false;  // the translator's increment already contains every weight term
         if (strata.values) {  // stratified initialise / update: one latent constrained, + log p(constraint) + log K
             const double val = strata.values[strata.stratum(e < valid ? start + e : 0, n)];
             l = Model::constrain(P, t, sp[k], sn[k], U, Z, strata.field, val) + log((double)strata.K);
+        } else if (strata.mode == kPropProposal) {
+            if constexpr (has_proposal<Model>::value) {
+                Model::propose(P, t, sp[k], obs, sn[k], U, Z);
+                l = Model::transition_logpdf(P, t, sp[k], sn[k]) - Model::proposal_logpdf(P, t, sp[k], obs, sn[k]);
+            }
+        } else if (strata.mode == kPropTranslate) {
+            if constexpr (has_translate<Model>::value) {
+                l = Model::translate(P, t, sp[k], obs, sn[k], U, Z);
+                weighted = true;
+            }
         } else {
             Model::transition(P, t, sp[k], sn[k], U, Z);
         }
-        l += Model::obs_logpdf(P, sn[k], obs);
+        if (!weighted) l += Model::obs_logpdf(P, sn[k], obs);
         if (e < valid) v[k] = INIT ? l : v[k] + l;
         else v[k] = -INFINITY;
     }
@@ -166,10 +182,10 @@ static __global__ void __launch_bounds__(kStateThreads)
 // REWEIGHT: pf_move_reweight! with move_reweight(trace, selection) (rejuvenate.jl:74-90,125-132): the regenerated
 // slice always replaces the current one and the same weight is added to the particle's log-weight.
 template <class Model, class Noise, bool REWEIGHT = false>
-static __global__ void __launch_bounds__(kStateThreads)
+GENPF_KERNEL void __launch_bounds__(kStateThreads)
     k_mh(ModelParams P, int64_t tau, int iter, int first_step, Cols prevprev, Cols cur, const double *obs_dev,
          double obs_val, int64_t n, int64_t tpf, Noise noise, uint8_t *accepts, unsigned long long *n_accept,
-         double *lw = nullptr, const Stats *gate_stats = nullptr) {
+         double *lw = nullptr, const Stats *gate_stats = nullptr, int use_proposal = 0) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ double sm[T / 32];
     int64_t f, tile;
@@ -196,8 +212,25 @@ static __global__ void __launch_bounds__(kStateThreads)
         double U = 0.5, Z = 0.0, U3 = 1.0;
         if (e < valid) noise.mh(base + e, iter, U, Z, U3);
         typename Model::Slice q;
-        Model::transition(P, tau, sp[k], q, U, Z);
-        double alpha = Model::obs_logpdf(P, q, obs) - Model::obs_logpdf(P, sc[k], obs);
+        double alpha;
+        bool proposed = false;
+        if constexpr (REWEIGHT && has_proposal<Model>::value) {
+            if (use_proposal) {
+                // move_reweight(trace, proposal, proposal_args) (rejuvenate.jl:134-148): rel. weight = up_weight -
+                // fwd_weight + bwd_weight = [p(q|pp) p(obs|q) / Q(q)] / [p(cur|pp) p(obs|cur) / Q(cur)]
+                Model::propose(P, tau, sp[k], obs, q, U, Z);
+                const double wn = Model::transition_logpdf(P, tau, sp[k], q) + Model::obs_logpdf(P, q, obs) -
+                                  Model::proposal_logpdf(P, tau, sp[k], obs, q);
+                const double wo = Model::transition_logpdf(P, tau, sp[k], sc[k]) + Model::obs_logpdf(P, sc[k], obs) -
+                                  Model::proposal_logpdf(P, tau, sp[k], obs, sc[k]);
+                alpha = wn - wo;
+                proposed = true;
+            }
+        }
+        if (!proposed) {
+            Model::transition(P, tau, sp[k], q, U, Z);
+            alpha = Model::obs_logpdf(P, q, obs) - Model::obs_logpdf(P, sc[k], obs);
+        }
         bool a;
         if (REWEIGHT) {
             a = e < valid;
@@ -217,6 +250,7 @@ static __global__ void __launch_bounds__(kStateThreads)
     }
 }
 
+#ifndef GENPF_PLUGIN_BUILD
 // ------------------------------------------------------------------ K8 ancestor gather
 // new_traces .= view(traces, parents) (resample.jl:60,102-104,114,169) over the window's columns.
 // Output centric, coalesced 16-byte stores; reads follow the (monotone for stratified/residual) parents.
@@ -310,5 +344,7 @@ static __global__ void k_write_field(const double *in, double *dcol, uint8_t *bc
         else bcol[j] = in[j] != 0.0 ? 1 : 0;
     }
 }
+
+#endif  // GENPF_PLUGIN_BUILD
 
 }  // namespace genpf

@@ -16,10 +16,13 @@ enum { kModelObjectMotion = 0, kModelLinGauss1D = 1, kNumModels = 2 };
 struct ModelInfo {
     const char *name;
     int nf, nb, np, naux;
+    int caps;  // bit 0: custom proposal (propose / proposal_logpdf / transition_logpdf), bit 1: translate
 };
 static const ModelInfo kModels[kNumModels] __attribute__((unused)) = {
-    {"object_motion", ObjectMotion::NF, ObjectMotion::NB, ObjectMotion::NP, ObjectMotion::NAUX},
-    {"lingauss1d", LinGauss1D::NF, LinGauss1D::NB, LinGauss1D::NP, LinGauss1D::NAUX},
+    {"object_motion", ObjectMotion::NF, ObjectMotion::NB, ObjectMotion::NP, ObjectMotion::NAUX,
+     (has_proposal<ObjectMotion>::value ? 1 : 0) | (has_translate<ObjectMotion>::value ? 2 : 0)},
+    {"lingauss1d", LinGauss1D::NF, LinGauss1D::NB, LinGauss1D::NP, LinGauss1D::NAUX,
+     (has_proposal<LinGauss1D>::value ? 1 : 0) | (has_translate<LinGauss1D>::value ? 2 : 0)},
 };
 
 struct Slab {  // one time slice's columns in one buffer

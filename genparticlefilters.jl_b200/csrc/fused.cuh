@@ -43,7 +43,7 @@ __device__ __forceinline__ void store_pair(X *p, int e, int valid, bool fast, X 
 #define GENPF_FUSED_MINB 4
 #endif
 template <class Model, class Noise, typename IdxT, int MH>
-static __global__ void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_FUSED_MINB : 4)
+GENPF_KERNEL void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_FUSED_MINB : 4)
     k_step_fused(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, Cols dst_cur,
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew,
@@ -152,6 +152,7 @@ static __global__ void __launch_bounds__(kStateThreads, kStateThreads == 512 ? G
     emit_partials<T>(v, partials, ps, -1, ew ? ew + obase : nullptr, valid);
 }
 
+#ifndef GENPF_PLUGIN_BUILD
 // ------------------------------------------------------------------ multi-GPU: source-side push
 // Particle sharding: rank r owns global particle slots [r*n_loc, (r+1)*n_loc).  After the shard-aware scan the
 // local O_k are GLOBAL cumulative offspring counts, so this rank's particles parent the contiguous global
@@ -458,5 +459,7 @@ static __global__ void k_shard_combine(const double *gathered, int world, int ra
 static __global__ void k_shard_oend(const int32_t *tile_last_O, int64_t tpf, long long *oend_local) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *oend_local = (long long)tile_last_O[tpf - 1];
 }
+
+#endif  // GENPF_PLUGIN_BUILD
 
 }  // namespace genpf

@@ -104,6 +104,7 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
     }
 }
 
+#ifndef GENPF_PLUGIN_BUILD  // weight-vector kernels: compiled into the library only
 // ------------------------------------------------------------------ K1/K2 reduce
 // Replaces: Gen.logsumexp, lognorm/softmax (utils.jl:100-107), safe_softmax's validity scan
 // (utils.jl:119-137), effective_sample_size (utils.jl:163-164).  Same block size and epilogue as the
@@ -818,6 +819,7 @@ static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
     }
 }
 
+#endif  // GENPF_PLUGIN_BUILD
 // ------------------------------------------------------------------ searches
 // smallest k in [0, n) with a[k] > t, clamped to n-1 (the reference would throw BoundsError, App. C)
 template <typename T, typename Q>
@@ -961,6 +963,7 @@ __device__ __forceinline__ int64_t block_expand(const IdxT *Of, const IdxT *tile
     return s0;
 }
 
+#ifndef GENPF_PLUGIN_BUILD
 // update_weights! without priorities fused into the kernels that write the ancestors: full state lw .= 0.0
 // (resample.jl:193-195), sub-state lw .= logsumexp(lw) - log(n_v) (resample.jl:208-210)
 struct LwFill {
@@ -1422,5 +1425,7 @@ static __global__ void k_convert_idx(const A *in, B *out, int64_t n, int64_t add
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (B)((int64_t)in[i] + add);
 }
+
+#endif  // GENPF_PLUGIN_BUILD
 
 }  // namespace genpf

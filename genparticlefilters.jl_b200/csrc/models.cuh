@@ -49,6 +49,22 @@ __device__ __forceinline__ bool mh_accept(double U3, double alpha) {
     return mh_accept_slow(U3, alpha);
 }
 
+// ------------------------------------------------------------------ optional members of a plugin (detected, never required)
+//   transition_logpdf(P, t, prev, x)            log p(x_t | x_{t-1})                         -- Gen `assess`/`update` weight
+//   propose(P, t, prev, obs, nxt, U, Z)         x_t ~ q(. | x_{t-1}, obs_t)                  -- Gen `propose` (initialize.jl:55,122; update.jl:85)
+//   proposal_logpdf(P, t, prev, obs, x)         log q(x | x_{t-1}, obs_t)                    -- its score
+//   translate(P, t, cur, obs, nxt, U, Z)        (new slice, log-weight increment)            -- translator(trace) (update.jl:35-44)
+template <class M, class = void>
+struct has_proposal { static constexpr bool value = false; };
+template <class M>
+struct has_proposal<M, decltype((void)&M::proposal_logpdf, (void)&M::propose, (void)&M::transition_logpdf)> {
+    static constexpr bool value = true;
+};
+template <class M, class = void>
+struct has_translate { static constexpr bool value = false; };
+template <class M>
+struct has_translate<M, decltype((void)&M::translate)> { static constexpr bool value = true; };
+
 // README.md:43-54 object_motion.  params: v[0]=p_stay .75, v[1]=p_start .25, v[2]=sigma_proc .01,
 // v[3]=sigma_obs .25, v[4]=log(sigma_obs), v[5]=1/sigma_obs (host filled).  aux[0] = vel_t = sin(t) from the caller.
 struct ObjectMotion {
@@ -86,6 +102,25 @@ struct ObjectMotion {
         nxt.b[0] = m;
         return normal_logpdf(val, mu, 1.0 / p.v[2], log(p.v[2]));
     }
+    // custom proposal (initialize.jl:46-62, update.jl:79-96): the motion flag is proposed from a fair coin instead of
+    // the sticky prior, y from its prior conditional; importance weight = p(m') / 0.5
+    static __device__ __forceinline__ double transition_logpdf(const ModelParams &p, int64_t, const Slice &prev, const Slice &x) {
+        const double pm = prev.b[0] ? p.v[0] : p.v[1];
+        const double mu = __dadd_rn(prev.f[0], x.b[0] ? p.aux[0] : 0.0);
+        return log(x.b[0] ? pm : 1.0 - pm) + normal_logpdf(x.f[0], mu, 1.0 / p.v[2], log(p.v[2]));
+    }
+    static __device__ __forceinline__ void propose(const ModelParams &p, int64_t, const Slice &prev, double, Slice &nxt,
+                                                   double U, double Z) {
+        const uint8_t m = U < 0.5;
+        const double mu = __dadd_rn(prev.f[0], m ? p.aux[0] : 0.0);
+        nxt.f[0] = __dadd_rn(mu, __dmul_rn(p.v[2], Z));
+        nxt.b[0] = m;
+    }
+    static __device__ __forceinline__ double proposal_logpdf(const ModelParams &p, int64_t, const Slice &prev, double,
+                                                             const Slice &x) {
+        const double mu = __dadd_rn(prev.f[0], x.b[0] ? p.aux[0] : 0.0);
+        return log(0.5) + normal_logpdf(x.f[0], mu, 1.0 / p.v[2], log(p.v[2]));
+    }
 };
 
 // 1-D linear-Gaussian tracker: x_0 ~ N(m0, s0) marginalised into the first transition,
@@ -113,6 +148,33 @@ struct LinGauss1D {
         nxt.f[0] = val;
         nxt.b[0] = 0;
         return normal_logpdf(val, __dmul_rn(p.v[0], prev.f[0]), 1.0 / sig, log(sig));
+    }
+    // custom proposal: the locally optimal one, q(x_t | x_{t-1}, y_t) = N(mu*, s*^2) with 1/s*^2 = 1/q^2 + 1/r^2 and
+    // mu* = s*^2 (a x_{t-1} / q^2 + y_t / r^2); the importance weight is then p(y_t | x_{t-1}) for every draw
+    static __device__ __forceinline__ void opt_moments(const ModelParams &p, int64_t t, const Slice &prev, double obs,
+                                                       double &mu, double &sd) {
+        const double sig = (t == 1) ? p.v[6] : p.v[1];
+        const double iq = 1.0 / (sig * sig), ir = 1.0 / (p.v[2] * p.v[2]);
+        const double var = 1.0 / (iq + ir);
+        mu = var * (__dmul_rn(p.v[0], prev.f[0]) * iq + obs * ir);
+        sd = sqrt(var);
+    }
+    static __device__ __forceinline__ double transition_logpdf(const ModelParams &p, int64_t t, const Slice &prev, const Slice &x) {
+        const double sig = (t == 1) ? p.v[6] : p.v[1];
+        return normal_logpdf(x.f[0], __dmul_rn(p.v[0], prev.f[0]), 1.0 / sig, log(sig));
+    }
+    static __device__ __forceinline__ void propose(const ModelParams &p, int64_t t, const Slice &prev, double obs, Slice &nxt,
+                                                   double, double Z) {
+        double mu, sd;
+        opt_moments(p, t, prev, obs, mu, sd);
+        nxt.f[0] = __dadd_rn(mu, __dmul_rn(sd, Z));
+        nxt.b[0] = 0;
+    }
+    static __device__ __forceinline__ double proposal_logpdf(const ModelParams &p, int64_t t, const Slice &prev, double obs,
+                                                             const Slice &x) {
+        double mu, sd;
+        opt_moments(p, t, prev, obs, mu, sd);
+        return normal_logpdf(x.f[0], mu, 1.0 / sd, log(sd));
     }
 };
 

@@ -172,6 +172,27 @@ typedef struct genpf_filter_s *genpf_filter_t;
 int32_t genpf_model_builtin(const char *name, int32_t *model_id);
 int32_t genpf_model_info(int32_t model_id, int32_t *n_f64_fields, int32_t *n_u8_fields, int32_t *n_params,
                          int32_t *n_aux);
+/* optional members of the model: bit 0 custom proposal, bit 1 translator */
+int32_t genpf_model_caps(int32_t model_id, int32_t *caps);
+
+/* ---- models registered at run time (north star "models registered as device plugins"; the reference's
+ * counterpart is handing ANY generative function to pf_initialize, initialize.jl:31-44).  `source` is CUDA C++ that
+ * defines one struct `struct_name` with the plugin interface (csrc/models.cuh; `#include "genpf_plugin.h"` is
+ * implied):  static constexpr int NF, NB, NP, NAUX;  using Slice = genpf::SliceT<NF, NB>;
+ *   initial(P, slice0)   transition(P, t, prev, next, U, Z)   obs_logpdf(P, slice, obs) -> double
+ *   optional: constrain(...) (stratified init/update), propose / proposal_logpdf / transition_logpdf (custom
+ *   proposals), translate (trace translators).
+ * The source is compiled by NVRTC for sm_100a together with the library's own kernel templates, so the plugin
+ * runs the same kernels (k_propagate, k_mh, k_step_fused) as the built-in models; compiling needs no GPU.
+ * genpf_model_builtin(name) finds it afterwards; ids of plugins start at 100.  `options`: extra NVRTC options or NULL.
+ * On a compile error the status is GENPF_ERR_INVALID_ARG and genpf_last_error() holds the compiler log. */
+int32_t genpf_model_compile(const char *name, const char *source, const char *struct_name, const char *options,
+                            int32_t *model_id);
+/* a compiled plugin as one relocatable image (kernel names + sm_100a cubin): size query with buf == NULL */
+int32_t genpf_model_export(int32_t model_id, void *buf, int64_t cap, int64_t *size);
+int32_t genpf_model_load_image(const void *image, int64_t size, int32_t *model_id);
+/* the kernel headers a plugin is compiled against, as embedded in this library (index 0 .. until an error) */
+int32_t genpf_model_plugin_sources(int32_t index, const char **name, const char **text);
 
 /* n_filters independent filters of n_particles each (views / batches, view.jl:16-48).  params may be NULL
  * (README constants). */
@@ -199,6 +220,16 @@ int32_t genpf_update_stratified(genpf_filter_t pf, int64_t t, const double *obs,
 
 /* pf_update!(state, (t,), (UnknownChange(),), obs_t), update.jl:12-25 */
 int32_t genpf_update(genpf_filter_t pf, int64_t t, const double *obs, const double *aux);
+/* Custom proposals (initialize.jl:46-62, update.jl:79-96) for models whose plugin defines propose / proposal_logpdf /
+ * transition_logpdf (genpf_model_caps bit 0): x ~ q(. | prev, obs); log-weight (+)= log p(x|prev) + log p(obs|x)
+ * - log q(x).  U, Z: the proposal's draws as columns (parity mode) or both NULL (library Philox noise). */
+int32_t genpf_initialize_proposal(genpf_filter_t pf, const double *obs, const double *aux, const double *U, const double *Z);
+int32_t genpf_update_proposal(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
+                              const double *Z);
+/* pf_update!(state, translator) (update.jl:35-44) for models whose plugin defines translate (caps bit 1): the
+ * translator maps the current slice to (new slice, log-weight increment); log_weights[i] += increment. */
+int32_t genpf_update_translate(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
+                               const double *Z);
 int32_t genpf_update_with_noise(genpf_filter_t pf, int64_t t, const double *obs, const double *aux, const double *U,
                                 const double *Z);
 
@@ -224,6 +255,12 @@ int32_t genpf_rejuvenate_mh_with_noise(genpf_filter_t pf, int64_t tau, const dou
 int32_t genpf_rejuvenate_reweight(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux, int32_t n_iters);
 int32_t genpf_rejuvenate_reweight_with_noise(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
                                              const double *U2, const double *Z2);
+
+/* pf_move_reweight! with move_reweight(trace, proposal, proposal_args) (rejuvenate.jl:74-90,134-148) for models that
+ * define a proposal: slice tau is re-proposed, log_weights += up_weight - fwd_weight + bwd_weight.  U2/Z2: the
+ * proposal's draws as columns (n_iters == 1) or both NULL. */
+int32_t genpf_rejuvenate_reweight_proposal(genpf_filter_t pf, int64_t tau, const double *obs, const double *aux,
+                                           int32_t n_iters, const double *U2, const double *Z2);
 
 /* One README loop iteration (README.md:66-77) fused on the device:
  *   ess = effective_sample_size(state); if ess < ess_frac*n: pf_resample!(method); pf_rejuvenate!(mh) end;
