@@ -22,6 +22,7 @@ LAYOUT_CONTIGUOUS, LAYOUT_INTERLEAVED = 0, 1
 KEEPFIRST, SAMPLE = 0, 1
 PRIO_NONE, PRIO_SCALE, PRIO_COLUMN = 0, 1, 2
 NOISE_LEAN, NOISE_PHILOX53, KEEP_HISTORY = 0, 1, 2
+RUN_GRAPH = 1
 
 METHODS = {"multinomial": MULTINOMIAL, "residual": RESIDUAL, "stratified": STRATIFIED}
 # the exact @warn texts of safe_softmax, utils.jl:120,124,132,135
@@ -88,6 +89,7 @@ SIGNATURES = {
     "genpf_rejuvenate_reweight": (i32, [_vp, i64, _vp, _vp, i32]),
     "genpf_rejuvenate_reweight_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     "genpf_step": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, f64, i32, _vp]),
+    "genpf_run_steps": (i32, [_vp, i64, i64, _vp, _vp, i32, f64, i32, u32]),
     "genpf_step_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, f64, i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "genpf_mean_var": (i32, [_vp, i32, i64, _vp, _vp]),
     "genpf_replicate": (i32, [_vp, i64, i32]),

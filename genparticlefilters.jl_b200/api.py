@@ -867,3 +867,19 @@ def pf_step_with_noise(state, t, obs_prev, obs_t, *, method="stratified", ess_th
                                            float(ess_thresh), int(mh_iters), *[L.ptr(c) for c in cols]))
     state.t = int(t)
     return state
+
+
+def pf_run(state, t_first, observations, *, method="stratified", ess_thresh=0.5, mh_iters=1, graph=False):
+    """The README loop (README.md:66-77) for steps t_first .. t_first + T - 1 in one asynchronous C-ABI call
+    (genpf_run_steps): `observations` has T + 1 rows, row 0 being the observation of step t_first - 1.  graph=True
+    replays steps 2.. as one CUDA graph.  Nothing is copied back; read ESS / fields afterwards."""
+    m = state.model
+    obs = _f64(np.asarray(observations, dtype=np.float64).reshape(-1, state.n_filters))
+    T = obs.shape[0] - 1
+    aux = None
+    if m.n_aux:
+        aux = _f64(np.concatenate([m.aux(t_first - 1 + r) for r in range(T + 1)]))
+    L.check(L.load().genpf_run_steps(state._h, int(t_first), T, L.ptr(obs), L.ptr(aux), L.METHODS[method],
+                                     float(ess_thresh), int(mh_iters), L.RUN_GRAPH if graph else 0))
+    state.t = int(t_first) + T - 1
+    return state

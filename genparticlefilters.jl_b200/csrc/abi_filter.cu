@@ -495,7 +495,7 @@ static int32_t step_fused_model(genpf_filter_t pf, const StepArgs &a, const Nois
 static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_prev, const double *aux_prev,
                              const double *obs_t, const double *aux_t, int32_t mh_iters, bool finalized,
                              const double *d_uniforms = nullptr, const NoiseCols *cols = nullptr, int gate = 0,
-                             double ess_frac = -1.0) {
+                             double ess_frac = -1.0, const double *d_obs_prev = nullptr, const double *d_obs_t = nullptr) {
     const ModelInfo &mi = *model_info(pf->model);
     const int64_t n = pf->n, nf = pf->nf;
     cudaStream_t s = pf->stream;
@@ -515,6 +515,10 @@ static int32_t do_step_fused(genpf_filter_t pf, int64_t t, const double *obs_pre
         a.obs_prev_dev = a.obs_t_dev = nullptr;
         a.obs_prev = obs_prev[0];
         a.obs_t = obs_t[0];
+    } else if (d_obs_prev && d_obs_t) {  // rows already staged on the device (genpf_run_steps)
+        a.obs_prev_dev = d_obs_prev;
+        a.obs_t_dev = d_obs_t;
+        a.obs_prev = a.obs_t = 0.0;
     } else {
         GENPF_TRY(pf->step_obs.ensure((size_t)nf * 16));
         double *d = pf->step_obs.as<double>();
@@ -650,6 +654,8 @@ int32_t genpf_filter_destroy(genpf_filter_t pf) {
     pf->cb.release();
     pf->ob.release();
     if (pf->h_opt_ctrl) cudaFreeHost(pf->h_opt_ctrl);
+    if (pf->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)pf->graph_exec);
+    pf->run_obs.release();
     pf->key_buf.release();
     for (DevBuf *b : {&pf->noise_buf[0], &pf->noise_buf[1], &pf->noise_buf[2], &pf->noise_buf[3], &pf->noise_buf[4], &pf->step_obs, &pf->strata_buf, &pf->uni_buf, &pf->tmp_col, &pf->tmp_idx, &pf->prio_buf})
         b->release();
@@ -802,6 +808,11 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
     bool any = false, every = true, finalized = false;
     if (ess_frac >= 1.0 && !ess_out) {
         any = true;
+    } else if (!ess_out && fusable) {
+        // asynchronous adaptive step: every filter decides ON THE DEVICE (ess < ess_frac * n, README.md:68); the
+        // finalize sets the per-filter flag that gates the scan and the fused kernel -- no host round trip
+        GENPF_TRY(pf->sc.O.ensure(4));
+        return do_step_fused(pf, t, obs_prev, aux_prev, obs_t, aux_t, mh_iters, false, nullptr, nullptr, 1, ess_frac);
     } else {
         // one finalize serves the decision, the scan's tile offsets and (if taken) update_lml_est!
         GENPF_TRY(pf->sc.O.ensure(4));
@@ -826,6 +837,66 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
         GENPF_TRY(do_mh(pf, t - 1, obs_prev, aux_prev, mh_iters, nullptr, nullptr, nullptr, nullptr, false, gate != 0));
     }
     return do_propagate(pf, false, t, obs_t, aux_t, nullptr, nullptr);
+}
+
+// T README iterations enqueued by ONE call ("T = 1000 is a host loop ... CUDA Graph the step"): nothing is
+// copied back and nothing synchronises; with GENPF_RUN_GRAPH steps 2..T are captured into a CUDA graph and launched
+// as one unit, which removes the per-kernel launch cost that dominates small filters (config 1: n = 100).
+int32_t genpf_run_steps(genpf_filter_t pf, int64_t t_first, int64_t n_steps, const double *obs, const double *aux,
+                        int32_t method, double ess_frac, int32_t mh_iters, uint32_t flags) {
+    GENPF_TRY(check_filter(pf));
+    if (pf->t_cur < 1) return fail(GENPF_ERR_STATE, "filter is not initialised");
+    if (t_first != pf->t_cur + 1) return fail(GENPF_ERR_INVALID_ARG, "genpf_run_steps must start at t_cur + 1");
+    if (n_steps < 1 || !obs) return fail(GENPF_ERR_INVALID_ARG, "genpf_run_steps: need n_steps >= 1 and observations");
+    if (method != GENPF_STRATIFIED || mh_iters < 0 || mh_iters > 255)
+        return fail(GENPF_ERR_UNSUPPORTED, "genpf_run_steps runs the fused stratified step (use genpf_step for the other methods)");
+    const ModelInfo &mi = *model_info(pf->model);
+    if (mi.naux > 0 && !aux) return fail(GENPF_ERR_INVALID_ARG, "aux is NULL");
+    const int64_t nf = pf->nf;
+    // row r of obs / aux belongs to time t_first - 1 + r: row 0 is the step the first mh move revisits
+    const double *d_rows = nullptr;
+    if (nf > 1) {
+        GENPF_TRY(pf->run_obs.ensure((size_t)((n_steps + 1) * nf) * 8));
+        GENPF_CUDA_TRY(cudaMemcpyAsync(pf->run_obs.p, obs, (size_t)((n_steps + 1) * nf) * 8, cudaMemcpyHostToDevice, pf->stream));
+        d_rows = pf->run_obs.as<double>();
+    }
+    const int gate = ess_frac < 1.0 ? 1 : 0;
+    auto one = [&](int64_t r) -> int32_t {
+        const double *ap = aux ? aux + (r - 1) * mi.naux : nullptr, *at = aux ? aux + r * mi.naux : nullptr;
+        return do_step_fused(pf, t_first + r - 1, obs + (r - 1) * nf, ap, obs + r * nf, at, mh_iters, false, nullptr, nullptr,
+                             gate, gate ? ess_frac : -1.0, d_rows ? d_rows + (r - 1) * nf : nullptr,
+                             d_rows ? d_rows + r * nf : nullptr);
+    };
+    GENPF_TRY(pf->sc.O.ensure(4));
+    const bool graph = (flags & GENPF_RUN_GRAPH) && n_steps > 1;
+    if (graph && (pf->flags & GENPF_KEEP_HISTORY)) return fail(GENPF_ERR_UNSUPPORTED, "graph capture with GENPF_KEEP_HISTORY");
+    GENPF_TRY(one(1));  // eager: sizes every scratch buffer, so the captured steps allocate nothing
+    if (!graph) {
+        for (int64_t r = 2; r <= n_steps; ++r) GENPF_TRY(one(r));
+        return GENPF_OK;
+    }
+    if (pf->graph_exec) {  // the previous run's graph: its launch has been ordered before us on the stream
+        GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
+        cudaGraphExecDestroy((cudaGraphExec_t)pf->graph_exec);
+        pf->graph_exec = nullptr;
+    }
+    GENPF_CUDA_TRY(cudaStreamBeginCapture(pf->stream, cudaStreamCaptureModeThreadLocal));
+    int32_t st = GENPF_OK;
+    for (int64_t r = 2; r <= n_steps && st == GENPF_OK; ++r) st = one(r);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(pf->stream, &g);
+    if (st != GENPF_OK) {
+        if (g) cudaGraphDestroy(g);
+        return st;
+    }
+    GENPF_CUDA_TRY(e);
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    GENPF_CUDA_TRY(e);
+    pf->graph_exec = ex;
+    GENPF_CUDA_TRY(cudaGraphLaunch(ex, pf->stream));
+    return GENPF_OK;
 }
 
 // One README iteration in parity mode: the resample is taken (forced), every random draw is supplied

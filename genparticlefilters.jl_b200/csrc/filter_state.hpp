@@ -76,7 +76,8 @@ struct genpf_filter_s {
     double *lml = nullptr;
     double *obs_dev = nullptr;
     double *noise_cols[3] = {nullptr, nullptr, nullptr};
-    DevBuf noise_buf[5], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf, strata_buf, step_obs;
+    DevBuf noise_buf[5], uni_buf, tmp_col, tmp_idx, prio_buf, key_buf, strata_buf, step_obs, run_obs;
+    void *graph_exec = nullptr;  // cudaGraphExec_t of the last genpf_run_steps(GENPF_RUN_GRAPH)
     CoalesceBufs cb;
     OptimalBufs ob;
     void *h_opt_ctrl = nullptr;  // pinned OptCtrl, allocated on first optimal resize

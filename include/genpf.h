@@ -270,6 +270,15 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
                    const double *obs_t, const double *aux_t, int32_t method, double ess_frac, int32_t mh_iters,
                    double *ess_out);
 
+/* n_steps README iterations (stratified resample + mh + update, the fused kernels of genpf_step) enqueued by one
+ * call: asynchronous, nothing copied back; ess_frac < 1: every filter decides on the device at every step.
+ * obs: (n_steps + 1) * n_filters doubles, row r belongs to time t_first - 1 + r (row 0 = the step the first mh move
+ * revisits); aux likewise with n_aux columns.  flags & GENPF_RUN_GRAPH: steps 2.. are captured into a CUDA graph and
+ * launched as one unit (SURVEY 5 "CUDA Graph the step": removes the launch latency that dominates small filters). */
+#define GENPF_RUN_GRAPH 1u
+int32_t genpf_run_steps(genpf_filter_t pf, int64_t t_first, int64_t n_steps, const double *obs, const double *aux,
+                        int32_t method, double ess_frac, int32_t mh_iters, uint32_t flags);
+
 /* The same iteration in parity mode (noise exported from the reference's RNG): the resample is taken
  * and EVERY random draw is an input column of n_particles*n_filters doubles indexed by output particle --
  * `uniforms` = the rand() of each stratum (resample.jl:162) / inverse-CDF draw (NULL: library Philox draws),
