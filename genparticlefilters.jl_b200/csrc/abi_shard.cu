@@ -23,7 +23,10 @@ struct ShardCtx {
     const long long *oend_all = nullptr;
     double *shard_info = nullptr;
     XchgPeers xp;                   // peer-mapped exchange blocks (xp.x[rank] is mine)
-    long long *oend_p2p = nullptr;  // oend_all for the p2p protocol (local copy filled by k_xchg_oend)
+    long long *oend_p2p = nullptr;  // oend_all for the p2p protocol (derived on every rank by the statistics combine)
+    unsigned long long epoch = 0;   // exchange epoch: grows by one per sharded step, never reset (re-initialising the
+                                    // filter resets n_resamples, and stale flags must not satisfy a wait)
+    XchgLink link(unsigned long long e) const { return XchgLink{xp, world, rank, e}; }
     std::vector<void *> opened;
 };
 
@@ -59,11 +62,13 @@ static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, N
     if (a.mh_iters == 1) {
         GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, 1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise);
+                     pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise,
+                     (const Stats *)pf->sc.st(0, 1));
     } else {
         GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, -1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
-                     pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise);
+                     pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise,
+                     (const Stats *)pf->sc.st(0, 1));
     }
     return GENPF_OK;
 }
@@ -116,10 +121,11 @@ int32_t genpf_shard_ipc_export(genpf_filter_t pf, void *handles, int64_t *n_bufs
     if (!pf->shard_xchg) {
         Xchg *x = nullptr;
         GENPF_TRY(pf->dalloc(&x, 1));
-        GENPF_CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(Xchg), pf->stream));
-        GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
         pf->shard_xchg = x;
     }
+    // every (re-)attach starts from a zeroed block on every rank: the group's epochs restart at 1 together
+    GENPF_CUDA_TRY(cudaMemsetAsync(pf->shard_xchg, 0, sizeof(Xchg), pf->stream));
+    GENPF_CUDA_TRY(cudaStreamSynchronize(pf->stream));
     std::vector<void *> bufs;
     list_bufs(pf, bufs);
     cudaIpcMemHandle_t *h = reinterpret_cast<cudaIpcMemHandle_t *>(handles);
@@ -278,23 +284,38 @@ static int32_t shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pr
     const int64_t n = pf->n, tpf = ceil_div(n, kTile);
     Scratch &sc = pf->sc;
     cudaStream_t s = pf->stream;
-    const unsigned long long epoch = (unsigned long long)pf->n_resamples + 1;
+    // No host synchronisation and TWO cross-GPU synchronisation points per step (statistics, done):
+    //   finalize (16 chunk blocks) -> k_chunk_combine: local totals, POST stats, wait, population statistics and
+    //               EVERY shard's closing offspring count (derived identically on every rank: no second exchange)
+    //   k_scan_hot: shard-aware offspring counts pinned to the agreed closing counts
+    //   k_step_push: offspring to their owners (NVLink P2P stores)
+    //   k_reduce_boundary: POST "my offspring have left" (stream order behind the push), wait for every producer's
+    //               flag, reduce the tiles two producers shared
+    const unsigned long long epoch = ++sh->epoch;
+    const XchgLink lk = sh->link(epoch);
     GENPF_TRY(sc.O.ensure((size_t)n * 4));
     GENPF_TRY(sc.tile_last.ensure((size_t)tpf * 4));
     // 1. local statistics (locally normalised tile offsets), post + gather + combine
-    GENPF_TRY(ensure_stats(pf, sc.tile_off.as<double>(), -1.0, nullptr));
-    GENPF_LAUNCH(k_xchg_stats_combine, 1, 32, s, (const Stats *)sc.st(0, 1), sh->xp, sh->world, sh->rank, epoch,
-                 sh->n_total, sc.st(0, 1), sh->shard_info, pf->lml);
-    // 2. shard-aware scan, closing counts exchanged
-    UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, epoch), 0};
+    if (!pf->part_valid) {
+        LwSrc src0{pf->lw, 1.0};
+        GENPF_TRY(launch_reduce(s, src0, n, 1, sc.partials(0), pf->ew));
+        pf->part_valid = true;
+    }
+    // the stratum uniforms of this resample: the combine derives every shard's closing count from them
+    UniSrc uni{d_uniforms, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), 0};
     StratArgs strat = make_strat(uni, sh->n_total);
+    bool exchanged = false;
+    GENPF_TRY(launch_finalize(s, sc, sc.partials(0), n, 1, sc.st(0, 1), sc.tile_off.as<double>(), -1.0, nullptr, &lk,
+                              sh->n_total, sh->shard_info, &exchanged, pf->lml, &strat, sh->oend_p2p));
+    if (!exchanged)  // small shard: one finalize block wrote the local Stats
+        GENPF_LAUNCH(k_xchg_stats_combine, 1, 32, s, (const Stats *)sc.st(0, 1), lk, sh->n_total, sc.st(0, 1), sh->shard_info,
+                     pf->lml, strat, sh->oend_p2p);
+    // 2. shard-aware scan, counts pinned to the agreed closing counts (no second exchange)
     LwSrc lw_src{pf->lw, 1.0};
     GENPF_TRY(launch_scan_counts<int32_t>(s, lw_src, n, tpf, 1, sc.st(0, 1), sc.tile_off.as<double>(), sc.O.as<int32_t>(),
                                           sc.tile_last.as<int32_t>(), strat, 0, sh->shard_info, (int64_t)sh->rank * n,
-                                          sc.chunk_info_ptr(n), pf->ew, sc.tile_scale.as<double>()));
-    GENPF_LAUNCH(k_xchg_oend, 1, 32, s, (const int32_t *)sc.tile_last.as<int32_t>(), tpf, sh->xp, sh->world, sh->rank,
-                 epoch, sh->oend_p2p);
-    // 3. offspring to their owners over NVLink, then the barrier
+                                          sc.chunk_info_ptr(n), pf->ew, sc.tile_scale.as<double>(), sh->oend_p2p, sh->rank));
+    // 3. offspring to their owners over NVLink
     int32_t st;
     switch (pf->model) {
         case kModelObjectMotion: st = push_model<ObjectMotion>(pf, sh, a, sh->oend_p2p, cols); break;
@@ -302,15 +323,14 @@ static int32_t shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pr
         default: return fail(GENPF_ERR_INVALID_ARG, "unknown model");
     }
     GENPF_TRY(st);
-    GENPF_LAUNCH(k_xchg_done, 1, 32, s, sh->xp, sh->world, sh->rank, epoch);
-    // 4. swap, K1 partials of the tiles two producers shared
+    // 4. swap; the closing barrier + K1 partials of the tiles two producers shared
     pf->t_cur = t;
     pf->buf ^= 1;
     std::swap(pf->lw, pf->lw_alt);
     pf->n_resamples += 1;
     LwSrc src{pf->lw, 1.0};
     GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, s, src, (const long long *)sh->oend_p2p,
-                 sh->world, sh->rank, n, sc.partials(0), pf->ew);
+                 sh->world, sh->rank, n, sc.partials(0), pf->ew, lk);
     pf->part_valid = true;
     return GENPF_OK;
 }
@@ -372,7 +392,7 @@ int32_t genpf_shard_finish(genpf_filter_t pf) {
     ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
     LwSrc src{pf->lw, 1.0};
     GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, pf->stream, src, sh->oend_all, sh->world,
-                 sh->rank, pf->n, pf->sc.partials(0), pf->ew);
+                 sh->rank, pf->n, pf->sc.partials(0), pf->ew, XchgLink{{}, 0, 0, 0});
     pf->part_valid = true;
     return GENPF_OK;
 }
@@ -381,8 +401,13 @@ int32_t genpf_shard_finish(genpf_filter_t pf) {
 int32_t genpf_shard_stats(genpf_filter_t pf, double *ess, double *lml_est, int32_t *invalid_kind) {
     GENPF_TRY(check_filter(pf));
     if (!pf->shard) return fail(GENPF_ERR_STATE, "filter is not attached to a shard group");
+    ShardCtx *sh = reinterpret_cast<ShardCtx *>(pf->shard);
     GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned, pf->lml, 8, cudaMemcpyDeviceToHost, pf->stream));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->h_pinned + 1, &sh->xp.x[sh->rank]->error, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
     GENPF_TRY(read_stats(pf, 0));
+    // a wait that ran into its bound (a lost or hung peer) left stale statistics / closing counts / payload behind
+    if (*reinterpret_cast<int *>(pf->h_pinned + 1) != 0)
+        return fail(GENPF_ERR_STATE, "peer exchange timed out: a rank of the shard group did not post (population is invalid)");
     if (ess) *ess = pf->h_stats[0].ess;
     if (lml_est) *lml_est = pf->h_pinned[0];  // log_ml_est accumulated by the resamples so far
     if (invalid_kind) *invalid_kind = pf->h_stats[0].invalid_kind;

@@ -58,6 +58,42 @@ struct Stats {
     int32_t do_resample;  // device-side predicate of the fused README step (ess < ess_frac * n)
 };
 
+// ------------------------------------------------------------------ peer-memory exchange (replaces NCCL)
+// The three per-step exchanges move 24, 8 and 0 bytes per rank: NCCL's launch + protocol latency (tens of
+// microseconds each at 8 ranks) dwarfs the payload.  Every rank instead owns an Xchg block that all peers
+// have mapped (CUDA IPC); a rank posts its value into slot [rank] of EVERY peer's block with plain NVLink
+// stores, fences, then stores the step's epoch into the matching flag; readers spin on their local flags.
+// Epochs only grow, so nothing is ever reset.  A bounded spin (about 20 s) turns a lost peer into an error
+// code instead of a hang.
+constexpr int kMaxPeers = 8;
+struct Xchg {
+    double stats[kMaxPeers][3];
+    long long oend[kMaxPeers];
+    unsigned long long flag_stats[kMaxPeers], flag_oend[kMaxPeers], flag_done[kMaxPeers];
+    int error;
+};
+struct XchgPeers {
+    Xchg *x[kMaxPeers];
+};
+__device__ __forceinline__ void xchg_wait(volatile unsigned long long *flag, unsigned long long epoch, int *error) {
+    const long long t0 = clock64();
+    while (*flag < epoch) {
+        if (clock64() - t0 > 40000000000ll) {  // ~20 s at 2 GHz
+            *error = 1;
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+// what a kernel needs to take part in an exchange; world == 0: the filter is not sharded (or exchanges through NCCL)
+struct XchgLink {
+    XchgPeers peers;
+    int world, rank;
+    unsigned long long epoch;  // monotone per shard group (never reset by re-initialisation)
+};
+
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {

@@ -54,9 +54,15 @@ inline int32_t launch_reduce(cudaStream_t s, LwSrc src, int64_t n, int64_t nf, P
     GENPF_LAUNCH(k_reduce, dim3((unsigned)tpf, (unsigned)nf), kReduceThreads, s, src, n, tpf, part, ew);
     return GENPF_OK;
 }
+// link / n_total / shard_info (a shard of a multi-GPU population): the large-filter path's combine kernel also runs the
+// statistics exchange (returns true through *exchanged); small shards exchange with a kernel of their own
 inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64_t n, int64_t nf, Stats *st,
-                               double *tile_off, double ess_frac, double *lml_accum) {
+                               double *tile_off, double ess_frac, double *lml_accum,
+                               const XchgLink *link = nullptr, int64_t n_total = 0, double *shard_info = nullptr,
+                               bool *exchanged = nullptr, double *xchg_lml = nullptr, const StratArgs *strat = nullptr,
+                               long long *oend_out = nullptr) {
     const int64_t tpf = ceil_div(n, kTile);
+    if (exchanged) *exchanged = false;
     if (tpf <= 64) {
         GENPF_LAUNCH((k_finalize_fast<64, 1>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf,
                      sc.tile_scale.as<double>());
@@ -72,8 +78,11 @@ inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64
         GENPF_LAUNCH((k_finalize_fast<512, 1>), dim3((unsigned)nchunks, (unsigned)nf), 512, s, part, n, tpf,
                      sc.chunk_stats.as<Stats>(), tile_off, -1.0, (double *)nullptr, Scratch::kChunkTiles,
                      sc.tile_scale.as<double>());
+        const XchgLink lk = link ? *link : XchgLink{{}, 0, 0, 0};
         GENPF_LAUNCH(k_chunk_combine, (unsigned)nf, 32, s, (const Stats *)sc.chunk_stats.as<Stats>(), (int)nchunks, n,
-                     Scratch::kChunkTiles * (int64_t)kTile, st, sc.chunk_info.as<double>(), ess_frac, lml_accum);
+                     Scratch::kChunkTiles * (int64_t)kTile, st, sc.chunk_info.as<double>(), ess_frac,
+                     lk.world > 0 ? xchg_lml : lml_accum, lk, n_total, shard_info, strat ? *strat : StratArgs{}, oend_out);
+        if (exchanged) *exchanged = lk.world > 0;
     }
     return GENPF_OK;
 }
@@ -95,20 +104,21 @@ template <typename IdxT>
 inline int32_t launch_scan_counts(cudaStream_t s, LwSrc sel, int64_t n, int64_t tpf, int64_t nf, const Stats *st,
                                   const double *tile_off, IdxT *O, IdxT *tile_last, const StratArgs &strat, int gate,
                                   const double *shard_info, int64_t global_base, const double *chunk_info,
-                                  const double *ew, const double *tile_scale) {
+                                  const double *ew, const double *tile_scale, const long long *oend_pin = nullptr,
+                                  int shard_rank = 0) {
     const dim3 grid((unsigned)tpf, (unsigned)nf);
     if (!strat.uni.col && !strat.guide && strat.pow2) {
         if (ew) {
             GENPF_LAUNCH((k_scan_hot<IdxT, true>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
-                         shard_info, global_base, chunk_info, ew, tile_scale);
+                         shard_info, global_base, chunk_info, ew, tile_scale, oend_pin, shard_rank);
         } else {
             GENPF_LAUNCH((k_scan_hot<IdxT, false>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
-                         shard_info, global_base, chunk_info, ew, tile_scale);
+                         shard_info, global_base, chunk_info, ew, tile_scale, oend_pin, shard_rank);
         }
         return GENPF_OK;
     }
     GENPF_LAUNCH((k_scan<IdxT>), grid, kScanThreads, s, sel, n, tpf, st, tile_off, WTables{nullptr}, O, tile_last, strat, gate,
-                 shard_info, global_base, chunk_info, Scratch::kChunkTiles, ew, tile_scale);
+                 shard_info, global_base, chunk_info, Scratch::kChunkTiles, ew, tile_scale, oend_pin, shard_rank);
     return GENPF_OK;
 }
 
@@ -163,7 +173,7 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
     } else if (method == GENPF_MULTINOMIAL) {
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
-        GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * sizeof(IdxT)));
+        GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * (sizeof(IdxT) == 4 ? sizeof(GuideRec) : sizeof(IdxT))));
         WTables wt{sc.W.as<double>()};
         StratArgs gs = make_strat(uni, n_in);
         gs.guide = B;  // O = guide-table counts of the weight CDF
@@ -171,16 +181,23 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
         GENPF_LAUNCH((k_scan<IdxT>), dim3((unsigned)tpf_in, (unsigned)nf), kScanThreads, s, sel, n_in, tpf_in, st_sel, tile_off,
                      wt, O, tile_last, gs, gate, (const double *)nullptr, (int64_t)0,
                      sc.chunk_info_ptr(n_in), Scratch::kChunkTiles);
-        GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, O, tile_last, n_in, B, tpf_b,
-                     (const int32_t *)nullptr, G, (int64_t)0, st_sel, gate, 0);
-        GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
-                     kThreads, s, (const double *)wt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)nullptr, parents,
-                     out_base, st_sel, gate, fill);
+        const dim3 lgrid((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf);
+        if constexpr (sizeof(IdxT) == 4) {  // one 32-byte record per bucket: a draw is one sector
+            GENPF_LAUNCH(k_guide_records, dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, (const int32_t *)O,
+                         (const int32_t *)tile_last, (const double *)wt.W, n_in, B, tpf_b, sc.guide.as<GuideRec>(), st_sel, gate);
+            GENPF_LAUNCH((k_lookup_rec<OutT>), lgrid, kThreads, s, (const double *)wt.W, (const GuideRec *)sc.guide.as<GuideRec>(),
+                         B, n_in, n_out, uni, (const int32_t *)nullptr, parents, out_base, st_sel, gate, fill);
+        } else {
+            GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, O, tile_last, n_in, B, tpf_b,
+                         (const int32_t *)nullptr, G, (int64_t)0, st_sel, gate, 0);
+            GENPF_LAUNCH((k_lookup<IdxT, OutT>), lgrid, kThreads, s, (const double *)wt.W, (const IdxT *)G, B, n_in, n_out, uni,
+                         (const IdxT *)nullptr, parents, out_base, st_sel, gate, fill);
+        }
     } else if (method == GENPF_RESIDUAL) {
         const size_t np = (size_t)(tpf_in * nf);
         GENPF_TRY(sc.W.ensure((size_t)(n_in * nf) * 8));
         const int64_t B = guide_buckets(n_in), tpf_b = ceil_div(B, kTile);
-        GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * sizeof(IdxT)));
+        GENPF_TRY(sc.guide.ensure((size_t)(B * nf) * (sizeof(IdxT) == 4 ? sizeof(GuideRec) : sizeof(IdxT))));
         GENPF_TRY(sc.guide_O.ensure((size_t)(n_in * nf) * sizeof(IdxT)));
         GENPF_TRY(sc.guide_tile_last.ensure((size_t)(tpf_in * nf) * sizeof(IdxT)));
         WTables rt{sc.W.as<double>()};
@@ -199,11 +216,18 @@ int32_t select_ancestors_t(cudaStream_t s, Scratch &sc, int method, LwSrc sel, i
                      tile_last, rt, GO, GTL, B);
         GENPF_LAUNCH((k_expand<IdxT, OutT>), dim3((unsigned)tpf_out, (unsigned)nf), kThreads, s, O, tile_last, n_in, n_out, tpf_out,
                      (const int32_t *)nullptr, parents, out_base, st_sel, gate, 1, fill);
-        GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, GO, GTL, n_in, B, tpf_b,
-                     (const int32_t *)nullptr, G, (int64_t)0, st_sel, 0, 0);
-        GENPF_LAUNCH((k_lookup<IdxT, OutT>), dim3((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf),
-                     kThreads, s, (const double *)rt.W, (const IdxT *)G, B, n_in, n_out, uni, (const IdxT *)O, parents,
-                     out_base, st_sel, gate, fill);
+        const dim3 lgrid((unsigned)ceil_div(n_out, (int64_t)kThreads * kLookupItems), (unsigned)nf);
+        if constexpr (sizeof(IdxT) == 4) {
+            GENPF_LAUNCH(k_guide_records, dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, (const int32_t *)GO,
+                         (const int32_t *)GTL, (const double *)rt.W, n_in, B, tpf_b, sc.guide.as<GuideRec>(), st_sel, 0);
+            GENPF_LAUNCH((k_lookup_rec<OutT>), lgrid, kThreads, s, (const double *)rt.W, (const GuideRec *)sc.guide.as<GuideRec>(),
+                         B, n_in, n_out, uni, (const int32_t *)O, parents, out_base, st_sel, gate, fill);
+        } else {
+            GENPF_LAUNCH((k_expand<IdxT, IdxT>), dim3((unsigned)tpf_b, (unsigned)nf), kThreads, s, GO, GTL, n_in, B, tpf_b,
+                         (const int32_t *)nullptr, G, (int64_t)0, st_sel, 0, 0);
+            GENPF_LAUNCH((k_lookup<IdxT, OutT>), lgrid, kThreads, s, (const double *)rt.W, (const IdxT *)G, B, n_in, n_out, uni,
+                         (const IdxT *)O, parents, out_base, st_sel, gate, fill);
+        }
     } else {
         return fail(GENPF_ERR_UNKNOWN_METHOD, "Resampling method not recognized.");
     }

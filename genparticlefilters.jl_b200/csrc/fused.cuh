@@ -161,7 +161,6 @@ GENPF_KERNEL void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_
 // independent of the number of GPUs) and stores them straight into the OWNER's buffers through peer-mapped
 // pointers (NVLink P2P stores; n_loc is a multiple of the 2048 tile so a tile never straddles two owners).
 // No all-to-all, no staging: stores are fire-and-forget, the ranks meet at one stream-ordered barrier after.
-constexpr int kMaxPeers = 8;
 struct PeerDst {
     Cols dst_cur[kMaxPeers], dst_new[kMaxPeers];
     double *lw[kMaxPeers];
@@ -181,10 +180,15 @@ __device__ __forceinline__ void shard_range(const long long *oend_all, int world
 template <class Model, class Noise, typename IdxT, int MH>
 static __global__ void __launch_bounds__(kStateThreads, 4)
     k_step_push(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, PeerDst peer,
-                const long long *oend_all, int world, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise) {
+                const long long *oend_all, int world, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise,
+                const Stats *stats = nullptr) {
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
+    if (stats) {  // invalid weights (NaN / +Inf): nothing is resampled, the population stays as it is
+        const int kind = stats[0].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+    }
     long long out_begin, out_end;
     shard_range(oend_all, world, rank, (long long)world * n_loc, out_begin, out_end);
     // grid ~ one block per local tile (+2): balanced shards do one tile per block, a shard that parents more
@@ -271,127 +275,32 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
     }
 }
 
-// ------------------------------------------------------------------ peer-memory exchange (replaces NCCL)
-// The three per-step exchanges move 24, 8 and 0 bytes per rank: NCCL's launch + protocol latency (tens of
-// microseconds each at 8 ranks) dwarfs the payload.  Every rank instead owns an Xchg block that all peers
-// have mapped (CUDA IPC); a rank posts its value into slot [rank] of EVERY peer's block with plain NVLink
-// stores, fences, then stores the step's epoch into the matching flag; readers spin on their local flags.
-// Epochs only grow, so nothing is ever reset.  A bounded spin (about 20 s) turns a lost peer into an error
-// code instead of a hang.
-struct Xchg {
-    double stats[kMaxPeers][3];
-    long long oend[kMaxPeers];
-    unsigned long long flag_stats[kMaxPeers], flag_oend[kMaxPeers], flag_done[kMaxPeers];
-    int error;
-};
-struct XchgPeers {
-    Xchg *x[kMaxPeers];
-};
-__device__ __forceinline__ void xchg_wait(volatile unsigned long long *flag, unsigned long long epoch, int *error) {
-    const long long t0 = clock64();
-    while (*flag < epoch) {
-        if (clock64() - t0 > 40000000000ll) {  // ~20 s at 2 GHz
-            *error = 1;
-            break;
-        }
-        __nanosleep(100);
-    }
-    __threadfence_system();
-}
-
-// post the local (M, S, S2), wait for everybody's, combine (k_shard_combine's arithmetic)
-static __global__ void k_xchg_stats_combine(const Stats *local, XchgPeers peers, int world, int rank,
-                                            unsigned long long epoch, int64_t n_total, Stats *stats,
-                                            double *shard_info, double *lml_accum) {
-    const int g = threadIdx.x;
-    Xchg *mine = peers.x[rank];
-    if (g < world) {
-        Xchg *dst = peers.x[g];
-        dst->stats[rank][0] = local->M;
-        dst->stats[rank][1] = local->S;
-        dst->stats[rank][2] = local->S2;
-        __threadfence_system();
-        *(volatile unsigned long long *)&dst->flag_stats[rank] = epoch;
-        xchg_wait(&mine->flag_stats[g], epoch, &mine->error);
-    }
-    __syncthreads();
-    if (g != 0) return;
-    const volatile double *gathered = &mine->stats[0][0];
-    double M = -INFINITY;
-    bool nan = false;
-    for (int r = 0; r < world; ++r) {
-        double m = gathered[3 * r];
-        if (isnan(m) || isnan(gathered[3 * r + 1])) nan = true;
-        M = fmax(M, m);
-    }
-    double S = 0.0, S2 = 0.0, prefix = 0.0, share_mine = 0.0;
-    const bool finite = M > -INFINITY && M < INFINITY;
-    for (int r = 0; r < world; ++r) {
-        double m = gathered[3 * r];
-        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
-        S += gathered[3 * r + 1] * sc;
-        S2 += gathered[3 * r + 2] * (sc * sc);
-    }
-    for (int r = 0; r < world; ++r) {
-        double m = gathered[3 * r];
-        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
-        double share = gathered[3 * r + 1] * sc / S;
-        if (r < rank) prefix += share;
-        if (r == rank) share_mine = share;
-    }
-    int kind = 0;
-    if (nan) kind = 1;
-    else if (M == -INFINITY) kind = 2;
-    else if (M == INFINITY || isnan(S)) kind = 4;
-    else if (S == 0.0) kind = 3;
-    Stats st;
-    st.M = M; st.S = S; st.S2 = S2;
-    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
-    st.ess = S * S / S2;
-    st.invalid_kind = kind;
-    st.do_resample = (kind == 1 || kind == 4) ? 0 : 1;
-    stats[0] = st;
-    if (kind == 2 || kind == 3) {
-        prefix = (double)rank / (double)world;
-        share_mine = 1.0 / (double)world;
-    }
-    shard_info[0] = prefix;
-    shard_info[1] = share_mine;
-    if (lml_accum && st.do_resample) lml_accum[0] += st.lse - log((double)n_total);
-}
-
-// post the shard's closing offspring count, wait for everybody's; oend_out[world] is what k_step_push reads
-static __global__ void k_xchg_oend(const int32_t *tile_last_O, int64_t tpf, XchgPeers peers, int world, int rank,
-                                   unsigned long long epoch, long long *oend_out) {
-    const int g = threadIdx.x;
-    Xchg *mine = peers.x[rank];
-    if (g < world) {
-        Xchg *dst = peers.x[g];
-        dst->oend[rank] = (long long)tile_last_O[tpf - 1];
-        __threadfence_system();
-        *(volatile unsigned long long *)&dst->flag_oend[rank] = epoch;
-        xchg_wait(&mine->flag_oend[g], epoch, &mine->error);
-        oend_out[g] = *(volatile long long *)&mine->oend[g];
-    }
-}
-
-// barrier after the push kernel (stream order makes its P2P stores precede this kernel's flag stores)
-static __global__ void k_xchg_done(XchgPeers peers, int world, int rank, unsigned long long epoch) {
-    const int g = threadIdx.x;
-    Xchg *mine = peers.x[rank];
-    if (g < world) {
-        __threadfence_system();
-        *(volatile unsigned long long *)&peers.x[g]->flag_done[rank] = epoch;
-        xchg_wait(&mine->flag_done[g], epoch, &mine->error);
-    }
+// small shards (one finalize block, no k_chunk_combine to ride on): the statistics exchange as a kernel of its own
+static __global__ void k_xchg_stats_combine(const Stats *local, XchgLink link, int64_t n_total, Stats *stats,
+                                            double *shard_info, double *lml_accum, StratArgs strat, long long *oend_out) {
+    const int kind = local->invalid_kind;
+    xchg_stats_combine(link, local->M, (kind == 1 || kind == 4) ? NAN : local->S, local->S2, n_total, stats, shard_info,
+                       lml_accum, &strat, oend_out);
 }
 
 // owner side: K1 partials of the tiles that two producers shared (global tile index = a range boundary)
 static __global__ void __launch_bounds__(kReduceThreads)
     k_reduce_boundary(LwSrc src, const long long *oend_all, int world, int rank, int64_t n_loc, Partials out,
-                      double *ew) {
+                      double *ew, XchgLink link) {
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
+    // The step's closing barrier, taken by the first reader of the pushed population.  Stream order puts the push
+    // kernel's P2P stores before this kernel, so block 0 first tells every peer "my offspring have left"; every
+    // block then waits for all producers' flags.  Everything later on this stream (the next finalize reads the
+    // pushed K1 partials) is ordered behind this kernel.
+    if (link.world > 0 && (int)threadIdx.x < link.world) {
+        Xchg *mine = link.peers.x[link.rank];
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            *(volatile unsigned long long *)&link.peers.x[threadIdx.x]->flag_done[link.rank] = link.epoch;
+        }
+        xchg_wait(&mine->flag_done[threadIdx.x], link.epoch, &mine->error);
+    }
     __syncthreads();
     long long b, e;
     shard_range(oend_all, world, (int)blockIdx.x, (long long)world * n_loc, b, e);

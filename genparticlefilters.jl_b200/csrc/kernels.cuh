@@ -270,79 +270,6 @@ static __global__ void __launch_bounds__(THREADS)
     }
 }
 
-// Large filters (more than kChunkTiles tiles): combine the per-chunk statistics into the filter's, and give every
-// chunk its {prefix, scale} (exclusive normalised mass before the chunk, the chunk's share).  One warp per filter;
-// lane l owns chunks l, l+32, ...; sums use fixed shuffle trees, the prefix is an ordered warp scan with a carry.
-static __global__ void __launch_bounds__(32)
-    k_chunk_combine(const Stats *chunk_stats, int nchunks, int64_t n, int64_t chunk_particles, Stats *stats,
-                    double *chunk_info, double ess_frac, double *lml_accum) {
-    const int64_t f = blockIdx.x;
-    const int lane = threadIdx.x;
-    const Stats *cs = chunk_stats + f * nchunks;
-    double M = -INFINITY;
-    int bits = 0;  // 1: NaN input somewhere, 2: NaN total somewhere, 4: some chunk is not all -Inf
-    for (int c = lane; c < nchunks; c += 32) {
-        M = fmax(M, cs[c].M);
-        const int k = cs[c].invalid_kind;
-        bits |= (k == 1 ? 1 : 0) | (k == 4 ? 2 : 0) | (k != 2 ? 4 : 0);
-    }
-    M = warp_max(M);
-    bits = __reduce_or_sync(0xffffffffu, (unsigned)bits);
-    const bool finite = M > -INFINITY && M < INFINITY;
-    double S = 0.0, S2 = 0.0;
-    for (int c = lane; c < nchunks; c += 32) {
-        const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
-        S += cs[c].S * sc;
-        S2 += cs[c].S2 * (sc * sc);
-    }
-    S = warp_sum(S);
-    S2 = warp_sum(S2);
-    int kind = 0;
-    if (bits & 1) kind = 1;
-    else if (!(bits & 4)) kind = 2;
-    else if ((bits & 2) || isnan(S)) kind = 4;
-    else if (S == 0.0) kind = 3;
-    double carry = 0.0;
-    for (int c0 = 0; c0 < nchunks; c0 += 32) {
-        const int c = c0 + lane;
-        double share = 0.0;
-        if (c < nchunks) {
-            if (kind == 2 || kind == 3) {
-                const int64_t cnt = min(chunk_particles, n - (int64_t)c * chunk_particles);
-                share = (double)cnt / (double)n;
-            } else {
-                const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
-                share = cs[c].S * sc / S;
-            }
-        }
-        double inc = share;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        double ex = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) ex = 0.0;
-        if (c < nchunks) {
-            chunk_info[2 * (f * nchunks + c)] = carry + ex;
-            chunk_info[2 * (f * nchunks + c) + 1] = share;
-        }
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane != 0) return;
-    Stats st;
-    st.M = M; st.S = S; st.S2 = S2;
-    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
-    st.ess = S * S / S2;
-    st.invalid_kind = kind;
-    int do_rs = 1;
-    if (ess_frac >= 0.0) do_rs = (st.ess < ess_frac * (double)n) ? 1 : 0;
-    if (kind == 1 || kind == 4) do_rs = 0;
-    st.do_resample = do_rs;
-    stats[f] = st;
-    if (lml_accum && do_rs) lml_accum[f] += st.lse - log((double)n);
-}
-
 // ------------------------------------------------------------------ stratified thresholds
 // u_i = r_i*(1/n) + lower_i with two roundings and no FMA (resample.jl:162); lower_i = element i of
 // 0.0:1/n:1.0-1/n, i.e. (i-1)/n (exact for power-of-two n).
@@ -484,6 +411,167 @@ static __device__ __noinline__ J strat_count_outline(const StratArgs &a, int64_t
     return strat_count<J>(a, slot0, W, StrataWindow{words, win_base, win_len});
 }
 
+// ------------------------------------------------------------------ multi-GPU statistics exchange
+// Post this shard's (M, S, S2) into every peer's exchange block, wait for everybody's, derive the population's
+// statistics and this shard's {prefix, share} of the normalised mass.  Called by ONE warp: lane g serves peer g,
+// lane 0 writes the results.  The posting rides on the kernel that produced the local statistics (k_chunk_combine),
+// so the exchange costs no launch of its own.
+// Closing offspring counts without an exchange: every rank derives ALL shards' cumulative mass W_end(g) = prefix(g+1)
+// from the same gathered totals with the same arithmetic, so O_end(g) = C(W_end(g)) (the exact stratified count; the
+// stratum uniforms are counter-based) is identical on every rank.  The scan then pins its shard to [O_end(rank-1),
+// O_end(rank)] (clamp + closing particle), which makes the ranks' output ranges an exact cover by construction; the
+// pinned value differs from the scan's own last count only when W_end computed by the two summation orders
+// straddles a stratum threshold -- inside the documented fp64 cumulative-sum tie class.
+__device__ __forceinline__ void xchg_stats_combine(const XchgLink &lk, double M_loc, double S_loc, double S2_loc,
+                                                   int64_t n_total, Stats *stats, double *shard_info, double *lml_accum,
+                                                   const StratArgs *strat = nullptr, long long *oend_out = nullptr) {
+    const int g = threadIdx.x & 31;
+    const int world = lk.world, rank = lk.rank;
+    Xchg *mine = lk.peers.x[rank];
+    if (g < world) {
+        Xchg *dst = lk.peers.x[g];
+        dst->stats[rank][0] = M_loc;
+        dst->stats[rank][1] = S_loc;
+        dst->stats[rank][2] = S2_loc;
+        __threadfence_system();
+        *(volatile unsigned long long *)&dst->flag_stats[rank] = lk.epoch;
+        xchg_wait(&mine->flag_stats[g], lk.epoch, &mine->error);
+    }
+    __syncwarp();
+    if (g != 0) return;
+    const volatile double *gathered = &mine->stats[0][0];
+    double M = -INFINITY;
+    bool nan = false;
+    for (int r = 0; r < world; ++r) {
+        double m = gathered[3 * r];
+        if (isnan(m) || isnan(gathered[3 * r + 1])) nan = true;
+        M = fmax(M, m);
+    }
+    double S = 0.0, S2 = 0.0, prefix = 0.0, share_mine = 0.0;
+    const bool finite = M > -INFINITY && M < INFINITY;
+    for (int r = 0; r < world; ++r) {
+        double m = gathered[3 * r];
+        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
+        S += gathered[3 * r + 1] * sc;
+        S2 += gathered[3 * r + 2] * (sc * sc);
+    }
+    int kind = 0;
+    if (nan) kind = 1;
+    else if (M == -INFINITY) kind = 2;
+    else if (M == INFINITY || isnan(S)) kind = 4;
+    else if (S == 0.0) kind = 3;
+    double run = 0.0;  // prefix(r): the same left-to-right sum on every rank
+    for (int r = 0; r < world; ++r) {
+        double m = gathered[3 * r];
+        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
+        double share = gathered[3 * r + 1] * sc / S;
+        if (kind == 2 || kind == 3) share = 1.0 / (double)world;  // uniform fallback (utils.jl:123-133)
+        if (r == rank) {
+            prefix = run;
+            share_mine = share;
+        }
+        run = (kind == 2 || kind == 3) ? (double)(r + 1) / (double)world : run + share;
+        if (oend_out) {
+            long long c;
+            if (r == world - 1 || kind == 1 || kind == 4) c = (n_total / world) * (long long)(r + 1);
+            else if (strat->n < 0x7FFFFFFFll) c = (long long)strat_count_slow<int32_t>(*strat, 0, run, nullptr, -1, 0);
+            else c = strat_count_slow<long long>(*strat, 0, run, nullptr, -1, 0);
+            oend_out[r] = c;
+        }
+    }
+    Stats st;
+    st.M = M; st.S = S; st.S2 = S2;
+    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    st.ess = S * S / S2;
+    st.invalid_kind = kind;
+    st.do_resample = (kind == 1 || kind == 4) ? 0 : 1;
+    stats[0] = st;
+    if (kind == 2 || kind == 3) prefix = (double)rank / (double)world;
+    shard_info[0] = prefix;
+    shard_info[1] = share_mine;
+    if (lml_accum && st.do_resample) lml_accum[0] += st.lse - log((double)n_total);
+}
+// Large filters (more than kChunkTiles tiles): combine the per-chunk statistics into the filter's, and give every
+// chunk its {prefix, scale} (exclusive normalised mass before the chunk, the chunk's share).  One warp per filter;
+// lane l owns chunks l, l+32, ...; sums use fixed shuffle trees, the prefix is an ordered warp scan with a carry.
+static __global__ void __launch_bounds__(32)
+    k_chunk_combine(const Stats *chunk_stats, int nchunks, int64_t n, int64_t chunk_particles, Stats *stats,
+                    double *chunk_info, double ess_frac, double *lml_accum, XchgLink link = XchgLink{{}, 0, 0, 0},
+                    int64_t n_total = 0, double *shard_info = nullptr, StratArgs strat = StratArgs{},
+                    long long *oend_out = nullptr) {
+    const int64_t f = blockIdx.x;
+    const int lane = threadIdx.x;
+    const Stats *cs = chunk_stats + f * nchunks;
+    double M = -INFINITY;
+    int bits = 0;  // 1: NaN input somewhere, 2: NaN total somewhere, 4: some chunk is not all -Inf
+    for (int c = lane; c < nchunks; c += 32) {
+        M = fmax(M, cs[c].M);
+        const int k = cs[c].invalid_kind;
+        bits |= (k == 1 ? 1 : 0) | (k == 4 ? 2 : 0) | (k != 2 ? 4 : 0);
+    }
+    M = warp_max(M);
+    bits = __reduce_or_sync(0xffffffffu, (unsigned)bits);
+    const bool finite = M > -INFINITY && M < INFINITY;
+    double S = 0.0, S2 = 0.0;
+    for (int c = lane; c < nchunks; c += 32) {
+        const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
+        S += cs[c].S * sc;
+        S2 += cs[c].S2 * (sc * sc);
+    }
+    S = warp_sum(S);
+    S2 = warp_sum(S2);
+    int kind = 0;
+    if (bits & 1) kind = 1;
+    else if (!(bits & 4)) kind = 2;
+    else if ((bits & 2) || isnan(S)) kind = 4;
+    else if (S == 0.0) kind = 3;
+    double carry = 0.0;
+    for (int c0 = 0; c0 < nchunks; c0 += 32) {
+        const int c = c0 + lane;
+        double share = 0.0;
+        if (c < nchunks) {
+            if (kind == 2 || kind == 3) {
+                const int64_t cnt = min(chunk_particles, n - (int64_t)c * chunk_particles);
+                share = (double)cnt / (double)n;
+            } else {
+                const double sc = (finite && cs[c].M > -INFINITY) ? exp(cs[c].M - M) : 0.0;
+                share = cs[c].S * sc / S;
+            }
+        }
+        double inc = share;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0.0;
+        if (c < nchunks) {
+            chunk_info[2 * (f * nchunks + c)] = carry + ex;
+            chunk_info[2 * (f * nchunks + c) + 1] = share;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (link.world > 0) {  // a shard of a multi-GPU population: the local totals go straight into the exchange
+        // NaN inputs only set a flag locally (fmax semantics): a NaN total carries the diagnosis to every rank
+        xchg_stats_combine(link, M, (kind == 1 || kind == 4) ? NAN : S, S2, n_total, stats, shard_info, lml_accum, &strat,
+                           oend_out);
+        return;
+    }
+    if (lane != 0) return;
+    Stats st;
+    st.M = M; st.S = S; st.S2 = S2;
+    st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
+    st.ess = S * S / S2;
+    st.invalid_kind = kind;
+    int do_rs = 1;
+    if (ess_frac >= 0.0) do_rs = (st.ess < ess_frac * (double)n) ? 1 : 0;
+    if (kind == 1 || kind == 4) do_rs = 0;
+    st.do_resample = do_rs;
+    stats[f] = st;
+    if (lml_accum && do_rs) lml_accum[f] += st.lse - log((double)n);
+}
+
 // ------------------------------------------------------------------ K3 normalise + scan
 // Replaces safe_softmax line utils.jl:139 and the running accum_weight of resample.jl:163-166.
 // Writes W (normalised inclusive cumulative weights) and/or O (cumulative offspring counts, stratified).
@@ -502,7 +590,8 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     k_scan(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, WTables wt, IdxT *O_out,
            IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info = nullptr,
            int64_t global_base = 0, const double *chunk_info = nullptr, int64_t chunk_tiles = 0,
-           const double *ew = nullptr, const double *tile_scale = nullptr) {
+           const double *ew = nullptr, const double *tile_scale = nullptr, const long long *oend_pin = nullptr,
+           int shard_rank = 0) {
     // ew / tile_scale (device filters): e_i = exp(lw_i - m_tile) stored by the kernel that produced lw and the
     // per-tile factor exp(m_tile - M)/S from the finalize: w_i = e_i * factor, no exp in this kernel.
     // shard_info (multi-GPU particle sharding): {prefix, scale}: this shard's cumulative weights are
@@ -625,6 +714,10 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
             else O[k] = strat_count<IdxT>(strat, slot0, W[k], win);
             // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
             if (global_base + start + e == strat.n - 1) O[k] = (IdxT)(strat.guide ? strat.guide : strat.n);
+            if (oend_pin && e < valid) {  // a shard's counts are pinned between the agreed closing counts
+                const IdxT lo_pin = shard_rank > 0 ? (IdxT)oend_pin[shard_rank - 1] : (IdxT)0, hi_pin = (IdxT)oend_pin[shard_rank];
+                O[k] = start + e == n - 1 ? hi_pin : min(max(O[k], lo_pin), hi_pin);
+            }
             if (tile_last_O && e == valid - 1) tile_last_O[f * tpf + tile] = O[k];
         }
         IdxT *po = O_out + f * n + start;
@@ -660,7 +753,10 @@ template <typename IdxT, bool USE_E, int T = kHotThreads>
 static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
     k_scan_hot(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, IdxT *O_out,
                IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info, int64_t global_base,
-               const double *chunk_info, const double *ew, const double *tile_scale) {
+               const double *chunk_info, const double *ew, const double *tile_scale,
+               const long long *oend_pin = nullptr, int shard_rank = 0) {
+    // oend_pin (multi-GPU particle sharding): the closing counts of all shards as every rank derived them from the
+    // exchanged totals (xchg_stats_combine); this shard's counts are pinned to [oend_pin[rank-1], oend_pin[rank]]
     constexpr int I = kTile / T, NW = T / 32;
     __shared__ double sm[NW + 1];
     __shared__ alignas(16) uint32_t swin[kHotWindow];
@@ -798,12 +894,21 @@ static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
         for (int k = 0; k < I; ++k)
             if (e0 + k >= valid) O[k] = (IdxT)0;
     }
-    // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C)
-    const bool closes = (global_base + start + valid == strat.n);
+    // the last particle closes the cumulative count at n (the reference's clamp at order[n], App. C); a shard's
+    // counts are pinned between the closing counts every rank agreed on
+    bool closes = (global_base + start + valid == strat.n);
+    IdxT close_at = nI;
+    if (oend_pin) {
+        const IdxT lo_pin = shard_rank > 0 ? (IdxT)oend_pin[shard_rank - 1] : (IdxT)0;
+        close_at = (IdxT)oend_pin[shard_rank];
+#pragma unroll
+        for (int k = 0; k < I; ++k) O[k] = min(max(O[k], lo_pin), close_at);
+        closes = (start + valid == n);
+    }
 #pragma unroll
     for (int k = 0; k < I; ++k) {
         if (e0 + k == valid - 1) {
-            if (closes) O[k] = nI;
+            if (closes) O[k] = close_at;
             tile_last_O[f * tpf + tile] = O[k];
         }
     }
@@ -1102,6 +1207,140 @@ static __global__ void __launch_bounds__(kThreads)
         }
         if (exact[k] && !below_known)
             while (kk > 0 && __ldg(Wf + kk - 1) > u[k]) --kk;
+        const int64_t j = j0 + k * kThreads + threadIdx.x;
+        parents[f * n_out + j] = (OutT)(kk + out_base);
+        if (fill.out) fill.out[f * n_out + j] = fill.value(f, n_src);
+    }
+}
+
+// ------------------------------------------------------------------ K5, one sector per draw
+// The inverse-CDF draws are a random gather over a table far larger than L2 (512 MB of W at 2^26), so a draw costs
+// what its scattered 32-byte sectors cost.  The guide table is therefore stored as one 32-BYTE RECORD per bucket,
+//   {g = G[b], span = G[b+1] - G[b], W[g], W[g+1], W[g+2]},
+// written by the pass that builds G (its reads of W are monotone, hence streaming): a lookup is ONE sector with no
+// dependent second load; only a draw with three or more cumulative weights of its bucket below it (rare: with
+// B = n/2 buckets a bucket holds two on average, and heavy particles span many buckets) continues in W itself,
+// by bisection inside [g+3, g+span].  Same answers as k_lookup: min{k : W_k > u} clamped to n_src-1.
+struct alignas(32) GuideRec {
+    int32_t g, span;  // span < 0: the next bucket's start is unknown (last bucket of a build tile)
+    double w[3];      // +Inf beyond n_src-1
+};
+static __global__ void __launch_bounds__(kThreads)
+    k_guide_records(const int32_t *O, const int32_t *tile_last_O, const double *W, int64_t n_src, int64_t B,
+                    int64_t tpf_b, GuideRec *rec, const Stats *stats, int gate) {
+    __shared__ ExpandSmem<int32_t> sm;
+    const int64_t f = blockIdx.y, tile = blockIdx.x;
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+        if (gate && !stats[f].do_resample) return;
+    }
+    const int64_t tpf_src = (n_src + kTile - 1) / kTile;
+    const int64_t i0 = tile * kTile;
+    const int valid = (int)min((int64_t)kTile, B - i0);
+    int32_t rel[kItems];
+    const int64_t s0 = block_expand<int32_t>(O + f * n_src, tile_last_O + f * tpf_src, n_src, tpf_src, i0, valid, sm, rel);
+    // span = the next bucket's start - g: the even slot's neighbour is the thread's own odd slot, the odd slot's is
+    // the next lane's even slot (unknown, -1, for lane 31: one bucket in 64 bisects up to n_src-1 instead)
+    const double *Wf = W + f * n_src;
+    GuideRec *out = rec + f * B + i0;
+    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+    int32_t nxt[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; k += 2) {
+        nxt[k] = rel[k + 1];
+        nxt[k + 1] = __shfl_down_sync(0xffffffffu, rel[k], 1);
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        const int e = tile_elem(k);
+        if (e >= valid) continue;
+        const int64_t g = s0 + rel[k];
+        int32_t span = -1;
+        if (e + 1 < valid && ((k & 1) == 0 || lane < 31)) span = nxt[k] - rel[k];
+        GuideRec r;
+        r.g = (int32_t)g;
+        r.span = span;
+        r.w[0] = __ldg(Wf + g);
+        r.w[1] = g + 1 < n_src ? __ldg(Wf + g + 1) : kInf;
+        r.w[2] = g + 2 < n_src ? __ldg(Wf + g + 2) : kInf;
+        int4 *q = reinterpret_cast<int4 *>(out + e);
+        q[0] = make_int4(r.g, r.span, __double2loint(r.w[0]), __double2hiint(r.w[0]));
+        q[1] = make_int4(__double2loint(r.w[1]), __double2hiint(r.w[1]), __double2loint(r.w[2]), __double2hiint(r.w[2]));
+    }
+}
+
+template <typename OutT>
+static __global__ void __launch_bounds__(kThreads)
+    k_lookup_rec(const double *W, const GuideRec *R, int64_t B, int64_t n_src, int64_t n_out, UniSrc uni,
+                 const int32_t *first_slot_O, OutT *parents, int64_t out_base, const Stats *stats, int gate,
+                 LwFill fill = LwFill{nullptr, nullptr, 0}) {
+    constexpr int K = kLookupItems;
+    const int64_t f = blockIdx.y;
+    if (stats) {
+        const int kind = stats[f].invalid_kind;
+        if (kind == 1 || kind == 4) return;
+        if (gate && !stats[f].do_resample) return;
+    }
+    const double *Wf = W + f * n_src;
+    const int4 *Rf = reinterpret_cast<const int4 *>(R + f * B);
+    const int64_t first = first_slot_O ? (int64_t)first_slot_O[f * n_src + n_src - 1] : 0;
+    const int64_t j0 = (int64_t)blockIdx.x * (kThreads * K);
+    if (j0 + kThreads * K <= first) return;  // residual: a block of deterministic copies only
+    const double nd = (double)B;
+    double u[K];
+    int64_t bk[K];
+    bool live[K], exact[K];
+    int4 qa[K], qb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t j = j0 + k * kThreads + threadIdx.x;
+        live[k] = j < n_out && j >= first;
+        u[k] = live[k] ? uni(f * n_out + j) : 0.0;
+        const double x = u[k] * nd;
+        const int64_t b = x >= nd ? B - 1 : (x <= 0.0 ? 0 : (int64_t)x);
+        exact[k] = !(x > (double)b && x < nd);  // n*u rounded onto the bucket boundary (or was clamped)
+        bk[k] = b;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        qa[k] = __ldg(Rf + 2 * bk[k]);
+        qb[k] = __ldg(Rf + 2 * bk[k] + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (!live[k]) continue;
+        const int64_t g = qa[k].x;
+        const double w0 = __hiloint2double(qa[k].w, qa[k].z), w1 = __hiloint2double(qb[k].y, qb[k].x),
+                     w2 = __hiloint2double(qb[k].w, qb[k].z);
+        const double uk = u[k];
+        int64_t kk;
+        bool below_known = true;  // W[kk-1] <= u established by the comparisons themselves
+        if (w0 > uk) {
+            kk = g;
+            below_known = false;
+        } else if (w1 > uk) {
+            kk = g + 1;
+        } else if (w2 > uk) {
+            kk = g + 2;
+        } else {
+            int64_t a = min(g + 3, n_src - 1), c = qa[k].y >= 0 ? min(g + (int64_t)qa[k].y, n_src - 1) : n_src - 1;
+            if (c < a) c = a;
+            while (a < c) {
+                const int64_t mid = a + ((c - a) >> 1);
+                if (__ldg(Wf + mid) > uk) c = mid; else a = mid + 1;
+            }
+            kk = a;
+            double w = __ldg(Wf + kk);
+            while (w <= uk && kk < n_src - 1) {  // the table only has to be monotone: the answer is checked against W
+                ++kk;
+                w = __ldg(Wf + kk);
+            }
+        }
+        if (kk > n_src - 1) kk = n_src - 1;
+        if (exact[k] && !below_known)
+            while (kk > 0 && __ldg(Wf + kk - 1) > uk) --kk;
         const int64_t j = j0 + k * kThreads + threadIdx.x;
         parents[f * n_out + j] = (OutT)(kk + out_base);
         if (fill.out) fill.out[f * n_out + j] = fill.value(f, n_src);

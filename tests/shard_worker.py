@@ -132,7 +132,9 @@ def noise_mode(g, ShardedFilter, dist, torch, model, rank, world, n_local, obs):
             assert np.array_equal(yt, st["y"]) and np.array_equal(mt, st["m"]) and np.array_equal(ym, st["y_pp"])
             np.testing.assert_allclose(lw, st["lw"], rtol=1e-10, atol=1e-12)
             print(f"[shard_worker] noise t={t} tie_ancestors={n_tie} cross_shard_fraction={frac:.5f}", flush=True)
-    assert ties <= 4
+    # validated cumulative-sum ties (tests/util.py::check_parents): the literal oracle's sequential sum drifts by a random
+    # walk against the tiled sums, same allowance as tests/test_gpu_step_parity.py at >= 2^22 particles
+    assert ties <= (4 if n < (1 << 22) else int(1e-4 * n * 3)), ties
     if rank == 0:
         print("[shard_worker] OK", flush=True)
     dist.barrier()

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--max-log2", type=int, default=26)
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--dists", default="ABC", help="subset of A (N(0,1)), B (N(0,25)), C (equal)")
     args = ap.parse_args()
     import torch
 
@@ -55,7 +56,11 @@ def main():
         n = 1 << lg
         gen = torch.Generator(device="cuda").manual_seed(0)
         base = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
-        for dist_name, lw in (("A:N(0,1)", base), ("B:N(0,25)", base * 5.0), ("C:equal", torch.zeros_like(base))):
+        for dist_name, mk in (("A:N(0,1)", lambda: base), ("B:N(0,25)", lambda: base * 5.0),
+                              ("C:equal", lambda: torch.zeros_like(base))):
+            if dist_name[0] not in args.dists:
+                continue
+            lw = mk()
             parents = torch.empty(n, dtype=torch.int64, device="cuda")
             lw_out = torch.empty(n, dtype=torch.float64, device="cuda")
             inc, kind, ess = C.c_double(), C.c_int32(), C.c_double()
