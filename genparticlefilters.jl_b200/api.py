@@ -219,8 +219,12 @@ class DevicePFState:
 
     @property
     def log_ml_est(self):
-        return log_ml_estimate(self) - (logsumexp_host(self.log_weights) - math.log(len(self))) \
-            if self.n_filters == 1 else None
+        """The accumulated field (update_lml_est!, resample.jl:178-182), without the current weights' term; one value
+        per filter for a batch."""
+        t, r = C.c_int64(), C.c_int64()
+        acc = np.empty(self.n_filters)
+        L.check(L.load().genpf_filter_get_progress(self._h, C.byref(t), C.byref(r), L.ptr(acc)))
+        return float(acc[0]) if self.n_filters == 1 else acc
 
     def field(self, name_or_idx, t=None):
         f = self.model.fields[name_or_idx] if isinstance(name_or_idx, str) else name_or_idx
@@ -654,8 +658,19 @@ def pf_introduce(state, model, model_args, observations, n_particles, *, proposa
     accumulated log_ml_est is folded into the existing weights first (resize.jl:362-365); `model` / `model_args`
     None reuse those of the first trace (trace.model, trace.args).  With a proposal (callable returning
     (choices, log_q)) the new weight is model_weight - log_q (resize.jl:410-413)."""
-    if isinstance(state, (ParticleFilterSubState, DevicePFState)):
-        raise TypeError("pf_introduce! takes a full host ParticleFilterState")
+    if isinstance(state, DevicePFState):
+        # device plugins: `observations` is the history [y_1, ..., y_t] (each a scalar or one value per filter); every
+        # new trace is a whole chain generated under it (genpf_introduce); proposal=True uses the plugin's proposal
+        t = state.t
+        obs = _f64(np.stack([state._obs(o) for o in observations]))
+        if obs.shape[0] != t:
+            raise ValueError(f"pf_introduce! on a device filter at time {t} needs {t} observations, got {obs.shape[0]}")
+        m = state.model
+        aux = _f64(np.concatenate([m.aux(tau) for tau in range(1, t + 1)])) if m.n_aux else None
+        L.check(L.load().genpf_introduce(state._h, int(n_particles), L.ptr(obs), L.ptr(aux), 1 if proposal else 0, None, None))
+        return state
+    if isinstance(state, ParticleFilterSubState):
+        raise TypeError("pf_introduce! takes a full ParticleFilterState")
     model = state.traces[0].model if model is None else model
     model_args = state.traces[0].args if model_args is None else model_args
     if state.log_ml_est != 0.0:

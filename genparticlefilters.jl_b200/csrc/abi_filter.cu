@@ -1115,6 +1115,41 @@ static int32_t check_resizable(genpf_filter_t pf, bool batched = false) {
     if (pf->shard) return fail(GENPF_ERR_UNSUPPORTED, "a sharded filter cannot be resized");
     return GENPF_OK;
 }
+// pf_introduce!, first half (resize.jl:362-371): the old particles keep their place, log_weights .+= log_ml_est and
+// log_ml_est = 0; the new slots get a placeholder ancestor until k_introduce fills them
+static __global__ void k_introduce_prepare(const double *lw, const double *lml, int64_t n_old, int64_t n_new, int32_t *parents,
+                                           double *lw_out) {
+    const int64_t f = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += (int64_t)gridDim.x * blockDim.x) {
+        parents[f * n_new + j] = j < n_old ? (int32_t)j : 0;
+        lw_out[f * n_new + j] = j < n_old ? lw[f * n_old + j] + lml[f] : 0.0;
+    }
+}
+template <class Model, class Noise>
+static int32_t launch_introduce(genpf_filter_t pf, int64_t n_old, int64_t m, const double *obs_hist, const double *aux_hist,
+                                Noise noise, int use_proposal) {
+    const ModelInfo &mi = *model_info(pf->model);
+    const void *fn = nullptr;
+    GENPF_PLUGIN_OR_BUILTIN(Model, kPlugIntro + NoiseIndex<Noise>::value, (&k_introduce<SigModel<Model>, Noise>), fn);
+    const int64_t t = pf->t_cur;
+    return launch_typed("k_introduce", &k_introduce<SigModel<Model>, Noise>, fn, dim3(grid_1d(m), (unsigned)pf->nf), dim3(256),
+                        pf->stream, pf->P, t, pf->slice(t - 1), pf->slice(t), pf->lw, obs_hist, aux_hist, mi.naux, n_old, m,
+                        noise, use_proposal);
+}
+template <class Model>
+static int32_t introduce_model(genpf_filter_t pf, int64_t n_old, int64_t m, const double *obs_hist, const double *aux_hist,
+                               const double *dU, const double *dZ, int use_proposal) {
+    if (dU || dZ) {
+        NoiseCols nz{nullptr, nullptr, nullptr, dU, dZ};
+        return launch_introduce<Model, NoiseCols>(pf, n_old, m, obs_hist, aux_hist, nz, use_proposal);
+    }
+    if (pf->flags & GENPF_NOISE_PHILOX53) {
+        NoisePhilox53 nz{pf->seed, 0, pf->rng_offset};
+        return launch_introduce<Model, NoisePhilox53>(pf, n_old, m, obs_hist, aux_hist, nz, use_proposal);
+    }
+    NoiseLean nz{pf->seed, 0, pf->rng_offset};
+    return launch_introduce<Model, NoiseLean>(pf, n_old, m, obs_hist, aux_hist, nz, use_proposal);
+}
 }  // namespace genpf
 
 extern "C" {
@@ -1128,6 +1163,43 @@ int32_t genpf_replicate(genpf_filter_t pf, int64_t k, int32_t layout) {
     GENPF_LAUNCH((k_replicate<int32_t>), dim3(grid_1d(n_out), (unsigned)pf->nf), 256, pf->stream, (const double *)pf->lw, pf->n, k,
                  layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, pf->parents, (int64_t)0, pf->lw_alt);
     return apply_parents_and_swap(pf, n_out);
+}
+
+// pf_introduce! (resize.jl:351-421) for device plugins: n_new particles generated under the whole observation history
+// obs[t_cur * n_filters] (row tau-1 = time tau; aux likewise with n_aux columns) are appended to every filter.
+int32_t genpf_introduce(genpf_filter_t pf, int64_t n_new, const double *obs, const double *aux, int32_t use_proposal,
+                        const double *U, const double *Z) {
+    GENPF_TRY(check_resizable(pf, true));
+    const ModelInfo &mi = *model_info(pf->model);
+    if (n_new < 1) return fail(GENPF_ERR_INVALID_ARG, "pf_introduce!: n_particles must be >= 1");
+    if (!obs || (mi.naux > 0 && !aux)) return fail(GENPF_ERR_INVALID_ARG, "pf_introduce!: the observation history is NULL");
+    if (use_proposal && !(mi.caps & 1)) return fail(GENPF_ERR_UNSUPPORTED, "this model has no custom proposal");
+    if (pf->flags & GENPF_KEEP_HISTORY) return fail(GENPF_ERR_UNSUPPORTED, "pf_introduce! with GENPF_KEEP_HISTORY");
+    const int64_t n_old = pf->n, n_out = n_old + n_new, t = pf->t_cur, nf = pf->nf;
+    if (n_out >= 0x7FFFFFF0ll) return fail(GENPF_ERR_UNSUPPORTED, "population must stay < 2^31");
+    // observation / aux history and (parity mode) the chains' noise columns [tau-1][filter][i]
+    const size_t hist = (size_t)(t * nf + t * mi.naux) * 8;
+    GENPF_TRY(pf->run_obs.ensure(hist + 16));
+    GENPF_CUDA_TRY(cudaMemcpyAsync(pf->run_obs.p, obs, (size_t)(t * nf) * 8, cudaMemcpyHostToDevice, pf->stream));
+    double *d_obs = pf->run_obs.as<double>(), *d_aux = d_obs + t * nf;
+    if (mi.naux > 0)
+        GENPF_CUDA_TRY(cudaMemcpyAsync(d_aux, aux, (size_t)(t * mi.naux) * 8, cudaMemcpyHostToDevice, pf->stream));
+    const double *dU = nullptr, *dZ = nullptr;
+    GENPF_TRY(stage_noise(pf, 3, U, &dU, t * nf * n_new));
+    GENPF_TRY(stage_noise(pf, 4, Z, &dZ, t * nf * n_new));
+    GENPF_TRY(resize_target(pf, n_out));
+    GENPF_LAUNCH(k_introduce_prepare, dim3(grid_1d(n_out), (unsigned)nf), 256, pf->stream, (const double *)pf->lw,
+                 (const double *)pf->lml, n_old, n_out, pf->parents, pf->lw_alt);
+    GENPF_TRY(apply_parents_and_swap(pf, n_out));
+    GENPF_CUDA_TRY(cudaMemsetAsync(pf->lml, 0, (size_t)nf * 8, pf->stream));
+    int32_t st;
+    switch (pf->model) {
+        case kModelObjectMotion: st = introduce_model<ObjectMotion>(pf, n_old, n_new, d_obs, d_aux, dU, dZ, use_proposal); break;
+        case kModelLinGauss1D: st = introduce_model<LinGauss1D>(pf, n_old, n_new, d_obs, d_aux, dU, dZ, use_proposal); break;
+        default: st = introduce_model<PluginTag>(pf, n_old, n_new, d_obs, d_aux, dU, dZ, use_proposal); break;
+    }
+    pf->part_valid = false;
+    return st;
 }
 
 int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t method, const double *uniforms) {

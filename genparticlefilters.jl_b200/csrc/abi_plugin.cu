@@ -112,6 +112,7 @@ static std::string kernel_expr(int k, const std::string &S) {
         const int nz = (k - kPlugMh) / 2, rw = (k - kPlugMh) % 2;
         return "genpf::k_mh<" + S + ", " + kNoiseNames[nz] + ", " + (rw ? "true" : "false") + ">";
     }
+    if (k >= kPlugIntro) return "genpf::k_introduce<" + S + ", " + kNoiseNames[k - kPlugIntro] + ">";
     const int nz = (k - kPlugFused) / 3, mh = (k - kPlugFused) % 3;
     return "genpf::k_step_fused<" + S + ", " + kNoiseNames[nz] + ", int, " + kFusedMh[mh] + ">";
 }
@@ -272,7 +273,7 @@ int32_t genpf_model_export(int32_t model_id, void *buf, int64_t cap, int64_t *si
     if (!pm || !size) return fail(GENPF_ERR_INVALID_ARG, "genpf_model_export: not a plugin model");
     std::string img = "GENPFPLG";
     auto put32 = [&](uint32_t v) { img.append(reinterpret_cast<const char *>(&v), 4); };
-    put32(1);
+    put32(2);  // version 2: 24 kernel slots (k_introduce added); version 1 images (21 slots) still load
     const int32_t dims[6] = {pm->info.nf, pm->info.nb, pm->info.np, pm->info.naux, pm->info.caps & 1, (pm->info.caps >> 1) & 1};
     img.append(reinterpret_cast<const char *>(dims), sizeof(dims));
     put32((uint32_t)pm->name.size());
@@ -304,7 +305,8 @@ int32_t genpf_model_load_image(const void *image, int64_t size, int32_t *model_i
         return true;
     };
     uint32_t ver = 0, len = 0;
-    if (!get32(ver) || ver != 1) return fail(GENPF_ERR_INVALID_ARG, "plugin image: unknown version");
+    if (!get32(ver) || (ver != 1 && ver != 2)) return fail(GENPF_ERR_INVALID_ARG, "plugin image: unknown version");
+    const int n_slots = ver == 1 ? kPlugKernelsV1 : kPlugKernels;
     int32_t dims[6];
     if (p + sizeof(dims) > end) return fail(GENPF_ERR_INVALID_ARG, "plugin image truncated");
     memcpy(dims, p, sizeof(dims));
@@ -315,7 +317,7 @@ int32_t genpf_model_load_image(const void *image, int64_t size, int32_t *model_i
         pm->name.assign(p, len);
         p += len;
     }
-    for (int k = 0; ok && k < kPlugKernels; ++k) {
+    for (int k = 0; ok && k < n_slots; ++k) {
         ok = get32(len) && p + len <= end;
         if (ok) {
             pm->lowered[k].assign(p, len);

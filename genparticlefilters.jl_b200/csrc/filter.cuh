@@ -250,6 +250,64 @@ GENPF_KERNEL void __launch_bounds__(kStateThreads)
     }
 }
 
+// ------------------------------------------------------------------ pf_introduce! (resize.jl:351-421)
+// m fresh particles appended to a filter at time t: generate(model, args, observations) simulates the whole chain
+// x_1 .. x_t from the prior (or the plugin's custom proposal) under the observations y_1 .. y_t; the new log-weight
+// is the sum of the observation log-densities (+ log p(x|prev) - log q(x) per step with a proposal).  Only the
+// fixed-lag window {t-1, t} is kept.  One thread per new particle; the chain's noise is the update noise of step tau
+// at the particle's (never used before) slot, or supplied columns [tau-1][filter][i] in parity mode.
+template <class N>
+__device__ __forceinline__ N noise_of_step(N nz, int64_t tau, int64_t) {
+    nz.step = (uint64_t)tau;
+    return nz;
+}
+__device__ __forceinline__ NoiseCols noise_of_step(NoiseCols nz, int64_t tau, int64_t stride) {
+    const double *pu = (nz.Uup || nz.Zup) ? nz.Uup : nz.U, *pz = (nz.Uup || nz.Zup) ? nz.Zup : nz.Z;
+    NoiseCols o{nullptr, nullptr, nullptr, pu ? pu + (tau - 1) * stride : nullptr, pz ? pz + (tau - 1) * stride : nullptr};
+    return o;
+}
+template <class Model, class Noise>
+GENPF_KERNEL void __launch_bounds__(256)
+    k_introduce(ModelParams P, int64_t t, Cols dst_prev, Cols dst_cur, double *lw, const double *obs_hist,
+                const double *aux_hist, int naux, int64_t n_old, int64_t m, Noise noise, int use_proposal) {
+    const int64_t f = blockIdx.y, nf = gridDim.y, n_new = n_old + m;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t slot = f * n_new + n_old + i;  // where the particle lives (and its Philox counter)
+    typename Model::Slice prev, cur;
+    Model::initial(P, cur);
+    double w = 0.0;
+    for (int64_t tau = 1; tau <= t; ++tau) {
+        prev = cur;
+        for (int a = 0; a < naux; ++a) P.aux[a] = aux_hist[(tau - 1) * naux + a];
+        const double obs = obs_hist[(tau - 1) * nf + f];
+        const Noise nz = noise_of_step(noise, tau, nf * m);
+        double U = 0.5, Z = 0.0;
+        nz.up(Noise::kIndexed ? f * m + i : slot, U, Z);
+        bool proposed = false;
+        if constexpr (has_proposal<Model>::value) {
+            if (use_proposal) {
+                Model::propose(P, tau, prev, obs, cur, U, Z);
+                w += Model::transition_logpdf(P, tau, prev, cur) - Model::proposal_logpdf(P, tau, prev, obs, cur);
+                proposed = true;
+            }
+        }
+        if (!proposed) Model::transition(P, tau, prev, cur, U, Z);
+        w += Model::obs_logpdf(P, cur, obs);
+    }
+#pragma unroll
+    for (int c = 0; c < Model::NF; ++c) {
+        dst_prev.f[c][slot] = prev.f[c];
+        dst_cur.f[c][slot] = cur.f[c];
+    }
+#pragma unroll
+    for (int c = 0; c < Model::NB; ++c) {
+        dst_prev.b[c][slot] = prev.b[c];
+        dst_cur.b[c][slot] = cur.b[c];
+    }
+    lw[slot] = w;
+}
+
 #ifndef GENPF_PLUGIN_BUILD
 // ------------------------------------------------------------------ K8 ancestor gather
 // new_traces .= view(traces, parents) (resample.jl:60,102-104,114,169) over the window's columns.

@@ -44,41 +44,52 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
     constexpr int NW = T / 32;
     constexpr long long kMinKey = (long long)0x8000000000000000ull;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long key = f64_key(v[0]);
-    int fl = (v[0] != v[0]) ? 1 : 0;
+    // thread maximum with fmax (NaN never wins), ONE key conversion per thread, REDUX across the warp
+    double mt = v[0];
 #pragma unroll
-    for (int k = 1; k < kTile / T; ++k) {
-        fl |= (v[k] != v[k]) ? 1 : 0;
-        key = max(key, f64_key(v[k]));
-    }
-    key = warp_max_key(key);
-    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    for (int k = 1; k < kTile / T; ++k) mt = fmax(mt, v[k]);
+    long long key = warp_max_key(f64_key(mt));
     long long *smk = reinterpret_cast<long long *>(ps.m);
     __syncthreads();
-    if (lane == 0) {
-        smk[warp] = key;
-        ps.fl[warp] = fl;
-    }
+    if (lane == 0) smk[warp] = key;
     __syncthreads();
     // every thread needs the block max: lane l reads cell l mod NW, REDUX over the warp
     key = warp_max_key(smk[lane & (NW - 1)]);
-    fl = __reduce_or_sync(0xffffffffu, (unsigned)ps.fl[lane & (NW - 1)]);
-    // all NaN / empty maps to the minimum key: treat as -Inf (the NaN flag carries the diagnosis)
+    // all NaN / empty maps to the minimum key: treat as -Inf
     const double m = key == kMinKey ? -INFINITY : f64_from_key(key);
     double s = 0.0, s2 = 0.0;
     double ev[kTile / T];
 #pragma unroll
     for (int k = 0; k < kTile / T; ++k) ev[k] = 0.0;
+    int fl = 0;
     if (m == INFINITY) {
-        fl |= 2;
+        fl = 2;
+#pragma unroll
+        for (int k = 0; k < kTile / T; ++k) fl |= (v[k] != v[k]) ? 1 : 0;
     } else if (m > -INFINITY) {
 #pragma unroll
         for (int k = 0; k < kTile / T; ++k) {
-            ev[k] = exp_nonpos(v[k] - m);
+            ev[k] = exp_nonpos(v[k] - m);  // NaN in, NaN out: the NaN flag is read off the sum (no per-element test)
             s += ev[k];
             s2 += ev[k] * ev[k];
         }
+        fl = (s != s) ? 1 : 0;
+        if (fl) {  // keep the sums finite like the per-element test did: NaN weights contribute nothing
+            s = 0.0;
+            s2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < kTile / T; ++k) {
+                if (ev[k] != ev[k]) ev[k] = 5e-308;
+                s += ev[k];
+                s2 += ev[k] * ev[k];
+            }
+        }
+    } else {  // every weight of the tile is -Inf or NaN (block-uniform, rare): look for the NaNs explicitly
+#pragma unroll
+        for (int k = 0; k < kTile / T; ++k) fl |= (v[k] != v[k]) ? 1 : 0;
     }
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    if (lane == 0) ps.fl[warp] = fl;
     if (e_tile) store_tile<double, T>(e_tile, 0, e_valid, ev);
     s = warp_sum(s);
     s2 = warp_sum(s2);
@@ -90,6 +101,7 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
     if (warp == 0) {
         s = ps.s[lane & (NW - 1)];
         s2 = ps.s2[lane & (NW - 1)];
+        fl = __reduce_or_sync(0xffffffffu, (unsigned)ps.fl[lane & (NW - 1)]);
 #pragma unroll
         for (int o = NW / 2; o > 0; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -35,7 +35,7 @@ struct SliceT {
 // (log-weights are compared at 1e-10 relative).
 __device__ __forceinline__ double normal_logpdf(double x, double mu, double inv_sigma, double log_sigma) {
     double z = (x - mu) * inv_sigma;
-    return -(__dmul_rn(z, z) + GENPF_LOG_2PI) / 2.0 - log_sigma;
+    return -(__dmul_rn(z, z) + kC[kcLog2Pi]) / 2.0 - log_sigma;
 }
 
 // accept iff log(U3) < alpha (Gen mh).  Decision-exact fast path: an fp32 log with a conservative error
@@ -257,13 +257,12 @@ __device__ __forceinline__ double log_unit(double u) {
     double sq = f * r;
     sq = fma(fma(-sq, d, f), r, sq);  // s = f / (2 + f), correctly rounded up to the last bit
     const double z = sq * sq, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                              6.666666666666735130e-01);
+    const double t1 = w * fma(w, fma(w, kC[kcLogA1], kC[kcLogA2]), kC[kcLogA3]);
+    const double t2 = z * fma(w, fma(w, fma(w, kC[kcLogB1], kC[kcLogB2]), kC[kcLogB3]), kC[kcLogB4]);
     const double R = t1 + t2;
     const double hfsq = 0.5 * f * f;
     const double dk = (double)k;
-    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+    return dk * kC[kcLn2Hi] - ((hfsq - fma(sq, hfsq + R, dk * kC[kcLn2Lo])) - f);
 }
 __device__ __forceinline__ double sqrt_pos(double x) {
     double y;
@@ -282,19 +281,19 @@ __device__ __forceinline__ void sincos_2pi(double a, double &sn, double &cs) {
     const double zq = fma(a, 4.0, SH);
     const int q = __double2loint(zq);             // rint(4a) in 0..4
     const double t = fma(zq - SH, -0.25, a);      // exact, |t| <= 1/8
-    const double phi = t * 6.283185307179586476925;
+    const double phi = t * kC[kcTwoPi];
     const double z = phi * phi;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kC[kcSinS6], kC[kcSinS5]);
+    ps = fma(z, ps, kC[kcSinS4]);
+    ps = fma(z, ps, kC[kcSinS3]);
+    ps = fma(z, ps, kC[kcSinS2]);
+    ps = fma(z, ps, kC[kcSinS1]);
     const double sp = fma(phi * z, ps, phi);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, kC[kcCosC6], kC[kcCosC5]);
+    pc = fma(z, pc, kC[kcCosC4]);
+    pc = fma(z, pc, kC[kcCosC3]);
+    pc = fma(z, pc, kC[kcCosC2]);
+    pc = fma(z, pc, kC[kcCosC1]);
     const double cp = fma(z * z, pc, fma(z, -0.5, 1.0));
     const bool swap = q & 1;
     double s0 = swap ? cp : sp, c0 = swap ? sp : cp;

@@ -12,8 +12,9 @@ namespace genpf {
 
 constexpr int kPluginIdBase = 100;  // model ids >= 100 are plugins registered at run time
 // kernel slots of a plugin image: k_propagate<M, Noise, INIT> (noise x {update, init}), k_mh<M, Noise, REWEIGHT>
-// (noise x {accept, reweight}), k_step_fused<M, Noise, int, MH> (noise x MH in {1, 0, -1}); noise order Lean, Philox53, Cols
-enum { kPlugProp = 0, kPlugMh = 6, kPlugFused = 12, kPlugKernels = 21 };
+// (noise x {accept, reweight}), k_step_fused<M, Noise, int, MH> (noise x MH in {1, 0, -1}), k_introduce<M, Noise> (image
+// version 2); noise order Lean, Philox53, Cols
+enum { kPlugProp = 0, kPlugMh = 6, kPlugFused = 12, kPlugIntro = 21, kPlugKernels = 24, kPlugKernelsV1 = 21 };
 enum { kNzLean = 0, kNzPhilox53 = 1, kNzCols = 2 };
 
 struct PluginModel {

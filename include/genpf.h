@@ -270,6 +270,16 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
                    const double *obs_t, const double *aux_t, int32_t method, double ess_frac, int32_t mh_iters,
                    double *ess_out);
 
+/* pf_introduce! (src/resize.jl:351-421) on a device filter: n_new particles are appended to every filter.  Like the
+ * reference's generate(model, model_args, observations), each new trace is a whole chain x_1..x_t simulated from the
+ * prior (use_proposal != 0: from the plugin's custom proposal, weight = model - proposal score, resize.jl:404-410) under
+ * the observation history obs[t_cur * n_filters] (row tau-1 = time tau; aux likewise, n_aux columns); its log-weight is
+ * the accumulated observation log-density.  The existing particles keep their place, log_weights .+= log_ml_est and
+ * log_ml_est = 0 (resize.jl:362-366).  U, Z: NULL (library Philox draws at the new slots) or the chains' noise,
+ * t_cur * n_filters * n_new doubles each, indexed [tau-1][filter][i] (parity mode). */
+int32_t genpf_introduce(genpf_filter_t pf, int64_t n_new, const double *obs, const double *aux, int32_t use_proposal,
+                        const double *U, const double *Z);
+
 /* n_steps README iterations (stratified resample + mh + update, the fused kernels of genpf_step) enqueued by one
  * call: asynchronous, nothing copied back; ess_frac < 1: every filter decides on the device at every step.
  * obs: (n_steps + 1) * n_filters doubles, row r belongs to time t_first - 1 + r (row 0 = the step the first mh move

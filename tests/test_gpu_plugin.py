@@ -48,6 +48,10 @@ def test_plugin_from_source_reproduces_builtin_bit_for_bit(g, plugin, noise):
     same()
     np.testing.assert_array_equal(dyn.accepts, ref.accepts)
     assert g.log_ml_estimate(dyn) == g.log_ml_estimate(ref)
+    for s in (ref, dyn):  # pf_introduce!: k_introduce from the plugin image
+        g.pf_introduce(s, None, None, list(obs[:7]), 1234)
+    assert len(dyn) == n + 1234
+    same()
     assert g.mean(dyn, (7, "x")) == g.mean(ref, (7, "x"))
 
 
