@@ -648,8 +648,8 @@ int32_t genpf_filter_destroy(genpf_filter_t pf) {
     genpf_shard_detach(pf);
     cudaSetDevice(pf->device);
     if (pf->stream) cudaStreamSynchronize(pf->stream);
-    for (void *p : pf->owned)
-        if (p) cudaFree(p);
+    for (auto &b : pf->live) cudaFree(b.p);
+    for (auto &b : pf->cache) cudaFree(b.p);
     pf->sc.release();
     pf->cb.release();
     pf->ob.release();

@@ -59,9 +59,25 @@ def main():
         lat.append((time.perf_counter() - t0) / 9)
         m5, m6 = g.mean(state, (5, "moving")), g.mean(state, (6, "moving"))
         flips += m5 < 0.5 < m6
+    # the same filter through genpf_run_steps: the 9 iterations enqueued by ONE asynchronous call, eager and as a CUDA
+    # graph (stratified resample decided per step on the device: the fused step has no residual form)
+    run_us = {}
+    for mode in ("eager", "graph"):
+        ts = []
+        for seed in range(21):
+            st = g.pf_initialize(model, (1,), obs[0], 100, seed=seed)
+            st.sync()
+            t0 = time.perf_counter()
+            g.pf_run(st, 2, np.array(obs), ess_thresh=0.5, graph=(mode == "graph"))
+            st.sync()
+            ts.append((time.perf_counter() - t0) / 9)
+        run_us[mode] = 1e6 * sorted(ts[1:])[10]
     print(json.dumps({"config": 1, "workload": "README object_motion T=10 n=100 residual+MH (README.md:60-79)",
                       "wall_us_per_step_median": 1e6 * sorted(lat)[len(lat) // 2], "posterior_flip_runs": f"{flips}/20",
-                      "last_run": {"mean_moving_5": m5, "mean_moving_6": m6}}), flush=True)
+                      "last_run": {"mean_moving_5": m5, "mean_moving_6": m6},
+                      "run_steps_us_per_step": run_us,
+                      "run_steps_note": "genpf_run_steps, stratified + mh + update, ess < n/2 decided on the device; "
+                                        "wall time of the whole call incl. graph capture + instantiate, / 9 steps"}), flush=True)
 
     # ---- config 3
     a, q, r, m0, s0 = 0.9, 1.0, 1.0, 0.0, 1.0
@@ -71,39 +87,50 @@ def main():
         x = a * x + q * rng.normal()
         obs3.append(x + r * rng.normal())
     model3 = g.DeviceModel("lingauss1d", (a, q, r, m0, s0))
-    state = g.pf_initialize(model3, (1,), obs3[0], args.n3, seed=5)
-    state.sync()
-    t0 = time.perf_counter()
-    for t in range(2, args.T3 + 1):
-        g.pf_step(state, t, obs3[t - 2], obs3[t - 1], method="stratified", ess_thresh=1.0, mh_iters=0, return_ess=False)
-    state.sync()
-    dt = time.perf_counter() - t0
     m, P, lz = kalman(obs3, a, q, r, m0, s0)
-    pm, pv, lml = g.mean(state, (args.T3, "x")), g.var(state, (args.T3, "x")), g.log_ml_estimate(state)
-    ups = args.n3 * (args.T3 - 1) / dt
-    print(json.dumps({"config": 3, "workload": f"lingauss1d n={args.n3} T={args.T3} stratified every step",
-                      "particle_updates_per_s": ups, "ms_per_step": 1e3 * dt / (args.T3 - 1),
-                      "frac_of_68B_roofline": ups * 68 / 6463.3e9,
-                      "pf_mean": pm, "kalman_mean": m, "pf_var": pv, "kalman_var": P, "pf_lml": lml, "kalman_logZ": lz}),
-          flush=True)
-    del state
+    for noise in ("philox53", "lean"):
+        state = g.pf_initialize(model3, (1,), obs3[0], args.n3, seed=5, noise=noise)
+        state.sync()
+        t0 = time.perf_counter()
+        for t in range(2, args.T3 + 1):
+            g.pf_step(state, t, obs3[t - 2], obs3[t - 1], method="stratified", ess_thresh=1.0, mh_iters=0, return_ess=False)
+        state.sync()
+        dt = time.perf_counter() - t0
+        pm, pv, lml = g.mean(state, (args.T3, "x")), g.var(state, (args.T3, "x")), g.log_ml_estimate(state)
+        ups = args.n3 * (args.T3 - 1) / dt
+        print(json.dumps({"config": 3, "workload": f"lingauss1d n={args.n3} T={args.T3} stratified every step", "noise": noise,
+                          "particle_updates_per_s": ups, "ms_per_step": 1e3 * dt / (args.T3 - 1),
+                          "frac_of_68B_roofline": ups * 68 / 6463.3e9,
+                          "pf_mean": pm, "kalman_mean": m, "pf_var": pv, "kalman_var": P, "pf_lml": lml, "kalman_logZ": lz}),
+              flush=True)
+        del state
 
     # ---- config 5 (one GPU's share of the 4096-filter batch)
     nf, n = args.filters5, 4096
     T5 = 50
     rng = np.random.default_rng(4)
     obs5 = np.cumsum(rng.normal(0, 0.3, (T5, nf)), axis=0)
-    state = g.pf_initialize(model, (1,), obs5[0], n, n_filters=nf, seed=9)
-    state.sync()
-    t0 = time.perf_counter()
-    for t in range(2, T5 + 1):
-        g.pf_step(state, t, obs5[t - 2], obs5[t - 1], method="stratified", ess_thresh=1.0, mh_iters=1, return_ess=False)
-    state.sync()
-    dt = time.perf_counter() - t0
-    ess = g.effective_sample_size(state)
-    print(json.dumps({"config": 5, "workload": f"{nf} independent object_motion filters x {n} particles, MH every step",
-                      "particle_updates_per_s": nf * n * (T5 - 1) / dt, "ms_per_step": 1e3 * dt / (T5 - 1),
-                      "ess_min": float(ess.min()), "ess_max": float(ess.max())}), flush=True)
+    for noise in ("philox53", "lean"):
+        state = g.pf_initialize(model, (1,), obs5[0], n, n_filters=nf, seed=9, noise=noise)
+        state.sync()
+        t0 = time.perf_counter()
+        for t in range(2, T5 + 1):
+            g.pf_step(state, t, obs5[t - 2], obs5[t - 1], method="stratified", ess_thresh=1.0, mh_iters=1, return_ess=False)
+        state.sync()
+        dt = time.perf_counter() - t0
+        ess = g.effective_sample_size(state)
+        # pf_replicate! x2 then residual resize back to n, per filter (resize.jl:87-124,236-244), timed on their own
+        state.sync()
+        t1 = time.perf_counter()
+        g.pf_replicate(state, 2)
+        g.pf_resize(state, n, "residual")
+        state.sync()
+        dt_rs = time.perf_counter() - t1
+        print(json.dumps({"config": 5, "workload": f"{nf} independent object_motion filters x {n} particles, MH every step",
+                          "noise": noise, "particle_updates_per_s": nf * n * (T5 - 1) / dt, "ms_per_step": 1e3 * dt / (T5 - 1),
+                          "ess_min": float(ess.min()), "ess_max": float(ess.max()),
+                          "replicate_x2_plus_residual_resize_ms": 1e3 * dt_rs}), flush=True)
+        del state
 
 
 if __name__ == "__main__":
