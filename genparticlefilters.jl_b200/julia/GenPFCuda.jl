@@ -11,6 +11,7 @@ module GenPFCuda
 
 using Gen, GenParticleFilters
 import GenParticleFilters: pf_resample!, pf_update!, pf_rejuvenate!, pf_replicate!, pf_dereplicate!
+import GenParticleFilters: pf_move_reweight!, pf_optimal_resize!, pf_introduce!  # extended below, not shadowed
 import GenParticleFilters: ParticleFilterView, ParticleFilterSubState, update_refs!
 import Gen: effective_sample_size, log_ml_estimate
 import Statistics: mean, var
@@ -221,5 +222,29 @@ pf_optimal_resize!(s::DevicePFState, n_particles::Int; check_=:warn) =
     (check(ccall((:genpf_optimal_resize_dev, LIB), Int32,
                  (Ptr{Cvoid}, Int64, Ptr{Cdouble}, UInt32, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int32}),
                  s.handle, n_particles, C_NULL, check_ == true ? CHECK : UInt32(0), C_NULL, C_NULL, C_NULL)); s)
+
+# pf_introduce!(state, observations, n_particles), src/resize.jl:351-421: y_hist[tau, filter] = the observation history
+# (the reference's `observations` choicemap covers every time step of the new traces); use_proposal: the plugin's proposal
+function pf_introduce!(s::DevicePFState, y_hist::Matrix{Float64}, n_particles::Int; use_proposal::Bool=false)
+    obs = permutedims(y_hist)  # row-major [tau][filter] for the C ABI
+    auxh = reduce(vcat, [aux(s, tau) for tau in 1:s.t]; init=Float64[])
+    check(ccall((:genpf_introduce, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                s.handle, n_particles, obs, isempty(auxh) ? C_NULL : auxh, use_proposal ? 1 : 0, C_NULL, C_NULL))
+    return s
+end
+
+"T README iterations enqueued by one asynchronous call (genpf_run_steps); graph=true replays steps 2.. as a CUDA graph"
+function pf_run!(s::DevicePFState, t_first::Int, y_rows::Matrix{Float64}; ess_thresh::Float64=0.5, mh_iters::Int=1,
+                 graph::Bool=false)
+    T = size(y_rows, 1) - 1
+    obs = permutedims(y_rows)
+    auxh = reduce(vcat, [aux(s, t_first - 1 + r) for r in 0:T]; init=Float64[])
+    check(ccall((:genpf_run_steps, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Cdouble, Int32, UInt32),
+                s.handle, t_first, T, obs, isempty(auxh) ? C_NULL : auxh, STRATIFIED, ess_thresh, mh_iters, graph ? UInt32(1) : UInt32(0)))
+    s.t = t_first + T - 1
+    return s
+end
 
 end # module
