@@ -91,6 +91,7 @@ SIGNATURES = {
     "genpf_step": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, f64, i32, _vp]),
     "genpf_run_steps": (i32, [_vp, i64, i64, _vp, _vp, i32, f64, i32, u32]),
     "genpf_introduce": (i32, [_vp, i64, _vp, _vp, i32, _vp, _vp]),
+    "genpf_filter_set_first_filter": (i32, [_vp, i64]),
     "genpf_step_with_noise": (i32, [_vp, i64, _vp, _vp, _vp, _vp, i32, f64, i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "genpf_mean_var": (i32, [_vp, i32, i64, _vp, _vp]),
     "genpf_replicate": (i32, [_vp, i64, i32]),

@@ -165,7 +165,9 @@ def _image_name(image):
 class DevicePFState:
     """Device-resident population (n_filters independent filters of n_particles)."""
 
-    def __init__(self, model, n_particles, n_filters=1, seed=0, keep_history=False, noise="lean"):
+    def __init__(self, model, n_particles, n_filters=1, seed=0, keep_history=False, noise="lean", first_filter=0):
+        """first_filter: position of this handle's filter 0 inside a larger batch that is split over several handles /
+        processes / GPUs (batch sharding needs no communication; the draws are those of the one big batch)."""
         lib = L.load()
         self.model = model
         flags = (L.KEEP_HISTORY if keep_history else 0) | (L.NOISE_PHILOX53 if noise == "philox53" else 0)
@@ -176,8 +178,10 @@ class DevicePFState:
         self._h = h
         self.n_filters = n_filters
         self.t = 0
+        if first_filter:
+            L.check(lib.genpf_filter_set_first_filter(h, int(first_filter)))
         self._ctor = dict(n_particles=int(n_particles), n_filters=int(n_filters), seed=int(seed),
-                          keep_history=bool(keep_history), noise=noise)
+                          keep_history=bool(keep_history), noise=noise, first_filter=int(first_filter))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -272,7 +276,8 @@ class DevicePFState:
         params = z["params"]
         model = DeviceModel(str(z["model"]), None if params.size == 0 else params)
         state = cls(model, int(z["ctor_n_particles"]), n_filters=int(z["ctor_n_filters"]), seed=int(z["ctor_seed"]),
-                    keep_history=False, noise=str(z["ctor_noise"]))
+                    keep_history=False, noise=str(z["ctor_noise"]),
+                    first_filter=int(z["ctor_first_filter"]) if "ctor_first_filter" in z else 0)
         t = int(z["t"])
         lml = _f64(z["lml"])
         L.check(L.load().genpf_filter_set_progress(state._h, t, int(z["n_resamples"]), L.ptr(lml)))

@@ -420,7 +420,10 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
         GENPF_CUDA_TRY(cudaMemcpyAsync(pf->uni_buf.p, uniforms_host, (size_t)(n_out * nf) * 8, cudaMemcpyHostToDevice, s));
         d_u = pf->uni_buf.as<double>();
     }
-    UniSrc uni{d_u, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    // the selection draws are indexed by OUTPUT slot (filter * n_out + j): a batch shard offsets by its position in
+    // output slots, which differs from rng_offset (input slots) when the call resizes
+    const int64_t uni_off = pf->first_filter ? pf->first_filter * n_out : pf->rng_offset;
+    UniSrc uni{d_u, pf->seed, make_stream(kPurposeResample, (uint64_t)pf->n_resamples + 1), uni_off};
     // every validation that can refuse the call is behind us: only now are the target buffers resized
     GENPF_TRY(resize_target(pf, n_out));
     GENPF_TRY_RB(pf, select_ancestors<int32_t>(s, sc, method, sel, n, n_out, nf, st_sel, uni, flags, pf->parents, 0, gate,
@@ -446,6 +449,7 @@ static int32_t do_resample(genpf_filter_t pf, int32_t method, int32_t prio_kind,
     GENPF_TRY(log_parents(pf, n, n_out));
     if (n_out != n) {
         pf->n = n_out;
+        if (pf->first_filter) pf->rng_offset = pf->first_filter * n_out;  // Philox counters stay global batch slots
         GENPF_TRY(resize_spare(pf, n_out));
     }
     return GENPF_OK;
@@ -639,6 +643,20 @@ int32_t genpf_filter_create(int32_t model_id, const double *params, int32_t n_pa
     GENPF_CUDA_TRY(cudaMallocHost(&pf->h_stats, pin * sizeof(Stats)));
     GENPF_CUDA_TRY(cudaMemsetAsync(pf->lml, 0, (size_t)n_filters * 8, pf->stream));
     *out = pf.release();
+    return GENPF_OK;
+}
+
+// Batch sharding ("batches of independent filters shard with no communication at all"): this handle holds
+// filters [first_filter, first_filter + n_filters) of a larger batch.  Every Philox counter of the library is a global
+// particle slot (filter * n_particles + i), so the shard draws exactly what the same filters would draw inside one
+// big batch: the result does not depend on how the batch is split over handles, processes or GPUs.
+int32_t genpf_filter_set_first_filter(genpf_filter_t pf, int64_t first_filter) {
+    GENPF_TRY(check_filter(pf));
+    if (first_filter < 0) return fail(GENPF_ERR_INVALID_ARG, "first_filter must be >= 0");
+    if (pf->shard) return fail(GENPF_ERR_STATE, "a particle-sharded filter has its own slot offset");
+    if (pf->t_cur != 0) return fail(GENPF_ERR_STATE, "set the batch position before the filter is initialised");
+    pf->first_filter = first_filter;
+    pf->rng_offset = first_filter * pf->n;
     return GENPF_OK;
 }
 
@@ -1102,6 +1120,7 @@ static int32_t apply_parents_and_swap(genpf_filter_t pf, int64_t n_out) {
     GENPF_TRY(log_parents(pf, n_prev, n_out));
     if (n_out != n_prev) {
         pf->n = n_out;
+        if (pf->first_filter) pf->rng_offset = pf->first_filter * n_out;  // Philox counters stay global batch slots
         GENPF_TRY(resize_spare(pf, n_out));
     }
     return GENPF_OK;
@@ -1213,7 +1232,8 @@ int32_t genpf_dereplicate(genpf_filter_t pf, int64_t k, int32_t layout, int32_t 
         d_u = pf->uni_buf.as<double>();
     }
     GENPF_TRY(resize_target(pf, n_out));
-    UniSrc uni{d_u, pf->seed, make_stream(kPurposeDerep, (uint64_t)pf->n_resamples + 1), pf->rng_offset};
+    UniSrc uni{d_u, pf->seed, make_stream(kPurposeDerep, (uint64_t)pf->n_resamples + 1),
+               pf->first_filter ? pf->first_filter * n_out : pf->rng_offset};  // indexed by output slot
     GENPF_LAUNCH((k_dereplicate<int32_t>), dim3(grid_1d(n_out), (unsigned)pf->nf), 256, pf->stream, (const double *)pf->lw, pf->n, k,
                  layout == GENPF_LAYOUT_INTERLEAVED ? 1 : 0, method == GENPF_SAMPLE ? 1 : 0, uni, pf->parents,
                  (int64_t)0, pf->lw_alt);

@@ -62,6 +62,7 @@ struct genpf_filter_s {
     ModelParams P{};
     int64_t t_cur = 0;
     int64_t n_resamples = 0;
+    int64_t first_filter = 0;  // index of filter 0 in a batch sharded over several handles / GPUs (rng_offset = first_filter * n)
     int64_t rng_offset = 0;
     Cols win[2][2];  // [buffer][slot parity]
     int buf = 0;

@@ -270,6 +270,12 @@ int32_t genpf_step(genpf_filter_t pf, int64_t t, const double *obs_prev, const d
                    const double *obs_t, const double *aux_t, int32_t method, double ess_frac, int32_t mh_iters,
                    double *ess_out);
 
+/* Batch sharding (north star: "batches of independent filters shard with no communication at all"): this handle holds
+ * filters [first_filter, first_filter + n_filters) of a larger batch; all Philox counters become the global batch
+ * slots, so results do not depend on how a batch is split over handles / processes / GPUs.  Call before
+ * genpf_initialize. */
+int32_t genpf_filter_set_first_filter(genpf_filter_t pf, int64_t first_filter);
+
 /* pf_introduce! (src/resize.jl:351-421) on a device filter: n_new particles are appended to every filter.  Like the
  * reference's generate(model, model_args, observations), each new trace is a whole chain x_1..x_t simulated from the
  * prior (use_proposal != 0: from the plugin's custom proposal, weight = model - proposal score, resize.jl:404-410) under

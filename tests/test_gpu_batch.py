@@ -174,3 +174,32 @@ def test_batch_sorted_stratified_vs_oracle(g, orc, n):
         np.testing.assert_array_equal(p[sl], p_ref)
         np.testing.assert_array_equal(y1[sl], y0[sl][p_ref])
     assert np.all(pf.log_weights == 0.0)
+
+
+@pytest.mark.parametrize("noise", ["lean", "philox53"])
+def test_batch_shards_reproduce_the_whole_batch(g, noise):
+    """Batch sharding (north star: "batches of independent filters shard with no communication at all", BASELINE
+    config 5): two handles holding filters [0, 3) and [3, 8) of a batch give, filter for filter and bit for bit, what
+    ONE handle holding all 8 gives -- every Philox counter is a global batch slot (genpf_filter_set_first_filter) --
+    through per-filter resample decisions, mh, updates and a replicate + residual-resize cycle."""
+    nf, n, T = 8, 4096, 12
+    rng = np.random.default_rng(77)
+    obs = np.cumsum(rng.normal(0, 0.3, (T + 1, nf)), axis=0)
+    model = g.DeviceModel("object_motion")
+
+    def run(f0, f1):
+        st = g.pf_initialize(model, (1,), obs[0, f0:f1], n, n_filters=f1 - f0, seed=5, noise=noise, first_filter=f0)
+        for t in range(2, T + 1):
+            g.pf_step(st, t, obs[t - 2, f0:f1], obs[t - 1, f0:f1], ess_thresh=0.5, return_ess=False)
+            if t == 6:
+                g.pf_replicate(st, 2)
+                g.pf_resize(st, n, "residual")
+        return (st.field("y", T).reshape(f1 - f0, -1), st.field("moving", T).reshape(f1 - f0, -1),
+                st.log_weights.reshape(f1 - f0, -1), np.atleast_1d(g.log_ml_estimate(st)))
+
+    whole = run(0, nf)
+    for f0, f1 in ((0, 3), (3, 8)):
+        part = run(f0, f1)
+        for a, b in zip(whole, part):
+            np.testing.assert_array_equal(a[f0:f1], b)
+    assert np.isfinite(whole[2]).all()

@@ -36,7 +36,7 @@ def main():
     obs_all = np.cumsum(rng.normal(0, 0.3, (T + W + 2, nf_total)), axis=0)
     obs = np.ascontiguousarray(obs_all[:, rank * nf:(rank + 1) * nf])  # this rank's filters
     model = g.DeviceModel("object_motion")
-    st = g.pf_initialize(model, (1,), obs[0], n, n_filters=nf, seed=9 + rank, noise=noise)
+    st = g.pf_initialize(model, (1,), obs[0], n, n_filters=nf, seed=9, noise=noise, first_filter=rank * nf)
     sp = C.c_void_p()
     g._lib.check(g.load().genpf_filter_stream(st._h, C.byref(sp)))
     stream = torch.cuda.ExternalStream(sp.value)
