@@ -310,7 +310,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     L.check(lib.genpf_set_device(local_rank))
-    if world > 1:
+    # GENPF_BENCH_SHARD1=1 (diagnostic, under torchrun --nproc-per-node 1): the sharded step with a world of one, to
+    # separate what the push kernel itself costs from what the peers cost
+    sharded = world > 1 or os.environ.get("GENPF_BENCH_SHARD1") == "1"
+    if sharded:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -331,7 +334,7 @@ def main():
     def measure(noise, sampler_on):
         """W warm-up + K timed steps (device resident) + K profiled steps + K end-to-end steps for one noise policy."""
         shard_info = None
-        if world == 1:
+        if not sharded:
             state = g.pf_initialize(model, (1,), obs[0], n, seed=1234, noise=noise)
             sp = C.c_void_p()
             L.check(lib.genpf_filter_stream(state._h, C.byref(sp)))
@@ -377,7 +380,7 @@ def main():
         barrier()
         launches = lib.genpf_launch_count() - launches0
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if sharded:
             ranges, frac = sf.exchange_summary()
             shard_info = {"cross_shard_offspring_fraction": frac,
                           "nvlink_bytes_per_step_per_gpu": frac * n * 38.0,  # parents 4 + two slices 18 + lw 8 + e 8
@@ -404,7 +407,7 @@ def main():
         assert np.isfinite(ess).all()
         clocks = sampler.stop() if sampler else None
         times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
+        if sharded:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
             sf.close()
         ms_max, e2e_ms_max = times.tolist()
@@ -500,7 +503,7 @@ def main():
                                 "sample": f"{n_sample} particles x {steps_cpu} steps of the same step "
                                           "(C/OpenMP port of the reference algorithms; Julia absent from the image)"}
     emit(line)
-    if world > 1:
+    if sharded:
         dist.destroy_process_group()
 
 

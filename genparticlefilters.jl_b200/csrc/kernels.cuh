@@ -450,47 +450,50 @@ __device__ __forceinline__ void xchg_stats_combine(const XchgLink &lk, double M_
         xchg_wait(&mine->flag_stats[g], lk.epoch, &mine->error);
     }
     __syncwarp();
-    if (g != 0) return;
+    // Lane r holds shard r; the exps, divisions and closing counts run in parallel lanes (a single thread doing them
+    // one after the other was ~9 us of dependent fp64 latency at 8 ranks), while every SUM is taken in rank order
+    // through shuffles, so all ranks (and the NCCL variant's one-thread combine) get bit-identical totals.
     const volatile double *gathered = &mine->stats[0][0];
-    double M = -INFINITY;
-    bool nan = false;
-    for (int r = 0; r < world; ++r) {
-        double m = gathered[3 * r];
-        if (isnan(m) || isnan(gathered[3 * r + 1])) nan = true;
-        M = fmax(M, m);
-    }
-    double S = 0.0, S2 = 0.0, prefix = 0.0, share_mine = 0.0;
+    const bool have = g < world;
+    const double m_r = have ? gathered[3 * g] : -INFINITY;
+    const double s_r = have ? gathered[3 * g + 1] : 0.0, s2_r = have ? gathered[3 * g + 2] : 0.0;
+    const bool nan = __any_sync(0xffffffffu, have && (isnan(m_r) || isnan(s_r)));
+    const double M = warp_max(m_r);
     const bool finite = M > -INFINITY && M < INFINITY;
+    const double sc = (have && finite && m_r > -INFINITY) ? exp(m_r - M) : 0.0;
+    const double a_r = s_r * sc, b_r = s2_r * (sc * sc);
+    double S = 0.0, S2 = 0.0;
     for (int r = 0; r < world; ++r) {
-        double m = gathered[3 * r];
-        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
-        S += gathered[3 * r + 1] * sc;
-        S2 += gathered[3 * r + 2] * (sc * sc);
+        S += __shfl_sync(0xffffffffu, a_r, r);
+        S2 += __shfl_sync(0xffffffffu, b_r, r);
     }
     int kind = 0;
     if (nan) kind = 1;
     else if (M == -INFINITY) kind = 2;
     else if (M == INFINITY || isnan(S)) kind = 4;
     else if (S == 0.0) kind = 3;
-    double run = 0.0;  // prefix(r): the same left-to-right sum on every rank
+    const bool uniform = kind == 2 || kind == 3;  // uniform fallback (utils.jl:123-133): every shard carries 1/world
+    const double share = uniform ? 1.0 / (double)world : a_r / S;
+    double prefix = 0.0, run = 0.0, run_mine = 0.0;  // prefix(r), run = prefix(r + 1): left-to-right sums
     for (int r = 0; r < world; ++r) {
-        double m = gathered[3 * r];
-        double sc = (finite && m > -INFINITY) ? exp(m - M) : 0.0;
-        double share = gathered[3 * r + 1] * sc / S;
-        if (kind == 2 || kind == 3) share = 1.0 / (double)world;  // uniform fallback (utils.jl:123-133)
-        if (r == rank) {
-            prefix = run;
-            share_mine = share;
-        }
-        run = (kind == 2 || kind == 3) ? (double)(r + 1) / (double)world : run + share;
-        if (oend_out) {
-            long long c;
-            if (r == world - 1 || kind == 1 || kind == 4) c = (n_total / world) * (long long)(r + 1);
-            else if (strat->n < 0x7FFFFFFFll) c = (long long)strat_count_slow<int32_t>(*strat, 0, run, nullptr, -1, 0);
-            else c = strat_count_slow<long long>(*strat, 0, run, nullptr, -1, 0);
-            oend_out[r] = c;
-        }
+        const double sh = __shfl_sync(0xffffffffu, share, r);
+        if (r == g) prefix = run;
+        run = uniform ? (double)(r + 1) / (double)world : run + sh;
+        if (r == g) run_mine = run;
     }
+    if (uniform) prefix = (double)g / (double)world;
+    if (oend_out && have) {
+        long long c;
+        if (g == world - 1 || kind == 1 || kind == 4) c = (n_total / world) * (long long)(g + 1);
+        else if (strat->n < 0x7FFFFFFFll) c = (long long)strat_count_slow<int32_t>(*strat, 0, run_mine, nullptr, -1, 0);
+        else c = strat_count_slow<long long>(*strat, 0, run_mine, nullptr, -1, 0);
+        oend_out[g] = c;
+    }
+    if (g == rank) {
+        shard_info[0] = prefix;
+        shard_info[1] = share;
+    }
+    if (g != 0) return;
     Stats st;
     st.M = M; st.S = S; st.S2 = S2;
     st.lse = (M == -INFINITY) ? -INFINITY : M + log(S);
@@ -498,9 +501,6 @@ __device__ __forceinline__ void xchg_stats_combine(const XchgLink &lk, double M_
     st.invalid_kind = kind;
     st.do_resample = (kind == 1 || kind == 4) ? 0 : 1;
     stats[0] = st;
-    if (kind == 2 || kind == 3) prefix = (double)rank / (double)world;
-    shard_info[0] = prefix;
-    shard_info[1] = share_mine;
     if (lml_accum && st.do_resample) lml_accum[0] += st.lse - log((double)n_total);
 }
 // Large filters (more than kChunkTiles tiles): combine the per-chunk statistics into the filter's, and give every
