@@ -443,12 +443,18 @@ def main():
     step_kernel_ms = prof_total / K
     algo_b = STEP_ALGO_BYTES * n
     achieved = algo_b / (step_kernel_ms * 1e-3) / 1e9
-    tkey = lambda k: k + ("" if args.noise == "lean" else "@" + args.noise)  # noqa: E731
-    tr = lambda k: traffic_of(tkey(k)) if traffic_of(tkey(k)) is not None else traffic_of(k)  # noqa: E731
+    def tr(k):
+        """DRAM bytes per launch of kernel k from the committed ncu capture of THIS build (profiles/traffic.json, written
+        by tools/ncu_traffic.py): the policy-specific entry first; the lean kernels move the same buffers as the
+        philox53 ones (same loads and stores, only the noise arithmetic differs), so they fall back to that capture."""
+        for key in (f"{k}@{args.noise}", k, f"{k}@philox53"):
+            v = traffic_of(key)
+            if v is not None:
+                return v
+        return None
+
     dom_traffic = tr(dom_name)
-    step_traffic = None
-    if all(tr(k) is not None for k in prof if k in ("k_scan", "k_step_fused")) and "k_step_fused" in prof:
-        step_traffic = sum(tr(k) or 0.0 for k in prof)
+    step_traffic = sum(tr(k) for k in prof) if all(tr(k) is not None for k in prof) else None
     dominant = {
         "name": dom_name, "ms_per_launch": per_launch_ms, "share_of_step": dom_ms / prof_total,
         "dram_bytes_per_launch": dom_traffic,

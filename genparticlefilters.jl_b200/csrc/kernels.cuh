@@ -879,13 +879,11 @@ static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
 #pragma unroll
     for (int k = 0; k < I; ++k) {
         const double Wk = base_w + W[k];
-        const double x = fmin(Wk * nd, nd);  // Wk >= 0
-        IdxT j = (IdxT)x;                     // floor(n*W) up to the rounding of the product
-        double lo = (double)j * step;         // exact: j/n
-        // one correction makes j/n <= W < (j+1)/n hold exactly (the product's rounding error is << 1 stratum)
-        const bool dn = Wk < lo, up = !dn && Wk >= lo + step;
-        j += (IdxT)(up ? 1 : 0) - (IdxT)(dn ? 1 : 0);
-        lo = dn ? lo - step : (up ? lo + step : lo);
+        // n is a power of two on this path, so n*W is an exact scaling: j = floor(n*W) and lo = j/n are exact and
+        // j/n <= W < (j+1)/n holds with no correction step (W >= 0; W marginally above 1 lands on j >= n below)
+        const double x = Wk * nd;
+        const IdxT j = (IdxT)x;
+        const double lo = (double)j * step;
         // stratum j+1 (1-based) is the only one that can straddle W: strata <= j lie below, strata >= j+2 above
         const IdxT rel = j - jw;
         uint32_t word;

@@ -37,5 +37,5 @@ for flt in filters:
         tot = sum(v[0] for _, v in items)
         tots = sum(v[1] for _, v in items)
         print(f"===== {fn}: {tot} warp-instructions, {tots} samples")
-        for k, v in sorted(items, key=lambda kv: -kv[1][0])[:30]:
+        for k, v in sorted(items, key=lambda kv: -kv[1][0])[:60]:
             print(f"{100 * v[0] / max(tot, 1):5.1f}% inst {100 * v[1] / max(tots, 1):5.1f}% smp  {k[1]}:{k[2]:4d}  {v[2]}")

@@ -31,6 +31,7 @@ def main():
 
     import genpf_b200 as g
     L, lib = g._lib, g.load()
+    L.check(lib.genpf_set_device(torch.cuda.current_device()))
     peak = 6463.3
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
