@@ -217,6 +217,62 @@ def test_production_noise_distribution(g):
         assert np.mean(s2.field("y", 1) == state.field("y", 1)) < 0.01
 
 
+def test_production_noise_tails_and_lattice(g):
+    """a KS test at 2^20 sees neither a truncated tail nor a coarse lattice.  At 2^26 draws the
+    philox53 normals (53-bit uniforms, fp64 Box-Muller) must populate the tails like N(0,1) -- |Z| > 4, > 5, the
+    maximum -- match the first four moments and take (almost) all-distinct values; the lean policy (24-bit radius
+    uniform, fp32 transcendentals) is checked against its DOCUMENTED limits: |Z| <= sqrt(-2 log(2^-25)) = 5.89 and a
+    2^24-point radius lattice, i.e. it is the throughput policy, not the production one."""
+    n, reps = 1 << 24, 4
+    model = g.DeviceModel("lingauss1d", (0.0, 1.0, 1.0, 0.0, 0.0))  # x_1 = Z exactly
+    for noise in ("philox53", "lean"):
+        z = np.concatenate([g.pf_initialize(model, (1,), 0.0, n, seed=1000 + k, noise=noise).field("x", 1)
+                            for k in range(reps)])
+        N = z.size
+        a = np.abs(z)
+        assert abs(z.mean()) < 5 / math.sqrt(N) and abs(z.var() - 1) < 5 * math.sqrt(2 / N)
+        assert abs(np.mean(z ** 3)) < 5 * math.sqrt(15 / N) and abs(np.mean(z ** 4) - 3) < 5 * math.sqrt(96 / N)
+        for thr, p in ((3.0, 2.6997960632601866e-03), (4.0, 6.334248366623973e-05), (5.0, 5.733031437583869e-07)):
+            cnt, exp = int(np.sum(a > thr)), N * p
+            if noise == "lean" and thr == 5.0:
+                continue  # the 24-bit radius grid is too coarse out there (documented)
+            assert abs(cnt - exp) < 5 * math.sqrt(exp) + 1, (noise, thr, cnt, exp)
+        distinct = np.unique(z).size / N
+        if noise == "philox53":
+            assert 5.2 < a.max() < 6.8            # E[max |Z|] of 2^26 draws = 5.6; 53-bit uniforms reach 8.57
+            assert distinct > 0.999               # 2^26 draws from a 2^53 x 2^53 grid: collisions are birthday-rare
+        else:
+            assert a.max() <= 5.8871 + 1e-3       # sqrt(-2 log((0 + 0.5) 2^-24))
+            assert 0.5 < distinct < 0.9           # fp32 values: 2^26 draws on a 2^23-per-binade lattice (measured 0.67)
+
+
+def test_multinomial_counts_chi_square(g):
+    """The reference draws multinomial ancestors with rand(Categorical(w), n) (resample.jl:59; an alias sampler, not
+    reproducible from uniforms), the library by inverse CDF of its Philox uniforms: the two must agree in
+    DISTRIBUTION.  Chi-square of the ancestor counts of 2^20 draws against n*w over 256 particles, device and
+    host-array paths, + independence of consecutive draws (lag-1 pairs)."""
+    from scipy import stats
+    n_src, n_out = 256, 1 << 20
+    rng = np.random.default_rng(4)
+    lw = rng.normal(0, 1.5, n_src)
+    w = np.exp(lw - lw.max())
+    w /= w.sum()
+    for seed in (1, 2):
+        state = g.ParticleFilterState(list(range(n_src)), lw.copy())
+        g.pf_resize(state, n_out, "multinomial", seed=seed)
+        p = np.asarray(state.parents)
+        counts = np.bincount(p, minlength=n_src)
+        chi2 = np.sum((counts - n_out * w) ** 2 / (n_out * w))
+        assert stats.chi2.sf(chi2, n_src - 1) > 1e-4, chi2
+        # lag-1 independence on a coarse 8 x 8 partition of the CDF
+        edges = np.searchsorted(np.cumsum(w), np.linspace(0, 1, 9)[1:-1])
+        cls = np.searchsorted(edges, p, side="right")
+        pair = np.bincount(cls[:-1] * 8 + cls[1:], minlength=64).reshape(8, 8)
+        pc = np.bincount(cls, minlength=8) / cls.size
+        exp = np.outer(pc, pc) * (cls.size - 1)
+        assert stats.chi2.sf(np.sum((pair - exp) ** 2 / exp), 49) > 1e-4
+
+
 def test_step_equals_separate_calls(g):
     """genpf_step (one C call per README iteration) == ESS / resample / mh / update issued separately."""
     obs = readme_observations()
