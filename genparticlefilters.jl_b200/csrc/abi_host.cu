@@ -1,6 +1,7 @@
 // abi_host.cu -- C ABI, host-array path: the caller (Julia via ccall) keeps its traces and hands over
 // only log_weights / uniforms; ancestors and new weights come back.  See include/genpf.h for the
 // reference function each entry point replaces.  No CPU fallback: every path launches CUDA kernels.
+#include <cstdlib>
 #include <cstring>
 
 #include "coalesce.cuh"
@@ -12,6 +13,7 @@ namespace genpf {
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 bool g_prof_on = false;
+bool g_pdl = []() { const char *e = getenv("GENPF_PDL"); return !(e && e[0] == '0'); }();
 std::vector<ProfRec> g_prof;
 
 // per-host-thread workspace: one stream, staging buffers, scratch

@@ -60,12 +60,12 @@ static int32_t launch_push(genpf_filter_t pf, ShardCtx *sh, const StepArgs &a, N
         if (((t - 1) & 1) == 1) std::swap(d.dst_cur[g], d.dst_new[g]);
     }
     if (a.mh_iters == 1) {
-        GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, 1>), grid, kStateThreads, pf->stream, a,
+        GENPF_LAUNCH_PDL((k_step_push<Model, Noise, int32_t, 1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                      pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise,
                      (const Stats *)pf->sc.st(0, 1));
     } else {
-        GENPF_LAUNCH((k_step_push<Model, Noise, int32_t, -1>), grid, kStateThreads, pf->stream, a,
+        GENPF_LAUNCH_PDL((k_step_push<Model, Noise, int32_t, -1>), grid, kStateThreads, pf->stream, a,
                      (const int32_t *)pf->sc.O.as<int32_t>(), (const int32_t *)pf->sc.tile_last.as<int32_t>(),
                      pf->slice(t - 2), pf->slice(t - 1), d, oend_all, sh->world, pf->n, tpf, sh->rank, noise,
                      (const Stats *)pf->sc.st(0, 1));
@@ -308,7 +308,7 @@ static int32_t shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pr
     GENPF_TRY(launch_finalize(s, sc, sc.partials(0), n, 1, sc.st(0, 1), sc.tile_off.as<double>(), -1.0, nullptr, &lk,
                               sh->n_total, sh->shard_info, &exchanged, pf->lml, &strat, sh->oend_p2p));
     if (!exchanged)  // small shard: one finalize block wrote the local Stats
-        GENPF_LAUNCH(k_xchg_stats_combine, 1, 32, s, (const Stats *)sc.st(0, 1), lk, sh->n_total, sc.st(0, 1), sh->shard_info,
+        GENPF_LAUNCH_PDL(k_xchg_stats_combine, 1, 32, s, (const Stats *)sc.st(0, 1), lk, sh->n_total, sc.st(0, 1), sh->shard_info,
                      pf->lml, strat, sh->oend_p2p);
     // 2. shard-aware scan, counts pinned to the agreed closing counts (no second exchange)
     LwSrc lw_src{pf->lw, 1.0};
@@ -329,7 +329,7 @@ static int32_t shard_step_p2p(genpf_filter_t pf, int64_t t, const double *obs_pr
     std::swap(pf->lw, pf->lw_alt);
     pf->n_resamples += 1;
     LwSrc src{pf->lw, 1.0};
-    GENPF_LAUNCH(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, s, src, (const long long *)sh->oend_p2p,
+    GENPF_LAUNCH_PDL(k_reduce_boundary, (unsigned)sh->world, kReduceThreads, s, src, (const long long *)sh->oend_p2p,
                  sh->world, sh->rank, n, sc.partials(0), pf->ew, lk);
     pf->part_valid = true;
     return GENPF_OK;

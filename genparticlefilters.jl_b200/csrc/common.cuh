@@ -94,6 +94,15 @@ struct XchgLink {
     unsigned long long epoch;  // monotone per shard group (never reset by re-initialisation)
 };
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// First statement of every kernel of the step chain (host.hpp::launch_pdl): let the NEXT kernel's blocks be scheduled
+// as soon as all of ours are running, then wait until the PREVIOUS kernel has completed and its writes are visible.
+// Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {

@@ -64,10 +64,10 @@ inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64
     const int64_t tpf = ceil_div(n, kTile);
     if (exchanged) *exchanged = false;
     if (tpf <= 64) {
-        GENPF_LAUNCH((k_finalize_fast<64, 1>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf,
+        GENPF_LAUNCH_PDL((k_finalize_fast<64, 1>), dim3(1, (unsigned)nf), 64, s, part, n, tpf, st, tile_off, ess_frac, lml_accum, tpf,
                      sc.tile_scale.as<double>());
     } else if (tpf <= Scratch::kChunkTiles) {
-        GENPF_LAUNCH((k_finalize_fast<512, 1>), dim3(1, (unsigned)nf), 512, s, part, n, tpf, st, tile_off, ess_frac,
+        GENPF_LAUNCH_PDL((k_finalize_fast<512, 1>), dim3(1, (unsigned)nf), 512, s, part, n, tpf, st, tile_off, ess_frac,
                      lml_accum, tpf, sc.tile_scale.as<double>());
     } else {
         // large filter: one block per chunk of 512 tiles (one tile per thread: the finalize is latency bound, so all
@@ -75,11 +75,11 @@ inline int32_t launch_finalize(cudaStream_t s, Scratch &sc, Partials part, int64
         const int64_t nchunks = ceil_div(tpf, Scratch::kChunkTiles);
         GENPF_TRY(sc.chunk_stats.ensure(sizeof(Stats) * (size_t)(nchunks * nf)));
         GENPF_TRY(sc.chunk_info.ensure(16 * (size_t)(nchunks * nf)));
-        GENPF_LAUNCH((k_finalize_fast<512, 1>), dim3((unsigned)nchunks, (unsigned)nf), 512, s, part, n, tpf,
+        GENPF_LAUNCH_PDL((k_finalize_fast<512, 1>), dim3((unsigned)nchunks, (unsigned)nf), 512, s, part, n, tpf,
                      sc.chunk_stats.as<Stats>(), tile_off, -1.0, (double *)nullptr, Scratch::kChunkTiles,
                      sc.tile_scale.as<double>());
         const XchgLink lk = link ? *link : XchgLink{{}, 0, 0, 0};
-        GENPF_LAUNCH(k_chunk_combine, (unsigned)nf, 32, s, (const Stats *)sc.chunk_stats.as<Stats>(), (int)nchunks, n,
+        GENPF_LAUNCH_PDL(k_chunk_combine, (unsigned)nf, 32, s, (const Stats *)sc.chunk_stats.as<Stats>(), (int)nchunks, n,
                      Scratch::kChunkTiles * (int64_t)kTile, st, sc.chunk_info.as<double>(), ess_frac,
                      lk.world > 0 ? xchg_lml : lml_accum, lk, n_total, shard_info, strat ? *strat : StratArgs{}, oend_out);
         if (exchanged) *exchanged = lk.world > 0;
@@ -109,15 +109,15 @@ inline int32_t launch_scan_counts(cudaStream_t s, LwSrc sel, int64_t n, int64_t 
     const dim3 grid((unsigned)tpf, (unsigned)nf);
     if (!strat.uni.col && !strat.guide && strat.pow2) {
         if (ew) {
-            GENPF_LAUNCH((k_scan_hot<IdxT, true>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
+            GENPF_LAUNCH_PDL((k_scan_hot<IdxT, true>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
                          shard_info, global_base, chunk_info, ew, tile_scale, oend_pin, shard_rank);
         } else {
-            GENPF_LAUNCH((k_scan_hot<IdxT, false>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
+            GENPF_LAUNCH_PDL((k_scan_hot<IdxT, false>), grid, kHotThreads, s, sel, n, tpf, st, tile_off, O, tile_last, strat, gate,
                          shard_info, global_base, chunk_info, ew, tile_scale, oend_pin, shard_rank);
         }
         return GENPF_OK;
     }
-    GENPF_LAUNCH((k_scan<IdxT>), grid, kScanThreads, s, sel, n, tpf, st, tile_off, WTables{nullptr}, O, tile_last, strat, gate,
+    GENPF_LAUNCH_PDL((k_scan<IdxT>), grid, kScanThreads, s, sel, n, tpf, st, tile_off, WTables{nullptr}, O, tile_last, strat, gate,
                  shard_info, global_base, chunk_info, Scratch::kChunkTiles, ew, tile_scale, oend_pin, shard_rank);
     return GENPF_OK;
 }

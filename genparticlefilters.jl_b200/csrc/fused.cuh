@@ -48,6 +48,7 @@ GENPF_KERNEL void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew,
                  const Stats *stats = nullptr, int gate = 0, const double *lw_src = nullptr) {
+    pdl_enter();
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
@@ -182,6 +183,7 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
     k_step_push(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, PeerDst peer,
                 const long long *oend_all, int world, int64_t n_loc, int64_t tpf_loc, int rank, Noise noise,
                 const Stats *stats = nullptr) {
+    pdl_enter();
     constexpr int T = kStateThreads, I = kTile / T;
     __shared__ ExpandSmem<IdxT> sm;
     __shared__ PartialSmem ps;
@@ -278,6 +280,7 @@ static __global__ void __launch_bounds__(kStateThreads, 4)
 // small shards (one finalize block, no k_chunk_combine to ride on): the statistics exchange as a kernel of its own
 static __global__ void k_xchg_stats_combine(const Stats *local, XchgLink link, int64_t n_total, Stats *stats,
                                             double *shard_info, double *lml_accum, StratArgs strat, long long *oend_out) {
+    pdl_enter();
     const int kind = local->invalid_kind;
     xchg_stats_combine(link, local->M, (kind == 1 || kind == 4) ? NAN : local->S, local->S2, n_total, stats, shard_info,
                        lml_accum, &strat, oend_out);
@@ -287,6 +290,7 @@ static __global__ void k_xchg_stats_combine(const Stats *local, XchgLink link, i
 static __global__ void __launch_bounds__(kReduceThreads)
     k_reduce_boundary(LwSrc src, const long long *oend_all, int world, int rank, int64_t n_loc, Partials out,
                       double *ew, XchgLink link) {
+    pdl_enter();
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
     // The step's closing barrier, taken by the first reader of the pushed population.  Stream order puts the push

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/genpf.h"
@@ -64,6 +65,37 @@ inline cudaEvent_t prof_mark(cudaStream_t s) {
         if (::genpf::g_prof_on) ::genpf::g_prof.push_back({#kernel, _e0, ::genpf::prof_mark(stream)}); \
         ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed);         \
         GENPF_CUDA_TRY(cudaGetLastError());                                  \
+    } while (0)
+
+// Programmatic dependent launch for the kernel chain of a step (finalize -> combine -> scan -> fused / push ->
+// boundary): the next kernel's blocks are scheduled while the previous kernel's last wave drains and park at
+// griddepcontrol.wait (common.cuh::pdl_enter) until it has completed and flushed -- same dependencies, but the
+// launch latency and the ramp of each kernel are hidden (4 boundaries per step).  Only kernels that call pdl_enter()
+// first thing may be launched this way.  GENPF_PDL=0 in the environment falls back to plain launches.
+extern bool g_pdl;
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A &&...a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(std::forward<A>(a))...);
+}
+#define GENPF_LAUNCH_PDL(kernel, grid, block, stream, ...)                                                     \
+    do {                                                                                                       \
+        cudaEvent_t _e0 = nullptr;                                                                             \
+        if (::genpf::g_prof_on) _e0 = ::genpf::prof_mark(stream);                                              \
+        cudaError_t _le = ::genpf::launch_pdl(kernel, dim3(grid), dim3(block), 0, (stream), __VA_ARGS__);      \
+        if (::genpf::g_prof_on) ::genpf::g_prof.push_back({#kernel, _e0, ::genpf::prof_mark(stream)});         \
+        ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
+        GENPF_CUDA_TRY(_le);                                                                                   \
+        GENPF_CUDA_TRY(cudaGetLastError());                                                                    \
     } while (0)
 
 // grow-only device allocation

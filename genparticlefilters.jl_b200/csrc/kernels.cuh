@@ -150,6 +150,7 @@ static __global__ void __launch_bounds__(THREADS)
     // finalises one CHUNK of a large filter as if it were a filter of its own (Stats at [f*chunks + c], tile
     // offsets normalised within the chunk); k_chunk_combine then produces the filter's statistics and each
     // chunk's {prefix, scale}, which k_scan composes -- the same mechanism as a multi-GPU shard.
+    pdl_enter();
     constexpr int NW = THREADS / 32;
     __shared__ double sm[3][NW];
     __shared__ int smi[NW];
@@ -511,6 +512,7 @@ static __global__ void __launch_bounds__(32)
                     double *chunk_info, double ess_frac, double *lml_accum, XchgLink link = XchgLink{{}, 0, 0, 0},
                     int64_t n_total = 0, double *shard_info = nullptr, StratArgs strat = StratArgs{},
                     long long *oend_out = nullptr) {
+    pdl_enter();
     const int64_t f = blockIdx.x;
     const int lane = threadIdx.x;
     const Stats *cs = chunk_stats + f * nchunks;
@@ -608,6 +610,7 @@ static __global__ void __launch_bounds__(kScanThreads, 4)
     // per-tile factor exp(m_tile - M)/S from the finalize: w_i = e_i * factor, no exp in this kernel.
     // shard_info (multi-GPU particle sharding): {prefix, scale}: this shard's cumulative weights are
     // prefix + scale * (locally normalised tile offsets) + in-tile sums of globally normalised weights.
+    pdl_enter();
     constexpr int T = kScanThreads, I = 4, NW = T / 32;
     static_assert(T * I == kTile, "blocked scan layout");
     __shared__ double sm[NW];
@@ -769,6 +772,7 @@ static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
                const long long *oend_pin = nullptr, int shard_rank = 0) {
     // oend_pin (multi-GPU particle sharding): the closing counts of all shards as every rank derived them from the
     // exchanged totals (xchg_stats_combine); this shard's counts are pinned to [oend_pin[rank-1], oend_pin[rank]]
+    pdl_enter();
     constexpr int I = kTile / T, NW = T / 32;
     __shared__ double sm[NW + 1];
     __shared__ alignas(16) uint32_t swin[kHotWindow];

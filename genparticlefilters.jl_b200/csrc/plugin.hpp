@@ -39,12 +39,23 @@ template <> struct NoiseIndex<NoiseCols> { static constexpr int value = kNzCols;
 
 // Launch `fn` (a __global__ function of this library or a cudaKernel_t of a plugin image) with the parameter list
 // of `sig`: every argument is converted to the exact parameter type first, as <<<>>> would.
+// pdl: programmatic dependent launch (host.hpp::launch_pdl) -- only for kernels that start with pdl_enter()
 template <typename... P, typename... A, size_t... I>
-inline cudaError_t launch_typed_impl(void (*)(P...), const void *fn, dim3 grid, dim3 block, cudaStream_t s,
+inline cudaError_t launch_typed_impl(void (*)(P...), const void *fn, dim3 grid, dim3 block, cudaStream_t s, bool pdl,
                                      std::index_sequence<I...>, A &&...a) {
     std::tuple<P...> args{static_cast<P>(std::forward<A>(a))...};
     void *argv[] = {(void *)&std::get<I>(args)...};
-    return cudaLaunchKernel(fn, grid, block, argv, 0, s);
+    if (!(pdl && g_pdl)) return cudaLaunchKernel(fn, grid, block, argv, 0, s);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, fn, argv);
 }
 template <typename... P, typename... A>
 inline int32_t launch_typed(const char *name, void (*sig)(P...), const void *fn, dim3 grid, dim3 block, cudaStream_t s,
@@ -52,7 +63,8 @@ inline int32_t launch_typed(const char *name, void (*sig)(P...), const void *fn,
     static_assert(sizeof...(P) == sizeof...(A), "argument count differs from the kernel's parameter list");
     cudaEvent_t e0 = nullptr;
     if (g_prof_on) e0 = prof_mark(s);
-    cudaError_t e = launch_typed_impl(sig, fn, grid, block, s, std::index_sequence_for<P...>{}, std::forward<A>(a)...);
+    const bool pdl = name[0] == 'k' && name[2] == 's' && name[3] == 't';  // "k_step_fused": the one chain kernel launched here
+    cudaError_t e = launch_typed_impl(sig, fn, grid, block, s, pdl, std::index_sequence_for<P...>{}, std::forward<A>(a)...);
     if (g_prof_on) g_prof.push_back({name, e0, prof_mark(s)});
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) {
