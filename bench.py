@@ -350,7 +350,8 @@ def main():
                                  return_ess=True)
         else:
             # ONE filter of world * n particles, slots sharded contiguously over the ranks:
-            # shard totals exchanged through peer memory inside 1-warp kernels + NVLink P2P push of offspring
+            # shard totals + closing barrier exchanged through peer memory by the step's own kernels (two
+            # synchronisation points, no NCCL) + NVLink P2P push of offspring
             from genpf_b200.sharded import ShardedFilter
             sf = ShardedFilter(model, n, seed=1234, noise=noise)
             sf.initialize(obs[0])
@@ -384,8 +385,9 @@ def main():
             ranges, frac = sf.exchange_summary()
             shard_info = {"cross_shard_offspring_fraction": frac,
                           "nvlink_bytes_per_step_per_gpu": frac * n * 38.0,  # parents 4 + two slices 18 + lw 8 + e 8
-                          "exchange_per_step": "24 B + 8 B + barrier per rank as NVLink P2P stores + epoch flags "
-                                               "polled in-kernel (no NCCL inside the step)"}
+                          "exchange_per_step": "24 B of shard totals + one closing barrier per rank as NVLink P2P stores "
+                                               "+ epoch flags polled by the step's own kernels (no NCCL inside the "
+                                               "step; closing counts derived on every rank)"}
         # ---- timed region 2: per-kernel CUDA events (same K steps again) for the roofline of the dominant kernel
         L.check(lib.genpf_profile_begin())
         for _ in range(K):

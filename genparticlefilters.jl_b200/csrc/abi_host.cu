@@ -13,6 +13,7 @@ namespace genpf {
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 bool g_prof_on = false;
+std::mutex g_prof_mu;
 bool g_pdl = []() { const char *e = getenv("GENPF_PDL"); return !(e && e[0] == '0'); }();
 std::vector<ProfRec> g_prof;
 

@@ -1,13 +1,18 @@
 // abi_shard.cu -- C ABI, multi-GPU particle sharding.  One process per GPU; rank r owns global
-// particle slots [r*n_loc, (r+1)*n_loc) of ONE filter of world*n_loc particles.  The library launches kernels
-// on the filter's stream; the three tiny collectives of a step (all-gather of 3 doubles, all-gather of one
-// int64, one barrier) are issued by the host language (torch.distributed/NCCL, or NCCL.jl) ON THE SAME STREAM
-// on device buffers it owns, so a step needs no host synchronisation:
+// particle slots [r*n_loc, (r+1)*n_loc) of ONE filter of world*n_loc particles.  Two ways to run a step, both
+// without host synchronisation:
+//
+//   genpf_shard_step_p2p     the whole step in one call: the statistics exchange and the closing barrier are done by
+//                            the step's own kernels over peer-mapped memory (NVLink stores + epoch flags), the closing
+//                            counts are derived identically on every rank, offspring are pushed to their owners with
+//                            P2P stores
 //
 //   genpf_shard_begin_step   K1 partials -> local (max, sum e, sum e^2)        -> stats_local   [allgather]
 //   genpf_shard_scan         global (M,S,ESS,lml), shard prefix, scan -> O_k    -> oend_local    [allgather]
 //   genpf_shard_push         offspring of local parents -> owner's buffers over NVLink P2P       [barrier]
 //   genpf_shard_finish       swap buffers, K1 partials of the received population
+//                            (the three tiny collectives issued by the host language -- torch.distributed / NCCL.jl --
+//                            on the filter's stream, on device buffers it owns)
 #include "filter_state.hpp"
 #include "plugin.hpp"
 

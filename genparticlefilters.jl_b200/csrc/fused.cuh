@@ -8,7 +8,7 @@
 // pins it.
 //
 // Traffic per particle: R O ~4, R window 18 (gathered, monotone), W parents 4, W slice t-1 9, W slice t 9,
-// W lw 8, W e 8 = 60 B (ncu: 64 B incl. evictions) against the 109 B the unfused kernels would move (slice t-2 is
+// W lw 8, W e 8 = 60 B (ncu, final build: 57 B) against the 109 B the unfused kernels would move (slice t-2 is
 // never copied: it leaves the window at this step).  The kernel is instruction-issue bound, not DRAM bound (ncu,
 // profiles/), hence 256 threads x 8 particles at 64 registers (4 blocks/SM, no spills; per-thread overheads amortised): small
 // per-thread footprint for occupancy, Philox + Box-Muller shared between the mh move and the update.

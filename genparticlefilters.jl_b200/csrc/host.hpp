@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -48,11 +49,16 @@ struct ProfRec {
 };
 extern bool g_prof_on;
 extern std::vector<ProfRec> g_prof;
+extern std::mutex g_prof_mu;  // launches may come from several host threads (one workspace / filter each)
 inline cudaEvent_t prof_mark(cudaStream_t s) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
     return e;
+}
+inline void prof_push(const char *name, cudaEvent_t e0, cudaEvent_t e1) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back({name, e0, e1});
 }
 
 // kernel launch + count (bench.py's gpu_launches) + launch-error check
@@ -62,7 +68,7 @@ inline cudaEvent_t prof_mark(cudaStream_t s) {
         cudaEvent_t _e0 = nullptr;                                           \
         if (::genpf::g_prof_on) _e0 = ::genpf::prof_mark(stream);            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
-        if (::genpf::g_prof_on) ::genpf::g_prof.push_back({#kernel, _e0, ::genpf::prof_mark(stream)}); \
+        if (::genpf::g_prof_on) ::genpf::prof_push(#kernel, _e0, ::genpf::prof_mark(stream)); \
         ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed);         \
         GENPF_CUDA_TRY(cudaGetLastError());                                  \
     } while (0)
@@ -92,7 +98,7 @@ inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_
         cudaEvent_t _e0 = nullptr;                                                                             \
         if (::genpf::g_prof_on) _e0 = ::genpf::prof_mark(stream);                                              \
         cudaError_t _le = ::genpf::launch_pdl(kernel, dim3(grid), dim3(block), 0, (stream), __VA_ARGS__);      \
-        if (::genpf::g_prof_on) ::genpf::g_prof.push_back({#kernel, _e0, ::genpf::prof_mark(stream)});         \
+        if (::genpf::g_prof_on) ::genpf::prof_push(#kernel, _e0, ::genpf::prof_mark(stream));                  \
         ::genpf::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
         GENPF_CUDA_TRY(_le);                                                                                   \
         GENPF_CUDA_TRY(cudaGetLastError());                                                                    \

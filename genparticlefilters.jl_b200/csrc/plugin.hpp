@@ -65,7 +65,7 @@ inline int32_t launch_typed(const char *name, void (*sig)(P...), const void *fn,
     if (g_prof_on) e0 = prof_mark(s);
     const bool pdl = name[0] == 'k' && name[2] == 's' && name[3] == 't';  // "k_step_fused": the one chain kernel launched here
     cudaError_t e = launch_typed_impl(sig, fn, grid, block, s, pdl, std::index_sequence_for<P...>{}, std::forward<A>(a)...);
-    if (g_prof_on) g_prof.push_back({name, e0, prof_mark(s)});
+    if (g_prof_on) prof_push(name, e0, prof_mark(s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) {
         cudaGetLastError();

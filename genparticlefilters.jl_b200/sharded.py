@@ -1,10 +1,12 @@
 """Multi-GPU particle sharding: one process per GPU, torch.distributed for the plumbing.
 
 ``ShardedFilter`` is ONE particle filter of ``world * n_local`` particles whose slots are split contiguously
-across ranks.  Per step the library launches its kernels on the filter's CUDA stream and this class issues
-the three tiny collectives (all-gather of 3 doubles, all-gather of one int64, a barrier) with NCCL *on that
-same stream*, so there is no host synchronisation inside a step; offspring travel to their owner as NVLink
-P2P stores from inside the fused step kernel.
+across ranks.  exchange="p2p" (default): one library call per step (genpf_shard_step_p2p) -- the per-shard totals and
+the closing barrier are exchanged by the step's own kernels over peer-mapped memory (NVLink stores + epoch flags, two
+synchronisation points, no NCCL inside the step).  exchange="nccl": the library launches its kernels on the filter's
+CUDA stream and this class issues three tiny collectives (all-gather of 3 doubles, all-gather of one int64, a barrier)
+with NCCL *on that same stream*.  Either way there is no host synchronisation inside a step, and offspring travel to
+their owner as NVLink P2P stores from inside the fused step kernel.
 
 The exchange logic is backend agnostic: tests/test_shard_host.py drives ``exchange_plan`` / ``ShardExchange``
 with the gloo backend at world_size 2 on CPU.
