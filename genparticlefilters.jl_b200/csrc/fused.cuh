@@ -42,8 +42,11 @@ __device__ __forceinline__ void store_pair(X *p, int e, int valid, bool fast, X 
 #ifndef GENPF_FUSED_MINB
 #define GENPF_FUSED_MINB 4
 #endif
+#ifndef GENPF_FUSED_MINB256
+#define GENPF_FUSED_MINB256 4  // 64 registers, no spills (3 -> 85 registers and 5 -> 51 were measured)
+#endif
 template <class Model, class Noise, typename IdxT, int MH>
-GENPF_KERNEL void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_FUSED_MINB : 4)
+GENPF_KERNEL void __launch_bounds__(kStateThreads, kStateThreads == 512 ? GENPF_FUSED_MINB : GENPF_FUSED_MINB256)
     k_step_fused(StepArgs a, const IdxT *O, const IdxT *tile_last_O, Cols src_pp, Cols src_cur, Cols dst_cur,
                  Cols dst_new, int32_t *parents, double *lw_dst, int64_t n, int64_t tpf, Noise noise,
                  uint8_t *accepts, unsigned long long *n_accept, Partials partials, double *ew,

@@ -122,7 +122,10 @@ __device__ __forceinline__ void emit_partials(const double (&v)[kTile / T], cons
 // (utils.jl:119-137), effective_sample_size (utils.jl:163-164).  Same block size and epilogue as the
 // state-producing kernels, so the partials are bit-identical to theirs.
 constexpr int kReduceThreads = 256;  // 8 particles per thread: four 16-byte loads in flight each, reductions amortised
-static __global__ void __launch_bounds__(kReduceThreads)
+#ifndef GENPF_REDUCE_MINB
+#define GENPF_REDUCE_MINB 8  // 32 registers (a few spilled words), 8 blocks/SM: 0.164 ms at 2^26 against 0.175 at 40 registers
+#endif                       // and 0.273 at 66 (the kernel lives on latency hiding: fp64 pipe + HBM both near half used)
+static __global__ void __launch_bounds__(kReduceThreads, GENPF_REDUCE_MINB)
     k_reduce(LwSrc src, int64_t n, int64_t tpf, Partials out, double *ew = nullptr) {
     constexpr int T = kReduceThreads;
     __shared__ PartialSmem ps;
@@ -763,9 +766,12 @@ constexpr int kHotWindow = 2560;  // stratum words staged per tile (2048 + 25 % 
 #ifndef GENPF_HOT_THREADS
 #define GENPF_HOT_THREADS 256
 #endif
+#ifndef GENPF_HOT_MINB
+#define GENPF_HOT_MINB 6  // 40 registers, no spills: 68 -> 62 us at 2^24 (4 -> 60 registers, 7 / 8 -> 32 registers + spills: 63.5 us)
+#endif
 constexpr int kHotThreads = GENPF_HOT_THREADS;  // 256 threads x 8 particles: per-thread overheads amortised over 8
 template <typename IdxT, bool USE_E, int T = kHotThreads>
-static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? 4 : 2048 / T)
+static __global__ void __launch_bounds__(T, 2048 / T >= 8 ? GENPF_HOT_MINB : 2048 / T)
     k_scan_hot(LwSrc src, int64_t n, int64_t tpf, const Stats *stats, const double *tile_off, IdxT *O_out,
                IdxT *tile_last_O, StratArgs strat, int gate, const double *shard_info, int64_t global_base,
                const double *chunk_info, const double *ew, const double *tile_scale,
@@ -1094,6 +1100,7 @@ struct LwFill {
     }
 };
 
+// (register budget left to the compiler: 44 registers; capping at 40 / 32 or letting it take 54 are all slower)
 template <typename IdxT, typename OutT>
 static __global__ void __launch_bounds__(kThreads)
     k_expand(const IdxT *O, const IdxT *tile_last_O, int64_t n_src, int64_t n_out, int64_t tpf_out,
@@ -1285,8 +1292,11 @@ static __global__ void __launch_bounds__(kThreads)
     }
 }
 
+#ifndef GENPF_LOOKUP_MINB
+#define GENPF_LOOKUP_MINB 5  // 48 registers: more gathers in flight (2.27 -> 2.11 ms at 2^26; 6 and 8 blocks spill too much)
+#endif
 template <typename OutT>
-static __global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads, GENPF_LOOKUP_MINB)
     k_lookup_rec(const double *W, const GuideRec *R, int64_t B, int64_t n_src, int64_t n_out, UniSrc uni,
                  const int32_t *first_slot_O, OutT *parents, int64_t out_base, const Stats *stats, int gate,
                  LwFill fill = LwFill{nullptr, nullptr, 0}) {
