@@ -247,4 +247,23 @@ function pf_run!(s::DevicePFState, t_first::Int, y_rows::Matrix{Float64}; ess_th
     return s
 end
 
+# ---- drop-in switch for ordinary (host-trace) states: after `GenPFCuda.enable!()` the reference's OWN entry points
+# run their array arithmetic on the GPU -- the same call sites, the same keyword arguments (`check` is spelled
+# `check_` inside this module only because `check` is the status helper above).  It re-defines the reference's
+# methods for `ParticleFilterView` in place (Julia prints "method overwritten"); `GenPFCuda.disable!()` needs a fresh
+# session, as for any method overwrite.  Untested here (no Julia in the build image), mechanically derived from
+# src/resample.jl:19-30, src/utils.jl:163-171, src/resize.jl:149-196.
+function enable!()
+    @eval GenParticleFilters begin
+        function pf_resample!(state::ParticleFilterView, method::Symbol=:multinomial;
+                              priority_fn=nothing, check=:warn, sort_particles::Bool=true)
+            return $(gpu_resample!)(state, method; priority_fn=priority_fn, check_=check, sort_particles=sort_particles)
+        end
+        pf_optimal_resize!(state::ParticleFilterState, n_particles::Int; check=:warn) =
+            $(gpu_optimal_resize!)(state, n_particles; check_=check)
+        Gen.effective_sample_size(state::ParticleFilterView) = $(gpu_effective_sample_size)(state)
+    end
+    return nothing
+end
+
 end # module
