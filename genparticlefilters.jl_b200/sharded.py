@@ -33,6 +33,28 @@ def exchange_plan(oend_all, n_total):
     return ranges
 
 
+def closing_counts_from_totals(totals, n_total, r):
+    """Host mirror of the device's exchange-free closing counts (csrc/kernels.cuh::xchg_stats_combine, DESIGN.md 5).
+    totals: per shard (max, sum e^{v-max}) of its log-weights -- what the ranks exchange; r: the n_total stratum
+    uniforms.  Every rank derives the same cumulative mass W_end(g) = prefix(g+1) (left-to-right sum of the shares) and
+    the same count O_end(g) = #{i : u_i <= W_end(g)} with u_i = r_i/n + (i-1)/n (resample.jl:162); the last shard closes
+    at n_total.  The scan pins each shard's counts to [O_end(g-1), O_end(g)], so exchange_plan(...) of the result is an
+    exact cover that agrees with the unsharded ancestors except at cumulative-sum ties on a shard boundary."""
+    totals = np.asarray(totals, dtype=np.float64).reshape(-1, 2)
+    world = totals.shape[0]
+    M = totals[:, 0].max()
+    a = totals[:, 1] * np.exp(totals[:, 0] - M)
+    S = 0.0
+    for g in range(world):  # rank order, like the device
+        S += a[g]
+    u = np.asarray(r, dtype=np.float64) * (1.0 / n_total) + np.arange(n_total) / n_total
+    oend, run = [], 0.0
+    for g in range(world):
+        run = run + a[g] / S
+        oend.append(int(n_total) if g == world - 1 else int(np.searchsorted(u, run, side="right")))
+    return oend
+
+
 def cross_shard_fraction(ranges, n_local):
     """Fraction of offspring whose owner differs from their parent's rank (NVLink traffic share)."""
     total = cross = 0

@@ -33,6 +33,38 @@ def test_exchange_plan_properties():
     assert cross_shard_fraction(exchange_plan([8192, 8192], 8192), 4096) == 0.5
 
 
+def test_closing_counts_from_totals_match_the_unsharded_ancestors():
+    """The two-synchronisation-point protocol exchanges only per-shard totals; every rank derives all closing counts
+    from them (sharded.closing_counts_from_totals mirrors the device code).  Against the CPU oracle's stratified
+    ancestors of the WHOLE population: the derived ranges are an exact cover, and the outputs of range g are parented
+    by shard g (a boundary output may differ only at a cumulative-sum tie)."""
+    from genpf_b200.sharded import closing_counts_from_totals, exchange_plan
+    from oracle import oracle as orc
+    rng = np.random.default_rng(5)
+    for world, n_local, tilt in ((2, 4096, 0.0), (4, 2048, 0.7), (8, 2048, 0.35), (8, 2048, 0.0)):
+        n = world * n_local
+        lw = rng.normal(0, 1.5, n) + tilt * np.repeat(np.arange(world), n_local)  # imbalanced shards when tilt > 0
+        r = rng.random(n)
+        totals = []
+        for g in range(world):
+            v = lw[g * n_local:(g + 1) * n_local]
+            totals.append((v.max(), np.exp(v - v.max()).sum()))
+        oend = closing_counts_from_totals(totals, n, r)
+        assert all(oend[i] <= oend[i + 1] for i in range(world - 1)) and oend[-1] == n
+        ranges = exchange_plan(oend, n)
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        p_ref = orc.resample("stratified", lw, r)[0]
+        owner_of_parent = p_ref // n_local
+        bad = 0
+        for g, (b, e) in enumerate(ranges):
+            bad += int(np.sum(owner_of_parent[b:e] != g))
+        assert bad <= world - 1, bad  # at most one tie per shard boundary (observed: 0)
+        if tilt > 0:
+            sizes = [e - b for b, e in ranges]
+            assert sizes[-1] > sizes[0]  # mass, and with it offspring, moved towards the tilted shards
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
