@@ -271,8 +271,9 @@ GENPF_KERNEL void __launch_bounds__(256)
     k_introduce(ModelParams P, int64_t t, Cols dst_prev, Cols dst_cur, double *lw, const double *obs_hist,
                 const double *aux_hist, int naux, int64_t n_old, int64_t m, Noise noise, int use_proposal) {
     const int64_t f = blockIdx.y, nf = gridDim.y, n_new = n_old + m;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+    const ModelParams P0 = P;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {  // grid-stride: the launch caps its blocks
+    P = P0;
     const int64_t slot = f * n_new + n_old + i;  // where the particle lives (and its Philox counter)
     typename Model::Slice prev, cur;
     Model::initial(P, cur);
@@ -306,6 +307,7 @@ GENPF_KERNEL void __launch_bounds__(256)
         dst_cur.b[c][slot] = cur.b[c];
     }
     lw[slot] = w;
+    }
 }
 
 #ifndef GENPF_PLUGIN_BUILD

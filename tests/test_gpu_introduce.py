@@ -90,6 +90,25 @@ def test_introduce_library_noise_is_a_prior_chain(g, orc, noise):
     assert abs(pf.field("moving", T)[n:].mean() - pf.field("moving", T)[:n].mean()) < 0.01
 
 
+def test_introduce_more_particles_than_one_launch_wave(g, orc):
+    """The kernel's grid is capped (grid-stride loop): 1.5 M new chains against the oracle at both ends of the range."""
+    L, lib = g._lib, g.load()
+    n, m, T = 4096, 1_500_000, 2
+    rng = np.random.default_rng(3)
+    obs = rng.normal(0, 0.5, (T, 1))
+    model = g.DeviceModel("object_motion")
+    pf = g.pf_initialize(model, (1,), obs[0], n, seed=4)
+    g.pf_update(pf, (2,), None, obs[1])
+    U, Z = rng.random((T, 1, m)), rng.normal(size=(T, 1, m))
+    aux = np.concatenate([model.aux(tau) for tau in range(1, T + 1)])
+    L.check(lib.genpf_introduce(pf._h, m, L.ptr(np.ascontiguousarray(obs)), L.ptr(aux), 0, L.ptr(np.ascontiguousarray(U)),
+                                L.ptr(np.ascontiguousarray(Z))))
+    y, yp, mv, mp, w = _oracle_chains(orc, obs[:, 0], U[:, 0], Z[:, 0])
+    np.testing.assert_array_equal(pf.field("y", T)[n:], y)
+    np.testing.assert_array_equal(pf.field("moving", T)[n:], mv)
+    np.testing.assert_allclose(pf.log_weights[n:], w, rtol=1e-10, atol=1e-12)
+
+
 def test_introduce_with_proposal_and_errors(g, orc):
     A, Q, R, M0, S0 = 0.9, 1.0, 0.8, 0.1, 1.3
     model = g.DeviceModel("lingauss1d", (A, Q, R, M0, S0))
